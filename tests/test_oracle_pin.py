@@ -1,0 +1,101 @@
+"""CPU: pin oracle/*.c against the reference itself (oracle/_ref, live) on fresh seeded inputs and edge cases.
+
+Skipped when oracle/_ref has not been built (it is built by `make -C oracle ref` / __graft_entry__.build() where
+/root/reference exists, and travels prebuilt to the GPU box).
+"""
+import numpy as np
+import pytest
+
+import oracle_c as O
+
+
+def _canon_q8K(b):
+    """quantize_row_q8_K_ref leaves bsums of an all-zero block unwritten (ggml-quants.c:2569-2574): ignore them."""
+    b = np.array(b, dtype=np.uint8).reshape(-1, 292).copy()
+    zero = (b[:, :4].view(np.float32)[:, 0] == 0)
+    b[zero, 260:] = 0
+    return b
+import refggml as R
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+QT = [O.Q4_0, O.Q8_0, O.Q4_K, O.Q5_K, O.Q6_K]
+
+
+@pytest.mark.parametrize("t", QT)
+@pytest.mark.parametrize("seed", [1, 2])
+def test_block_decode_matches_reference(t, seed):
+    rng = np.random.default_rng(seed)
+    k = 2048
+    x = (rng.standard_normal((6, k)) * rng.choice([1e-3, 1.0, 30.0], (6, 1))).astype(np.float32)
+    x[0, :256] = 0.0
+    q = R.quantize(t, x)
+    assert np.array_equal(O.dequant(t, q, k), R.dequantize(t, q, k))
+
+
+def test_random_bytes_decode():
+    """decoders must agree on arbitrary bit patterns, not only on quantiser output (all 6-bit scale/min codes, all nibbles)."""
+    rng = np.random.default_rng(3)
+    for t in QT:
+        bs = O.BLOCK[t]
+        raw = rng.integers(0, 256, (4, 8 * bs[1]), dtype=np.uint8)
+        k = 8 * bs[0]
+        blk = raw.reshape(4, 8, bs[1])
+        # keep the f16 scale fields finite
+        for off in {O.Q4_0: [0], O.Q8_0: [0], O.Q4_K: [0, 2], O.Q5_K: [0, 2], O.Q6_K: [208]}[t]:
+            blk[:, :, off + 1] &= 0x3B
+        assert np.array_equal(O.dequant(t, raw, k), R.dequantize(t, raw, k))
+
+
+@pytest.mark.parametrize("seed", [0, 7])
+def test_activation_quantisers(seed):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(4096) * 2.5).astype(np.float32)
+    x[256:512] = 0.0
+    x[700] = -40.0            # negative max: q8_K keeps the sign in iscale
+    assert np.array_equal(_canon_q8K(O.quantize_q8_K(x)), _canon_q8K(R.quantize_act(R.Q8_K, x)))
+    assert np.array_equal(_canon_q8K(O.quantize_q8_K(x)), _canon_q8K(R.quantize_act(R.Q8_K, x, simd=True)))
+    assert np.array_equal(O.quantize_q8_0(x, 0), R.quantize_act(R.Q8_0, x))
+    assert np.array_equal(O.quantize_q8_0(x, 1), R.quantize_act(R.Q8_0, x, simd=True))
+
+
+@pytest.mark.parametrize("t", QT)
+def test_vec_dot_and_mul_mat(t):
+    rng = np.random.default_rng(11 + t)
+    m, k, n = 32, 4096, 2
+    w = (rng.standard_normal((m, k)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    wq = R.quantize(t, w)
+    ref = R.mul_mat(t, wq, x, m, k)
+    got = O.mul_mat(t, wq, x, m, k)
+    mag = np.abs(x) @ np.abs(O.dequant(t, wq, k)).T
+    assert np.all(np.abs(got - ref) <= 2e-6 * mag)
+    # the generic C vec_dot and the SIMD one of the reference agree with the port to the same bar
+    act = R.quantize_act(R.Q8_0 if t in (O.Q4_0, O.Q8_0) else R.Q8_K, x[0], simd=True)
+    for r in range(4):
+        a = R.vec_dot(t, wq[r], act, k, generic=True)
+        b = R.vec_dot(t, wq[r], act, k, generic=False)
+        assert abs(a - got[0, r]) <= 2e-6 * mag[0, r] and abs(b - got[0, r]) <= 2e-6 * mag[0, r]
+
+
+def test_ops_match_reference():
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((5, 4096)) * 2).astype(np.float32)
+    assert np.allclose(O.rms_norm(x, 1e-6), R.rms_norm(x, 1e-6), rtol=2e-7, atol=0)
+    qk = rng.standard_normal((3, 8, 128)).astype(np.float32)
+    pos = np.array([3, 2047, 40000], np.int32)
+    assert np.abs(O.rope(qk, pos, 128, 2) - R.rope(qk, pos, 128, 2, 40960, 1e6)).max() <= 2e-6
+    g, u = (rng.standard_normal(4096) * 5).astype(np.float32), rng.standard_normal(4096).astype(np.float32)
+    assert np.allclose(O.swiglu(g, u), R.swiglu(g, u), rtol=1e-6, atol=1e-7)
+
+
+def test_flash_attn_matches_reference():
+    rng = np.random.default_rng(9)
+    D, n_head, n_head_kv, n_kv = 128, 8, 2, 512
+    q = rng.standard_normal((1, n_head, D)).astype(np.float32)
+    k = (rng.standard_normal((n_head_kv, n_kv, D)) * 0.3).astype(np.float16)
+    v = rng.standard_normal((n_head_kv, n_kv, D)).astype(np.float16)
+    mask = np.zeros((64, n_kv), np.float16)
+    mask[:, 400:] = -np.inf
+    ref = R.flash_attn(q, k, v, mask, 1 / np.sqrt(D))
+    got = O.flash_attn(q, k, v, mask, 1 / np.sqrt(D), f16_acc=True)
+    assert np.abs(got - ref).max() <= 3e-3 * np.abs(ref).max()
