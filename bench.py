@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: Qwen3-8B (MiniCPM-o-4.5 LLM) Q4_K_M batch-1 decode tok/s on B200, with the HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--depth D] [--impl b200|reference]
+
+A "step" = one decoded token = one pass of the hot path (36 layers + lm_head) over synthetic weights of the named shape
+(BASELINE.json configs[1]; ctx = 4096, KV depth D, default 2048 = the mean depth of a 4096-token generation).
+  value : tok/s, inputs resident in HBM, the step replayed as ONE CUDA graph, CUDA-event timed on the launching stream.
+  e2e   : tok/s through the C-ABI with HOST buffers: per step the token's embedding row, pos, KV index and the F32 KQ mask are
+          copied from pinned host memory (what the ggml scheduler copies per split, ggml-backend.cpp:1435-1442), the graph is
+          replayed, and the logits are read back (llama-context.cpp:1144) — all inside the timed region.
+  roofline : algorithmic bytes/token (weights + KV read/write) / measured time vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference : the reference's own ggml CPU backend (oracle/_ref, built from /root/reference by oracle/Makefile)
+          on a bounded sample of the same workload (whole layers of the same shapes/types), all host threads.
+N > 1: layer-split pipeline (LLAMA_SPLIT_MODE_LAYER, src/llama-model.cpp:2130-2185): rank r owns a contiguous layer range and its KV
+cache; the only exchange is one NCCL send/recv of the 16 KiB hidden state per boundary.  N independent decode streams are kept in
+flight (one per stage) so every GPU works every step; value = tokens of all streams / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int = 0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                                          str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------ reference arm
+def reference_layer_sample(cfg, n_layers: int, threads: int, steps: int, warmup: int) -> dict:
+    """The reference CPU backend (oracle/_ref libggml-cpu.so, unmodified) on `n_layers` whole layers' worth of decode matvecs +
+    swiglu/norms at the Qwen3-8B shapes; tok/s is extrapolated to the 36-layer + lm_head token by BYTES (the CPU path is as
+    bandwidth-bound as ours)."""
+    import numpy as np
+    import refggml as R
+    from __graft_entry__ import load_package
+    dec = load_package().decode
+    assert R.available(), "oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists"
+    rng = np.random.default_rng(0)
+    E, F, q, kv = cfg.n_embd, cfg.n_ff, cfg.n_head * cfg.head_dim, cfg.n_head_kv * cfg.head_dim
+    shapes = [("wq", q, E), ("wk", kv, E), ("wv", kv, E), ("wo", E, q), ("gate", F, E), ("up", F, E), ("down", E, F)]
+    tmap = {12: R.Q4_K, 14: R.Q6_K}
+    sample_bytes = 0
+    with R.Graph(mem_mb=2048) as g:
+        x = g.tensor(R.F32, [E, 1], rng.standard_normal((1, E)).astype(np.float32))
+        outs = []
+        for il in range(n_layers):
+            ty = dec.layer_types(cfg, il)
+            for name, m, k in shapes:
+                t = tmap[ty[name]]
+                nbytes = m * R.row_size(t, k)
+                raw = rng.integers(0, 256, nbytes, dtype=np.uint8)
+                blk = raw.reshape(-1, R.BLOCK[t][1])
+                sc = np.float16(rng.uniform(2e-5, 2e-4, blk.shape[0])).view(np.uint8).reshape(-1, 2)
+                if t == R.Q4_K:
+                    blk[:, 0:2], blk[:, 2:4] = sc, sc
+                else:
+                    blk[:, 208:210] = sc
+                w = g.tensor(t, [k, m], raw)
+                xin = x if k == E else g.tensor(R.F32, [k, 1], rng.standard_normal((1, k)).astype(np.float32))
+                outs.append(g.op("ggml_mul_mat", w, xin))
+                sample_bytes += nbytes
+        gr = g.base.ggml_new_graph(g.ctx)
+        for o in outs:
+            g.base.ggml_build_forward_expand(gr, o)
+        for _ in range(warmup):
+            assert g.cpu.ggml_graph_compute_with_ctx(g.ctx, gr, threads) == 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            assert g.cpu.ggml_graph_compute_with_ctx(g.ctx, gr, threads) == 0
+        dt = (time.perf_counter() - t0) / steps
+    full = dec.weight_bytes_per_token(cfg)
+    ms_token = dt * 1e3 * full / sample_bytes
+    return {"ms_per_step": ms_token, "value": 1e3 / ms_token, "sample_ms": dt * 1e3, "sample_bytes": sample_bytes,
+            "sample": f"{n_layers} of {cfg.n_layer} layers (7 weight matvecs each, {sample_bytes / 1e6:.0f} MB of Q4_K/Q6_K rows) per step on the "
+                      f"reference ggml CPU backend, {threads} threads; extrapolated to one token by weight bytes ({full / 1e9:.3f} GB)"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from __graft_entry__ import load_package
+    cfg = load_package().decode.LLMConfig()
+    threads = os.cpu_count() or 1
+    r = reference_layer_sample(cfg, 2, threads, max(1, args.steps), max(1, args.warmup))
+    line = {"impl": "reference", "metric": "decode_tok_per_s", "value": round(r["value"], 3), "unit": "tok/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations)", "data": "synthetic",
+            "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}", "timing": "weights (>1 GB sample) exceed the CPU caches"},
+            "cpu_baseline": {"value": round(r["value"], 3), "unit": "tok/s", "cores": threads, "kind": "reference", "sample": r["sample"]},
+            "e2e": {"value": round(r["value"], 3), "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    ops, dec = pkg.ops, pkg.decode
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.lib()
+    cfg = dec.LLMConfig.tiny() if args.tiny else dec.LLMConfig()
+    per = (cfg.n_layer + world - 1) // world
+    layers = range(rank * per, min(cfg.n_layer, (rank + 1) * per))
+    last = rank == world - 1
+    D = dec.Qwen3Decoder(cfg, dev, layers=layers, has_head=last, seed=rank)
+    depth = min(args.depth, cfg.n_ctx - args.steps - args.warmup - 2)
+    n_kv = min(cfg.n_ctx, (depth + args.steps + args.warmup + 1 + 255) // 256 * 256)
+    # pre-fill the KV cache up to `depth` so attention reads real (finite) rows
+    for lw in D.L:
+        lw["k_cache"][:depth].normal_(0, 0.5)
+        lw["v_cache"][:depth].normal_(0, 1.0)
+    E = cfg.n_embd
+    host_embd = (torch.randn(args.steps + args.warmup + 1, E) * 0.05).pin_memory()     # rows of token_embd gathered on the host
+    host_logits = torch.empty(cfg.n_vocab).pin_memory()
+    stream = torch.cuda.Stream(device=dev)
+    n_streams = world                                      # decode streams in flight across the pipeline
+
+    def set_inputs(i: int):
+        hi = dec.Qwen3Decoder.host_inputs(cfg, depth + i, n_kv)
+        D.pos.copy_(hi["pos"], non_blocking=True)
+        D.kv_idx.copy_(hi["kv_idx"], non_blocking=True)
+        D.mask_f32[:, :n_kv].copy_(hi["mask"], non_blocking=True)
+        return hi["pos"].numel() * 4 + 8 + hi["mask"].numel() * 4
+
+    with torch.cuda.stream(stream):
+        set_inputs(0)
+        D.x_in.copy_(host_embd[0], non_blocking=True)
+        D.step(n_kv)                                       # eager once (module load, attribute setup)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            launches = D.step(n_kv)
+    hidden = D.x_in
+
+    def pipeline_step(i: int, e2e: bool) -> tuple[int, int]:
+        """One step of every in-flight stream through this rank's stage.  Returns (h2d, d2h) bytes when e2e."""
+        h2d = d2h = 0
+        for _s in range(n_streams):
+            if e2e or world > 1:
+                h2d += set_inputs(i)
+            if rank == 0:
+                if e2e:
+                    D.x_in.copy_(host_embd[i], non_blocking=True)
+                    h2d += E * 4
+            else:
+                dist.recv(hidden, src=rank - 1)
+            graph.replay()
+            if not last:
+                dist.send(D.x_out, dst=rank + 1)
+            elif e2e:
+                host_logits.copy_(D.logits, non_blocking=True)
+                d2h += cfg.n_vocab * 4
+        if e2e and last:
+            torch.cuda.current_stream().synchronize()       # the sampler needs the logits before the next token
+        return h2d, d2h
+
+    def timed(e2e: bool, steps: int, warmup: int):
+        with torch.cuda.stream(stream):
+            for i in range(warmup):
+                pipeline_step(i, e2e)
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            hb = db = 0
+            for i in range(steps):
+                a, b = pipeline_step(warmup + i, e2e)
+                hb, db = hb + a, db + b
+            ev1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            if world > 1:
+                dist.barrier()
+            ms = ev0.elapsed_time(ev1)
+        if e2e:
+            ms = max(ms, wall)                              # host copies/syncs are part of the end-to-end time
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), hb // max(steps, 1), db // max(steps, 1)
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total, _, _ = timed(False, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, h2d, d2h = timed(True, args.steps, args.warmup)
+    if world > 1:
+        hb = torch.tensor([h2d, d2h], device=dev)
+        dist.all_reduce(hb)
+        h2d, d2h = int(hb[0]), int(hb[1])
+
+    tokens = args.steps * n_streams
+    ms_step = ms_total / args.steps
+    value = tokens / (ms_total / 1e3)
+    e2e_value = tokens / (ms_e2e / 1e3)
+    peak, peak_src = peaks()
+    # roofline of the dominant kernel class (the weight matvecs + KV reads = the whole step's algorithmic bytes; one launch = one
+    # graph replay = one token through this rank's stage).  At N > 1 every rank moves 1/N of the bytes per stream-step.
+    w_bytes = dec.weight_bytes_per_token(cfg, layers, with_head=last)
+    kv_bytes = dec.kv_bytes_per_token(cfg, n_kv, layers)
+    step_bytes = (w_bytes + kv_bytes) * n_streams
+    achieved = step_bytes / (ms_step / 1e3) / 1e9
+    line = {"metric": "decode_tok_per_s", "value": round(value, 2), "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations), f16 KV", "data": "synthetic",
+            "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}, KV depth {depth}..{depth + args.steps + args.warmup} (n_kv={n_kv})",
+                       "streams_in_flight": n_streams, "parallelism": "single GPU" if world == 1 else f"layer-split pipeline pp{world}",
+                       "timing": f"one CUDA graph per token; weights {w_bytes / 1e9:.2f} GB/rank exceed the 126 MB L2, so no flush is needed"},
+            "gpu_launches": launches * args.steps * n_streams,
+            "e2e": {"value": round(e2e_value, 2), "unit": "tok/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "peak_source": peak_src, "bytes_per_step": int(step_bytes),
+                         "kernel": "k_mmvq (decode matvec) + k_fa_decode: algorithmic weight+KV bytes of one token / graph-replay time"},
+            "clocks": clk}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = reference_layer_sample(cfg, 1, os.cpu_count() or 1, 3, 1)
+            line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tok/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                    "sample": r["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--depth", type=int, default=2048)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tiny", action="store_true", help="tiny model (plumbing checks only; not a bench line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

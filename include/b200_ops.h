@@ -1,0 +1,167 @@
+/* include/b200_ops.h — C-ABI of the hand-written sm_100a kernels (libb200ops.so).
+ *
+ * This is the "thin C-ABI of hand-written sm_100a kernels" the host side calls (BASELINE.json north_star): plain
+ * pointers, sizes and strides, no C++/torch/ggml types.  The ggml backend plugin (include/ggml-b200.h,
+ * libggml-b200.so) maps each ggml op onto one of these entry points; parity tests call them through ctypes.
+ *
+ * Every entry point cites the reference CUDA-backend interface it replaces (paths relative to the reference root,
+ * ggml/src/ggml-cuda/...) and follows the arithmetic of the reference CPU backend (the parity oracle, oracle/*.c).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless named host_*; `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 = launched OK; B200_ERR_UNSUPPORTED = shape/type outside what the kernel handles (caller must not
+ *     have routed it here: the plugin's supports_op mirrors b200_*_supported); other negative = CUDA error code negated.
+ *   - tensors follow ggml's convention: ne[0] is the contiguous dimension, nb[] are BYTE strides.
+ */
+#ifndef B200_OPS_H
+#define B200_OPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+#define B200_OK               0
+#define B200_ERR_UNSUPPORTED (-1000)
+#define B200_ERR_ARG         (-1001)
+
+/* ggml_type ids this library understands (ggml/include/ggml.h:379-421) */
+enum b200_type {
+    B200_F32 = 0, B200_F16 = 1, B200_Q4_0 = 2, B200_Q8_0 = 8, B200_Q4_K = 12, B200_Q5_K = 13, B200_Q6_K = 14,
+    B200_I32 = 26, B200_I64 = 27, B200_BF16 = 30,
+};
+
+/* Strided 4-D tensor view: the fields of struct ggml_tensor (ggml.h:626-658) a kernel needs. */
+typedef struct b200_tensor {
+    void *  data;
+    int32_t type;      /* enum b200_type */
+    int32_t layout;    /* B200_LAYOUT_*: only quantised weights can be non-native */
+    int64_t ne[4];
+    int64_t nb[4];
+} b200_tensor;
+
+/* Weight layouts in HBM.  NATIVE = ggml block structs back to back (ggml-common.h).  PLANAR = the same bytes split
+ * into a 16-byte aligned payload plane followed by a scale plane, so that q4_0 / q8_0 / q6_K rows can be streamed with
+ * 128-bit loads (their native blocks are 18 / 34 / 210 bytes).  See DESIGN.md "Data layout in HBM".
+ *   q4_0 : payload 16 B (qs)                  | scale plane: f16 d
+ *   q8_0 : payload 32 B (qs)                  | scale plane: f16 d
+ *   q6_K : payload 208 B (ql, qh, scales)     | scale plane: f16 d
+ * q4_K (144 B) and q5_K (176 B) are already 16-byte multiples and are never repacked. */
+enum { B200_LAYOUT_NATIVE = 0, B200_LAYOUT_PLANAR = 1 };
+
+/* ---- library / device --------------------------------------------------------------------------------------------- */
+B200_API int          b200_abi_version(void);                      /* bumps when any signature below changes */
+B200_API const char * b200_error_string(int code);
+B200_API int          b200_device_sm_count(int device);
+
+/* ---- weight repack (buffer set_tensor / get_tensor path; replaces nothing in the reference: ggml-cuda keeps native
+ *      blocks and pays for it with 2-/4-byte loads, vecdotq.cuh:103-122,580-600) ---------------------------------------
+ * Scatter `size` bytes that sit at native byte offset `offset` of a [nblocks] block array into the planar layout at
+ * `dst_planar` (and the inverse).  Any offset/size works (llama-model-loader.cpp:1077-1093 uploads 1 MiB chunks). */
+B200_API int b200_repack_supported(int type);
+B200_API int b200_repack_scatter(int type, const void * src_native_chunk, void * dst_planar, int64_t nblocks_total,
+                                 int64_t offset, int64_t size, void * stream);
+B200_API int b200_repack_gather (int type, const void * src_planar, void * dst_native_chunk, int64_t nblocks_total,
+                                 int64_t offset, int64_t size, void * stream);
+
+/* ---- activation quantisation (replaces quantize_q8_1, ggml-cuda/quantize.cu:4-48; arithmetic of the CPU oracle:
+ *      quantize_row_q8_K_ref ggml-quants.c:2555-2592 for K-quant weights, quantize_row_q8_0 for q4_0/q8_0) ---------------
+ * Device-side activation buffer ("act"), one record per column, planar:
+ *     int8  qs[k]            quantised values
+ *     float d[k/G]           G = 256 for K-quant weights (q8_K), 32 for q4_0/q8_0 weights (q8_0; value is f16-rounded)
+ *     int16 bsum[k/16|k/32]  partial sums of qs (16-wide for G = 256, 32-wide for G = 32)
+ * b200_act_bytes gives the size of one record; records are laid out back to back, 16-byte aligned. */
+B200_API size_t b200_act_bytes(int weight_type, int64_t k);
+B200_API int    b200_quantize_act(int weight_type, const float * x, int64_t x_col_stride_elems, void * act,
+                                  int64_t k, int64_t ncols, void * stream);
+
+/* ---- MUL_MAT (replaces ggml_cuda_mul_mat ggml-cuda.cu:2001-2084: mmvq.cu mul_mat_vec_q for n <= 8, mmq.cu mul_mat_q
+ *      beyond; oracle: ggml_compute_forward_mul_mat ggml-cpu.c:1210-1402) ------------------------------------------------
+ * dst[m, n] (F32) = W[m, k] (any supported type) . X[n, k]^T (F32), batched over ne[2], ne[3] with ggml broadcast rules.
+ * `scratch` must hold b200_mul_mat_scratch_bytes(...) bytes (activation records / tile buffers). */
+B200_API int    b200_mul_mat_supported(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst);
+B200_API size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x);
+B200_API int    b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
+                             size_t scratch_bytes, void * stream);
+
+/* Decode fast path: y[m] (+= residual) = W[m, k] . act, activations already quantised by b200_quantize_act /
+ * a fused producer.  Up to 4 weight matrices that share the same activation run in ONE launch (q/k/v, gate/up).
+ * `residual` may be NULL; when not NULL, y[i] = dot + residual[i] (fuses the ADD that follows wo / ffn_down). */
+typedef struct b200_matvec_job {
+    const void * w; int32_t type; int32_t layout; int64_t m; int64_t row_stride_bytes;
+    float * y; const float * residual;
+} b200_matvec_job;
+B200_API int b200_matvec_q(const b200_matvec_job * jobs, int njobs, const void * act, int64_t k, void * stream);
+/* gate/up pair with the swiglu epilogue fused: y[m] = silu(Wg.act) * (Wu.act)   (GLU: ggml-cuda/unary.cu:208-228) */
+B200_API int b200_matvec_q_swiglu(const b200_matvec_job * gate, const b200_matvec_job * up, float * y, const void * act,
+                                  int64_t k, void * stream);
+
+/* ---- normalisation (replaces rms_norm_f32<.., do_mul, do_add> ggml-cuda/norm.cu:107-185; oracle ops.cpp:3517-3565) ---
+ * y = x * rsqrt(mean(x^2) + eps) [* w] [+ add].  w broadcasts over rows (ne[0] == x->ne[0]) or is NULL. */
+B200_API int b200_rms_norm(const b200_tensor * x, const b200_tensor * w, const b200_tensor * add, const b200_tensor * dst,
+                           float eps, void * stream);
+/* fused producer for the decode path: y = rms_norm(x) * w, quantised straight to act records (one per column; no F32 round
+ * trip unless y_f32_or_null is given).  x: ncols columns of k floats, x_col_stride elements apart. */
+B200_API int b200_rms_norm_quantize(const float * x, int64_t x_col_stride, const float * w, float * y_f32_or_null,
+                                    int64_t y_col_stride, void * act, int weight_type, int64_t k, int64_t ncols, float eps,
+                                    void * stream);
+
+/* ---- ROPE (replaces rope_norm / rope_neox ggml-cuda/rope.cu:40-123; oracle ops.cpp:5436-5720) --------------------------- */
+typedef struct b200_rope_params {
+    int32_t n_dims, mode, n_ctx_orig;      /* mode: 0 = norm, 2 = neox (GGML_ROPE_TYPE_NEOX) */
+    float freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow;
+} b200_rope_params;
+B200_API int b200_rope(const b200_tensor * x, const int32_t * pos, const float * freq_factors, const b200_tensor * dst,
+                       const b200_rope_params * p, void * stream);
+
+/* ---- fused q/k post-processing (replaces, per layer, 2 x rms_norm_f32 norm.cu:107-185 + 2 x rope_neox rope.cu:83-123 +
+ *      2 x k_set_rows set-rows.cu:264; graph side: llm_build_qwen3 src/llama-model.cpp:9320-9350, llama-kv-cache.cpp:1021-1110) ---
+ * For each of n_tok tokens: q heads are RMS-normed (if q_norm_w), multiplied by the norm weight and rotated IN PLACE; k heads get
+ * the same treatment and are written as F16 to k_cache row kv_idx[t]; v is converted to F16 into v_cache row kv_idx[t].
+ * Strides: *_tok_stride in elements between tokens; cache row strides in bytes.  head_dim 64 or 128, p->n_dims == head_dim. */
+B200_API int b200_qkv_post(float * q, const float * k, const float * v, const float * q_norm_w, const float * k_norm_w,
+                           const int32_t * pos, const void * kv_idx, int idx_type, void * k_cache, void * v_cache,
+                           int64_t k_row_stride_bytes, int64_t v_row_stride_bytes, int head_dim, int n_head, int n_head_kv,
+                           int64_t n_tok, int64_t q_tok_stride, int64_t k_tok_stride, int64_t v_tok_stride,
+                           const b200_rope_params * p, float eps, void * stream);
+
+/* ---- KV-cache write / gathers / copies ----------------------------------------------------------------------------------
+ * SET_ROWS (set-rows.cu:264; oracle ggml_compute_forward_set_rows): dst[idx[r], :] = convert(src[r, :]), idx I64 or I32.
+ * GET_ROWS (getrows.cu:238): dst[r, :] = float(src[idx[r], :]).  CPY (cpy.cu:280): strided copy with F32/F16/BF16 casts. */
+B200_API int b200_set_rows(const b200_tensor * src, const b200_tensor * idx, const b200_tensor * dst, void * stream);
+B200_API int b200_get_rows(const b200_tensor * src, const b200_tensor * idx, const b200_tensor * dst, void * stream);
+B200_API int b200_cpy(const b200_tensor * src, const b200_tensor * dst, void * stream);
+
+/* ---- elementwise (binbcast.cu:395-443, unary.cu, scale.cu) -------------------------------------------------------------- */
+enum b200_binop { B200_ADD = 0, B200_SUB = 1, B200_MUL = 2, B200_DIV = 3 };
+B200_API int b200_binary(int op, const b200_tensor * a, const b200_tensor * b, const b200_tensor * dst, void * stream);
+enum b200_unop { B200_SILU = 0, B200_GELU = 1, B200_RELU = 2, B200_GELU_QUICK = 3, B200_TANH = 4, B200_SIGMOID = 5,
+                 B200_GELU_ERF = 6, B200_NEG = 7, B200_EXP = 8, B200_SQR = 9, B200_SQRT = 10, B200_ABS = 11 };
+B200_API int b200_unary(int op, const b200_tensor * x, const b200_tensor * dst, void * stream);
+enum b200_gluop { B200_GLU_REGLU = 0, B200_GLU_GEGLU = 1, B200_GLU_SWIGLU = 2, B200_GLU_GEGLU_ERF = 4, B200_GLU_GEGLU_QUICK = 5 };
+/* GLU: dst = act(gate) * up.  up == NULL: single-tensor form, halves of x's rows (swapped selects which half gates). */
+B200_API int b200_glu(int op, const b200_tensor * gate_or_x, const b200_tensor * up, const b200_tensor * dst, int swapped,
+                      void * stream);
+B200_API int b200_scale(const b200_tensor * x, const b200_tensor * dst, float scale, float bias, void * stream);
+/* SOFT_MAX (softmax.cu:253): dst = softmax(x*scale + mask) over ne[0]; mask F32/F16 [ne0, ne1, ..] broadcast or NULL */
+B200_API int b200_soft_max(const b200_tensor * x, const b200_tensor * mask, const b200_tensor * dst, float scale,
+                           float max_bias, void * stream);
+
+/* ---- FLASH_ATTN_EXT (replaces fattn.cu:195-341 -> fattn-vec.cuh / fattn-mma-f16.cuh; oracle ops.cpp:7912-8148) ----------
+ * q F32 [D, n_q, n_head, n_b], k/v F16 [D, n_kv, n_head_kv, n_b], mask F16 [n_kv, >= n_q, ...] or NULL,
+ * dst F32 [D, n_head, n_q, n_b].  `scratch`: b200_flash_attn_scratch_bytes (split-KV partials). */
+B200_API int    b200_flash_attn_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v,
+                                          const b200_tensor * mask, const b200_tensor * dst);
+B200_API size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b200_tensor * k);
+B200_API int    b200_flash_attn(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask,
+                                const b200_tensor * dst, float scale, float max_bias, float logit_softcap, void * scratch,
+                                size_t scratch_bytes, void * stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_OPS_H */

@@ -1,0 +1,280 @@
+// flash_attn.cu — GGML_OP_FLASH_ATTN_EXT over the F16 KV cache, decode / small-batch form (split-KV, online softmax).
+//
+// Replaces ggml-cuda/fattn.cu:195-341 -> flash_attn_ext_vec (fattn-vec.cuh:19) + flash_attn_combine_results
+// (fattn-common.cuh).  Arithmetic follows the CPU oracle (ggml-cpu/ops.cpp:7912-8148): Q rounded to f16, K.Q products of
+// f16 values accumulated in f32, s = dot*scale + mask, online softmax in f32; V is accumulated in f32 here (the CPU backend
+// accumulates in f16 — lossier; the reference's own backend test allows NMSE 5e-4, tests/test-backend-ops.cpp:5085).
+//
+// B200-first: HBM-bound on the K/V read.  One CTA owns (KV-chunk, kv-head, q-token) and serves all G query heads of the GQA
+// group from ONE pass over K and V, so every cache byte is read once per token; a D-half row (256 B at D = 128) is read by
+// 16 lanes x 16 B, rows whose mask is -inf are never fetched (the reference pre-scans the mask for that,
+// fattn-common.cuh flash_attn_mask_to_KV_max); the grid is sized to ~2 CTAs per SM and a tiny second kernel merges the
+// per-chunk (m, l, acc) partials.
+#include "common.cuh"
+#include <math.h>
+
+namespace b200 {
+
+constexpr int FA_THREADS = 256;
+constexpr int FA_TILE    = 256;      // KV positions per softmax tile
+
+struct FaArgs {
+    const char * q; const char * k; const char * v; const char * mask; char * dst;
+    int64_t q_nb1, q_nb2, q_nb3, k_nb1, k_nb2, k_nb3, v_nb1, v_nb2, v_nb3, m_nb1, m_nb2, m_nb3, d_nb1, d_nb2, d_nb3;
+    int64_t n_q, n_kv, n_head, n_head_kv, k_ne3, m_ne2, m_ne3;
+    int ratio, groups, splits; int64_t chunk;
+    float scale;
+    float * part_acc; float2 * part_ml;
+};
+
+struct FaPlan { int G, groups, splits; int64_t chunk; };
+static FaPlan fa_plan(int64_t n_q_total, int64_t n_kv, int64_t n_head, int64_t n_head_kv) {
+    FaPlan P;
+    const int ratio = (int) (n_head / n_head_kv);
+    P.G = ratio % 4 == 0 ? 4 : ratio % 2 == 0 ? 2 : 1;
+    P.groups = ratio / P.G;
+    const int64_t base = n_head_kv * P.groups * n_q_total;
+    int64_t splits = (2 * (int64_t) sm_count() + base - 1) / base;
+    const int64_t max_splits = (n_kv + 63) / 64;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int64_t chunk = (n_kv + splits - 1) / splits;
+    chunk = (chunk + 31) / 32 * 32;
+    P.chunk = chunk;
+    P.splits = (int) ((n_kv + chunk - 1) / chunk);
+    if (P.splits < 1) P.splits = 1;
+    return P;
+}
+
+template <int D, int G>
+__global__ void __launch_bounds__(FA_THREADS) k_fa_decode(const FaArgs A) {
+    constexpr int LPR = D / 8;                 // lanes per K/V row (16 B each)
+    constexpr int RPW = 32 / LPR;              // rows per warp-load
+    constexpr int NRG = (FA_THREADS / 32) * RPW;
+    constexpr int U   = 4;                     // rows in flight per lane
+    static_assert(FA_TILE % (NRG * U) == 0, "tile");
+    __shared__ float S[FA_TILE][G];
+    __shared__ float s_corr[G], s_m[G], s_l[G];
+    __shared__ float red[NRG][G * D + 4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = warp * RPW + lane / LPR, hl = lane % LPR;
+    const int split = blockIdx.x;
+    const int kvh = blockIdx.y / A.groups, grp = blockIdx.y % A.groups;
+    const int64_t iq = blockIdx.z % A.n_q, ib = blockIdx.z / A.n_q;
+    const int head0 = kvh * A.ratio + grp * G;
+
+    float qreg[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float * qp = (const float *) (A.q + iq * A.q_nb1 + (int64_t) (head0 + g) * A.q_nb2 + ib * A.q_nb3) + hl * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qreg[g][i] = __half2float(__float2half_rn(qp[i]));
+    }
+    if (tid < G) { s_m[tid] = -INFINITY; s_l[tid] = 0.0f; }
+    float acc[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[g][i] = 0.0f;
+
+    const char * kb = A.k + (int64_t) kvh * A.k_nb2 + (ib % A.k_ne3) * A.k_nb3 + hl * 16;
+    const char * vb = A.v + (int64_t) kvh * A.v_nb2 + (ib % A.k_ne3) * A.v_nb3 + hl * 16;
+    const __half * mrow = A.mask ? (const __half *) (A.mask + iq * A.m_nb1 + ((int64_t) head0 % A.m_ne2) * A.m_nb2 + (ib % A.m_ne3) * A.m_nb3) : nullptr;
+    const int64_t c0 = (int64_t) split * A.chunk, c1 = min(c0 + A.chunk, A.n_kv);
+    __syncthreads();
+
+    for (int64_t t0 = c0; t0 < c1; t0 += FA_TILE) {
+        // ---- S = scale * K.q + mask for the tile --------------------------------------------------------------------
+        for (int j0 = rg; j0 < FA_TILE; j0 += NRG * U) {
+            uint4 kk[U]; float mv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t pos = t0 + j0 + u * NRG;
+                mv[u] = pos < c1 ? (mrow ? __half2float(mrow[pos]) : 0.0f) : -INFINITY;
+                kk[u] = make_uint4(0, 0, 0, 0);
+                if (mv[u] != -INFINITY) kk[u] = ldg_stream16(kb + pos * A.k_nb1);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const __half2 * h2 = (const __half2 *) &kk[u];
+                float kf[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h2[i]); kf[2 * i] = f.x; kf[2 * i + 1] = f.y; }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float d = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d = fmaf(kf[i], qreg[g][i], d);
+#pragma unroll
+                    for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                    if (hl == 0) S[j0 + u * NRG][g] = mv[u] != -INFINITY ? d * A.scale + mv[u] : -INFINITY;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- online softmax bookkeeping: warp g owns head g ------------------------------------------------------------
+        if (warp < G) {
+            const int g = warp;
+            float mx = -INFINITY;
+            for (int j = lane; j < FA_TILE; j += 32) mx = fmaxf(mx, S[j][g]);
+            mx = warp_max(mx);
+            const float m_old = s_m[g], m_new = fmaxf(m_old, mx);
+            float sum = 0.0f;
+            for (int j = lane; j < FA_TILE; j += 32) {
+                const float s = S[j][g];
+                const float p = s == -INFINITY ? 0.0f : expf(s - m_new);
+                S[j][g] = p; sum += p;
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) {
+                const float corr = m_old == -INFINITY ? 1.0f : expf(m_old - m_new);     // m_new >= m_old; acc is 0 while m_old = -inf
+                s_corr[g] = corr; s_m[g] = m_new; s_l[g] = s_l[g] * corr + sum;
+            }
+        }
+        __syncthreads();
+        // ---- acc = acc*corr + P.V ------------------------------------------------------------------------------------
+#pragma unroll
+        for (int g = 0; g < G; ++g) { const float c = s_corr[g];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[g][i] *= c; }
+        for (int j0 = rg; j0 < FA_TILE; j0 += NRG * U) {
+            uint4 vv[U]; float pv[U][G];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * NRG;
+                bool any = false;
+#pragma unroll
+                for (int g = 0; g < G; ++g) { pv[u][g] = S[j][g]; any |= pv[u][g] != 0.0f; }
+                vv[u] = make_uint4(0, 0, 0, 0);
+                if (any) vv[u] = ldg_stream16(vb + (t0 + j) * A.v_nb1);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const __half2 * h2 = (const __half2 *) &vv[u];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) { acc[g][2 * i] = fmaf(pv[u][g], f.x, acc[g][2 * i]); acc[g][2 * i + 1] = fmaf(pv[u][g], f.y, acc[g][2 * i + 1]); }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- reduce the NRG row-group accumulators ------------------------------------------------------------------------
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[rg][g * D + hl * 8 + i] = acc[g][i];
+    __syncthreads();
+    const int64_t z = blockIdx.z;
+    for (int o = tid; o < G * D; o += FA_THREADS) {
+        float v = 0.0f;
+#pragma unroll
+        for (int r = 0; r < NRG; ++r) v += red[r][o];
+        const int g = o / D, d = o % D;
+        const int head = head0 + g;
+        if (A.splits == 1) {
+            const float l = s_l[g];
+            *(float *) (A.dst + (int64_t) d * 4 + (int64_t) head * A.d_nb1 + iq * A.d_nb2 + ib * A.d_nb3) = l == 0.0f ? 0.0f : v / l;
+        } else {
+            const int64_t slot = (z * A.n_head + head) * A.splits + split;
+            A.part_acc[slot * D + d] = v;
+            if (d == 0) A.part_ml[slot] = make_float2(s_m[g], s_l[g]);
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(D) k_fa_combine(const FaArgs A) {
+    const int head = blockIdx.x; const int64_t z = blockIdx.y;
+    const int64_t iq = z % A.n_q, ib = z / A.n_q;
+    const int64_t slot0 = (z * A.n_head + head) * A.splits;
+    float M = -INFINITY;
+    for (int s = 0; s < A.splits; ++s) M = fmaxf(M, A.part_ml[slot0 + s].x);
+    float L = 0.0f, v = 0.0f;
+    for (int s = 0; s < A.splits; ++s) {
+        const float2 ml = A.part_ml[slot0 + s];
+        if (ml.x == -INFINITY) continue;
+        const float w = expf(ml.x - M);
+        L += ml.y * w;
+        v += A.part_acc[(slot0 + s) * D + threadIdx.x] * w;
+    }
+    *(float *) (A.dst + (int64_t) threadIdx.x * 4 + (int64_t) head * A.d_nb1 + iq * A.d_nb2 + ib * A.d_nb3) = L == 0.0f ? 0.0f : v / L;
+}
+
+template <int D>
+static int fa_launch(const FaArgs & A, int G, int64_t nz, cudaStream_t st) {
+    dim3 grid((unsigned) A.splits, (unsigned) (A.n_head_kv * A.groups), (unsigned) nz);
+    if      (G == 4) k_fa_decode<D, 4><<<grid, FA_THREADS, 0, st>>>(A);
+    else if (G == 2) k_fa_decode<D, 2><<<grid, FA_THREADS, 0, st>>>(A);
+    else             k_fa_decode<D, 1><<<grid, FA_THREADS, 0, st>>>(A);
+    B200_LAUNCH_CHECK();
+    if (A.splits > 1) {
+        k_fa_combine<D><<<dim3((unsigned) A.n_head, (unsigned) nz), D, 0, st>>>(A);
+        B200_LAUNCH_CHECK();
+    }
+    return B200_OK;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_flash_attn_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask,
+                                         const b200_tensor * dst) {
+    if (!q || !k || !v || !dst) return 0;
+    if (q->type != B200_F32 || k->type != B200_F16 || v->type != B200_F16 || dst->type != B200_F32) return 0;
+    const int64_t D = q->ne[0];
+    if ((D != 64 && D != 128) || k->ne[0] != D || v->ne[0] != D) return 0;
+    if (k->ne[1] != v->ne[1] || k->ne[2] != v->ne[2] || k->ne[3] != v->ne[3] || k->ne[2] == 0 || k->ne[3] == 0) return 0;
+    if (q->ne[2] % k->ne[2] != 0 || q->ne[3] % k->ne[3] != 0) return 0;
+    if (q->nb[0] != 4 || k->nb[0] != 2 || v->nb[0] != 2 || dst->nb[0] != 4) return 0;
+    if (((uintptr_t) k->data | (uintptr_t) v->data) % 16 || (k->nb[1] | k->nb[2] | k->nb[3] | v->nb[1] | v->nb[2] | v->nb[3]) % 16) return 0;
+    if (dst->ne[0] != D || dst->ne[1] != q->ne[2] || dst->ne[2] != q->ne[1] || dst->ne[3] != q->ne[3]) return 0;
+    if (mask) {
+        if (mask->type != B200_F16 || mask->nb[0] != 2 || mask->ne[0] != k->ne[1] || mask->ne[1] < q->ne[1]) return 0;
+        if (mask->ne[2] == 0 || mask->ne[3] == 0 || q->ne[2] % mask->ne[2] || q->ne[3] % mask->ne[3]) return 0;
+        if (mask->ne[2] != 1) return 0;            // per-head masks (ALiBi-style) are not on this path
+    }
+    return 1;
+}
+
+extern "C" size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b200_tensor * k) {
+    const int64_t nz = q->ne[1] * q->ne[3];
+    if (nz == 0 || k->ne[1] == 0 || k->ne[2] == 0) return 0;
+    const FaPlan P = fa_plan(nz, k->ne[1], q->ne[2], k->ne[2]);
+    if (P.splits <= 1) return 0;
+    const size_t slots = (size_t) nz * q->ne[2] * P.splits;
+    return slots * q->ne[0] * 4 + slots * 8 + 16;
+}
+
+extern "C" int b200_flash_attn(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask,
+                               const b200_tensor * dst, float scale, float max_bias, float logit_softcap, void * scratch,
+                               size_t scratch_bytes, void * stream) {
+    if (!b200_flash_attn_supported(q, k, v, mask, dst) || max_bias != 0.0f || logit_softcap != 0.0f) return B200_ERR_UNSUPPORTED;
+    const int64_t nz = q->ne[1] * q->ne[3];
+    if (nz == 0 || q->ne[2] == 0) return B200_OK;
+    if (nz > 65535) return B200_ERR_UNSUPPORTED;
+    const FaPlan P = fa_plan(nz, k->ne[1], q->ne[2], k->ne[2]);
+    FaArgs A = {};
+    A.q = (const char *) q->data; A.k = (const char *) k->data; A.v = (const char *) v->data; A.mask = mask ? (const char *) mask->data : nullptr;
+    A.dst = (char *) dst->data;
+    A.q_nb1 = q->nb[1]; A.q_nb2 = q->nb[2]; A.q_nb3 = q->nb[3];
+    A.k_nb1 = k->nb[1]; A.k_nb2 = k->nb[2]; A.k_nb3 = k->nb[3];
+    A.v_nb1 = v->nb[1]; A.v_nb2 = v->nb[2]; A.v_nb3 = v->nb[3];
+    if (mask) { A.m_nb1 = mask->nb[1]; A.m_nb2 = mask->nb[2]; A.m_nb3 = mask->nb[3]; A.m_ne2 = mask->ne[2]; A.m_ne3 = mask->ne[3]; } else { A.m_ne2 = A.m_ne3 = 1; }
+    A.d_nb1 = dst->nb[1]; A.d_nb2 = dst->nb[2]; A.d_nb3 = dst->nb[3];
+    A.n_q = q->ne[1]; A.n_kv = k->ne[1]; A.n_head = q->ne[2]; A.n_head_kv = k->ne[2]; A.k_ne3 = k->ne[3];
+    A.ratio = (int) (q->ne[2] / k->ne[2]); A.groups = P.groups; A.splits = P.splits; A.chunk = P.chunk; A.scale = scale;
+    if (k->ne[1] == 0) { A.splits = 1; A.chunk = 32; }
+    if (A.splits > 1) {
+        if (!scratch || scratch_bytes < b200_flash_attn_scratch_bytes(q, k) || (uintptr_t) scratch % 16) return B200_ERR_ARG;
+        const size_t slots = (size_t) nz * q->ne[2] * P.splits;
+        A.part_acc = (float *) scratch;
+        A.part_ml  = (float2 *) ((char *) scratch + ((slots * q->ne[0] * 4 + 15) & ~(size_t) 15));
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    return q->ne[0] == 128 ? fa_launch<128>(A, P.G, nz, st) : fa_launch<64>(A, P.G, nz, st);
+}

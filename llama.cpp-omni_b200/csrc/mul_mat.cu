@@ -1,0 +1,150 @@
+// mul_mat.cu — GGML_OP_MUL_MAT entry point (replaces ggml_cuda_mul_mat dispatcher, ggml-cuda.cu:2001-2084).
+//   quantised W : activations -> q8 records (quant_act.cu) -> mmvq (<= 8 columns per pass)
+//   f32/f16/bf16 W: mmvf-style warp-per-row kernel below (replaces mul_mat_vec_f, ggml-cuda/mmvf.cu); activations are rounded to
+//                   the weight type first exactly like the CPU oracle does (vec_dot_type, ggml-cpu.c:196-350)
+// Batch dims follow ggml broadcast rules: w.ne[2] divides x.ne[2], w.ne[3] divides x.ne[3].
+#include "common.cuh"
+
+namespace b200 {
+
+int matvec_q_cols(const void * w, int type, int layout, int64_t m, int64_t row_stride, const void * act, int64_t k, int ncols,
+                  float * y, int64_t y_col_stride, cudaStream_t st);
+
+template <typename WT> __device__ __forceinline__ float w2f(WT v);
+template <> __device__ __forceinline__ float w2f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float w2f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float w2f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename WT> __device__ __forceinline__ float round_like(float v);
+template <> __device__ __forceinline__ float round_like<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_like<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> __device__ __forceinline__ float round_like<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+struct MmvfArgs {
+    const char * w; const char * x; char * y;
+    int64_t m, k, n;
+    int64_t w_nb1, w_nb2, w_nb3, x_nb1, x_nb2, x_nb3, y_nb1, y_nb2, y_nb3;
+    int64_t ne2, ne3, r2, r3;        // dst batch dims and broadcast ratios
+};
+
+// one warp per (row, batch); up to NC columns per pass; 16-byte loads when the row is aligned, scalar otherwise
+template <typename WT, int NC>
+__global__ void __launch_bounds__(256) k_mmvf(const MmvfArgs A, int64_t col0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t rows_total = A.m * A.ne2 * A.ne3;
+    if (warp >= rows_total) return;
+    const int64_t r = warp % A.m, i2 = (warp / A.m) % A.ne2, i3 = warp / (A.m * A.ne2);
+    const WT * w = (const WT *) (A.w + r * A.w_nb1 + (i2 / A.r2) * A.w_nb2 + (i3 / A.r3) * A.w_nb3);
+    const char * xb = A.x + i2 * A.x_nb2 + i3 * A.x_nb3;
+    float acc[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) acc[n] = 0.0f;
+    constexpr int VEC = 16 / sizeof(WT);
+    const bool vec_ok = ((uintptr_t) w % 16 == 0) && (A.k % VEC == 0) && ((uintptr_t) xb % 16 == 0) && (A.x_nb1 % 16 == 0);
+    if (vec_ok) {
+        for (int64_t i = (int64_t) lane * VEC; i < A.k; i += 32 * VEC) {
+            const uint4 raw = ldg_stream16(w + i);
+            const WT * wv = (const WT *) &raw;
+#pragma unroll
+            for (int n = 0; n < NC; ++n) {
+                if (col0 + n < A.n) {
+                    const float * x = (const float *) (xb + (col0 + n) * A.x_nb1) + i;
+#pragma unroll
+                    for (int e = 0; e < VEC; e += 4) {
+                        const float4 xv = *(const float4 *) (x + e);
+                        acc[n] += w2f<WT>(wv[e]) * round_like<WT>(xv.x) + w2f<WT>(wv[e + 1]) * round_like<WT>(xv.y)
+                                + w2f<WT>(wv[e + 2]) * round_like<WT>(xv.z) + w2f<WT>(wv[e + 3]) * round_like<WT>(xv.w);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int64_t i = lane; i < A.k; i += 32) {
+            const float wv = w2f<WT>(w[i]);
+#pragma unroll
+            for (int n = 0; n < NC; ++n)
+                if (col0 + n < A.n) acc[n] += wv * round_like<WT>(((const float *) (xb + (col0 + n) * A.x_nb1))[i]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        const float v = warp_sum(acc[n]);
+        if (lane == 0 && col0 + n < A.n) *(float *) (A.y + r * 4 + (col0 + n) * A.y_nb1 + i2 * A.y_nb2 + i3 * A.y_nb3) = v;
+    }
+}
+
+template <typename WT>
+static int run_mmvf(const MmvfArgs & A, cudaStream_t st) {
+    const int64_t warps = A.m * A.ne2 * A.ne3;
+    const unsigned grid = (unsigned) ((warps + 7) / 8);
+    for (int64_t c0 = 0; c0 < A.n; c0 += 8) {
+        const int64_t nc = A.n - c0;
+        if      (nc == 1) k_mmvf<WT, 1><<<grid, 256, 0, st>>>(A, c0);
+        else if (nc == 2) k_mmvf<WT, 2><<<grid, 256, 0, st>>>(A, c0);
+        else if (nc <= 4) k_mmvf<WT, 4><<<grid, 256, 0, st>>>(A, c0);
+        else              k_mmvf<WT, 8><<<grid, 256, 0, st>>>(A, c0);
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_mul_mat_supported(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst) {
+    if (!w || !x || !dst) return 0;
+    if (x->type != B200_F32 || dst->type != B200_F32) return 0;
+    const int t = w->type;
+    if (!(is_quant(t) || t == B200_F32 || t == B200_F16 || t == B200_BF16)) return 0;
+    const int64_t k = w->ne[0];
+    if (k != x->ne[0] || k % blck_size(t) != 0) return 0;
+    if (dst->ne[0] != w->ne[1] || dst->ne[1] != x->ne[1] || dst->ne[2] != x->ne[2] || dst->ne[3] != x->ne[3]) return 0;
+    if (w->ne[2] == 0 || w->ne[3] == 0 || x->ne[2] % w->ne[2] != 0 || x->ne[3] % w->ne[3] != 0) return 0;
+    if (w->nb[0] != type_size(t) || x->nb[0] != 4 || dst->nb[0] != 4) return 0;       // rows contiguous
+    if (is_quant(t)) {
+        if ((uintptr_t) x->data % 16 || x->nb[1] % 16 || x->nb[2] % 16 || x->nb[3] % 16) return 0;
+        if (dst->nb[1] % 4) return 0;
+        if (w->layout == B200_LAYOUT_PLANAR && (w->ne[2] != 1 || w->ne[3] != 1)) return 0;
+    }
+    return 1;
+}
+
+extern "C" size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x) {
+    if (!is_quant(w->type)) return 0;
+    return (size_t) act_layout(w->type, w->ne[0]).bytes * (size_t) (x->ne[1] * x->ne[2] * x->ne[3]);
+}
+
+extern "C" int b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
+                            size_t scratch_bytes, void * stream) {
+    if (!b200_mul_mat_supported(w, x, dst)) return B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t) stream;
+    const int t = w->type;
+    const int64_t k = w->ne[0], m = w->ne[1], n = x->ne[1];
+    if (m == 0 || n == 0 || dst->ne[2] * dst->ne[3] == 0) return B200_OK;
+    const int64_t r2 = x->ne[2] / w->ne[2], r3 = x->ne[3] / w->ne[3];
+    if (!is_quant(t)) {
+        MmvfArgs A = { (const char *) w->data, (const char *) x->data, (char *) dst->data, m, k, n,
+                       w->nb[1], w->nb[2], w->nb[3], x->nb[1], x->nb[2], x->nb[3], dst->nb[1], dst->nb[2], dst->nb[3],
+                       dst->ne[2], dst->ne[3], r2, r3 };
+        if (t == B200_F32)  return run_mmvf<float>(A, st);
+        if (t == B200_F16)  return run_mmvf<__half>(A, st);
+        return run_mmvf<__nv_bfloat16>(A, st);
+    }
+    if (scratch_bytes < b200_mul_mat_scratch_bytes(w, x) || ((uintptr_t) scratch % 16)) return B200_ERR_ARG;
+    const int64_t act_b = act_layout(t, k).bytes;
+    for (int64_t i3 = 0; i3 < x->ne[3]; ++i3) for (int64_t i2 = 0; i2 < x->ne[2]; ++i2) {
+        const float * xs = (const float *) ((const char *) x->data + i2 * x->nb[2] + i3 * x->nb[3]);
+        uint8_t * act = (uint8_t *) scratch + (i3 * x->ne[2] + i2) * n * act_b;
+        int rc = b200_quantize_act(t, xs, x->nb[1] / 4, act, k, n, stream);
+        if (rc) return rc;
+        const char * wb = (const char *) w->data + (i2 / r2) * w->nb[2] + (i3 / r3) * w->nb[3];
+        float * yb = (float *) ((char *) dst->data + i2 * dst->nb[2] + i3 * dst->nb[3]);
+        for (int64_t c0 = 0; c0 < n; c0 += 8) {
+            const int nc = (int) (n - c0 < 8 ? n - c0 : 8);
+            rc = matvec_q_cols(wb, t, w->layout, m, w->nb[1], act + c0 * act_b, k, nc, yb + c0 * (dst->nb[1] / 4), dst->nb[1] / 4, st);
+            if (rc) return rc;
+        }
+    }
+    return B200_OK;
+}

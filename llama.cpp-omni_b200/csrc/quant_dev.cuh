@@ -1,0 +1,86 @@
+// quant_dev.cuh — device-side activation quantisers shared by quant_act.cu (stand-alone launch) and the fused producers.
+// Arithmetic = the CPU oracle's, bit for bit (see quant_act.cu header): q8_K per 256 (ggml-quants.c:2555-2592) and q8_0 per 32
+// (ggml-cpu/arch/x86/quants.c:297-360).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// One warp quantises one 256-element super-block held in `v` (lane owns elements [8*lane, 8*lane+8)) into the planar record.
+__device__ __forceinline__ void quant_block_q8K(const float (&v)[8], uint8_t * rec, int64_t blk, int64_t d_off, int64_t bsum_off) {
+    const int lane = threadIdx.x & 31;
+    // (amax, first index attaining it): strict '>' in the reference keeps the FIRST maximum
+    float amax = 0.0f; int imax = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float a = fabsf(v[i]); if (a > amax) { amax = a; imax = lane * 8 + i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oa = __shfl_xor_sync(0xffffffffu, amax, o); const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
+        if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }
+    }
+    int8_t q[8]; int s = 0;
+    float d = 0.0f;
+    if (amax != 0.0f) {
+        float mine = 0.0f;                                             // the SIGNED value at imax
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if ((imax & 7) == i) mine = v[i];
+        const float vmax = __shfl_sync(0xffffffffu, mine, (imax >> 3) & 31);
+        const float iscale = __fdiv_rn(-127.0f, vmax);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { int t = __float2int_rn(__fmul_rn(iscale, v[i])); t = t > 127 ? 127 : t; q[i] = (int8_t) t; s += t; }
+        d = __fdiv_rn(1.0f, iscale);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = 0;
+    }
+    *(uint2 *) (rec + blk * 256 + lane * 8) = *(const uint2 *) q;
+    const int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);            // 16-wide partial sums
+    if ((lane & 1) == 0) ((int16_t *) (rec + bsum_off))[blk * 16 + (lane >> 1)] = (int16_t) s2;
+    if (lane == 0) ((float *) (rec + d_off))[blk] = d;
+}
+
+// 8 lanes quantise one 32-element block (lane part = lane & 7 owns 4 elements); `live` = block index in range.
+__device__ __forceinline__ void quant_block_q8_0(const float4 v, bool live, uint8_t * rec, int64_t blk, int64_t d_off, int64_t bsum_off) {
+    const int lane = threadIdx.x & 31;
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float d  = __fdiv_rn(amax, 127.0f);
+    const float id = amax != 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+    const int q0 = __float2int_rn(__fmul_rn(v.x, id)), q1 = __float2int_rn(__fmul_rn(v.y, id));
+    const int q2 = __float2int_rn(__fmul_rn(v.z, id)), q3 = __float2int_rn(__fmul_rn(v.w, id));
+    int s = q0 + q1 + q2 + q3;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (!live) return;
+    const uint32_t packed = (uint32_t) (uint8_t) q0 | ((uint32_t) (uint8_t) q1 << 8) | ((uint32_t) (uint8_t) q2 << 16) | ((uint32_t) (uint8_t) q3 << 24);
+    *(uint32_t *) (rec + blk * 32 + (lane & 7) * 4) = packed;
+    if ((lane & 7) == 0) {
+        ((__half *) (rec + d_off))[blk] = __float2half_rn(d);
+        ((int16_t *) (rec + bsum_off))[blk] = (int16_t) s;
+    }
+}
+
+// A whole CTA quantises `k` floats at `src` (global or shared, 16-byte aligned) into one record.
+__device__ __forceinline__ void quant_row_cta(const float * src, uint8_t * rec, int64_t k, const ActLayout & L) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (L.group == 256) {
+        for (int64_t blk = warp; blk < k / 256; blk += nw) {
+            const float * xs = src + blk * 256 + lane * 8;
+            const float4 v0 = *(const float4 *) xs, v1 = *(const float4 *) (xs + 4);
+            const float v[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+            quant_block_q8K(v, rec, blk, L.d_off, L.bsum_off);
+        }
+    } else {
+        const int64_t nblk = k / 32;
+        for (int64_t b0 = (int64_t) warp * 4; b0 < nblk; b0 += (int64_t) nw * 4) {
+            const int64_t blk = b0 + (lane >> 3);
+            const bool live = blk < nblk;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (live) v = *(const float4 *) (src + blk * 32 + (lane & 7) * 4);
+            quant_block_q8_0(v, live, rec, blk, L.d_off, L.bsum_off);
+        }
+    }
+}
+
+} // namespace b200

@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library loads and exports every symbol include/b200_ops.h declares (no compute calls without a GPU),
+and the host-side accounting (Q4_K_M type recipe, algorithmic bytes/token) matches SURVEY.md §8d."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from __graft_entry__ import load_package, ROOT
+
+HDR = ROOT / "include" / "b200_ops.h"
+SO = ROOT / "llama.cpp-omni_b200" / "lib" / "libb200ops.so"
+
+
+def declared():
+    txt = HDR.read_text()
+    return sorted(set(re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", txt)))
+
+
+def test_header_declares_what_python_binds():
+    ops = load_package().ops
+    assert set(ops.EXPORTS) == set(declared())
+
+
+@pytest.mark.skipif(not SO.exists(), reason="libb200ops.so not built (run __graft_entry__.build())")
+def test_library_exports_every_declared_symbol():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", str(SO)], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    missing = [s for s in declared() if s not in exported]
+    assert not missing, missing
+    extra = [s for s in exported if not s.startswith("b200_")]
+    assert not extra, f"non-API symbols leak from the library: {extra[:5]}"
+    lib = C.CDLL(str(SO))
+    assert lib.b200_abi_version() == 1
+    lib.b200_error_string.restype = C.c_char_p
+    assert b"unsupported" in lib.b200_error_string(-1000)
+    lib.b200_act_bytes.restype, lib.b200_act_bytes.argtypes = C.c_size_t, [C.c_int, C.c_int64]
+    assert lib.b200_act_bytes(12, 4096) == 4096 + 4 * 16 + 2 * 256            # q8_K record: qs | f32 d per 256 | i16 bsum per 16
+    assert lib.b200_act_bytes(8, 4096) == 4096 + 2 * 128 + 2 * 128             # q8_0 record: qs | f16 d per 32 | i16 sum per 32
+
+
+def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
+    ops = load_package().ops
+    monkeypatch.setattr(ops, "_lib", None)
+    monkeypatch.setattr(ops, "SO", tmp_path / "nope.so")
+    with pytest.raises(ops.B200Error):
+        ops.lib()
+
+
+def test_q4_k_m_recipe_and_bytes_per_token():
+    dec = load_package().decode
+    cfg = dec.LLMConfig()
+    hi = [il for il in range(cfg.n_layer) if dec.use_more_bits(il, cfg.n_layer)]
+    assert len(hi) == 18                                                       # 18 of 36 layers carry Q6_K wv / ffn_down
+    assert dec.weight_bytes_per_token(cfg) == 4_671_134_848
+    assert dec.kv_bytes_per_token(cfg, 4096) == 147_456 * 4097
+    # layer-split sharding covers every layer exactly once
+    for world in (1, 2, 4, 8):
+        per = (cfg.n_layer + world - 1) // world
+        cover = [il for r in range(world) for il in range(r * per, min(cfg.n_layer, (r + 1) * per))]
+        assert cover == list(range(cfg.n_layer))
+        total = sum(dec.weight_bytes_per_token(cfg, range(r * per, min(cfg.n_layer, (r + 1) * per)), with_head=(r == world - 1)) for r in range(world))
+        assert total == 4_671_134_848

@@ -1,0 +1,432 @@
+"""GPU parity: the sm_100a kernels, called through the C-ABI (include/b200_ops.h via ctypes), against the CPU oracle
+(oracle/*.c restating the reference's ggml CPU backend) and the committed golden vectors minted from the reference itself.
+
+Bars (BASELINE.json north_star): integer / byte / index work BIT-EXACT (activation quantisers, repack, KV-cache writes, gathers);
+MUL_MAT: the integer sub-block dot products are exact, only the order of the final f32 accumulation differs -> |err| <=
+2e-6 * sum|w||x| (a few ulp of the summand scale; far inside the reference's own NMSE 5e-4 bar, tests/test-backend-ops.cpp:3300);
+float ops within the tolerance written in each test.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_c as O
+
+pytestmark = pytest.mark.gpu
+
+from __graft_entry__ import load_package  # noqa: E402
+
+QT = {"q4_0": O.Q4_0, "q8_0": O.Q8_0, "q4_K": O.Q4_K, "q5_K": O.Q5_K, "q6_K": O.Q6_K}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    return load_package().ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rand_blocks(rng, t, nblocks):
+    """Random but VALID quantised blocks (no quantiser needed): random payload bytes, f16 scales in a sane range."""
+    bs = O.BLOCK[t][1]
+    b = rng.integers(0, 256, (nblocks, bs), dtype=np.uint8)
+
+    def h(n, lo=1e-3, hi=1e-2, signed=False):
+        v = rng.uniform(lo, hi, n).astype(np.float16)
+        if signed:
+            v *= rng.choice([-1, 1], n).astype(np.float16)
+        return v.view(np.uint8).reshape(n, 2)
+    if t in (O.Q4_0, O.Q8_0):
+        b[:, 0:2] = h(nblocks, signed=True)
+    elif t in (O.Q4_K, O.Q5_K):
+        b[:, 0:2] = h(nblocks)
+        b[:, 2:4] = h(nblocks)
+    elif t == O.Q6_K:
+        b[:, 208:210] = h(nblocks, 1e-4, 1e-3, signed=True)
+    return b
+
+
+def mm_check(got, ref, w_deq, x, factor=2e-6):
+    mag = np.abs(x) @ np.abs(w_deq).T
+    err = np.abs(got - ref)
+    assert np.all(err <= factor * mag + 1e-12), (err.max(), (err / (mag + 1e-30)).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------- quantisers
+def _canon_q8K(rec, k):
+    return rec
+
+
+@pytest.mark.parametrize("k", [256, 1024, 4096, 12288])
+def test_quantize_q8K_bit_exact(ops, k):
+    rng = np.random.default_rng(k)
+    x = rng.standard_normal((3, k)).astype(np.float32) * 2
+    x[1] *= 1e-3
+    x[2, :256] = 0.0
+    x[0, 5] = -x[0, 7]                     # tie in |x|: the reference keeps the FIRST maximum
+    act = ops.quantize_act(ops.Q4_K, dev(x)).cpu().numpy()
+    nb = k // 256
+    for i in range(3):
+        ref = O.quantize_q8_K(x[i]).reshape(nb, 292)
+        d_ref = ref[:, :4].copy().view(np.float32)[:, 0]
+        qs_ref = ref[:, 4:260].reshape(-1)
+        bs_ref = ref[:, 260:292].copy().view(np.int16).reshape(-1)
+        zero = np.repeat(d_ref == 0, 16)
+        rec = act[i]
+        assert np.array_equal(rec[:k], qs_ref)
+        assert np.array_equal(rec[k:k + 4 * nb].view(np.float32), d_ref)
+        got_bs = rec[k + 4 * nb:k + 4 * nb + 2 * (k // 16)].view(np.int16)
+        assert np.array_equal(got_bs[~zero], bs_ref[~zero])      # ref leaves bsums of an all-zero block unwritten
+        assert np.all(got_bs[zero] == 0)
+
+
+@pytest.mark.parametrize("k", [32, 1024, 4096])
+def test_quantize_q8_0_bit_exact(ops, k):
+    rng = np.random.default_rng(k + 1)
+    x = rng.standard_normal((2, k)).astype(np.float32)
+    x[1, :32] = 0
+    act = ops.quantize_act(ops.Q8_0, dev(x)).cpu().numpy()
+    nb = k // 32
+    for i in range(2):
+        ref = O.quantize_q8_0(x[i], variant=1).reshape(nb, 34)
+        assert np.array_equal(act[i][:k], ref[:, 2:].reshape(-1))
+        assert np.array_equal(act[i][k:k + 2 * nb].view(np.uint16), ref[:, :2].copy().view(np.uint16).reshape(-1))
+        bs = act[i][k + 2 * nb:k + 4 * nb].view(np.int16)
+        assert np.array_equal(bs, ref[:, 2:].view(np.int8).astype(np.int32).sum(1).astype(np.int16))
+
+
+# ---------------------------------------------------------------------------------------------------------------- MUL_MAT
+@pytest.mark.parametrize("name", list(QT) + ["f16"])
+@pytest.mark.parametrize("planar", [False, True])
+def test_mul_mat_golden(ops, golden, name, planar):
+    g = golden["mul_mat"]
+    t = QT.get(name, O.F16)
+    if planar and t not in ops.PAYLOAD:
+        pytest.skip("type is never repacked")
+    w, x, ref = g[f"w_{name}"], g["x"], g[f"y_{name}"]
+    wd = dev(w.view(np.uint8))
+    layout = ops.LAYOUT_NATIVE
+    if planar:
+        wd, layout = ops.to_planar(t, wd), ops.LAYOUT_PLANAR
+    wf = O.dequant(t, w, 1024) if name != "f16" else w.view(np.float16).astype(np.float32).reshape(48, 1024)
+    for n in (1, 3):
+        got = ops.mul_mat(wd, t, 48, 1024, dev(x[:n]), layout=layout).cpu().numpy()
+        mm_check(got, ref[:n], wf, x[:n], 3e-6 if name != "f16" else 1e-5)
+
+
+SHAPES = [(4096, 4096, 1), (1024, 4096, 1), (12288, 4096, 1), (4096, 12288, 1), (40, 256, 1), (7, 512, 5), (33, 256, 8), (64, 1024, 11)]
+
+
+@pytest.mark.parametrize("name", QT)
+@pytest.mark.parametrize("m,k,n", SHAPES)
+def test_mul_mat_vs_oracle(ops, name, m, k, n):
+    """Seeded random blocks at the BASELINE.json layer shapes (Qwen3-8B: 4096x4096, 1024x4096, 12288x4096, 4096x12288) and ragged
+    small ones; n > 8 exercises the column chunking."""
+    t = QT[name]
+    rng = np.random.default_rng(hash((name, m, k, n)) & 0xffff)
+    blocks = rand_blocks(rng, t, m * k // O.BLOCK[t][0])
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    ref = O.mul_mat(t, blocks, x, m, k)
+    wf = O.dequant(t, blocks, k)
+    wd = dev(blocks)
+    got = ops.mul_mat(wd, t, m, k, dev(x)).cpu().numpy()
+    mm_check(got, ref, wf, x)
+    if t in ops.PAYLOAD:
+        got = ops.mul_mat(ops.to_planar(t, wd), t, m, k, dev(x), layout=ops.LAYOUT_PLANAR).cpu().numpy()
+        mm_check(got, ref, wf, x)
+
+
+def test_mul_mat_lm_head_shape(ops):
+    """output.weight of MiniCPM-o-4.5: Q6_K [4096, 151748]; oracle on a row sample, linearity on the full output."""
+    m, k = 151748, 4096
+    rng = np.random.default_rng(7)
+    blocks = rand_blocks(rng, O.Q6_K, m * k // 256)
+    x = rng.standard_normal((1, k)).astype(np.float32)
+    wd = ops.to_planar(ops.Q6_K, dev(blocks))
+    got = ops.mul_mat(wd, ops.Q6_K, m, k, dev(x), layout=ops.LAYOUT_PLANAR).cpu().numpy()
+    rows = np.concatenate([np.arange(0, 64), np.arange(m - 64, m), rng.integers(0, m, 128)])
+    sub = blocks.reshape(m, -1)[rows]
+    ref = O.mul_mat(O.Q6_K, sub, x, len(rows), k)
+    mm_check(got[:, rows], ref, O.dequant(O.Q6_K, sub, k), x)
+    # homogeneity: q8_K quantisation is scale-equivariant for power-of-two scales -> y(2x) == 2 y(x) exactly
+    got2 = ops.mul_mat(wd, ops.Q6_K, m, k, dev(2 * x), layout=ops.LAYOUT_PLANAR).cpu().numpy()
+    assert np.array_equal(got2, 2 * got)
+
+
+def test_mul_mat_empty_and_batched(ops):
+    rng = np.random.default_rng(3)
+    blocks = rand_blocks(rng, O.Q4_K, 16 * 512 // 256)
+    wd = dev(blocks)
+    y = ops.mul_mat(wd, ops.Q4_K, 16, 512, torch.empty((0, 512), device="cuda"))
+    assert y.shape == (0, 16)
+    # batch dims with broadcast: x [2, 3, n=2, k], w 2-D
+    x = rng.standard_normal((2, 3, 2, 512)).astype(np.float32)
+    got = ops.mul_mat(wd, ops.Q4_K, 16, 512, dev(x)).cpu().numpy()
+    ref = O.mul_mat(O.Q4_K, blocks, x.reshape(-1, 512), 16, 512).reshape(2, 3, 2, 16)
+    mm_check(got.reshape(-1, 16), ref.reshape(-1, 16), O.dequant(O.Q4_K, blocks, 512), x.reshape(-1, 512))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+def test_mul_mat_float_weights(ops, dt):
+    rng = np.random.default_rng(11)
+    m, k, n = 96, 768, 3
+    w = (rng.standard_normal((m, k)) * 0.05).astype(np.float32)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    tdt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[dt]
+    wt = torch.from_numpy(w).cuda().to(tdt)
+    got = ops.mul_mat(wt, {"f32": ops.F32, "f16": ops.F16, "bf16": ops.BF16}[dt], m, k, dev(x), w_ne=[k, m]).cpu().numpy()
+    xr = torch.from_numpy(x).to(tdt).double()             # the CPU backend rounds activations to the weight type (vec_dot_type)
+    ref = (xr @ wt.cpu().double().T).numpy()
+    assert np.abs(got - ref).max() <= 1e-5 * (np.abs(x) @ np.abs(w).T).max()
+
+
+def test_matvec_jobs_residual_swiglu(ops):
+    rng = np.random.default_rng(5)
+    k = 1024
+    x = rng.standard_normal((1, k)).astype(np.float32)
+    act = ops.quantize_act(ops.Q4_K, dev(x))
+    ms = [256, 64, 64]
+    ws = [rand_blocks(rng, O.Q4_K, m * k // 256) for m in ms]
+    ys = [torch.zeros(m, device="cuda") for m in ms]
+    res = rng.standard_normal(ms[0]).astype(np.float32)
+    jobs = [ops.make_job(dev(w), ops.Q4_K, m, k, y) for w, m, y in zip(ws, ms, ys)]
+    keep = [dev(w) for w in ws]
+    jobs = [ops.make_job(kw, ops.Q4_K, m, k, y) for kw, m, y in zip(keep, ms, ys)]
+    rd = dev(res)
+    jobs[0].residual = rd.data_ptr()
+    ops.matvec_q(jobs, act, k)
+    for i, (w, m) in enumerate(zip(ws, ms)):
+        ref = O.mul_mat(O.Q4_K, w, x, m, k)[0] + (res if i == 0 else 0)
+        mm_check(ys[i].cpu().numpy()[None], ref[None], O.dequant(O.Q4_K, w, k), x)
+    # gate/up + swiglu epilogue
+    m = 384
+    wg, wu = rand_blocks(rng, O.Q4_K, m * k // 256), rand_blocks(rng, O.Q4_K, m * k // 256)
+    dg, du = dev(wg), dev(wu)
+    y = torch.zeros(m, device="cuda")
+    ops.matvec_q_swiglu(ops.make_job(dg, ops.Q4_K, m, k, y), ops.make_job(du, ops.Q4_K, m, k, y), y, act, k)
+    g, u = O.mul_mat(O.Q4_K, wg, x, m, k)[0], O.mul_mat(O.Q4_K, wu, x, m, k)[0]
+    ref = O.swiglu(g, u)
+    assert np.allclose(y.cpu().numpy(), ref, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["q4_0", "q8_0", "q6_K"])
+def test_repack_round_trip(ops, name):
+    t = QT[name]
+    rng = np.random.default_rng(9)
+    nblocks = 70001                     # odd count: chunk boundaries fall inside blocks
+    raw = rng.integers(0, 256, nblocks * O.BLOCK[t][1], dtype=np.uint8)
+    wd = dev(raw)
+    planar = ops.to_planar(t, wd)
+    back = ops.from_planar(t, planar)
+    assert torch.equal(back, wd)
+    pay = ops.PAYLOAD[t]
+    p = planar.cpu().numpy()
+    nat = raw.reshape(nblocks, -1)
+    d_off = 208 if t == O.Q6_K else 0
+    p_off = 0 if t == O.Q6_K else 2
+    assert np.array_equal(p[:nblocks * pay].reshape(nblocks, pay), nat[:, p_off:p_off + pay])
+    assert np.array_equal(p[nblocks * pay:].reshape(nblocks, 2), nat[:, d_off:d_off + 2])
+
+
+# ---------------------------------------------------------------------------------------------------------------- norm / rope / kv
+def test_rms_norm_golden_and_fused_forms(ops, golden):
+    g = golden["ops"]
+    got = ops.rms_norm(dev(g["rms_x"]), 1e-6).cpu().numpy()
+    assert np.allclose(got, g["rms_y"], rtol=1e-6, atol=0)
+    rng = np.random.default_rng(2)
+    for rows, n in ((1, 4096), (40, 128), (5, 1000), (3, 12288)):
+        x = rng.standard_normal((rows, n)).astype(np.float32) * 3
+        w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+        a = rng.standard_normal((rows, n)).astype(np.float32)
+        ref = O.rms_norm(x, 1e-6)
+        assert np.allclose(ops.rms_norm(dev(x), 1e-6).cpu().numpy(), ref, rtol=1e-6, atol=0)
+        assert np.allclose(ops.rms_norm(dev(x), 1e-6, w=dev(w)).cpu().numpy(), ref * w, rtol=1e-6, atol=0)
+        assert np.allclose(ops.rms_norm(dev(x), 1e-6, w=dev(w), add=dev(a)).cpu().numpy(), ref * w + a, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("wtype", ["q4_K", "q8_0"])
+def test_rms_norm_quantize_fused(ops, wtype):
+    """The fused producer must equal rms_norm -> mul -> quantize run as separate C-ABI calls (same f32 op sequence)."""
+    t = QT[wtype]
+    rng = np.random.default_rng(4)
+    for n, k in ((1, 4096), (3, 1024), (2, 12288)):
+        x = rng.standard_normal((n, k)).astype(np.float32) * 2
+        w = (1 + 0.1 * rng.standard_normal(k)).astype(np.float32)
+        xd, wd = dev(x), dev(w)
+        act, y = ops.rms_norm_quantize(xd, wd, t, 1e-6, want_f32=True)
+        y_sep = ops.rms_norm(xd, 1e-6, w=wd)
+        assert np.allclose(y.cpu().numpy(), y_sep.cpu().numpy(), rtol=3e-7, atol=0)
+        act_sep = ops.quantize_act(t, y)                      # quantising the fused kernel's own f32 output must be identical
+        assert torch.equal(act, act_sep)
+        ref = O.rms_norm(x, 1e-6) * w
+        assert np.allclose(y.cpu().numpy(), ref, rtol=1e-6, atol=0)
+
+
+def test_rope_golden(ops, golden):
+    g = golden["ops"]
+    x, pos = dev(g["rope_x"]), dev(g["rope_pos"])
+    for key, nd, mode, ctx, base in (("rope_neox", 128, 2, 40960, 1e6), ("rope_norm", 128, 0, 4096, 1e4),
+                                     ("rope_neox_partial", 64, 2, 40960, 1e6)):
+        got = ops.rope(x, pos, nd, mode, ctx, base).cpu().numpy()
+        assert np.abs(got - g[key]).max() <= 4e-6, key         # theta chain identical; CUDA sincosf vs glibc <= 2 ulp
+
+
+def test_rope_yarn_and_freq_factors(ops):
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((3, 4, 64)).astype(np.float32)
+    pos = np.array([3, 500, 9000], np.int32)
+    ff = (1 + rng.uniform(0, 1, 32)).astype(np.float32)
+    ref = O.rope(x, pos, 64, 0, 4096, 1e4, freq_scale=0.25, ext_factor=1.0, attn_factor=1.1, freq_factors=ff)
+    got = ops.rope(dev(x), dev(pos), 64, 0, 4096, 1e4, freq_scale=0.25, ext_factor=1.0, attn_factor=1.1, freq_factors=dev(ff)).cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-5
+
+
+def test_set_rows_get_rows_cpy(ops, golden):
+    g = golden["ops"]
+    dst = torch.zeros((12, 256), dtype=torch.float16, device="cuda")
+    ops.set_rows(dev(g["sr_src"]), dev(g["sr_idx"]), dst)
+    assert np.array_equal(dst.cpu().numpy().view(np.uint16), g["sr_dst"].view(np.uint16))
+    # i32 indices, f32 destination, strided destination rows (a KV-cache view)
+    rng = np.random.default_rng(8)
+    src = rng.standard_normal((5, 1024)).astype(np.float32)
+    idx = np.array([7, 0, 3, 9, 1], np.int32)
+    big = torch.zeros((10, 2048), dtype=torch.float16, device="cuda")
+    ops.set_rows(dev(src), dev(idx), big[:, :1024])
+    exp = np.zeros((10, 2048), np.float16)
+    exp[idx, :1024] = src.astype(np.float16)
+    assert np.array_equal(big.cpu().numpy().view(np.uint16), exp.view(np.uint16))
+    # get_rows f32 / f16
+    table = rng.standard_normal((50, 96)).astype(np.float32)
+    ids = np.array([[49, 0, 7], [7, 7, 1]], np.int32)[0]
+    assert np.array_equal(ops.get_rows(dev(table), dev(ids)).cpu().numpy(), table[ids])
+    assert np.array_equal(ops.get_rows(dev(table.astype(np.float16)), dev(ids)).cpu().numpy(), table.astype(np.float16)[ids].astype(np.float32))
+    # cpy: f32 -> f16 contiguous (the KQ-mask cast), f16 -> f32, transposed source
+    m = rng.standard_normal((64, 320)).astype(np.float32)
+    m[m > 1] = -np.inf
+    out = torch.empty((64, 320), dtype=torch.float16, device="cuda")
+    ops.cpy(dev(m), out)
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), m.astype(np.float16).view(np.uint16))
+    back = torch.empty((64, 320), dtype=torch.float32, device="cuda")
+    ops.cpy(out, back)
+    assert np.array_equal(back.cpu().numpy(), m.astype(np.float16).astype(np.float32))
+    tr = torch.empty((320, 64), dtype=torch.float32, device="cuda")
+    ops.cpy(dev(m).t(), tr)
+    assert np.array_equal(tr.cpu().numpy(), m.T)
+
+
+def test_elementwise(ops, golden):
+    g = golden["ops"]
+    got = ops.glu(ops.GLU_SWIGLU, dev(g["glu_gate"]), dev(g["glu_up"])).cpu().numpy()
+    assert np.allclose(got, g["glu_y"], rtol=2e-6, atol=1e-7)
+    rng = np.random.default_rng(10)
+    a = rng.standard_normal((2, 3, 5, 64)).astype(np.float32)
+    for op, f in ((ops.ADD, np.add), (ops.SUB, np.subtract), (ops.MUL, np.multiply), (ops.DIV, np.divide)):
+        for bshape in ((2, 3, 5, 64), (64,), (1, 3, 1, 64), (2, 1, 5, 1)):
+            b = rng.standard_normal(bshape).astype(np.float32) + 3
+            assert np.array_equal(ops.binary(op, dev(a), dev(b)).cpu().numpy(), f(a, b).astype(np.float32)), (op, bshape)
+    x = rng.standard_normal(1000).astype(np.float32) * 3
+    xt = torch.from_numpy(x)
+    F = torch.nn.functional
+    for op, ref in ((ops.SILU, F.silu(xt)), (ops.RELU, F.relu(xt)), (ops.GELU, F.gelu(xt, approximate="tanh")), (ops.TANH, torch.tanh(xt)),
+                    (ops.SIGMOID, torch.sigmoid(xt)), (ops.GELU_ERF, F.gelu(xt)), (ops.NEG, -xt), (ops.EXP, torch.exp(xt)),
+                    (ops.SQR, xt * xt), (ops.ABS, xt.abs()), (ops.GELU_QUICK, xt * torch.sigmoid(1.702 * xt))):
+        assert np.allclose(ops.unary(op, dev(x)).cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-6), op
+    assert np.allclose(ops.scale(dev(x), 0.5, 1.0).cpu().numpy(), x * 0.5 + 1.0)
+    # single-tensor GLU (halves of a row), swapped or not
+    xx = rng.standard_normal((4, 128)).astype(np.float32)
+    assert np.allclose(ops.glu(ops.GLU_SWIGLU, dev(xx)).cpu().numpy(), O.swiglu(xx[:, :64], xx[:, 64:]), rtol=2e-6, atol=1e-7)
+    assert np.allclose(ops.glu(ops.GLU_SWIGLU, dev(xx), swapped=True).cpu().numpy(), O.swiglu(xx[:, 64:], xx[:, :64]), rtol=2e-6, atol=1e-7)
+    # soft_max with f16 mask
+    s = rng.standard_normal((6, 300)).astype(np.float32) * 4
+    mask = np.zeros((6, 300), np.float32)
+    mask[:, 250:] = -np.inf
+    got = ops.soft_max(dev(s), dev(mask.astype(np.float16)), 0.3).cpu().numpy()
+    assert np.allclose(got, O.soft_max(s, mask, 0.3), rtol=2e-6, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("tag", ["dec", "pre"])
+def test_flash_attn_golden(ops, golden, tag):
+    g = golden["flash_attn"]
+    q, k, v, mask, ref = g[f"{tag}_q"], g[f"{tag}_k"], g[f"{tag}_v"], g[f"{tag}_mask"], g[f"{tag}_out"]
+    qd = dev(q).permute(1, 0, 2)                                         # [n_head, n_q, D] view, as llama-graph.cpp:1303 permutes
+    got = ops.flash_attn(qd, dev(k), dev(v), dev(mask), 1.0 / np.sqrt(128)).cpu().numpy()
+    # the reference CPU backend accumulates V in f16 (ops.cpp:8040-8060); we accumulate in f32 -> compare at its own noise level
+    assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max()
+    exact = O.flash_attn(q, k, v, mask, 1.0 / np.sqrt(128), f16_acc=False)
+    assert np.abs(got - exact).max() <= 2e-5 * np.abs(exact).max() + 1e-6
+
+
+@pytest.mark.parametrize("n_kv,cur,D,n_head,n_head_kv", [(4096, 4000, 128, 32, 8), (256, 0, 128, 32, 8), (512, 300, 64, 12, 12),
+                                                         (1024, 1023, 128, 8, 4), (8192, 5000, 128, 32, 8)])
+def test_flash_attn_decode_cache_views(ops, n_kv, cur, D, n_head, n_head_kv):
+    """Decode at the BASELINE.json shapes over a strided F16 KV-cache view (row stride = n_head_kv*D halves, head stride = D)."""
+    rng = np.random.default_rng(n_kv + cur)
+    q = rng.standard_normal((1, n_head, D)).astype(np.float32)
+    kc = (rng.standard_normal((n_kv, n_head_kv, D)) * 0.5).astype(np.float16)
+    vc = rng.standard_normal((n_kv, n_head_kv, D)).astype(np.float16)
+    kc[cur + 1:] = np.float16(np.nan)                                    # never-written cells: must not leak through the mask
+    vc[cur + 1:] = np.float16(np.nan)
+    mask = np.zeros((64, n_kv), np.float16)
+    mask[:, cur + 1:] = -np.inf
+    kd, vd = dev(kc).permute(1, 0, 2), dev(vc).permute(1, 0, 2)          # [n_head_kv, n_kv, D] views with cache strides
+    got = ops.flash_attn(dev(q).permute(1, 0, 2), kd, vd, dev(mask), 1.0 / np.sqrt(D)).cpu().numpy()
+    kk, vv = np.ascontiguousarray(kc.transpose(1, 0, 2)), np.ascontiguousarray(vc.transpose(1, 0, 2))
+    kk[:, cur + 1:], vv[:, cur + 1:] = 0, 0
+    ref = O.flash_attn(q, kk, vv, mask, 1.0 / np.sqrt(D), f16_acc=False)
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6
+
+
+def test_flash_attn_small_batch_causal(ops):
+    rng = np.random.default_rng(12)
+    n_q, n_kv, D, n_head, n_head_kv = 7, 448, 128, 16, 4
+    q = rng.standard_normal((n_q, n_head, D)).astype(np.float32)
+    k = (rng.standard_normal((n_head_kv, n_kv, D)) * 0.5).astype(np.float16)
+    v = rng.standard_normal((n_head_kv, n_kv, D)).astype(np.float16)
+    mask = np.zeros((64, n_kv), np.float16)
+    for i in range(n_q):
+        mask[i, 400 + i + 1:] = -np.inf
+    got = ops.flash_attn(dev(q).permute(1, 0, 2), dev(k), dev(v), dev(mask), 0.088).cpu().numpy()
+    ref = O.flash_attn(q, k, v, mask, 0.088, f16_acc=False)
+    assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6
+
+
+def test_qkv_post_matches_separate_ops(ops):
+    """b200_qkv_post == rms_norm*w -> rope -> set_rows run as separate C-ABI calls (Qwen3 shapes; 2 tokens)."""
+    rng = np.random.default_rng(13)
+    D, n_head, n_head_kv, n_tok, n_ctx = 128, 32, 8, 2, 64
+    q = rng.standard_normal((n_tok, n_head, D)).astype(np.float32)
+    k = rng.standard_normal((n_tok, n_head_kv, D)).astype(np.float32)
+    v = rng.standard_normal((n_tok, n_head_kv * D)).astype(np.float32)
+    qw = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    kw = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    pos = np.array([17, 4000], np.int32)
+    idx = np.array([5, 41], np.int64)
+    qd, kd, vd, qwd, kwd, posd, idxd = map(dev, (q, k, v, qw, kw, pos, idx))
+    # separate ops
+    q_ref = ops.rope(ops.rms_norm(qd, 1e-6, w=qwd), posd, D, 2)
+    k_ref = ops.rope(ops.rms_norm(kd, 1e-6, w=kwd), posd, D, 2)
+    kc_ref = torch.zeros((n_ctx, n_head_kv * D), dtype=torch.float16, device="cuda")
+    vc_ref = torch.zeros_like(kc_ref)
+    ops.set_rows(k_ref.reshape(n_tok, -1), idxd, kc_ref)
+    ops.set_rows(vd, idxd, vc_ref)
+    # fused
+    kc, vc = torch.zeros_like(kc_ref), torch.zeros_like(vc_ref)
+    p = ops.RopeParams(D, 2, 40960, 1e6, 1.0, 0.0, 1.0, 32.0, 1.0)
+    P = C.c_void_p
+    ops.check(ops.lib().b200_qkv_post(P(qd.data_ptr()), P(kd.data_ptr()), P(vd.data_ptr()), P(qwd.data_ptr()), P(kwd.data_ptr()),
+                                      P(posd.data_ptr()), P(idxd.data_ptr()), ops.I64, P(kc.data_ptr()), P(vc.data_ptr()),
+                                      C.c_int64(n_head_kv * D * 2), C.c_int64(n_head_kv * D * 2), D, n_head, n_head_kv,
+                                      C.c_int64(n_tok), C.c_int64(n_head * D), C.c_int64(n_head_kv * D), C.c_int64(n_head_kv * D),
+                                      C.byref(p), C.c_float(1e-6), ops.stream()))
+    assert torch.allclose(qd, q_ref, rtol=2e-6, atol=2e-6)
+    assert torch.equal(vc, vc_ref)
+    assert (kc.float() - kc_ref.float()).abs().max().item() <= 2e-3        # one f16 ulp at |k| <= 4
+    ref_np = O.rope(O.rms_norm(q.reshape(-1, D), 1e-6).reshape(q.shape) * qw, pos, D, 2)
+    assert np.abs(qd.cpu().numpy() - ref_np).max() <= 1e-5
