@@ -161,6 +161,35 @@ B200_API int    b200_flash_attn(const b200_tensor * q, const b200_tensor * k, co
                                 const b200_tensor * dst, float scale, float max_bias, float logit_softcap, void * scratch,
                                 size_t scratch_bytes, void * stream);
 
+/* ---- persistent decode engine (replaces, for a batch-1 token, the whole per-node launch sequence ggml_backend_cuda_graph_compute
+ *      ggml-cuda.cu:3085-3164 issues for llm_build_qwen3's graph, src/llama-model.cpp:9287-9406: 868 node launches + 253 quantize_q8_1) ---
+ * ONE cooperative kernel, one CTA per SM, walks 5 phases per layer + lm_head with grid barriers; weights stream through per-warp TMA
+ * rings that keep filling across the barriers (csrc/stream_decode.cu).  All pointers are device pointers and are baked into the program:
+ * the host updates the CONTENTS of x_in / pos / kv_idx / mask before each step (what the ggml scheduler's input copies do).
+ * Requirements (else B200_ERR_UNSUPPORTED and the caller uses the per-op entry points): head_dim 128, n_head = 4 * n_head_kv, K-quant
+ * weights (q4_K / q5_K native, q6_K planar), n_embd and n_ff multiples of 256. */
+typedef struct b200_weight { const void * data; int32_t type; int32_t layout; } b200_weight;
+typedef struct b200_decode_layer {
+    b200_weight wq, wk, wv, wo, gate, up, down;
+    const float * attn_norm, * ffn_norm, * q_norm, * k_norm;      /* q_norm/k_norm NULL: no per-head norm (llama arch) */
+    void * k_cache, * v_cache;                                   /* F16 [n_ctx][n_head_kv * head_dim] */
+    int64_t k_row_bytes, v_row_bytes;
+} b200_decode_layer;
+typedef struct b200_decode_desc {
+    int32_t n_layer, n_embd, n_head, n_head_kv, head_dim, n_ff, n_vocab;
+    float rms_eps, attn_scale;
+    b200_rope_params rope;
+    const b200_decode_layer * layers;
+    const float * out_norm; b200_weight lm_head;                 /* lm_head.data NULL: stage without head, x_out receives the residual stream */
+    const float * x_in;                                          /* [n_embd] embedding row of the token (or the previous stage's x_out) */
+    const int32_t * pos; const int64_t * kv_idx; const void * mask;   /* pos[1], kv_idx[1], F16 mask row [n_kv] (0 / -inf) */
+    float * logits; float * hidden_out; float * x_out;           /* [n_vocab]; optional [n_embd] result_norm; optional [n_embd] */
+} b200_decode_desc;
+B200_API int  b200_decoder_create(const b200_decode_desc * desc, void ** handle);
+B200_API int  b200_decoder_step(void * handle, int32_t n_kv, void * stream);
+B200_API int  b200_decoder_n_phases(void * handle);
+B200_API void b200_decoder_destroy(void * handle);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 //   * persistent grid sized to the SM count; several weight matrices sharing one activation (q/k/v, gate/up) run as
 //     "jobs" of ONE launch; optional fused residual add and swiglu epilogues remove 3 launches per layer.
 #include "common.cuh"
+#include "stream_decode.cuh"
 
 namespace b200 {
 
@@ -299,15 +300,46 @@ int matvec_launch(MatvecArgs & A, int type, bool aligned, int ncols, cudaStream_
     return B200_ERR_UNSUPPORTED;
 }
 
+static bool try_stream(const b200_matvec_job * jobs, int njobs, const void * act, int64_t k, bool swiglu, float * y_swiglu, cudaStream_t st, int & rc);
+
 // used by mul_mat.cu: single job, ncols <= 8, explicit y column stride
 int matvec_q_cols(const void * w, int type, int layout, int64_t m, int64_t row_stride, const void * act, int64_t k, int ncols,
                   float * y, int64_t y_col_stride, cudaStream_t st) {
+    if (ncols == 1) {
+        b200_matvec_job job = { w, type, layout, m, row_stride, y, nullptr };
+        int rc = 0;
+        if (try_stream(&job, 1, act, k, false, nullptr, st, rc)) return rc;
+    }
     MatvecArgs A = {};
     const ActLayout L = act_layout(type, k);
     A.njobs = 1; A.act = (const uint8_t *) act; A.act_bytes = L.bytes; A.act_d_off = L.d_off; A.act_bsum_off = L.bsum_off; A.k = k;
     const bool al = setup_job(A, 0, w, type, layout, m, row_stride, k);
     A.y[0] = y; A.residual[0] = nullptr; A.row_begin[0] = 0; A.row_begin[1] = m; A.y_col_stride[0] = y_col_stride;
     return matvec_launch(A, type, al, ncols, st);
+}
+
+bool sd_fill_mat(SdMat & M, const void * w, int type, int layout, int64_t m, int64_t k, int64_t row_stride_bytes, float * y, const float * residual);
+bool sd_phase_ok(const SdPhase & P);
+int  sd_launch(const SdPhase * phases_dev, int n_phases, const SdPhase * single, unsigned * gbar, const SdRuntime & rt, cudaStream_t st);
+
+// batch-1 jobs whose rows can be bulk-copied go to the persistent streaming kernel (stream_decode.cu); anything else (native
+// q4_0/q8_0/q6_K blocks, strided rows, k beyond the shared-memory record) stays on k_mmvq above.
+static bool try_stream(const b200_matvec_job * jobs, int njobs, const void * act, int64_t k, bool swiglu, float * y_swiglu, cudaStream_t st, int & rc) {
+    if (njobs > 3) return false;
+    SdPhase P = {};
+    P.ksplit = 1;
+    P.kind = SD_MATVEC; P.n_mat = njobs; P.epilogue = swiglu ? SD_EPI_SWIGLU : SD_EPI_STORE; P.prologue = SD_PRO_ACT;
+    P.k = (int32_t) k; P.act_group = is_kquant(jobs[0].type) ? 256 : 32; P.act = (const uint8_t *) act;
+    if ((uintptr_t) act % 16) return false;
+    for (int i = 0; i < njobs; ++i) {
+        if ((is_kquant(jobs[i].type) ? 256 : 32) != P.act_group) return false;
+        if (!sd_fill_mat(P.mat[i], jobs[i].w, jobs[i].type, jobs[i].layout, jobs[i].m, k, jobs[i].row_stride_bytes,
+                         swiglu ? y_swiglu : jobs[i].y, swiglu ? nullptr : jobs[i].residual)) return false;
+    }
+    if (!sd_phase_ok(P)) return false;
+    SdRuntime rt = {};
+    rc = sd_launch(nullptr, 1, &P, nullptr, rt, st);
+    return true;
 }
 
 } // namespace b200
@@ -318,6 +350,7 @@ extern "C" int b200_matvec_q(const b200_matvec_job * jobs, int njobs, const void
     if (njobs < 1 || njobs > MAX_JOBS || !jobs || !act) return B200_ERR_ARG;
     const int type = jobs[0].type;
     if (!is_quant(type) || k % blck_size(type) != 0) return B200_ERR_UNSUPPORTED;
+    { int rc = 0; if (try_stream(jobs, njobs, act, k, false, nullptr, (cudaStream_t) stream, rc)) return rc; }
     MatvecArgs A = {};
     const ActLayout L = act_layout(type, k);
     A.njobs = njobs; A.act = (const uint8_t *) act; A.act_bytes = L.bytes; A.act_d_off = L.d_off; A.act_bsum_off = L.bsum_off; A.k = k;
@@ -336,6 +369,7 @@ extern "C" int b200_matvec_q_swiglu(const b200_matvec_job * gate, const b200_mat
     if (!gate || !up || !y || !act) return B200_ERR_ARG;
     const int type = gate->type;
     if (!is_quant(type) || up->type != type || up->m != gate->m || k % blck_size(type) != 0) return B200_ERR_UNSUPPORTED;
+    { const b200_matvec_job two[2] = { *gate, *up }; int rc = 0; if (try_stream(two, 2, act, k, true, y, (cudaStream_t) stream, rc)) return rc; }
     MatvecArgs A = {};
     const ActLayout L = act_layout(type, k);
     A.njobs = 2; A.swiglu = 1; A.act = (const uint8_t *) act; A.act_bytes = L.bytes; A.act_d_off = L.d_off; A.act_bsum_off = L.bsum_off; A.k = k;

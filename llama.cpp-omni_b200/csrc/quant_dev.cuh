@@ -6,7 +6,12 @@
 
 namespace b200 {
 
+// Shared-memory copies of the record (stream_decode.cu) store the int8 plane with a 16-byte-segment swizzle so that the matvec's
+// fragment loads are bank-conflict free: segment bit 3 is XORed into segment bits 1 and 2.  SWZ = false: linear (global records).
+template <bool SWZ> __device__ __forceinline__ int64_t act_qs_off(int64_t off) { return SWZ ? (off ^ (((off >> 7) & 1) * 0x60)) : off; }
+
 // One warp quantises one 256-element super-block held in `v` (lane owns elements [8*lane, 8*lane+8)) into the planar record.
+template <bool SWZ = false>
 __device__ __forceinline__ void quant_block_q8K(const float (&v)[8], uint8_t * rec, int64_t blk, int64_t d_off, int64_t bsum_off) {
     const int lane = threadIdx.x & 31;
     // (amax, first index attaining it): strict '>' in the reference keeps the FIRST maximum
@@ -33,13 +38,14 @@ __device__ __forceinline__ void quant_block_q8K(const float (&v)[8], uint8_t * r
 #pragma unroll
         for (int i = 0; i < 8; ++i) q[i] = 0;
     }
-    *(uint2 *) (rec + blk * 256 + lane * 8) = *(const uint2 *) q;
+    *(uint2 *) (rec + act_qs_off<SWZ>(blk * 256 + lane * 8)) = *(const uint2 *) q;
     const int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);            // 16-wide partial sums
     if ((lane & 1) == 0) ((int16_t *) (rec + bsum_off))[blk * 16 + (lane >> 1)] = (int16_t) s2;
     if (lane == 0) ((float *) (rec + d_off))[blk] = d;
 }
 
 // 8 lanes quantise one 32-element block (lane part = lane & 7 owns 4 elements); `live` = block index in range.
+template <bool SWZ = false>
 __device__ __forceinline__ void quant_block_q8_0(const float4 v, bool live, uint8_t * rec, int64_t blk, int64_t d_off, int64_t bsum_off) {
     const int lane = threadIdx.x & 31;
     float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
@@ -54,7 +60,7 @@ __device__ __forceinline__ void quant_block_q8_0(const float4 v, bool live, uint
     for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (!live) return;
     const uint32_t packed = (uint32_t) (uint8_t) q0 | ((uint32_t) (uint8_t) q1 << 8) | ((uint32_t) (uint8_t) q2 << 16) | ((uint32_t) (uint8_t) q3 << 24);
-    *(uint32_t *) (rec + blk * 32 + (lane & 7) * 4) = packed;
+    *(uint32_t *) (rec + act_qs_off<SWZ>(blk * 32 + (lane & 7) * 4)) = packed;
     if ((lane & 7) == 0) {
         ((__half *) (rec + d_off))[blk] = __float2half_rn(d);
         ((int16_t *) (rec + bsum_off))[blk] = (int16_t) s;

@@ -1,0 +1,410 @@
+// stream_decode.cu — the B200 decode engine: ONE persistent kernel (one CTA per SM) that streams quantised weight rows through
+// TMA (cp.async.bulk) shared-memory rings and executes a whole sequence of decode "phases" with grid barriers between them.
+//
+// Why (SURVEY.md §7 hard parts): a Qwen3-8B Q4_K_M token reads 4.67 GB of weights -> 0.71 ms at the measured 6.54 TB/s, but the
+// reference needs 868 node launches + 253 quantize launches per token; kernel boundaries, not bytes, dominate.  Here
+//   * each of the 12 warps of a CTA owns a private 3-slot ring and is its own producer: while it computes the unit in one slot its
+//     elected lane has two more 4.6 KB bulk copies in flight (12 x 2 x 4.6 KB = 110 KB per SM, independent of occupancy), and when a
+//     phase runs out of rows it prefetches the first units of the NEXT matvec phase before entering the grid barrier — weights never
+//     depend on activations, so HBM keeps streaming through barriers, prologues and the attention phase;
+//   * the arithmetic is the reference CPU backend's (q8_K / q8_0 activations, dp4a sub-block dots, one f32 multiply per block:
+//     ggml-cpu/quants.c:115-149, 305-333, 550-758), computed out of shared memory, activation fragments held in registers;
+//   * phase prologues (sum of partials -> RMS_NORM * weight -> q8 record, or plain quantisation) are recomputed by every CTA into its own
+//     shared memory instead of being separate launches; epilogues fuse the residual ADD and SWIGLU; reductions longer than 4096
+//     (ffn_down) are K-split across CTA groups and summed, in a fixed order, by the next prologue;
+//   * a split-KV attention phase (same arithmetic as flash_attn.cu) runs on the same CTAs while wo's first rows are already resident.
+// Replaces, for batch-1 decode, mul_mat_vec_q + quantize_q8_1 + rms_norm_f32 + rope_neox + k_set_rows + flash_attn_ext_vec +
+// unary_gated_op_kernel + k_bin_bcast of the reference (ggml-cuda/mmvq.cu:139-227, quantize.cu:4-48, norm.cu:107-185,
+// rope.cu:83-123, set-rows.cu:264, fattn-vec.cuh:19, unary.cu:208-228, binbcast.cu:395-443).
+#include "quant_dev.cuh"
+#include "stream_decode.cuh"
+#include <math.h>
+#include <mutex>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds16(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
+__device__ __forceinline__ uint32_t lds4(uint32_t a) { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ int lds_s16(uint32_t a) { int r; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t r; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float r; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a)); return r; }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned * p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// ---------------------------------------------------------------------------------------------------------------- geometry
+// A matvec phase hands CTA c a K-slice (c % ksplit) and the rows [T*g/G, T*(g+1)/G) (g = c / ksplit, G = gridDim / ksplit) of the
+// concatenated row space of its matrices (T rows in total; for SWIGLU the gate/up row PAIRS).  Those rows are cut into UNITS of rpu (1 or
+// 2) consecutive rows of one matrix; unit u of the phase belongs to warp u % SD_WARPS.  Everything is derived arithmetically from u.
+__device__ __forceinline__ void seg_build(SegTab & S, const SdPhase & P, int cta, int ncta) {
+    const bool sw = P.epilogue == SD_EPI_SWIGLU;
+    const int nmat = sw ? 1 : P.n_mat, ks = P.ksplit;
+    const int grp = cta / ks, ngrp = ncta / ks;
+    S.kpart = cta % ks;
+    int64_t T = 0;
+    for (int j = 0; j < nmat; ++j) T += P.mat[j].rows;
+    const int r0 = grp < ngrp ? (int) (T * grp / ngrp) : 0, r1 = grp < ngrp ? (int) (T * (grp + 1) / ngrp) : 0;   // leftover CTAs idle
+    int mb = 0; S.upre[0] = 0;
+    for (int j = 0; j < 3; ++j) {
+        if (j < nmat) {
+            const int lo = max(r0, mb), hi = min(r1, mb + P.mat[j].rows);
+            S.first[j] = lo - mb; S.nrows[j] = max(0, hi - lo);
+            S.sub_p[j] = P.mat[j].row_bytes_p / ks; S.sub_d[j] = P.mat[j].row_bytes_d / ks;
+            const int unit_row = (S.sub_p[j] + S.sub_d[j]) * (sw ? 2 : 1);
+            S.rpu[j] = (P.act_group == 256 && unit_row * 2 <= SD_SLOT_BYTES) ? 2 : 1;
+            mb += P.mat[j].rows;
+        } else { S.first[j] = 0; S.nrows[j] = 0; S.rpu[j] = 1; S.sub_p[j] = 0; S.sub_d[j] = 0; }
+        S.upre[j + 1] = S.upre[j] + (S.nrows[j] + S.rpu[j] - 1) / S.rpu[j];
+    }
+}
+__device__ __forceinline__ void seg_unit(const SegTab & S, int u, int & j, int & row, int & n) {
+    j = u < S.upre[1] ? 0 : u < S.upre[2] ? 1 : 2;
+    const int off = (u - S.upre[j]) * S.rpu[j];
+    row = S.first[j] + off; n = min(S.rpu[j], S.nrows[j] - off);
+}
+
+#include "stream_dot.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------- block sync
+__device__ __forceinline__ float cta_sum(float v, float * red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = lane < SD_WARPS ? red[lane] : 0.0f;
+    t = warp_sum(t);
+    __syncthreads();
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- prologues
+// Build the q8 activation record of the phase's K-slice in shared memory (`act`).  The inputs were written by other CTAs in an earlier
+// phase -> read through L2 (__ldcg).  x = x[0] + x[1] + ... in that fixed order (residual + K-split partials).
+__device__ __forceinline__ float4 sd_load_x4(const SdPhase & P, int i) {
+    float4 v = __ldcg((const float4 *) (P.x[0] + i));
+    for (int s = 1; s < P.n_x; ++s) { const float4 a = __ldcg((const float4 *) (P.x[s] + i)); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+    return v;
+}
+
+// the shared-memory copy of the record keeps every plane 16-byte aligned (the global record packs d right after qs)
+__device__ __forceinline__ ActLayout sd_act_layout(int act_group, int kl) {
+    ActLayout L = act_layout(act_group == 256 ? B200_Q4_K : B200_Q8_0, kl);
+    L.bsum_off = (L.bsum_off + 15) & ~(int64_t) 15;
+    return L;
+}
+
+__device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_t * act, float * red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = P.k, kl = k / P.ksplit, k0 = kpart * kl;                 // this CTA quantises [k0, k0 + kl)
+    const ActLayout L = sd_act_layout(P.act_group, kl);
+    const bool writer = blockIdx.x == 0;
+    if (P.prologue == SD_PRO_ACT) {
+        const ActLayout G = act_layout(P.act_group == 256 ? B200_Q4_K : B200_Q8_0, kl);     // layout of the global record
+        const uint4 * src = (const uint4 *) P.act;
+        for (int i = threadIdx.x; i < (kl >> 4); i += SD_THREADS) *(uint4 *) (act + act_qs_off<true>(i * 16)) = __ldcg(src + i);
+        const int dwords = (int) (G.bsum_off - G.d_off) >> 2, bwords = (int) (G.bytes - G.bsum_off) >> 2;    // small planes: 4-byte words
+        for (int i = threadIdx.x; i < dwords; i += SD_THREADS) ((uint32_t *) (act + L.d_off))[i] = __ldcg((const uint32_t *) (P.act + G.d_off) + i);
+        for (int i = threadIdx.x; i < bwords; i += SD_THREADS) ((uint32_t *) (act + L.bsum_off))[i] = __ldcg((const uint32_t *) (P.act + G.bsum_off) + i);
+        __syncthreads();
+        return;
+    }
+    float scale = 1.0f;
+    const bool norm = P.prologue == SD_PRO_RMSNORM_QUANT;
+    if (norm) {                                                            // the norm spans the whole row, not just this CTA's K-slice
+        float ss = 0.0f;
+        for (int i = threadIdx.x * 4; i < k; i += SD_THREADS * 4) {
+            const float4 v = sd_load_x4(P, i);
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
+    }
+    if (P.act_group == 256) {
+        for (int blk = warp; blk < (kl >> 8); blk += SD_WARPS) {
+            const int e = k0 + blk * 256 + lane * 8;
+            const float4 v0 = sd_load_x4(P, e), v1 = sd_load_x4(P, e + 4);
+            float v[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+            if (writer && P.x_out) { *(float4 *) (P.x_out + e) = v0; *(float4 *) (P.x_out + e + 4) = v1; }
+            if (norm) {
+                const float4 w0 = __ldg((const float4 *) (P.norm_w + e)), w1 = __ldg((const float4 *) (P.norm_w + e + 4));
+                const float w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __fmul_rn(__fmul_rn(v[i], scale), w[i]);
+                if (writer && P.norm_out) {
+                    *(float4 *) (P.norm_out + e) = make_float4(v[0], v[1], v[2], v[3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+            quant_block_q8K<true>(v, act, blk, L.d_off, L.bsum_off);
+        }
+    } else {
+        const int nblk = kl >> 5;
+        for (int b0 = warp * 4; b0 < nblk; b0 += SD_WARPS * 4) {
+            const int blk = b0 + (lane >> 3);
+            const bool live = blk < nblk;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (live) {
+                const int e = k0 + blk * 32 + (lane & 7) * 4;
+                v = sd_load_x4(P, e);
+                if (writer && P.x_out) *(float4 *) (P.x_out + e) = v;
+                if (norm) {
+                    const float4 w = __ldg((const float4 *) (P.norm_w + e));
+                    v.x = __fmul_rn(__fmul_rn(v.x, scale), w.x); v.y = __fmul_rn(__fmul_rn(v.y, scale), w.y);
+                    v.z = __fmul_rn(__fmul_rn(v.z, scale), w.z); v.w = __fmul_rn(__fmul_rn(v.w, scale), w.w);
+                    if (writer && P.norm_out) *(float4 *) (P.norm_out + e) = v;
+                }
+            }
+            quant_block_q8_0<true>(v, live, act, blk, L.d_off, L.bsum_off);
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------- grid barrier
+// count/generation barrier in global memory; self-resetting, so a captured CUDA graph can replay the kernel without host help.
+__device__ __forceinline__ void sd_grid_barrier(unsigned * bar) {       // bar[0] = count, bar[32] = generation (separate 128-B lines)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned gen = ld_acquire_u32(bar + 32);
+        __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 32, 1u);
+        } else {
+            while (ld_acquire_u32(bar + 32) == gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+#include "stream_attn.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------- the kernel
+__device__ __forceinline__ void sd_copy_phase(SdPhase * dst, const SdPhase * src, int lane, int nlanes) {
+    static_assert(sizeof(SdPhase) % 16 == 0, "SdPhase must be a multiple of 16 bytes");
+    for (int i = lane; i < (int) (sizeof(SdPhase) / 16); i += nlanes) ((uint4 *) dst)[i] = ((const uint4 *) src)[i];
+}
+
+// per-warp streaming state: `issued` / `consumed` count this warp's units since kernel start; unit n sits in slot n % SD_DEPTH
+struct WarpStream {
+    uint32_t issued, consumed;
+    int iss_mv, iss_u;                // phase slot (mv index & 1) and phase-local unit index of the next unit this warp will request
+};
+
+// lane 0: request one unit (bulk copies of its rows' K-slices into the warp's next ring slot)
+__device__ __forceinline__ void sd_issue(const SdPhase & P, const SegTab & S, int u, uint32_t slot_addr, uint32_t bar, uint64_t pol) {
+    int j, row, n; seg_unit(S, u, j, row, n);
+    const int nm = P.epilogue == SD_EPI_SWIGLU ? 2 : 1;
+    const uint32_t sp = S.sub_p[j], sd = S.sub_d[j];
+    const int64_t rbp = P.mat[j].row_bytes_p, rbd = P.mat[j].row_bytes_d;
+    mbar_expect_tx(bar, (uint32_t) n * (sp + sd) * nm);
+    uint32_t dst = slot_addr;
+    for (int w = 0; w < nm; ++w) {
+        const uint8_t * pay = P.mat[j + w].payload + row * rbp + (int64_t) S.kpart * sp;
+        if (P.ksplit == 1) { bulk_g2s(dst, pay, (uint32_t) n * sp, bar, pol); dst += n * sp; }           // full rows are back to back
+        else for (int i = 0; i < n; ++i) { bulk_g2s(dst, pay + i * rbp, sp, bar, pol); dst += sp; }
+        if (sd) {
+            const uint8_t * dpl = P.mat[j + w].dplane + row * rbd + (int64_t) S.kpart * sd;
+            if (P.ksplit == 1) { bulk_g2s(dst, dpl, (uint32_t) n * sd, bar, pol); dst += n * sd; }
+            else for (int i = 0; i < n; ++i) { bulk_g2s(dst, dpl + i * rbd, sd, bar, pol); dst += sd; }
+        }
+    }
+}
+
+// keep the warp's ring full: request units of the current phase, then of the next matvec phase (whose descriptor is already staged)
+__device__ __forceinline__ void sd_top_up(WarpStream & W, const SdPhase * sP, const SegTab * sS, int cur_mv, bool have_next,
+                                          uint32_t ring_w, uint32_t bars_w, uint64_t pol) {
+    while (W.issued - W.consumed < SD_DEPTH) {
+        if (W.iss_u >= sS[W.iss_mv].upre[3]) {
+            if (W.iss_mv == (cur_mv & 1) && have_next) { W.iss_mv ^= 1; W.iss_u = threadIdx.x >> 5; continue; }
+            break;
+        }
+        const uint32_t slot = W.issued % SD_DEPTH;
+        sd_issue(sP[W.iss_mv], sS[W.iss_mv], W.iss_u, ring_w + slot * SD_SLOT_BYTES, bars_w + 8 * slot, pol);
+        W.iss_u += SD_WARPS; ++W.issued;
+    }
+}
+
+// one matvec phase.  REGS: K-slice <= 4096 and q4_K / q6_K only -> activation fragments live in registers; otherwise fragments are
+// re-read from shared memory (two rows share each read).
+template <bool REGS>
+__device__ __forceinline__ void sd_consume(const SdPhase & P, const SegTab & S, const ActS & A, WarpStream & W, const SdPhase * sP, const SegTab * sS,
+                                           int cur_mv, bool have_next, uint32_t ring_w, uint32_t bars_w, uint64_t pol) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kl = P.k / P.ksplit, nblk = kl >> 8;
+    const bool swiglu = P.epilogue == SD_EPI_SWIGLU;
+    HFrag fr;
+    if (REGS) hfrag_fill(A, nblk, fr);
+    const int nunits = S.upre[3];
+    for (int u = warp; u < nunits; u += SD_WARPS) {
+        if (lane == 0) sd_top_up(W, sP, sS, cur_mv, have_next, ring_w, bars_w, pol);
+        int j, row, n; seg_unit(S, u, j, row, n);
+        const uint32_t slot = W.consumed % SD_DEPTH, par = (W.consumed / SD_DEPTH) & 1;
+        const int type = P.mat[j].type;
+        const uint32_t rbp = S.sub_p[j], rbd = S.sub_d[j];
+        const uint32_t base = ring_w + slot * SD_SLOT_BYTES;
+        const uint32_t bp = (uint32_t) n * rbp, bd = (uint32_t) n * rbd;     // slot: [payload rows][d rows] (+ the same again for `up`)
+        float * y = P.mat[j].y + (int64_t) S.kpart * P.y_part_stride + row;
+        const float * resid = P.mat[j].residual ? P.mat[j].residual + row : nullptr;
+        mbar_wait(bars_w + 8 * slot, par);
+        float2 g2 = make_float2(0.0f, 0.0f), v;
+        if (REGS) {
+            if (type == B200_Q4_K) { v = krow_regs<B200_Q4_K>(base, rbp, base + bp, rbd, nblk, n, fr); if (swiglu) { g2 = v; v = krow_regs<B200_Q4_K>(base + bp + bd, rbp, base + 2 * bp + bd, rbd, nblk, n, fr); } }
+            else                   { v = krow_regs<B200_Q6_K>(base, rbp, base + bp, rbd, nblk, n, fr); if (swiglu) { g2 = v; v = krow_regs<B200_Q6_K>(base + bp + bd, rbp, base + 2 * bp + bd, rbd, nblk, n, fr); } }
+        } else {
+            v = unit_dots_lds(type, n, base, rbp, base + bp, rbd, A, kl);
+            if (swiglu) { g2 = v; v = unit_dots_lds(type, n, base + bp + bd, rbp, base + 2 * bp + bd, rbd, A, kl); }
+        }
+        if (lane < n) {
+            float o = lane == 0 ? v.x : v.y;
+            if (swiglu) { const float gg = lane == 0 ? g2.x : g2.y; o = (gg / (1.0f + expf(-gg))) * o; }
+            if (resid) o += __ldcg(resid + lane);
+            y[lane] = o;
+        }
+        __syncwarp();
+        fence_proxy_async();                                               // the slot's generic-proxy reads precede its next bulk write
+        ++W.consumed;
+    }
+    if (lane == 0) sd_top_up(W, sP, sS, cur_mv, have_next, ring_w, bars_w, pol);   // prefetch into the next phase through the barrier
+}
+
+__global__ void __launch_bounds__(SD_THREADS, 1) k_stream(const SdPhase * __restrict__ phases_g, int n_phases, unsigned * gbar,
+                                                          const __grid_constant__ SdPhase single, const SdRuntime rt) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t  * ring = smem;
+    uint8_t  * act  = smem + SD_RING_BYTES;
+    uint8_t  * attn_scratch = act + SD_ACT_BYTES;
+    uint64_t * bars = (uint64_t *) (attn_scratch + SD_ATTN_BYTES);       // full[warp][slot]
+    float    * red  = (float *) (bars + SD_WARPS * SD_DEPTH);
+    SdPhase  * sP   = (SdPhase *) (red + 64);                            // [0], [1]: matvec phases (alternating); [2]: attention phase
+    SegTab   * sS   = (SegTab *) (sP + 3);                               // [0], [1]: this CTA's share of the matvec phase in sP[0], sP[1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const SdPhase * src = phases_g ? phases_g : &single;
+    const uint32_t ring_w = smem_u32(ring) + warp * SD_DEPTH * SD_SLOT_BYTES, bars_w = smem_u32(bars) + warp * SD_DEPTH * 8;
+
+    // stage the first matvec phase (its successor is staged at the start of every matvec phase)
+    int first_mv = 0;
+    while (first_mv < n_phases && src[first_mv].kind != SD_MATVEC) ++first_mv;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SD_WARPS * SD_DEPTH; ++s) mbar_init(smem_u32(bars) + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && first_mv < n_phases) sd_copy_phase(&sP[0], src + first_mv, lane, 32);
+    __syncthreads();
+    if (threadIdx.x == 0 && first_mv < n_phases) seg_build(sS[0], sP[0], blockIdx.x, gridDim.x);
+    __syncthreads();
+
+    const uint64_t pol = policy_evict_first();
+    WarpStream W; W.issued = 0; W.consumed = 0; W.iss_mv = 0; W.iss_u = warp;
+    int mv = 0;                                                           // index of the current matvec phase among matvec phases
+    if (lane == 0 && first_mv < n_phases) sd_top_up(W, sP, sS, 0, false, ring_w, bars_w, pol);   // weights first: they depend on nothing
+
+    for (int p = 0; p < n_phases; ++p) {
+        const int kind = p == first_mv ? (int) SD_MATVEC : src[p].kind;
+        if (kind == SD_MATVEC) {
+            const SdPhase & P = sP[mv & 1];
+            // stage the next matvec phase's descriptor + segment table (published by the prologue's __syncthreads)
+            int nxt = p + 1;
+            while (nxt < n_phases && src[nxt].kind != SD_MATVEC) ++nxt;
+            const bool have_next = nxt < n_phases;
+            if (warp == 1 && have_next) {
+                sd_copy_phase(&sP[(mv + 1) & 1], src + nxt, lane, 32);
+                __syncwarp();
+                if (lane == 0) seg_build(sS[(mv + 1) & 1], sP[(mv + 1) & 1], blockIdx.x, gridDim.x);
+            }
+            const SegTab & S = sS[mv & 1];
+            sd_prologue(P, S.kpart, act, red);
+            const int kl = P.k / P.ksplit;
+            const ActLayout L = sd_act_layout(P.act_group, kl);
+            ActS A; A.qs = smem_u32(act); A.d = A.qs + (uint32_t) L.d_off; A.bsum = A.qs + (uint32_t) L.bsum_off;
+            bool regs = P.act_group == 256 && kl <= 4096;                 // q8_K fragments of a 4096-wide record fit in registers
+            for (int m = 0; m < P.n_mat; ++m) regs = regs && (P.mat[m].type == B200_Q4_K || P.mat[m].type == B200_Q6_K);
+            if (regs) sd_consume<true >(P, S, A, W, sP, sS, mv, have_next, ring_w, bars_w, pol);
+            else      sd_consume<false>(P, S, A, W, sP, sS, mv, have_next, ring_w, bars_w, pol);
+            ++mv;
+        } else if (kind == SD_ATTN) {
+            if (warp == 0) sd_copy_phase(&sP[2], src + p, lane, 32);
+            __syncthreads();
+            sd_attention(sP[2], rt, attn_scratch, red);
+        }
+        if (p + 1 < n_phases) sd_grid_barrier(gbar);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- host side
+bool sd_fill_mat(SdMat & M, const void * w, int type, int layout, int64_t m, int64_t k, int64_t row_stride_bytes, float * y, const float * residual) {
+    if (!is_quant(type) || k % blck_size(type) || m <= 0 || m > INT32_MAX) return false;
+    const int64_t nblk = k / blck_size(type);
+    const bool split = payload_size(type) != type_size(type);            // q4_0 / q8_0 / q6_K: streamable only from the planar layout
+    if (split && layout != B200_LAYOUT_PLANAR) return false;
+    const int64_t rb_p = nblk * payload_size(type), rb_d = split ? nblk * 2 : 0;
+    if (!split && row_stride_bytes != rb_p) return false;                 // rows must be back to back for 1-D bulk copies
+    if (rb_p % 16 || rb_d % 16 || (uintptr_t) w % 16) return false;
+    M.payload = (const uint8_t *) w; M.dplane = split ? (const uint8_t *) w + m * rb_p : nullptr;
+    if (split && ((uintptr_t) M.dplane % 16)) return false;
+    M.y = y; M.residual = residual; M.type = type; M.rows = (int32_t) m; M.row_bytes_p = (int32_t) rb_p; M.row_bytes_d = (int32_t) rb_d;
+    return true;
+}
+
+// a phase is streamable when one row's K-slice (x2 for gate/up pairs) fits a ring slot and every slice is 16-byte granular
+bool sd_phase_ok(const SdPhase & P) {
+    if (P.kind != SD_MATVEC) return true;
+    const int ks = P.ksplit;
+    if (ks < 1 || P.k % ks) return false;
+    const int64_t kl = P.k / ks;
+    if (act_layout(P.act_group == 256 ? B200_Q4_K : B200_Q8_0, kl).bytes + 16 > SD_ACT_BYTES) return false;
+    const int nm = P.epilogue == SD_EPI_SWIGLU ? 2 : 1;
+    for (int j = 0; j < P.n_mat; ++j) {
+        const SdMat & M = P.mat[j];
+        if (M.row_bytes_p % ks || M.row_bytes_d % ks) return false;
+        const int sp = M.row_bytes_p / ks, sd = M.row_bytes_d / ks;
+        if (sp % 16 || sd % 16 || (sp + sd) * nm > SD_SLOT_BYTES) return false;
+        if (ks > 1 && (kl % 256 || !is_kquant(M.type))) return false;      // K-split: whole super-blocks per slice, K-quants only
+        if ((is_kquant(M.type) ? 256 : 32) != P.act_group) return false;
+    }
+    if (nm == 2 && (P.n_mat != 2 || P.mat[0].type != P.mat[1].type || P.mat[0].rows != P.mat[1].rows || P.mat[0].row_bytes_p != P.mat[1].row_bytes_p)) return false;
+    return true;
+}
+
+static int sd_setup() {
+    static std::once_flag once; static int rc = B200_OK;
+    std::call_once(once, [] {
+        cudaError_t e = cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
+        if (e != cudaSuccess) rc = -(int) e;
+    });
+    return rc;
+}
+
+// one launch of the persistent kernel.  phases_dev == nullptr: run `single` (no grid barrier needed -> ordinary launch);
+// otherwise a cooperative launch guarantees the one-CTA-per-SM grid is co-resident for the grid barriers.
+int sd_launch(const SdPhase * phases_dev, int n_phases, const SdPhase * single, unsigned * gbar, const SdRuntime & rt, cudaStream_t st) {
+    int rc = sd_setup();
+    if (rc) return rc;
+    static const SdPhase zero = {};
+    const SdPhase & S = single ? *single : zero;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) sm_count()); cfg.blockDim = dim3(SD_THREADS); cfg.dynamicSmemBytes = SD_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = (phases_dev && n_phases > 1) ? 1 : 0;
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stream, phases_dev, n_phases, gbar, S, rt));
+    return B200_OK;
+}
+
+} // namespace b200

@@ -192,6 +192,44 @@ class Qwen3Decoder:
         self.launches_per_step = n
         return n
 
+    # ---- the persistent decode engine: the whole step as ONE cooperative kernel (include/b200_ops.h b200_decoder_*) ---------------
+    def build_engine(self, x_out: torch.Tensor | None = None, hidden_out: torch.Tensor | None = None):
+        cfg = self.cfg
+        kvb = cfg.n_head_kv * cfg.head_dim * 2
+
+        def W(t, wtype):
+            return ops.Weight(t.data_ptr(), wtype, ops.LAYOUT_PLANAR if wtype == ops.Q6_K else ops.LAYOUT_NATIVE)
+        layers = (ops.DecodeLayer * len(self.L))()
+        for i, lw in enumerate(self.L):
+            ty = lw["types"]
+            for n in ("wq", "wk", "wv", "wo", "gate", "up", "down"):
+                setattr(layers[i], n, W(lw[n], ty[n]))
+            for n in ("attn_norm", "ffn_norm", "q_norm", "k_norm", "k_cache", "v_cache"):
+                setattr(layers[i], n, lw[n].data_ptr())
+            layers[i].k_row_bytes = layers[i].v_row_bytes = kvb
+        d = ops.DecodeDesc()
+        d.n_layer, d.n_embd, d.n_head, d.n_head_kv, d.head_dim, d.n_ff, d.n_vocab = (len(self.L), cfg.n_embd, cfg.n_head, cfg.n_head_kv,
+                                                                                   cfg.head_dim, cfg.n_ff, cfg.n_vocab)
+        d.rms_eps, d.attn_scale, d.rope, d.layers = cfg.rms_eps, 1.0 / cfg.head_dim ** 0.5, self.rope, layers
+        if self.has_head:
+            d.out_norm, d.lm_head, d.logits = self.out_norm.data_ptr(), W(self.lm_head, ops.Q6_K), self.logits.data_ptr()
+        self.engine_x_out = x_out if x_out is not None else torch.zeros(cfg.n_embd, device=self.dev)
+        d.x_out = self.engine_x_out.data_ptr()
+        d.hidden_out = hidden_out.data_ptr() if hidden_out is not None else None
+        d.x_in, d.pos, d.kv_idx = self.x_in.data_ptr(), self.pos.data_ptr(), self.kv_idx.data_ptr()
+        d.mask = self.mask_f16.data_ptr()                                 # row 0 of the [64, n_ctx] F16 mask
+        h = C.c_void_p()
+        ops.check(ops.lib().b200_decoder_create(C.byref(d), C.byref(h)))
+        self._engine, self._engine_keep = h, (layers, d)
+        return h
+
+    def step_engine(self, n_kv: int) -> int:
+        """mask cast (F32 -> F16, as llama-graph.cpp:1532 does) + the one-kernel decode step.  Returns #launches."""
+        ops.cpy(self.mask_f32[:1, :n_kv], self.mask_f16[:1, :n_kv])
+        ops.check(ops.lib().b200_decoder_step(self._engine, n_kv, ops.stream()))
+        self.x_out = self.engine_x_out
+        return 2
+
     def _matvec(self, jobs, act, k) -> int:
         """One launch per run of equal weight type (a Q4_K_M layer mixes Q4_K and Q6_K in q/k/v)."""
         n, i = 0, 0

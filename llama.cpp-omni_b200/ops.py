@@ -22,7 +22,8 @@ EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b20
            "b200_repack_gather", "b200_act_bytes", "b200_quantize_act", "b200_mul_mat_supported", "b200_mul_mat_scratch_bytes",
            "b200_mul_mat", "b200_matvec_q", "b200_matvec_q_swiglu", "b200_rms_norm", "b200_rms_norm_quantize", "b200_rope",
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
-           "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post"]
+           "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
+           "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_destroy"]
 
 
 class Tensor(C.Structure):
@@ -38,6 +39,23 @@ class RopeParams(C.Structure):
     _fields_ = [("n_dims", C.c_int32), ("mode", C.c_int32), ("n_ctx_orig", C.c_int32), ("freq_base", C.c_float),
                 ("freq_scale", C.c_float), ("ext_factor", C.c_float), ("attn_factor", C.c_float), ("beta_fast", C.c_float),
                 ("beta_slow", C.c_float)]
+
+
+class Weight(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("type", C.c_int32), ("layout", C.c_int32)]
+
+
+class DecodeLayer(C.Structure):
+    _fields_ = [(n, Weight) for n in ("wq", "wk", "wv", "wo", "gate", "up", "down")] + \
+               [(n, C.c_void_p) for n in ("attn_norm", "ffn_norm", "q_norm", "k_norm", "k_cache", "v_cache")] + \
+               [("k_row_bytes", C.c_int64), ("v_row_bytes", C.c_int64)]
+
+
+class DecodeDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_layer", "n_embd", "n_head", "n_head_kv", "head_dim", "n_ff", "n_vocab")] + \
+               [("rms_eps", C.c_float), ("attn_scale", C.c_float), ("rope", RopeParams), ("layers", C.POINTER(DecodeLayer)),
+                ("out_norm", C.c_void_p), ("lm_head", Weight)] + \
+               [(n, C.c_void_p) for n in ("x_in", "pos", "kv_idx", "mask", "logits", "hidden_out", "x_out")]
 
 
 class B200Error(RuntimeError):
@@ -59,6 +77,10 @@ def lib():
         L.b200_act_bytes.argtypes = [C.c_int, C.c_int64]
         L.b200_mul_mat_scratch_bytes.restype = C.c_size_t
         L.b200_flash_attn_scratch_bytes.restype = C.c_size_t
+        L.b200_decoder_destroy.restype = None
+        L.b200_decoder_destroy.argtypes = [C.c_void_p]
+        L.b200_decoder_step.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.b200_decoder_n_phases.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -203,8 +225,9 @@ def rms_norm_quantize(x: torch.Tensor, w: torch.Tensor, wtype: int, eps: float, 
     ab = L.b200_act_bytes(wtype, k)
     act = torch.empty((n, ab), dtype=torch.uint8, device=x.device)
     y = torch.empty_like(x) if want_f32 else None
-    check(L.b200_rms_norm_quantize(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(y.data_ptr() if want_f32 else None),
-                                   C.c_void_p(act.data_ptr()), wtype, C.c_int64(k), C.c_int64(n), C.c_float(eps), stream()))
+    check(L.b200_rms_norm_quantize(C.c_void_p(x.data_ptr()), C.c_int64(x.stride(0)), C.c_void_p(w.data_ptr()),
+                                   C.c_void_p(y.data_ptr() if want_f32 else None), C.c_int64(k), C.c_void_p(act.data_ptr()), wtype,
+                                   C.c_int64(k), C.c_int64(n), C.c_float(eps), stream()))
     return act, y
 
 

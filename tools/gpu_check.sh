@@ -10,7 +10,7 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 python bench.py --steps 64 --warmup 8 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${1:-}" != "quick" ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 1300 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   tail -3 gpurun_out/ncu_bench.log
 fi
