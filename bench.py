@@ -178,14 +178,17 @@ def run_b200(args) -> None:
         D.mask_f32[:, :n_kv].copy_(hi["mask"], non_blocking=True)
         return hi["pos"].numel() * 4 + 8 + hi["mask"].numel() * 4
 
+    engine = not args.per_op
     with torch.cuda.stream(stream):
         set_inputs(0)
         D.x_in.copy_(host_embd[0], non_blocking=True)
-        D.step(n_kv)                                       # eager once (module load, attribute setup)
+        if engine:
+            D.build_engine()
+        D.step(n_kv, engine)                               # eager once (module load, attribute setup)
         stream.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
-            launches = D.step(n_kv)
+            launches = D.step(n_kv, engine)
     hidden = D.x_in
 
     def pipeline_step(i: int, e2e: bool) -> tuple[int, int]:
@@ -266,12 +269,14 @@ def run_b200(args) -> None:
             "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations), f16 KV", "data": "synthetic",
             "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}, KV depth {depth}..{depth + args.steps + args.warmup} (n_kv={n_kv})",
                        "streams_in_flight": n_streams, "parallelism": "single GPU" if world == 1 else f"layer-split pipeline pp{world}",
+                       "engine": "persistent (1 kernel/token)" if engine else "per-op launches",
                        "timing": f"one CUDA graph per token; weights {w_bytes / 1e9:.2f} GB/rank exceed the 126 MB L2, so no flush is needed"},
             "gpu_launches": launches * args.steps * n_streams,
             "e2e": {"value": round(e2e_value, 2), "unit": "tok/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": None, "peak_source": peak_src, "bytes_per_step": int(step_bytes),
-                         "kernel": "k_mmvq (decode matvec) + k_fa_decode: algorithmic weight+KV bytes of one token / graph-replay time"},
+                         "kernel": ("k_stream (persistent decode engine: all weight matvecs + attention of the token in one launch)" if engine else
+                                    "k_stream / k_mmvq per-op launches + k_fa_decode") + ": algorithmic weight+KV bytes of one token / graph-replay time"},
             "clocks": clk}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -292,6 +297,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tiny", action="store_true", help="tiny model (plumbing checks only; not a bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-op", action="store_true", help="one launch per (fused) op instead of the persistent decode engine")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,8 +24,8 @@ struct Decoder {
     char * scratch = nullptr;
     unsigned * gbar = nullptr;
     SdRuntime rt = {};
-    int launches = 0;
-    ~Decoder() { if (phases_dev) cudaFree(phases_dev); if (scratch) cudaFree(scratch); }
+    unsigned long long * prof_dev = nullptr;
+    ~Decoder() { if (phases_dev) cudaFree(phases_dev); if (scratch) cudaFree(scratch); if (prof_dev) cudaFree(prof_dev); }
 };
 
 static int64_t row_bytes(int type, int64_t k) { return k / blck_size(type) * type_size(type); }
@@ -131,11 +131,19 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
         ok = ok && sd_phase_ok(P); ph.push_back(P);
     }
     if (!ok) { delete dec; return B200_ERR_UNSUPPORTED; }
+    for (size_t p = 0; p < ph.size(); ++p) {                             // let every phase know what follows it (no descriptor reads on the critical path)
+        ph[p].next_kind = p + 1 < ph.size() ? ph[p + 1].kind : -1;
+        ph[p].next_mv = -1;
+        for (size_t n = p + 1; n < ph.size(); ++n) if (ph[n].kind == SD_MATVEC) { ph[p].next_mv = (int) n; break; }
+    }
     dec->n_phases = (int) ph.size();
     e = cudaMalloc(&dec->phases_dev, ph.size() * sizeof(SdPhase));
     if (e == cudaSuccess) e = cudaMemcpy(dec->phases_dev, ph.data(), ph.size() * sizeof(SdPhase), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { delete dec; return -(int) e; }
     dec->rt.pos = d->pos; dec->rt.kv_idx = d->kv_idx; dec->rt.mask = (const __half *) d->mask;
+    dec->rt.theta_scale = powf(d->rope.freq_base, -2.0f / D); dec->rt.freq_scale = d->rope.freq_scale; dec->rt.ext_factor = d->rope.ext_factor;
+    dec->rt.attn_factor = d->rope.attn_factor; dec->rt.corr0 = lo < 0 ? 0 : lo; dec->rt.corr1 = hi > D - 1 ? D - 1 : hi;
+    dec->rt.rope_mode = d->rope.mode; dec->rt.has_rope = d->n_layer > 0;
     *handle = dec;
     return B200_OK;
 }
@@ -145,6 +153,21 @@ extern "C" int b200_decoder_step(void * handle, int32_t n_kv, void * stream) {
     if (!dec || n_kv <= 0) return B200_ERR_ARG;
     SdRuntime rt = dec->rt; rt.n_kv = n_kv;
     return sd_launch(dec->phases_dev, dec->n_phases, nullptr, dec->gbar, rt, (cudaStream_t) stream);
+}
+
+// debugging aid: run one step with per-phase globaltimer stamps of CTA 0 ([n_phases][4] ns: start, prologue done, work done, barrier done)
+extern "C" int b200_decoder_profile(void * handle, int32_t n_kv, unsigned long long * host_out, void * stream) {
+    Decoder * dec = (Decoder *) handle;
+    if (!dec || !host_out) return B200_ERR_ARG;
+    const size_t bytes = (size_t) dec->n_phases * 8 * sizeof(unsigned long long);
+    if (!dec->prof_dev) B200_CUDA_TRY(cudaMalloc(&dec->prof_dev, bytes));
+    B200_CUDA_TRY(cudaMemsetAsync(dec->prof_dev, 0, bytes, (cudaStream_t) stream));
+    SdRuntime rt = dec->rt; rt.n_kv = n_kv; rt.prof = dec->prof_dev;
+    int rc = sd_launch(dec->phases_dev, dec->n_phases, nullptr, dec->gbar, rt, (cudaStream_t) stream);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(host_out, dec->prof_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+    B200_CUDA_TRY(cudaStreamSynchronize((cudaStream_t) stream));
+    return B200_OK;
 }
 
 extern "C" int b200_decoder_n_phases(void * handle) { return handle ? ((Decoder *) handle)->n_phases : 0; }

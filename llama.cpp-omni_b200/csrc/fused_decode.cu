@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_qkv_post(const QkvPostArgs A) {
             if (A.ext_factor != 0.0f) {
                 const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
                 const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
-                th = th * (1.0f - ramp) + theta * ramp;
+                th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(theta, ramp));
                 ms *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
             }
             float sn, cs; sincosf(th, &sn, &cs); sn *= ms; cs *= ms;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) k_qkv_post(const QkvPostArgs A) {
             if (A.ext_factor != 0.0f) {
                 const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
                 const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
-                th = th * (1.0f - ramp) + theta * ramp;
+                th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(theta, ramp));
                 ms *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
             }
             float sn, cs; sincosf(th, &sn, &cs); sn *= ms; cs *= ms;

@@ -327,7 +327,7 @@ int  sd_launch(const SdPhase * phases_dev, int n_phases, const SdPhase * single,
 static bool try_stream(const b200_matvec_job * jobs, int njobs, const void * act, int64_t k, bool swiglu, float * y_swiglu, cudaStream_t st, int & rc) {
     if (njobs > 3) return false;
     SdPhase P = {};
-    P.ksplit = 1;
+    P.ksplit = 1; P.next_kind = -1; P.next_mv = -1;
     P.kind = SD_MATVEC; P.n_mat = njobs; P.epilogue = swiglu ? SD_EPI_SWIGLU : SD_EPI_STORE; P.prologue = SD_PRO_ACT;
     P.k = (int32_t) k; P.act_group = is_kquant(jobs[0].type) ? 256 : 32; P.act = (const uint8_t *) act;
     if ((uintptr_t) act % 16) return false;

@@ -122,11 +122,11 @@ __global__ void __launch_bounds__(256) k_rope(const RopeArgs A, int64_t total_pa
         for (int j = 0; j < (int) p; ++j) theta = __fmul_rn(theta, A.theta_scale);
         const float ffv = A.ff ? A.ff[p] : 1.0f;
         const float th_extrap = theta / ffv;
-        float th = A.freq_scale * th_extrap, mscale = A.attn_factor;
+        float th = __fmul_rn(A.freq_scale, th_extrap), mscale = A.attn_factor;
         if (A.ext_factor != 0.0f) {
             const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
             const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
-            th = th * (1.0f - ramp) + th_extrap * ramp;
+            th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(th_extrap, ramp));     // no FMA contraction: the oracle's rounding
             mscale *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
         }
         float sn, cs; sincosf(th, &sn, &cs);

@@ -18,8 +18,27 @@ struct SaSmem {                         // carved from the phase scratch (SD_ATT
 };
 static_assert(sizeof(SaSmem) <= SD_ATTN_BYTES, "attention scratch");
 
+// (cos, sin) * mscale of the token's position for the 64 rotation pairs: computed ONCE per launch (every layer rotates by the same
+// angles), with the oracle's theta chain (theta *= theta_scale per pair, ops.cpp ggml_rope_cache_init) and the accurate sincosf
+__device__ __forceinline__ void sa_rope_table(float2 * tab, const SdRuntime & rt, int lane) {
+    const float posf = (float) rt.pos[0];
+    for (int p = lane; p < 64; p += 32) {
+        float theta = posf;
+        for (int j = 0; j < p; ++j) theta = __fmul_rn(theta, rt.theta_scale);
+        float th = __fmul_rn(rt.freq_scale, theta), ms = rt.attn_factor;
+        if (rt.ext_factor != 0.0f) {
+            const float yv = ((float) p - rt.corr0) / fmaxf(0.001f, rt.corr1 - rt.corr0);
+            const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * rt.ext_factor;
+            th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(theta, ramp));
+            ms *= 1.0f + 0.1f * logf(1.0f / rt.freq_scale);
+        }
+        float sn, cs; sincosf(th, &sn, &cs);
+        tab[p] = make_float2(cs * ms, sn * ms);
+    }
+}
+
 // warp-level: RMS-norm (optional) + weight + rotary embedding of one 128-wide head held as 4 contiguous elements per lane
-__device__ __forceinline__ void sa_norm_rope(float (&v)[4], const float * w, float eps, float posf, const SdAttn & A) {
+__device__ __forceinline__ void sa_norm_rope(float (&v)[4], const float * w, float eps, int rope_mode, const float2 * tab) {
     const int lane = threadIdx.x & 31;
     if (w) {
         float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
@@ -29,46 +48,25 @@ __device__ __forceinline__ void sa_norm_rope(float (&v)[4], const float * w, flo
         for (int i = 0; i < 4; ++i) v[i] = __fmul_rn(__fmul_rn(v[i], scale), w[lane * 4 + i]);
     }
     float out[4];
-    if (A.rope_mode & 2) {              // neox: pairs (p, p + 64) live in lanes (l, l + 16)
+    if (rope_mode & 2) {                // neox: pairs (p, p + 64) live in lanes (l, l + 16)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int p = (lane & 15) * 4 + i;
-            float theta = posf;
-            for (int j = 0; j < p; ++j) theta = __fmul_rn(theta, A.theta_scale);
-            float th = A.freq_scale * theta, ms = A.attn_factor;
-            if (A.ext_factor != 0.0f) {
-                const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
-                const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
-                th = th * (1.0f - ramp) + theta * ramp;
-                ms *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
-            }
-            float sn, cs; sincosf(th, &sn, &cs); sn *= ms; cs *= ms;
+            const float2 cs = tab[(lane & 15) * 4 + i];
             const float other = __shfl_xor_sync(0xffffffffu, v[i], 16);
-            out[i] = lane < 16 ? v[i] * cs - other * sn : other * sn + v[i] * cs;
+            out[i] = lane < 16 ? v[i] * cs.x - other * cs.y : other * cs.y + v[i] * cs.x;
         }
     } else {                            // norm: pairs (2p, 2p + 1) inside a lane
 #pragma unroll
         for (int i = 0; i < 4; i += 2) {
-            const int p = (lane * 4 + i) / 2;
-            float theta = posf;
-            for (int j = 0; j < p; ++j) theta = __fmul_rn(theta, A.theta_scale);
-            float th = A.freq_scale * theta, ms = A.attn_factor;
-            if (A.ext_factor != 0.0f) {
-                const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
-                const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
-                th = th * (1.0f - ramp) + theta * ramp;
-                ms *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
-            }
-            float sn, cs; sincosf(th, &sn, &cs); sn *= ms; cs *= ms;
-            out[i] = v[i] * cs - v[i + 1] * sn; out[i + 1] = v[i] * sn + v[i + 1] * cs;
+            const float2 cs = tab[(lane * 4 + i) / 2];
+            out[i] = v[i] * cs.x - v[i + 1] * cs.y; out[i + 1] = v[i] * cs.y + v[i + 1] * cs.x;
         }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = out[i];
 }
 
-__device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * scratch, float * red) {
-    (void) red;
+__device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * scratch, const float2 * rope_tab, unsigned long long * pf) {
     const SdAttn & A = P.attn;
     SaSmem & sm = *(SaSmem *) scratch;
     constexpr int D = 128, LPR = 16, NRG = SD_WARPS * 2, U = 4;
@@ -83,21 +81,20 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
     const int ratio = A.n_head / A.n_head_kv, head0 = kvh * ratio;           // ratio == SA_G (checked on the host)
     const int c0 = split * chunk, c1 = min(c0 + chunk, n_kv);
     const int64_t slot = rt.kv_idx[0];
-    const float posf = (float) rt.pos[0];
     const bool owner = slot >= c0 && slot < c1;
 
     // ---- q heads (warps 0..3), new K row (warp 4), new V row (warp 5) ---------------------------------------------------------------
     if (warp < SA_G) {
         const float4 r = __ldcg((const float4 *) (A.q + (head0 + warp) * D + lane * 4));
         float v[4] = { r.x, r.y, r.z, r.w };
-        sa_norm_rope(v, A.q_norm_w, A.eps, posf, A);
+        sa_norm_rope(v, A.q_norm_w, A.eps, rt.rope_mode, rope_tab);
 #pragma unroll
         for (int i = 0; i < 4; ++i) sm.q[warp][lane * 4 + i] = __half2float(__float2half_rn(v[i]));       // the oracle rounds Q to f16
         if (lane == 0) { sm.m[warp] = -INFINITY; sm.l[warp] = 0.0f; }
     } else if (warp == SA_G && owner) {
         const float4 r = __ldcg((const float4 *) (A.k_new + kvh * D + lane * 4));
         float v[4] = { r.x, r.y, r.z, r.w };
-        sa_norm_rope(v, A.k_norm_w, A.eps, posf, A);
+        sa_norm_rope(v, A.k_norm_w, A.eps, rt.rope_mode, rope_tab);
         __half * dst = (__half *) (A.k_cache + slot * A.k_row_bytes) + kvh * D + lane * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { const __half hv = __float2half_rn(v[i]); dst[i] = hv; sm.knew[lane * 4 + i] = hv; }
@@ -109,6 +106,7 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
         for (int i = 0; i < 4; ++i) { const __half hv = __float2half_rn(v[i]); dst[i] = hv; sm.vnew[lane * 4 + i] = hv; }
     }
     __syncthreads();
+    if (pf) pf[4] = globaltimer();
 
     float qreg[SA_G][8], acc[SA_G][8];
 #pragma unroll
@@ -197,6 +195,7 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
         }
         __syncthreads();
     }
+    if (pf) pf[5] = globaltimer();
     // ---- reduce the 24 row-group accumulators: the two groups of a warp by shuffle, the 12 warps through shared memory --------------------
 #pragma unroll
     for (int g = 0; g < SA_G; ++g)
@@ -220,6 +219,7 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
             if (d == 0) A.part_ml[ps] = make_float2(sm.m[g], sm.l[g]);
         }
     }
+    if (pf) pf[6] = globaltimer();
     if (splits == 1) return;
     // ---- the last chunk of this kv head to finish merges the partials ---------------------------------------------------------------------
     __syncthreads();
@@ -230,20 +230,40 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
         if (sm.is_last) { A.tickets[kvh] = 0; __threadfence(); }
     }
     __syncthreads();
+    if (pf) pf[7] = globaltimer();
     if (!sm.is_last) return;
+    // merge weights: warp g (one head) turns the chunks' (m, l) into w_s = exp(m_s - M) / sum_s l_s w_s, lanes = chunks
+    float * wgt = &sm.S[0][0];                                              // [SA_G][splits], the score tile is free now
+    if (warp < SA_G) {
+        const int64_t ps0 = (int64_t) (head0 + warp) * splits;
+        float M = -INFINITY;
+        for (int s = lane; s < splits; s += 32) M = fmaxf(M, __ldcg(&A.part_ml[ps0 + s]).x);
+        M = warp_max(M);
+        float L = 0.0f;
+        for (int s = lane; s < splits; s += 32) {
+            const float2 ml = __ldcg(&A.part_ml[ps0 + s]);
+            const float w = ml.x == -INFINITY ? 0.0f : expf(ml.x - M);
+            wgt[warp * splits + s] = w; L += ml.y * w;
+        }
+        L = warp_sum(L);
+        __syncwarp();
+        const float inv = L == 0.0f ? 0.0f : 1.0f / L;
+        for (int s = lane; s < splits; s += 32) wgt[warp * splits + s] *= inv;
+    }
+    __syncthreads();
     for (int o = tid; o < SA_G * D; o += SD_THREADS) {
         const int g = o / D, d = o % D, head = head0 + g;
-        const int64_t ps0 = (int64_t) head * splits;
-        float M = -INFINITY;
-        for (int s = 0; s < splits; ++s) M = fmaxf(M, __ldcg(&A.part_ml[ps0 + s]).x);
-        float L = 0.0f, v = 0.0f;
-        for (int s = 0; s < splits; ++s) {
-            const float2 ml = __ldcg(&A.part_ml[ps0 + s]);
-            if (ml.x == -INFINITY) continue;
-            const float w = expf(ml.x - M);
-            L += ml.y * w;
-            v += __ldcg(&A.part_acc[(ps0 + s) * D + d]) * w;
+        const float * pa = A.part_acc + (int64_t) head * splits * D + d;
+        float v = 0.0f;
+        int s = 0;
+        for (; s + 6 <= splits; s += 6) {                                   // six independent L2 loads in flight per thread
+            float t[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) t[i] = __ldcg(pa + (int64_t) (s + i) * D);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) v = fmaf(t[i], wgt[g * splits + s + i], v);
         }
-        A.out[head * D + d] = L == 0.0f ? 0.0f : v / L;
+        for (; s < splits; ++s) v = fmaf(__ldcg(pa + (int64_t) s * D), wgt[g * splits + s], v);
+        A.out[head * D + d] = v;
     }
 }

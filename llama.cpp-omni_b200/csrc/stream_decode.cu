@@ -20,6 +20,7 @@
 #include "stream_decode.cuh"
 #include <math.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -40,12 +41,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void * src, uint32_
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds16(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
 __device__ __forceinline__ uint32_t lds4(uint32_t a) { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ int lds_s16(uint32_t a) { int r; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t r; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float r; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a)); return r; }
+__device__ __forceinline__ unsigned long long globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned * p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // ---------------------------------------------------------------------------------------------------------------- geometry
@@ -56,27 +61,37 @@ __device__ __forceinline__ void seg_build(SegTab & S, const SdPhase & P, int cta
     const bool sw = P.epilogue == SD_EPI_SWIGLU;
     const int nmat = sw ? 1 : P.n_mat, ks = P.ksplit;
     const int grp = cta / ks, ngrp = ncta / ks;
-    S.kpart = cta % ks;
-    int64_t T = 0;
-    for (int j = 0; j < nmat; ++j) T += P.mat[j].rows;
-    const int r0 = grp < ngrp ? (int) (T * grp / ngrp) : 0, r1 = grp < ngrp ? (int) (T * (grp + 1) / ngrp) : 0;   // leftover CTAs idle
+    S.kpart = cta % ks; S.nm = sw ? 2 : 1; S.ksplit = ks;
+    uint32_t T = 0;                                                       // T * ngrp < 2^32 (checked on the host): 32-bit divisions only
+    for (int j = 0; j < nmat; ++j) T += (uint32_t) P.mat[j].rows;
+    const int r0 = grp < ngrp ? (int) (T * (uint32_t) grp / (uint32_t) ngrp) : 0, r1 = grp < ngrp ? (int) (T * (uint32_t) (grp + 1) / (uint32_t) ngrp) : 0;   // leftover CTAs idle
     int mb = 0; S.upre[0] = 0;
     for (int j = 0; j < 3; ++j) {
         if (j < nmat) {
-            const int lo = max(r0, mb), hi = min(r1, mb + P.mat[j].rows);
-            S.first[j] = lo - mb; S.nrows[j] = max(0, hi - lo);
-            S.sub_p[j] = P.mat[j].row_bytes_p / ks; S.sub_d[j] = P.mat[j].row_bytes_d / ks;
+            const SdMat & M = P.mat[j];
+            const int lo = max(r0, mb), hi = min(r1, mb + M.rows), first = lo - mb;
+            S.nrows[j] = max(0, hi - lo);
+            S.rbp[j] = M.row_bytes_p; S.rbd[j] = M.row_bytes_d; S.sub_p[j] = M.row_bytes_p / ks; S.sub_d[j] = M.row_bytes_d / ks; S.type[j] = M.type;
             const int unit_row = (S.sub_p[j] + S.sub_d[j]) * (sw ? 2 : 1);
             S.rpu[j] = (P.act_group == 256 && unit_row * 2 <= SD_SLOT_BYTES) ? 2 : 1;
-            mb += P.mat[j].rows;
-        } else { S.first[j] = 0; S.nrows[j] = 0; S.rpu[j] = 1; S.sub_p[j] = 0; S.sub_d[j] = 0; }
+            S.pay[j] = M.payload + (int64_t) first * M.row_bytes_p + (int64_t) S.kpart * S.sub_p[j];
+            S.dpl[j] = M.dplane ? M.dplane + (int64_t) first * M.row_bytes_d + (int64_t) S.kpart * S.sub_d[j] : nullptr;
+            S.y[j] = M.y + (int64_t) S.kpart * P.y_part_stride + first;
+            S.resid[j] = M.residual ? M.residual + first : nullptr;
+            if (sw) {
+                S.pay2 = P.mat[1].payload + (int64_t) first * M.row_bytes_p;
+                S.dpl2 = P.mat[1].dplane ? P.mat[1].dplane + (int64_t) first * M.row_bytes_d : nullptr;
+            }
+            mb += M.rows;
+        } else { S.nrows[j] = 0; S.rpu[j] = 1; S.sub_p[j] = 0; S.sub_d[j] = 0; S.rbp[j] = 0; S.rbd[j] = 0; S.type[j] = 0; }
         S.upre[j + 1] = S.upre[j] + (S.nrows[j] + S.rpu[j] - 1) / S.rpu[j];
     }
 }
-__device__ __forceinline__ void seg_unit(const SegTab & S, int u, int & j, int & row, int & n) {
+// unit u -> matrix j, first row (relative to this CTA's first row of j), row count
+__device__ __forceinline__ void seg_unit(const SegTab & S, int u, int & j, int & off, int & n) {
     j = u < S.upre[1] ? 0 : u < S.upre[2] ? 1 : 2;
-    const int off = (u - S.upre[j]) * S.rpu[j];
-    row = S.first[j] + off; n = min(S.rpu[j], S.nrows[j] - off);
+    off = (u - S.upre[j]) * S.rpu[j];
+    n = min(S.rpu[j], S.nrows[j] - off);
 }
 
 #include "stream_dot.cuh"
@@ -109,7 +124,7 @@ __device__ __forceinline__ ActLayout sd_act_layout(int act_group, int kl) {
     return L;
 }
 
-__device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_t * act, float * red) {
+__device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_t * act, float * red, unsigned long long * pf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = P.k, kl = k / P.ksplit, k0 = kpart * kl;                 // this CTA quantises [k0, k0 + kl)
     const ActLayout L = sd_act_layout(P.act_group, kl);
@@ -126,13 +141,54 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
     }
     float scale = 1.0f;
     const bool norm = P.prologue == SD_PRO_RMSNORM_QUANT;
-    if (norm) {                                                            // the norm spans the whole row, not just this CTA's K-slice
+    if (P.act_group == 256 && (kl >> 8) <= 2 * SD_WARPS && (P.ksplit == 1 || !norm)) {
+        // fast path (every phase of the decode program): ONE pass over the inputs — each warp keeps its <= 2 super-blocks in registers
+        // between the sum of squares and the quantisation, and the loads of the up-to-4 summands are issued together
+        const int nb = kl >> 8, n_x = P.n_x;
+        float v[2][8];
         float ss = 0.0f;
-        for (int i = threadIdx.x * 4; i < k; i += SD_THREADS * 4) {
-            const float4 v = sd_load_x4(P, i);
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int blk = warp + SD_WARPS * t;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[t][i] = 0.0f;
+            if (blk < nb) {
+                const int e = k0 + blk * 256 + lane * 8;
+                float4 a[4][2];
+#pragma unroll
+                for (int sx = 0; sx < 4; ++sx) if (sx < n_x) { a[sx][0] = __ldcg((const float4 *) (P.x[sx] + e)); a[sx][1] = __ldcg((const float4 *) (P.x[sx] + e + 4)); }
+#pragma unroll
+                for (int sx = 0; sx < 4; ++sx) if (sx < n_x) {
+                    if (sx == 0) { v[t][0] = a[0][0].x; v[t][1] = a[0][0].y; v[t][2] = a[0][0].z; v[t][3] = a[0][0].w; v[t][4] = a[0][1].x; v[t][5] = a[0][1].y; v[t][6] = a[0][1].z; v[t][7] = a[0][1].w; }
+                    else { v[t][0] += a[sx][0].x; v[t][1] += a[sx][0].y; v[t][2] += a[sx][0].z; v[t][3] += a[sx][0].w; v[t][4] += a[sx][1].x; v[t][5] += a[sx][1].y; v[t][6] += a[sx][1].z; v[t][7] += a[sx][1].w; }
+                }
+                if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
+            }
         }
-        scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
+        if (pf) pf[4] = globaltimer();
+        if (norm) scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
+        if (pf) pf[5] = globaltimer();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int blk = warp + SD_WARPS * t;
+            if (blk < nb) {
+                const int e = k0 + blk * 256 + lane * 8;
+                if (norm) {
+                    const float4 w0 = __ldg((const float4 *) (P.norm_w + e)), w1 = __ldg((const float4 *) (P.norm_w + e + 4));
+                    const float w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[t][i] = __fmul_rn(__fmul_rn(v[t][i], scale), w[i]);
+                    if (writer && P.norm_out) {
+                        *(float4 *) (P.norm_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]);
+                    }
+                }
+                quant_block_q8K<true>(v[t], act, blk, L.d_off, L.bsum_off);
+            }
+        }
+        __syncthreads();
+        return;
     }
     if (P.act_group == 256) {
         for (int blk = warp; blk < (kl >> 8); blk += SD_WARPS) {
@@ -179,16 +235,18 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
 __device__ __forceinline__ void sd_grid_barrier(unsigned * bar) {       // bar[0] = count, bar[32] = generation (separate 128-B lines)
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned gen = ld_acquire_u32(bar + 32);
-        __threadfence();
-        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(bar + 32, 1u);
+        // release/acquire ride on the atomics themselves (no separate membar.gl): the CTA's writes are ordered before thread 0's
+        // release by the bar.sync above (cumulativity), and the acquire load orders the other CTAs' writes before the bar.sync below
+        unsigned gen, old;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 32) : "memory");
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+        if (old == gridDim.x - 1) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(bar), "r"(0u) : "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar + 32) : "memory");
         } else {
-            while (ld_acquire_u32(bar + 32) == gen) { }
+            unsigned g2;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 32) : "memory"); } while (g2 == gen);
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -207,36 +265,41 @@ struct WarpStream {
     int iss_mv, iss_u;                // phase slot (mv index & 1) and phase-local unit index of the next unit this warp will request
 };
 
-// lane 0: request one unit (bulk copies of its rows' K-slices into the warp's next ring slot)
-__device__ __forceinline__ void sd_issue(const SdPhase & P, const SegTab & S, int u, uint32_t slot_addr, uint32_t bar, uint64_t pol) {
-    int j, row, n; seg_unit(S, u, j, row, n);
-    const int nm = P.epilogue == SD_EPI_SWIGLU ? 2 : 1;
+// lane 0: request one unit (bulk copies of its rows' K-slices into the warp's next ring slot).  Everything it needs was precomputed
+// into the segment table: this runs once per unit on ONE lane while 31 wait, so it must stay a few dozen instructions.
+__device__ __forceinline__ void sd_issue(const SegTab & S, int u, uint32_t dst, uint32_t bar, uint64_t pol) {
+    int j, off, n; seg_unit(S, u, j, off, n);
     const uint32_t sp = S.sub_p[j], sd = S.sub_d[j];
-    const int64_t rbp = P.mat[j].row_bytes_p, rbd = P.mat[j].row_bytes_d;
-    mbar_expect_tx(bar, (uint32_t) n * (sp + sd) * nm);
-    uint32_t dst = slot_addr;
-    for (int w = 0; w < nm; ++w) {
-        const uint8_t * pay = P.mat[j + w].payload + row * rbp + (int64_t) S.kpart * sp;
-        if (P.ksplit == 1) { bulk_g2s(dst, pay, (uint32_t) n * sp, bar, pol); dst += n * sp; }           // full rows are back to back
-        else for (int i = 0; i < n; ++i) { bulk_g2s(dst, pay + i * rbp, sp, bar, pol); dst += sp; }
-        if (sd) {
-            const uint8_t * dpl = P.mat[j + w].dplane + row * rbd + (int64_t) S.kpart * sd;
-            if (P.ksplit == 1) { bulk_g2s(dst, dpl, (uint32_t) n * sd, bar, pol); dst += n * sd; }
-            else for (int i = 0; i < n; ++i) { bulk_g2s(dst, dpl + i * rbd, sd, bar, pol); dst += sd; }
+    const int64_t rbp = S.rbp[j], rbd = S.rbd[j];
+    mbar_expect_tx(bar, (uint32_t) n * (sp + sd) * S.nm);
+    const uint8_t * pay = S.pay[j] + off * rbp;
+    const uint8_t * dpl = S.dpl[j] + off * rbd;
+    if (S.ksplit == 1) {                                                   // full rows are back to back: one copy per plane
+        bulk_g2s(dst, pay, (uint32_t) n * sp, bar, pol); dst += n * sp;
+        if (sd) { bulk_g2s(dst, dpl, (uint32_t) n * sd, bar, pol); dst += n * sd; }
+        if (S.nm == 2) {
+            bulk_g2s(dst, S.pay2 + off * rbp, (uint32_t) n * sp, bar, pol); dst += n * sp;
+            if (sd) bulk_g2s(dst, S.dpl2 + off * rbd, (uint32_t) n * sd, bar, pol);
         }
+    } else {                                                               // K-slices of consecutive rows are rbp apart
+        for (int i = 0; i < n; ++i) { bulk_g2s(dst, pay + i * rbp, sp, bar, pol); dst += sp; }
+        if (sd) for (int i = 0; i < n; ++i) { bulk_g2s(dst, dpl + i * rbd, sd, bar, pol); dst += sd; }
     }
 }
 
 // keep the warp's ring full: request units of the current phase, then of the next matvec phase (whose descriptor is already staged)
-__device__ __forceinline__ void sd_top_up(WarpStream & W, const SdPhase * sP, const SegTab * sS, int cur_mv, bool have_next,
+__device__ __forceinline__ void sd_top_up(WarpStream & W, const SegTab * sS, int cur_mv, bool have_next, const volatile int * staged,
                                           uint32_t ring_w, uint32_t bars_w, uint64_t pol) {
     while (W.issued - W.consumed < SD_DEPTH) {
         if (W.iss_u >= sS[W.iss_mv].upre[3]) {
-            if (W.iss_mv == (cur_mv & 1) && have_next) { W.iss_mv ^= 1; W.iss_u = threadIdx.x >> 5; continue; }
+            if (W.iss_mv == (cur_mv & 1) && have_next) {
+                while (*staged < cur_mv + 1) { }                            // the staging warp publishes the next phase's table
+                W.iss_mv ^= 1; W.iss_u = threadIdx.x >> 5; continue;
+            }
             break;
         }
         const uint32_t slot = W.issued % SD_DEPTH;
-        sd_issue(sP[W.iss_mv], sS[W.iss_mv], W.iss_u, ring_w + slot * SD_SLOT_BYTES, bars_w + 8 * slot, pol);
+        sd_issue(sS[W.iss_mv], W.iss_u, ring_w + slot * SD_SLOT_BYTES, bars_w + 8 * slot, pol);
         W.iss_u += SD_WARPS; ++W.issued;
     }
 }
@@ -245,7 +308,7 @@ __device__ __forceinline__ void sd_top_up(WarpStream & W, const SdPhase * sP, co
 // re-read from shared memory (two rows share each read).
 template <bool REGS>
 __device__ __forceinline__ void sd_consume(const SdPhase & P, const SegTab & S, const ActS & A, WarpStream & W, const SdPhase * sP, const SegTab * sS,
-                                           int cur_mv, bool have_next, uint32_t ring_w, uint32_t bars_w, uint64_t pol) {
+                                           int cur_mv, bool have_next, const volatile int * staged, uint32_t ring_w, uint32_t bars_w, uint64_t pol) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kl = P.k / P.ksplit, nblk = kl >> 8;
     const bool swiglu = P.epilogue == SD_EPI_SWIGLU;
@@ -253,15 +316,15 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, const SegTab & S, 
     if (REGS) hfrag_fill(A, nblk, fr);
     const int nunits = S.upre[3];
     for (int u = warp; u < nunits; u += SD_WARPS) {
-        if (lane == 0) sd_top_up(W, sP, sS, cur_mv, have_next, ring_w, bars_w, pol);
+        if (lane == 0) sd_top_up(W, sS, cur_mv, have_next, staged, ring_w, bars_w, pol);
         int j, row, n; seg_unit(S, u, j, row, n);
         const uint32_t slot = W.consumed % SD_DEPTH, par = (W.consumed / SD_DEPTH) & 1;
-        const int type = P.mat[j].type;
+        const int type = S.type[j];
         const uint32_t rbp = S.sub_p[j], rbd = S.sub_d[j];
         const uint32_t base = ring_w + slot * SD_SLOT_BYTES;
         const uint32_t bp = (uint32_t) n * rbp, bd = (uint32_t) n * rbd;     // slot: [payload rows][d rows] (+ the same again for `up`)
-        float * y = P.mat[j].y + (int64_t) S.kpart * P.y_part_stride + row;
-        const float * resid = P.mat[j].residual ? P.mat[j].residual + row : nullptr;
+        float * y = S.y[j] + row;
+        const float * resid = S.resid[j] ? S.resid[j] + row : nullptr;
         mbar_wait(bars_w + 8 * slot, par);
         float2 g2 = make_float2(0.0f, 0.0f), v;
         if (REGS) {
@@ -281,7 +344,7 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, const SegTab & S, 
         fence_proxy_async();                                               // the slot's generic-proxy reads precede its next bulk write
         ++W.consumed;
     }
-    if (lane == 0) sd_top_up(W, sP, sS, cur_mv, have_next, ring_w, bars_w, pol);   // prefetch into the next phase through the barrier
+    if (lane == 0) sd_top_up(W, sS, cur_mv, have_next, staged, ring_w, bars_w, pol);   // prefetch into the next phase through the barrier
 }
 
 __global__ void __launch_bounds__(SD_THREADS, 1) k_stream(const SdPhase * __restrict__ phases_g, int n_phases, unsigned * gbar,
@@ -294,56 +357,69 @@ __global__ void __launch_bounds__(SD_THREADS, 1) k_stream(const SdPhase * __rest
     float    * red  = (float *) (bars + SD_WARPS * SD_DEPTH);
     SdPhase  * sP   = (SdPhase *) (red + 64);                            // [0], [1]: matvec phases (alternating); [2]: attention phase
     SegTab   * sS   = (SegTab *) (sP + 3);                               // [0], [1]: this CTA's share of the matvec phase in sP[0], sP[1]
+    float2   * rope_tab = (float2 *) (((uintptr_t) (sS + 2) + 15) & ~(uintptr_t) 15);   // [64] (cos, sin) of the token's position
+    volatile int * staged = (volatile int *) (rope_tab + 64);          // index of the last matvec phase whose descriptor + table are staged
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SdPhase * src = phases_g ? phases_g : &single;
     const uint32_t ring_w = smem_u32(ring) + warp * SD_DEPTH * SD_SLOT_BYTES, bars_w = smem_u32(bars) + warp * SD_DEPTH * 8;
 
-    // stage the first matvec phase (its successor is staged at the start of every matvec phase)
-    int first_mv = 0;
-    while (first_mv < n_phases && src[first_mv].kind != SD_MATVEC) ++first_mv;
+    // stage the first phase(s): phase 0, and the first matvec phase if phase 0 is not one (later ones are staged one phase ahead)
     if (threadIdx.x == 0) {
         for (int s = 0; s < SD_WARPS * SD_DEPTH; ++s) mbar_init(smem_u32(bars) + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0 && first_mv < n_phases) sd_copy_phase(&sP[0], src + first_mv, lane, 32);
+    const int kind0 = src[0].kind;
+    const int first_mv = kind0 == SD_MATVEC ? 0 : src[0].next_mv;
+    if (warp == 0 && first_mv >= 0) sd_copy_phase(&sP[0], src + first_mv, lane, 32);
+    if (warp == 1 && kind0 == SD_ATTN) sd_copy_phase(&sP[2], src, lane, 32);
+    if (warp == 2 && rt.has_rope) sa_rope_table(rope_tab, rt, lane);
     __syncthreads();
-    if (threadIdx.x == 0 && first_mv < n_phases) seg_build(sS[0], sP[0], blockIdx.x, gridDim.x);
+    if (threadIdx.x == 0) { if (first_mv >= 0) seg_build(sS[0], sP[0], blockIdx.x, gridDim.x); *staged = 0; }
     __syncthreads();
 
-    const uint64_t pol = policy_evict_first();
+    const uint64_t pol = rt.flags & 1 ? policy_evict_normal() : policy_evict_first();
     WarpStream W; W.issued = 0; W.consumed = 0; W.iss_mv = 0; W.iss_u = warp;
     int mv = 0;                                                           // index of the current matvec phase among matvec phases
-    if (lane == 0 && first_mv < n_phases) sd_top_up(W, sP, sS, 0, false, ring_w, bars_w, pol);   // weights first: they depend on nothing
+    if (lane == 0 && first_mv >= 0) sd_top_up(W, sS, 0, false, staged, ring_w, bars_w, pol);   // weights first: they depend on nothing
+    const bool prof = rt.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 
+    int kind = kind0;
     for (int p = 0; p < n_phases; ++p) {
-        const int kind = p == first_mv ? (int) SD_MATVEC : src[p].kind;
+        if (prof) rt.prof[p * 8 + 0] = globaltimer();
+        int next_kind;
         if (kind == SD_MATVEC) {
             const SdPhase & P = sP[mv & 1];
-            // stage the next matvec phase's descriptor + segment table (published by the prologue's __syncthreads)
-            int nxt = p + 1;
-            while (nxt < n_phases && src[nxt].kind != SD_MATVEC) ++nxt;
-            const bool have_next = nxt < n_phases;
-            if (warp == 1 && have_next) {
+            next_kind = P.next_kind;
+            const int nxt = P.next_mv;
+            const bool have_next = nxt >= 0;
+            // stage, one phase ahead and off the critical path: the next matvec phase's descriptor + segment table (warp 1) and the
+            // attention phase that follows this one (warp 2); both are published by the prologue's __syncthreads
+            const SegTab & S = sS[mv & 1];
+            sd_prologue(P, S.kpart, act, red, prof ? rt.prof + p * 8 : nullptr);
+            if (warp == SD_WARPS - 1 && have_next) {                      // after the prologue: off the CTA's critical path
                 sd_copy_phase(&sP[(mv + 1) & 1], src + nxt, lane, 32);
                 __syncwarp();
-                if (lane == 0) seg_build(sS[(mv + 1) & 1], sP[(mv + 1) & 1], blockIdx.x, gridDim.x);
+                if (lane == 0) { seg_build(sS[(mv + 1) & 1], sP[(mv + 1) & 1], blockIdx.x, gridDim.x); __threadfence_block(); *staged = mv + 1; }
             }
-            const SegTab & S = sS[mv & 1];
-            sd_prologue(P, S.kpart, act, red);
+            if (warp == SD_WARPS - 2 && next_kind == SD_ATTN) sd_copy_phase(&sP[2], src + p + 1, lane, 32);   // published by the grid barrier
+            if (prof) rt.prof[p * 8 + 1] = globaltimer();
             const int kl = P.k / P.ksplit;
             const ActLayout L = sd_act_layout(P.act_group, kl);
             ActS A; A.qs = smem_u32(act); A.d = A.qs + (uint32_t) L.d_off; A.bsum = A.qs + (uint32_t) L.bsum_off;
             bool regs = P.act_group == 256 && kl <= 4096;                 // q8_K fragments of a 4096-wide record fit in registers
             for (int m = 0; m < P.n_mat; ++m) regs = regs && (P.mat[m].type == B200_Q4_K || P.mat[m].type == B200_Q6_K);
-            if (regs) sd_consume<true >(P, S, A, W, sP, sS, mv, have_next, ring_w, bars_w, pol);
-            else      sd_consume<false>(P, S, A, W, sP, sS, mv, have_next, ring_w, bars_w, pol);
+            if (regs) sd_consume<true >(P, S, A, W, sP, sS, mv, have_next, staged, ring_w, bars_w, pol);
+            else      sd_consume<false>(P, S, A, W, sP, sS, mv, have_next, staged, ring_w, bars_w, pol);
             ++mv;
-        } else if (kind == SD_ATTN) {
-            if (warp == 0) sd_copy_phase(&sP[2], src + p, lane, 32);
-            __syncthreads();
-            sd_attention(sP[2], rt, attn_scratch, red);
+        } else {
+            next_kind = sP[2].next_kind;
+            if (prof) rt.prof[p * 8 + 1] = globaltimer();
+            sd_attention(sP[2], rt, attn_scratch, rope_tab, prof ? rt.prof + p * 8 : nullptr);
         }
+        if (prof) rt.prof[p * 8 + 2] = globaltimer();
         if (p + 1 < n_phases) sd_grid_barrier(gbar);
+        if (prof) rt.prof[p * 8 + 3] = globaltimer();
+        kind = next_kind;
     }
 }
 
@@ -398,12 +474,14 @@ int sd_launch(const SdPhase * phases_dev, int n_phases, const SdPhase * single, 
     if (rc) return rc;
     static const SdPhase zero = {};
     const SdPhase & S = single ? *single : zero;
+    static const int env_flags = getenv("B200_SD_FLAGS") ? atoi(getenv("B200_SD_FLAGS")) : 0;     // experiment switches (bit 0: no evict_first hint)
+    SdRuntime rt2 = rt; rt2.flags = env_flags;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) sm_count()); cfg.blockDim = dim3(SD_THREADS); cfg.dynamicSmemBytes = SD_SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = (phases_dev && n_phases > 1) ? 1 : 0;
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stream, phases_dev, n_phases, gbar, S, rt));
+    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stream, phases_dev, n_phases, gbar, S, rt2));
     return B200_OK;
 }
 

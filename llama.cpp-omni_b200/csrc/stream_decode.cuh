@@ -35,6 +35,7 @@ struct SdAttn {                                           // batch-1 attention o
 
 struct alignas(16) SdPhase {
     int32_t kind, n_mat, epilogue, prologue, k, act_group;
+    int32_t next_kind, next_mv, pad1_, pad2_;             // kind of phase p+1 (-1: none) and index of the next matvec phase (-1: none)
     float eps; int32_t ksplit;                            // ksplit > 1: CTA c reduces over K-slice c % ksplit and stores a PARTIAL y
     const float * x[4]; int32_t n_x, pad0_;               // prologue input = x[0] + x[1] + ... (fixed order: deterministic)
     float * x_out;                                        // optional: CTA 0 stores the summed input (the new residual stream)
@@ -46,14 +47,20 @@ struct alignas(16) SdPhase {
 
 struct SdRuntime {                                        // per-step inputs (device pointers; contents change every token)
     const int32_t * pos; const int64_t * kv_idx; const __half * mask; int32_t n_kv;
+    float theta_scale, freq_scale, ext_factor, attn_factor, corr0, corr1; int32_t rope_mode, has_rope;   // RoPE of the token (all layers)
+    int32_t flags, pad_;
+    unsigned long long * prof;                            // optional [n_phases][4] globaltimer stamps of CTA 0: start, prologue done, work done, barrier done
 };
 
 struct SegTab {                                           // a CTA's share of one matvec phase (see stream_decode.cu "geometry")
-    int first[3], nrows[3], rpu[3], upre[4];
-    int kpart, sub_p[3], sub_d[3];                        // K-slice of this CTA, bytes of one row's slice in each plane
+    int nrows[3], rpu[3], upre[4];                        // per matrix: rows of this CTA, rows per unit; unit prefix sums
+    int kpart, nm, ksplit, pad_;                          // K-slice of this CTA; matrices per unit (2 = gate/up pair)
+    int sub_p[3], sub_d[3], rbp[3], rbd[3], type[3];      // bytes of one row's K-slice / of one full row, per plane; weight type
+    const uint8_t * pay[3], * dpl[3], * pay2, * dpl2;     // first row's slice of this CTA in each plane (pay2/dpl2: the `up` matrix)
+    float * y[3]; const float * resid[3];                 // output / residual at this CTA's first row
 };
 
 constexpr int SD_SMEM_BYTES = SD_RING_BYTES + SD_ACT_BYTES + SD_ATTN_BYTES + SD_WARPS * SD_DEPTH * 8 + 64 * 4 + 3 * (int) sizeof(SdPhase)
-                            + 2 * (int) sizeof(SegTab) + 64;
+                            + 2 * (int) sizeof(SegTab) + 64 + 64 * 8 + 16;
 
 } // namespace b200

@@ -126,6 +126,14 @@ __device__ __forceinline__ int dot16u(uint32_t w0, uint32_t w1, uint32_t w2, uin
     acc = __dp4a((int) w0, (int) a.x, acc); acc = __dp4a((int) w1, (int) a.y, acc); acc = __dp4a((int) w2, (int) a.z, acc); return __dp4a((int) w3, (int) a.w, acc);
 }
 
+// unsigned-weight x signed-activation dp4a: lets a nibble stay in the HIGH half of its byte (value x16) and a 2-bit field stay where it
+// is in qh (value x4^q) — the shifts the unpacking would need move to ONE exact shift of the accumulated sum.  The logic pipe (LOP3/SHF),
+// not HBM, is what bounds this kernel (ncu: math_pipe_throttle), so every removed shift counts.
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dot16m(const uint4 & w, uint32_t mask, const uint4 & a, int acc) {     // sum over 16 bytes of (w & mask) * a
+    acc = dp4a_us(w.x & mask, a.x, acc); acc = dp4a_us(w.y & mask, a.y, acc); acc = dp4a_us(w.z & mask, a.z, acc); return dp4a_us(w.w & mask, a.w, acc);
+}
+
 template <int T> __device__ __forceinline__ float hblock_dot(uint32_t pb, uint32_t dp, int h, const HFrag & f);
 
 template <> __device__ __forceinline__ float hblock_dot<B200_Q4_K>(uint32_t pb, uint32_t, int h, const HFrag & f) {
@@ -139,12 +147,11 @@ template <> __device__ __forceinline__ float hblock_dot<B200_Q4_K>(uint32_t pb, 
     int isum = 0;
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {                      // pair jj: low nibbles = sub-block 2jj (acts a[4jj], a[4jj+1]), high = 2jj+1 (a[4jj+2], a[4jj+3])
-        const uint4 u0 = q[2 * jj], u1 = q[2 * jj + 1];
-        int dlo = dot16u(u0.x & 0x0f0f0f0fu, u0.y & 0x0f0f0f0fu, u0.z & 0x0f0f0f0fu, u0.w & 0x0f0f0f0fu, f.a[4 * jj], 0);
-        dlo     = dot16u(u1.x & 0x0f0f0f0fu, u1.y & 0x0f0f0f0fu, u1.z & 0x0f0f0f0fu, u1.w & 0x0f0f0f0fu, f.a[4 * jj + 1], dlo);
-        int dhi = dot16u((u0.x >> 4) & 0x0f0f0f0fu, (u0.y >> 4) & 0x0f0f0f0fu, (u0.z >> 4) & 0x0f0f0f0fu, (u0.w >> 4) & 0x0f0f0f0fu, f.a[4 * jj + 2], 0);
-        dhi     = dot16u((u1.x >> 4) & 0x0f0f0f0fu, (u1.y >> 4) & 0x0f0f0f0fu, (u1.z >> 4) & 0x0f0f0f0fu, (u1.w >> 4) & 0x0f0f0f0fu, f.a[4 * jj + 3], dhi);
-        isum += (int) ((scw >> (16 * jj)) & 0xff) * dlo + (int) ((scw >> (16 * jj + 8)) & 0xff) * dhi;
+        int dlo  = dot16m(q[2 * jj], 0x0f0f0f0fu, f.a[4 * jj], 0);
+        dlo      = dot16m(q[2 * jj + 1], 0x0f0f0f0fu, f.a[4 * jj + 1], dlo);
+        int dh16 = dot16m(q[2 * jj], 0xf0f0f0f0u, f.a[4 * jj + 2], 0);           // 16 x the high-nibble dot product
+        dh16     = dot16m(q[2 * jj + 1], 0xf0f0f0f0u, f.a[4 * jj + 3], dh16);
+        isum += (int) ((scw >> (16 * jj)) & 0xff) * dlo + (int) ((scw >> (16 * jj + 8)) & 0xff) * (dh16 >> 4);
     }
     // mins: sub-block s' of this half sums the 16-element groups 2s', 2s'+1 -> dp2a of the packed s16 pair with the min byte duplicated
     int msum = dp2a_lo((int) f.bs.x, (int) __byte_perm(mnw, 0, 0x4400), 0);
@@ -166,19 +173,17 @@ template <> __device__ __forceinline__ float hblock_dot<B200_Q6_K>(uint32_t pb, 
     const int16_t * bs = (const int16_t *) &f.bs;
     int isum = 0;
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {                         // s: positions l = 16s .. 16s+15 of each quad
-        const uint32_t qa[4] = { l[s].x, l[s].y, l[s].z, l[s].w }, qb[4] = { l[2 + s].x, l[2 + s].y, l[2 + s].z, l[2 + s].w };
-        const uint32_t hh[4] = { hq[s].x, hq[s].y, hq[s].z, hq[s].w };
-        int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-        const uint32_t a0[4] = { f.a[s].x, f.a[s].y, f.a[s].z, f.a[s].w }, a1[4] = { f.a[2 + s].x, f.a[2 + s].y, f.a[2 + s].z, f.a[2 + s].w };
-        const uint32_t a2[4] = { f.a[4 + s].x, f.a[4 + s].y, f.a[4 + s].z, f.a[4 + s].w }, a3[4] = { f.a[6 + s].x, f.a[6 + s].y, f.a[6 + s].z, f.a[6 + s].w };
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            d0 = __dp4a((int) ((qa[i] & 0x0f0f0f0fu)        | ((hh[i] << 4) & 0x30303030u)), (int) a0[i], d0);
-            d1 = __dp4a((int) ((qb[i] & 0x0f0f0f0fu)        | ((hh[i] << 2) & 0x30303030u)), (int) a1[i], d1);
-            d2 = __dp4a((int) (((qa[i] >> 4) & 0x0f0f0f0fu) | ( hh[i]       & 0x30303030u)), (int) a2[i], d2);
-            d3 = __dp4a((int) (((qb[i] >> 4) & 0x0f0f0f0fu) | ((hh[i] >> 2) & 0x30303030u)), (int) a3[i], d3);
-        }
+    for (int s = 0; s < 2; ++s) {                         // s: positions l = 16s .. 16s+15 of each quad; activations of quad q: f.a[2q + s]
+        // w = nibble + 16 * (2-bit field): by linearity dot(w, a) = dot(nibble, a) + 16 * dot(field, a); fields stay in place (x 4^q)
+        const int n0 = dot16m(l[s],     0x0f0f0f0fu, f.a[s],     0);          // quad 0: low nibbles of ql[.. 0..31]
+        const int n1 = dot16m(l[2 + s], 0x0f0f0f0fu, f.a[2 + s], 0);          // quad 1: low nibbles of ql[.. 32..63]
+        const int n2 = dot16m(l[s],     0xf0f0f0f0u, f.a[4 + s], 0);          // quad 2: high nibbles, x16
+        const int n3 = dot16m(l[2 + s], 0xf0f0f0f0u, f.a[6 + s], 0);          // quad 3: high nibbles, x16
+        const int h0 = dot16m(hq[s], 0x03030303u, f.a[s],     0);             // x1
+        const int h1 = dot16m(hq[s], 0x0c0c0c0cu, f.a[2 + s], 0);             // x4
+        const int h2 = dot16m(hq[s], 0x30303030u, f.a[4 + s], 0);             // x16
+        const int h3 = dot16m(hq[s], 0xc0c0c0c0u, f.a[6 + s], 0);             // x64
+        const int d0 = n0 + 16 * h0, d1 = n1 + 4 * h1, d2 = (n2 >> 4) + h2, d3 = (n3 >> 4) + (h3 >> 2);      // all exact
         // quad q, half s -> 16-element group 2q + s of this block half; scale byte index 2q + s (sc0: q = 0, 1; sc1: q = 2, 3)
         isum += (int) (int8_t) (sc0 >> (8 * s))      * (d0 - 32 * (int) bs[s]);
         isum += (int) (int8_t) (sc0 >> (8 * s + 16)) * (d1 - 32 * (int) bs[2 + s]);

@@ -147,8 +147,10 @@ class Qwen3Decoder:
         layout = ops.LAYOUT_PLANAR if wtype == ops.Q6_K else ops.LAYOUT_NATIVE
         return ops.make_job(w, wtype, m, k, y, residual, layout)
 
-    def step(self, n_kv: int) -> int:
+    def step(self, n_kv: int, engine: bool = False) -> int:
         """Enqueue one decode step on the current stream (capturable).  x_in/pos/kv_idx/mask_f32[:, :n_kv] must be set.  Returns #launches."""
+        if engine:
+            return self.step_engine(n_kv)
         cfg, L = self.cfg, ops.lib()
         E, F, D = cfg.n_embd, cfg.n_ff, cfg.head_dim
         q, kv = cfg.n_head * D, cfg.n_head_kv * D
