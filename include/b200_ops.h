@@ -188,7 +188,8 @@ typedef struct b200_decode_desc {
 B200_API int  b200_decoder_create(const b200_decode_desc * desc, void ** handle);
 B200_API int  b200_decoder_step(void * handle, int32_t n_kv, void * stream);
 B200_API int  b200_decoder_n_phases(void * handle);
-/* debugging aid: one step with per-phase device timestamps of CTA 0 -> host_out[n_phases][8] (ns; 0..3: start, prologue, work, barrier; 4..7: finer marks) */
+/* debugging aid: one step with per-phase device timestamps of every CTA -> host_out[n_phases][b200_device_sm_count][8]
+ * (ns; 0..3: phase start, prologue done, work done, barrier left; 4..7: finer marks) */
 B200_API int  b200_decoder_profile(void * handle, int32_t n_kv, unsigned long long * host_out, void * stream);
 B200_API void b200_decoder_destroy(void * handle);
 

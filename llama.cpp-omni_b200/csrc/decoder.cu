@@ -155,11 +155,11 @@ extern "C" int b200_decoder_step(void * handle, int32_t n_kv, void * stream) {
     return sd_launch(dec->phases_dev, dec->n_phases, nullptr, dec->gbar, rt, (cudaStream_t) stream);
 }
 
-// debugging aid: run one step with per-phase globaltimer stamps of CTA 0 ([n_phases][4] ns: start, prologue done, work done, barrier done)
+// debugging aid: run one step with per-phase globaltimer stamps of every CTA ([n_phases][n_sm][8] ns: start, prologue done, work done, barrier done, 4 finer marks)
 extern "C" int b200_decoder_profile(void * handle, int32_t n_kv, unsigned long long * host_out, void * stream) {
     Decoder * dec = (Decoder *) handle;
     if (!dec || !host_out) return B200_ERR_ARG;
-    const size_t bytes = (size_t) dec->n_phases * 8 * sizeof(unsigned long long);
+    const size_t bytes = (size_t) dec->n_phases * sm_count() * 8 * sizeof(unsigned long long);
     if (!dec->prof_dev) B200_CUDA_TRY(cudaMalloc(&dec->prof_dev, bytes));
     B200_CUDA_TRY(cudaMemsetAsync(dec->prof_dev, 0, bytes, (cudaStream_t) stream));
     SdRuntime rt = dec->rt; rt.n_kv = n_kv; rt.prof = dec->prof_dev;

@@ -30,6 +30,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
                  :: "r"(bar), "r"(parity) : "memory");
@@ -97,14 +98,18 @@ __device__ __forceinline__ void seg_unit(const SegTab & S, int u, int & j, int &
 #include "stream_dot.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------- block sync
+// The CTA is warp-specialised: warps 0 .. SD_WARPS-1 are CONSUMERS (prologues, dot products, attention, grid barriers), warp SD_WARPS
+// is the PRODUCER (phase staging + every bulk copy).  Consumers synchronise among themselves on named barrier 1.
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" :: "n"(SD_THREADS) : "memory"); }
+
 __device__ __forceinline__ float cta_sum(float v, float * red) {
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) red[warp] = v;
-    __syncthreads();
+    cons_sync();
     float t = lane < SD_WARPS ? red[lane] : 0.0f;
     t = warp_sum(t);
-    __syncthreads();
+    cons_sync();
     return t;
 }
 
@@ -136,36 +141,44 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
         const int dwords = (int) (G.bsum_off - G.d_off) >> 2, bwords = (int) (G.bytes - G.bsum_off) >> 2;    // small planes: 4-byte words
         for (int i = threadIdx.x; i < dwords; i += SD_THREADS) ((uint32_t *) (act + L.d_off))[i] = __ldcg((const uint32_t *) (P.act + G.d_off) + i);
         for (int i = threadIdx.x; i < bwords; i += SD_THREADS) ((uint32_t *) (act + L.bsum_off))[i] = __ldcg((const uint32_t *) (P.act + G.bsum_off) + i);
-        __syncthreads();
+        cons_sync();
         return;
     }
     float scale = 1.0f;
     const bool norm = P.prologue == SD_PRO_RMSNORM_QUANT;
     if (P.act_group == 256 && (kl >> 8) <= 2 * SD_WARPS && (P.ksplit == 1 || !norm)) {
         // fast path (every phase of the decode program): ONE pass over the inputs — each warp keeps its <= 2 super-blocks in registers
-        // between the sum of squares and the quantisation, and the loads of the up-to-4 summands are issued together
+        // between the sum of squares and the quantisation.  A round trip to L2 costs ~1 us while the weight stream saturates HBM, so ALL
+        // loads of the prologue (up to 4 summands x 2 blocks, and the norm weights) are issued back to back, branch-free, before any use.
         const int nb = kl >> 8, n_x = P.n_x;
+        const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 a[2][4][2], w[2][2];
+        if (pf) pf[6] = globaltimer();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const bool live = warp + SD_WARPS * t < nb;
+            const int e = k0 + (live ? warp + SD_WARPS * t : warp) * 256 + lane * 8;
+#pragma unroll
+            for (int sx = 0; sx < 4; ++sx) {
+                const bool on = live && sx < n_x;
+                const float * px = P.x[on ? sx : 0] + e;
+                a[t][sx][0] = on ? __ldcg((const float4 *) px) : z4; a[t][sx][1] = on ? __ldcg((const float4 *) (px + 4)) : z4;
+            }
+            w[t][0] = norm && live ? __ldg((const float4 *) (P.norm_w + e)) : z4; w[t][1] = norm && live ? __ldg((const float4 *) (P.norm_w + e + 4)) : z4;
+        }
         float v[2][8];
         float ss = 0.0f;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-            const int blk = warp + SD_WARPS * t;
+            v[t][0] = a[t][0][0].x; v[t][1] = a[t][0][0].y; v[t][2] = a[t][0][0].z; v[t][3] = a[t][0][0].w;
+            v[t][4] = a[t][0][1].x; v[t][5] = a[t][0][1].y; v[t][6] = a[t][0][1].z; v[t][7] = a[t][0][1].w;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[t][i] = 0.0f;
-            if (blk < nb) {
-                const int e = k0 + blk * 256 + lane * 8;
-                float4 a[4][2];
-#pragma unroll
-                for (int sx = 0; sx < 4; ++sx) if (sx < n_x) { a[sx][0] = __ldcg((const float4 *) (P.x[sx] + e)); a[sx][1] = __ldcg((const float4 *) (P.x[sx] + e + 4)); }
-#pragma unroll
-                for (int sx = 0; sx < 4; ++sx) if (sx < n_x) {
-                    if (sx == 0) { v[t][0] = a[0][0].x; v[t][1] = a[0][0].y; v[t][2] = a[0][0].z; v[t][3] = a[0][0].w; v[t][4] = a[0][1].x; v[t][5] = a[0][1].y; v[t][6] = a[0][1].z; v[t][7] = a[0][1].w; }
-                    else { v[t][0] += a[sx][0].x; v[t][1] += a[sx][0].y; v[t][2] += a[sx][0].z; v[t][3] += a[sx][0].w; v[t][4] += a[sx][1].x; v[t][5] += a[sx][1].y; v[t][6] += a[sx][1].z; v[t][7] += a[sx][1].w; }
-                }
-                if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
+            for (int sx = 1; sx < 4; ++sx) if (sx < n_x) {                 // fixed order x[0] + x[1] + ...: deterministic
+                v[t][0] += a[t][sx][0].x; v[t][1] += a[t][sx][0].y; v[t][2] += a[t][sx][0].z; v[t][3] += a[t][sx][0].w;
+                v[t][4] += a[t][sx][1].x; v[t][5] += a[t][sx][1].y; v[t][6] += a[t][sx][1].z; v[t][7] += a[t][sx][1].w;
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
         }
         if (pf) pf[4] = globaltimer();
         if (norm) scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
@@ -175,11 +188,11 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
             const int blk = warp + SD_WARPS * t;
             if (blk < nb) {
                 const int e = k0 + blk * 256 + lane * 8;
+                if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
                 if (norm) {
-                    const float4 w0 = __ldg((const float4 *) (P.norm_w + e)), w1 = __ldg((const float4 *) (P.norm_w + e + 4));
-                    const float w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+                    const float wv[8] = { w[t][0].x, w[t][0].y, w[t][0].z, w[t][0].w, w[t][1].x, w[t][1].y, w[t][1].z, w[t][1].w };
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[t][i] = __fmul_rn(__fmul_rn(v[t][i], scale), w[i]);
+                    for (int i = 0; i < 8; ++i) v[t][i] = __fmul_rn(__fmul_rn(v[t][i], scale), wv[i]);
                     if (writer && P.norm_out) {
                         *(float4 *) (P.norm_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]);
                     }
@@ -187,8 +200,13 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
                 quant_block_q8K<true>(v[t], act, blk, L.d_off, L.bsum_off);
             }
         }
-        __syncthreads();
+        cons_sync();
         return;
+    }
+    if (norm) {                                                           // generic path: separate sum-of-squares pass over the FULL row
+        float ss = 0.0f;
+        for (int i = threadIdx.x * 4; i < k; i += SD_THREADS * 4) { const float4 v = sd_load_x4(P, i); ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+        scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
     }
     if (P.act_group == 256) {
         for (int blk = warp; blk < (kl >> 8); blk += SD_WARPS) {
@@ -227,51 +245,54 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
             quant_block_q8_0<true>(v, live, act, blk, L.d_off, L.bsum_off);
         }
     }
-    __syncthreads();
+    cons_sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------------- grid barrier
-// count/generation barrier in global memory; self-resetting, so a captured CUDA graph can replay the kernel without host help.
-__device__ __forceinline__ void sd_grid_barrier(unsigned * bar) {       // bar[0] = count, bar[32] = generation (separate 128-B lines)
-    __syncthreads();
+// A monotonic arrival counter in global memory: every CTA adds 1 (release) and polls the SAME word (acquire) until it reaches the phase's
+// target — one hop after the last arrival, instead of "last arriver sees the returned count, then flips a generation flag" (two).  The
+// counter is never reset: bar[32] holds the value it had when the launch began (written by CTA 0 at the very end of the previous launch),
+// so a captured CUDA graph can replay the kernel without host help.  `done` (shared) tells the producer warp that this CTA's consumers
+// have left phase `phase_done - 1` (its staging slot may be reused).
+__device__ __forceinline__ void sd_grid_barrier(unsigned * bar, unsigned target, volatile int * done, int phase_done, bool sync_grid) {
+    cons_sync();
     if (threadIdx.x == 0) {
-        // release/acquire ride on the atomics themselves (no separate membar.gl): the CTA's writes are ordered before thread 0's
-        // release by the bar.sync above (cumulativity), and the acquire load orders the other CTAs' writes before the bar.sync below
-        unsigned gen, old;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 32) : "memory");
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
-        if (old == gridDim.x - 1) {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(bar), "r"(0u) : "memory");
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar + 32) : "memory");
-        } else {
-            unsigned g2;
-            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(bar + 32) : "memory"); } while (g2 == gen);
+        *done = phase_done;
+        if (sync_grid) {
+            // the CTA's writes are ordered before thread 0's release by the bar.sync above (cumulativity); the acquire load orders the other
+            // CTAs' writes before the bar.sync below
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
+            unsigned v;                                                    // (polling relaxed + one acquire fence measured slower)
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int) (v - target) < 0);
         }
     }
-    __syncthreads();
+    if (sync_grid) cons_sync();
 }
 
 #include "stream_attn.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------- the kernel
 __device__ __forceinline__ void sd_copy_phase(SdPhase * dst, const SdPhase * src, int lane, int nlanes) {
+    static_assert(SD_WARPS % 4 == 0, "rings are split evenly over the 4 producer warps");
     static_assert(sizeof(SdPhase) % 16 == 0, "SdPhase must be a multiple of 16 bytes");
     for (int i = lane; i < (int) (sizeof(SdPhase) / 16); i += nlanes) ((uint4 *) dst)[i] = ((const uint4 *) src)[i];
 }
 
-// per-warp streaming state: `issued` / `consumed` count this warp's units since kernel start; unit n sits in slot n % SD_DEPTH
-struct WarpStream {
-    uint32_t issued, consumed;
-    int iss_mv, iss_u;                // phase slot (mv index & 1) and phase-local unit index of the next unit this warp will request
-};
+// what a consumer warp needs to know about the unit sitting in one of its ring slots (written by the producer before the copy is issued,
+// published by the slot's full-barrier): 32 bytes
+struct alignas(16) SlotDesc { uint32_t type_n; uint32_t sub_p, sub_d; uint32_t pad_; float * y; const float * resid; };
 
-// lane 0: request one unit (bulk copies of its rows' K-slices into the warp's next ring slot).  Everything it needs was precomputed
-// into the segment table: this runs once per unit on ONE lane while 31 wait, so it must stay a few dozen instructions.
-__device__ __forceinline__ void sd_issue(const SegTab & S, int u, uint32_t dst, uint32_t bar, uint64_t pol) {
+struct StagedPhase { SdPhase P; SegTab S; };                           // ring of SD_NPH entries in shared memory, entry of phase p: p % SD_NPH
+
+// producer lane (= consumer warp index): request unit u of the staged phase into the warp's ring slot
+__device__ __forceinline__ void sd_issue(const SegTab & S, int u, uint32_t dst, uint32_t bar, SlotDesc * desc, uint64_t pol, bool dry) {
     int j, off, n; seg_unit(S, u, j, off, n);
     const uint32_t sp = S.sub_p[j], sd = S.sub_d[j];
     const int64_t rbp = S.rbp[j], rbd = S.rbd[j];
-    mbar_expect_tx(bar, (uint32_t) n * (sp + sd) * S.nm);
+    desc->type_n = (uint32_t) S.type[j] | ((uint32_t) n << 8); desc->sub_p = sp; desc->sub_d = sd;
+    desc->y = S.y[j] + off; desc->resid = S.resid[j] ? S.resid[j] + off : nullptr;
+    if (dry) { mbar_arrive(bar); return; }                                // experiment: control path without any weight traffic
+    mbar_expect_tx(bar, (uint32_t) n * (sp + sd) * S.nm);                 // release: orders the descriptor before the consumer's acquire
     const uint8_t * pay = S.pay[j] + off * rbp;
     const uint8_t * dpl = S.dpl[j] + off * rbd;
     if (S.ksplit == 1) {                                                   // full rows are back to back: one copy per plane
@@ -287,140 +308,171 @@ __device__ __forceinline__ void sd_issue(const SegTab & S, int u, uint32_t dst, 
     }
 }
 
-// keep the warp's ring full: request units of the current phase, then of the next matvec phase (whose descriptor is already staged)
-__device__ __forceinline__ void sd_top_up(WarpStream & W, const SegTab * sS, int cur_mv, bool have_next, const volatile int * staged,
-                                          uint32_t ring_w, uint32_t bars_w, uint64_t pol) {
-    while (W.issued - W.consumed < SD_DEPTH) {
-        if (W.iss_u >= sS[W.iss_mv].upre[3]) {
-            if (W.iss_mv == (cur_mv & 1) && have_next) {
-                while (*staged < cur_mv + 1) { }                            // the staging warp publishes the next phase's table
-                W.iss_mv ^= 1; W.iss_u = threadIdx.x >> 5; continue;
+// The producer warp group (4 warps): warp 0 of the group stages phase descriptors + this CTA's segment tables two phases ahead of the one
+// being issued; every producer warp keeps the rings of 3 consumer warps full (lanes 0..2, one ring each — bulk copies are issued from
+// uniform registers, i.e. serially per lane, so the rings are spread over four warps rather than twelve lanes of one).  Producers never
+// wait for a grid barrier (weights depend on nothing), only for free ring slots, so HBM keeps streaming through the consumers' barriers,
+// prologues and attention phases.
+__device__ __forceinline__ void sd_producer(const SdPhase * src, int n_phases, StagedPhase * ring_ph, volatile int * staged, volatile int * done,
+                                            uint32_t ring, uint32_t full, uint32_t empty, SlotDesc * descs, uint64_t pol, uint32_t inflight, const SdRuntime & rt) {
+    const int lane = threadIdx.x & 31, pw = (threadIdx.x >> 5) - SD_WARPS;
+    constexpr int RPW = SD_WARPS / 4;                                      // rings per producer warp
+    const int cw = pw * RPW + lane;                                        // the consumer warp this lane feeds (lanes < RPW)
+    int staged_n = 0;
+    uint32_t issued = 0;
+    for (int p = 0; p < n_phases; ++p) {
+        if (pw == 0) {
+            while (staged_n < n_phases && staged_n <= p + SD_STAGE_AHEAD) {
+                if (staged_n >= SD_NPH) while (*done < staged_n - SD_NPH + 1) { }      // the slot's previous tenant has been left by the consumers
+                StagedPhase & E = ring_ph[staged_n % SD_NPH];
+                sd_copy_phase(&E.P, src + staged_n, lane, 32);
+                __syncwarp();
+                // an attention phase's old KV rows do not depend on this token: pull this CTA's chunk into L2 now, two phases early
+                if (E.P.kind == SD_ATTN && !(rt.flags & 2)) sa_prefetch_kv(E.P.attn, rt, lane, 32);
+                if (lane == 0) {
+                    if (E.P.kind == SD_MATVEC) seg_build(E.S, E.P, blockIdx.x, gridDim.x); else E.S.upre[3] = 0;
+                    __threadfence_block();
+                    *staged = staged_n + 1;
+                }
+                __syncwarp();
+                ++staged_n;
             }
-            break;
+        } else {
+            while (*staged <= p) { }
+            __threadfence_block();
         }
-        const uint32_t slot = W.issued % SD_DEPTH;
-        sd_issue(sS[W.iss_mv], W.iss_u, ring_w + slot * SD_SLOT_BYTES, bars_w + 8 * slot, pol);
-        W.iss_u += SD_WARPS; ++W.issued;
+        const StagedPhase & E = ring_ph[p % SD_NPH];
+        if (E.P.kind != SD_MATVEC) continue;
+        const int nunits = E.S.upre[3];
+        if (lane < RPW) {
+            const uint32_t ring_w = ring + cw * SD_DEPTH * SD_SLOT_BYTES, full_w = full + cw * SD_DEPTH * 8, empty_w = empty + cw * SD_DEPTH * 8;
+            for (int u = cw; u < nunits; u += SD_WARPS) {
+                const uint32_t slot = issued % SD_DEPTH, use = issued / SD_DEPTH;
+                if (use) mbar_wait(empty_w + 8 * slot, (use - 1) & 1);
+                // pacing: at most `inflight` units of this ring on the wire
+                if (issued >= inflight) { const uint32_t o = issued - inflight; mbar_wait(full_w + 8 * (o % SD_DEPTH), (o / SD_DEPTH) & 1); }
+                sd_issue(E.S, u, ring_w + slot * SD_SLOT_BYTES, full_w + 8 * slot, descs + cw * SD_DEPTH + slot, pol, (rt.flags & 4) != 0);
+                ++issued;
+            }
+        }
+        __syncwarp();
     }
 }
 
-// one matvec phase.  REGS: K-slice <= 4096 and q4_K / q6_K only -> activation fragments live in registers; otherwise fragments are
-// re-read from shared memory (two rows share each read).
+// one matvec phase on a consumer warp.  REGS: K-slice <= 4096 and q4_K / q6_K only -> activation fragments live in registers; otherwise
+// fragments are re-read from shared memory (two rows share each read).
 template <bool REGS>
-__device__ __forceinline__ void sd_consume(const SdPhase & P, const SegTab & S, const ActS & A, WarpStream & W, const SdPhase * sP, const SegTab * sS,
-                                           int cur_mv, bool have_next, const volatile int * staged, uint32_t ring_w, uint32_t bars_w, uint64_t pol) {
+__device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const ActS & A, uint32_t & consumed, uint32_t ring_w, uint32_t full_w, uint32_t empty_w,
+                                           const SlotDesc * descs_w, unsigned long long * pf, int flags) {
+    long long waited = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kl = P.k / P.ksplit, nblk = kl >> 8;
     const bool swiglu = P.epilogue == SD_EPI_SWIGLU;
     HFrag fr;
     if (REGS) hfrag_fill(A, nblk, fr);
-    const int nunits = S.upre[3];
     for (int u = warp; u < nunits; u += SD_WARPS) {
-        if (lane == 0) sd_top_up(W, sS, cur_mv, have_next, staged, ring_w, bars_w, pol);
-        int j, row, n; seg_unit(S, u, j, row, n);
-        const uint32_t slot = W.consumed % SD_DEPTH, par = (W.consumed / SD_DEPTH) & 1;
-        const int type = S.type[j];
-        const uint32_t rbp = S.sub_p[j], rbd = S.sub_d[j];
+        const uint32_t slot = consumed % SD_DEPTH, par = (consumed / SD_DEPTH) & 1;
         const uint32_t base = ring_w + slot * SD_SLOT_BYTES;
+        const long long tw = pf ? clock64() : 0;
+        mbar_wait(full_w + 8 * slot, par);
+        if (pf) waited += clock64() - tw;
+        const SlotDesc d = descs_w[slot];
+        const int type = d.type_n & 0xff, n = d.type_n >> 8;
+        const uint32_t rbp = d.sub_p, rbd = d.sub_d;
         const uint32_t bp = (uint32_t) n * rbp, bd = (uint32_t) n * rbd;     // slot: [payload rows][d rows] (+ the same again for `up`)
-        float * y = S.y[j] + row;
-        const float * resid = S.resid[j] ? S.resid[j] + row : nullptr;
-        mbar_wait(bars_w + 8 * slot, par);
-        float2 g2 = make_float2(0.0f, 0.0f), v;
-        if (REGS) {
+        float2 g2 = make_float2(0.0f, 0.0f), v = make_float2(0.0f, 0.0f);
+        if (flags & 8) { }                                                 // experiment: handshake only, no arithmetic
+        else if (REGS) {
             if (type == B200_Q4_K) { v = krow_regs<B200_Q4_K>(base, rbp, base + bp, rbd, nblk, n, fr); if (swiglu) { g2 = v; v = krow_regs<B200_Q4_K>(base + bp + bd, rbp, base + 2 * bp + bd, rbd, nblk, n, fr); } }
             else                   { v = krow_regs<B200_Q6_K>(base, rbp, base + bp, rbd, nblk, n, fr); if (swiglu) { g2 = v; v = krow_regs<B200_Q6_K>(base + bp + bd, rbp, base + 2 * bp + bd, rbd, nblk, n, fr); } }
         } else {
             v = unit_dots_lds(type, n, base, rbp, base + bp, rbd, A, kl);
             if (swiglu) { g2 = v; v = unit_dots_lds(type, n, base + bp + bd, rbp, base + 2 * bp + bd, rbd, A, kl); }
         }
+        __syncwarp();                                                      // every lane's reads of the slot are done
+        if (lane == 0) mbar_arrive(empty_w + 8 * slot);                    // hand it back to the producer before the epilogue's global traffic
         if (lane < n) {
             float o = lane == 0 ? v.x : v.y;
             if (swiglu) { const float gg = lane == 0 ? g2.x : g2.y; o = (gg / (1.0f + expf(-gg))) * o; }
-            if (resid) o += __ldcg(resid + lane);
-            y[lane] = o;
+            if (d.resid) o += __ldcg(d.resid + lane);
+            d.y[lane] = o;
         }
-        __syncwarp();
-        fence_proxy_async();                                               // the slot's generic-proxy reads precede its next bulk write
-        ++W.consumed;
+        ++consumed;
     }
-    if (lane == 0) sd_top_up(W, sS, cur_mv, have_next, staged, ring_w, bars_w, pol);   // prefetch into the next phase through the barrier
+    if (pf) pf[7] = (unsigned long long) waited;                           // cycles warp 0 spent waiting for weights in this phase
 }
 
-__global__ void __launch_bounds__(SD_THREADS, 1) k_stream(const SdPhase * __restrict__ phases_g, int n_phases, unsigned * gbar,
-                                                          const __grid_constant__ SdPhase single, const SdRuntime rt) {
+__global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * __restrict__ phases_g, int n_phases, unsigned * gbar,
+                                                               const __grid_constant__ SdPhase single, const SdRuntime rt) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t  * ring = smem;
     uint8_t  * act  = smem + SD_RING_BYTES;
     uint8_t  * attn_scratch = act + SD_ACT_BYTES;
-    uint64_t * bars = (uint64_t *) (attn_scratch + SD_ATTN_BYTES);       // full[warp][slot]
-    float    * red  = (float *) (bars + SD_WARPS * SD_DEPTH);
-    SdPhase  * sP   = (SdPhase *) (red + 64);                            // [0], [1]: matvec phases (alternating); [2]: attention phase
-    SegTab   * sS   = (SegTab *) (sP + 3);                               // [0], [1]: this CTA's share of the matvec phase in sP[0], sP[1]
-    float2   * rope_tab = (float2 *) (((uintptr_t) (sS + 2) + 15) & ~(uintptr_t) 15);   // [64] (cos, sin) of the token's position
-    volatile int * staged = (volatile int *) (rope_tab + 64);          // index of the last matvec phase whose descriptor + table are staged
+    uint64_t * bars = (uint64_t *) (attn_scratch + SD_ATTN_BYTES);       // full[warp][slot], then empty[warp][slot]
+    SlotDesc * descs = (SlotDesc *) (bars + 2 * SD_WARPS * SD_DEPTH);
+    float    * red  = (float *) (descs + SD_WARPS * SD_DEPTH);
+    StagedPhase * ring_ph = (StagedPhase *) (red + 64);
+    float2   * rope_tab = (float2 *) (((uintptr_t) (ring_ph + SD_NPH) + 15) & ~(uintptr_t) 15);   // [64] (cos, sin) of the token's position
+    volatile int * staged = (volatile int *) (rope_tab + 64);          // number of phases staged so far (producer -> consumers)
+    volatile int * done   = staged + 1;                                // number of phases the consumers have left (consumers -> producer)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SdPhase * src = phases_g ? phases_g : &single;
-    const uint32_t ring_w = smem_u32(ring) + warp * SD_DEPTH * SD_SLOT_BYTES, bars_w = smem_u32(bars) + warp * SD_DEPTH * 8;
+    const uint32_t full = smem_u32(bars), empty = full + SD_WARPS * SD_DEPTH * 8;
 
-    // stage the first phase(s): phase 0, and the first matvec phase if phase 0 is not one (later ones are staged one phase ahead)
     if (threadIdx.x == 0) {
-        for (int s = 0; s < SD_WARPS * SD_DEPTH; ++s) mbar_init(smem_u32(bars) + 8 * s, 1);
+        for (int s = 0; s < 2 * SD_WARPS * SD_DEPTH; ++s) mbar_init(full + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *staged = 0; *done = 0;
     }
-    const int kind0 = src[0].kind;
-    const int first_mv = kind0 == SD_MATVEC ? 0 : src[0].next_mv;
-    if (warp == 0 && first_mv >= 0) sd_copy_phase(&sP[0], src + first_mv, lane, 32);
-    if (warp == 1 && kind0 == SD_ATTN) sd_copy_phase(&sP[2], src, lane, 32);
-    if (warp == 2 && rt.has_rope) sa_rope_table(rope_tab, rt, lane);
-    __syncthreads();
-    if (threadIdx.x == 0) { if (first_mv >= 0) seg_build(sS[0], sP[0], blockIdx.x, gridDim.x); *staged = 0; }
-    __syncthreads();
+    __syncthreads();                                                     // the only CTA-wide barrier: roles split here
 
-    const uint64_t pol = rt.flags & 1 ? policy_evict_normal() : policy_evict_first();
-    WarpStream W; W.issued = 0; W.consumed = 0; W.iss_mv = 0; W.iss_u = warp;
-    int mv = 0;                                                           // index of the current matvec phase among matvec phases
-    if (lane == 0 && first_mv >= 0) sd_top_up(W, sS, 0, false, staged, ring_w, bars_w, pol);   // weights first: they depend on nothing
-    const bool prof = rt.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    // register reallocation between the warp groups (512 threads start with 128 registers each): the producer group gives most of its
+    // registers back, the three consumer groups grow to 152
+    if (warp >= SD_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const uint64_t pol = rt.flags & 1 ? policy_evict_normal() : policy_evict_first();
+        const uint32_t infl = (rt.flags >> 4) & 15;
+        sd_producer(src, n_phases, ring_ph, staged, done, smem_u32(ring), full, empty, descs, pol, infl ? infl : SD_INFLIGHT, rt);
+        return;
+    }
 
-    int kind = kind0;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    if (warp == 2 && rt.has_rope) sa_rope_table(rope_tab, rt, lane);     // published by the first prologue's barrier
+    const uint32_t ring_w = smem_u32(ring) + warp * SD_DEPTH * SD_SLOT_BYTES, full_w = full + warp * SD_DEPTH * 8, empty_w = empty + warp * SD_DEPTH * 8;
+    const SlotDesc * descs_w = descs + warp * SD_DEPTH;
+    uint32_t consumed = 0;
+    unsigned bar_base = 0;                                                // value of the arrival counter when this launch began
+    if (threadIdx.x == 0 && n_phases > 1) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bar_base) : "l"(gbar + 32) : "memory");
+    const bool prof = rt.prof != nullptr && threadIdx.x == 0;
+    unsigned long long * const pbase = prof ? rt.prof + (size_t) blockIdx.x * 8 : nullptr;      // [phase][cta][8]
+    const size_t pstr = (size_t) gridDim.x * 8;
+
     for (int p = 0; p < n_phases; ++p) {
-        if (prof) rt.prof[p * 8 + 0] = globaltimer();
-        int next_kind;
-        if (kind == SD_MATVEC) {
-            const SdPhase & P = sP[mv & 1];
-            next_kind = P.next_kind;
-            const int nxt = P.next_mv;
-            const bool have_next = nxt >= 0;
-            // stage, one phase ahead and off the critical path: the next matvec phase's descriptor + segment table (warp 1) and the
-            // attention phase that follows this one (warp 2); both are published by the prologue's __syncthreads
-            const SegTab & S = sS[mv & 1];
-            sd_prologue(P, S.kpart, act, red, prof ? rt.prof + p * 8 : nullptr);
-            if (warp == SD_WARPS - 1 && have_next) {                      // after the prologue: off the CTA's critical path
-                sd_copy_phase(&sP[(mv + 1) & 1], src + nxt, lane, 32);
-                __syncwarp();
-                if (lane == 0) { seg_build(sS[(mv + 1) & 1], sP[(mv + 1) & 1], blockIdx.x, gridDim.x); __threadfence_block(); *staged = mv + 1; }
-            }
-            if (warp == SD_WARPS - 2 && next_kind == SD_ATTN) sd_copy_phase(&sP[2], src + p + 1, lane, 32);   // published by the grid barrier
-            if (prof) rt.prof[p * 8 + 1] = globaltimer();
+        if (prof) pbase[p * pstr + 0] = globaltimer();
+        while (*staged <= p) { }
+        __threadfence_block();
+        const StagedPhase & E = ring_ph[p % SD_NPH];
+        const SdPhase & P = E.P;
+        if (P.kind == SD_MATVEC) {
+            sd_prologue(P, E.S.kpart, act, red, prof ? pbase + p * pstr : nullptr);
+            if (prof) pbase[p * pstr + 1] = globaltimer();
             const int kl = P.k / P.ksplit;
             const ActLayout L = sd_act_layout(P.act_group, kl);
             ActS A; A.qs = smem_u32(act); A.d = A.qs + (uint32_t) L.d_off; A.bsum = A.qs + (uint32_t) L.bsum_off;
             bool regs = P.act_group == 256 && kl <= 4096;                 // q8_K fragments of a 4096-wide record fit in registers
             for (int m = 0; m < P.n_mat; ++m) regs = regs && (P.mat[m].type == B200_Q4_K || P.mat[m].type == B200_Q6_K);
-            if (regs) sd_consume<true >(P, S, A, W, sP, sS, mv, have_next, staged, ring_w, bars_w, pol);
-            else      sd_consume<false>(P, S, A, W, sP, sS, mv, have_next, staged, ring_w, bars_w, pol);
-            ++mv;
+            if (regs) sd_consume<true >(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, prof ? pbase + p * pstr : nullptr, rt.flags);
+            else      sd_consume<false>(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, prof ? pbase + p * pstr : nullptr, rt.flags);
         } else {
-            next_kind = sP[2].next_kind;
-            if (prof) rt.prof[p * 8 + 1] = globaltimer();
-            sd_attention(sP[2], rt, attn_scratch, rope_tab, prof ? rt.prof + p * 8 : nullptr);
+            if (prof) pbase[p * pstr + 1] = globaltimer();
+            sd_attention(P, rt, attn_scratch, rope_tab, prof ? pbase + p * pstr : nullptr);
         }
-        if (prof) rt.prof[p * 8 + 2] = globaltimer();
-        if (p + 1 < n_phases) sd_grid_barrier(gbar);
-        if (prof) rt.prof[p * 8 + 3] = globaltimer();
-        kind = next_kind;
+        if (prof) pbase[p * pstr + 2] = globaltimer();
+        sd_grid_barrier(gbar, bar_base + (unsigned) (p + 1) * gridDim.x, done, p + 1, p + 1 < n_phases);
+        if (prof) pbase[p * pstr + 3] = globaltimer();
     }
+    // every CTA read bar[32] before its first barrier, and CTA 0 is past the last one: safe to publish the next launch's base
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_phases > 1) gbar[32] = bar_base + (unsigned) (n_phases - 1) * gridDim.x;
 }
 
 // ---------------------------------------------------------------------------------------------------------------- host side
@@ -477,7 +529,7 @@ int sd_launch(const SdPhase * phases_dev, int n_phases, const SdPhase * single, 
     static const int env_flags = getenv("B200_SD_FLAGS") ? atoi(getenv("B200_SD_FLAGS")) : 0;     // experiment switches (bit 0: no evict_first hint)
     SdRuntime rt2 = rt; rt2.flags = env_flags;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned) sm_count()); cfg.blockDim = dim3(SD_THREADS); cfg.dynamicSmemBytes = SD_SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned) sm_count()); cfg.blockDim = dim3(SD_THREADS + 128); cfg.dynamicSmemBytes = SD_SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = (phases_dev && n_phases > 1) ? 1 : 0;

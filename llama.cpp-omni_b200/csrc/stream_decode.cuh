@@ -4,13 +4,16 @@
 
 namespace b200 {
 
-constexpr int SD_WARPS       = 12;                                 // 384 threads -> 168 registers each, no spills
+constexpr int SD_WARPS       = 12;                                 // CONSUMER warps (384 threads); one more warp is the producer -> 416 threads, 152 registers each
 constexpr int SD_THREADS     = SD_WARPS * 32;
 constexpr int SD_DEPTH       = 3;                                  // ring slots per warp: 1 being computed + 2 in flight
 constexpr int SD_SLOT_BYTES  = 4608;                               // one unit: 2 q4_K rows of k=4096, 1 q6_K row, or 1 gate/up pair
 constexpr int SD_RING_BYTES  = SD_WARPS * SD_DEPTH * SD_SLOT_BYTES;   // 162 KB of weights in flight per SM
 constexpr int SD_ACT_BYTES   = 16 * 1024;                          // q8 activation record, k <= 12288
-constexpr int SD_ATTN_BYTES  = 40 * 1024;                          // attention phase: score tile + cross-warp reduction
+constexpr int SD_ATTN_BYTES  = 40 * 1024;                          // attention phase: cross-warp reduction of the split-KV partials
+constexpr int SD_NPH         = 6;                                  // staged phase descriptors (ring in shared memory)
+constexpr int SD_INFLIGHT    = 3;                                  // bulk copies on the wire per consumer ring (pacing, see sd_producer)
+constexpr int SD_STAGE_AHEAD = 2;                                  // the producer stages this many phases ahead of the one it issues
 
 enum { SD_MATVEC = 0, SD_ATTN = 1 };
 enum { SD_EPI_STORE = 0, SD_EPI_SWIGLU = 1 };
@@ -60,7 +63,8 @@ struct SegTab {                                           // a CTA's share of on
     float * y[3]; const float * resid[3];                 // output / residual at this CTA's first row
 };
 
-constexpr int SD_SMEM_BYTES = SD_RING_BYTES + SD_ACT_BYTES + SD_ATTN_BYTES + SD_WARPS * SD_DEPTH * 8 + 64 * 4 + 3 * (int) sizeof(SdPhase)
-                            + 2 * (int) sizeof(SegTab) + 64 + 64 * 8 + 16;
+constexpr int SD_SMEM_BYTES = SD_RING_BYTES + SD_ACT_BYTES + SD_ATTN_BYTES + 2 * SD_WARPS * SD_DEPTH * 8 /* full + empty barriers */
+                            + SD_WARPS * SD_DEPTH * 32 /* slot descriptors */ + 64 * 4 + SD_NPH * (int) (sizeof(SdPhase) + sizeof(SegTab)) + 64 + 64 * 8 + 16;
+static_assert(SD_SMEM_BYTES <= 227 * 1024, "k_stream shared memory");
 
 } // namespace b200
