@@ -1,0 +1,729 @@
+// ggml-b200.cpp — the drop-in boundary: a ggml backend plugin (libggml-b200.so) that the reference loads with
+//   GGML_BACKEND_PATH=/path/libggml-b200.so        (ggml_backend_load_all, ggml/src/ggml-backend-reg.cpp:581-608)
+// and that then sits behind the reference's own ggml_backend_t interface (ggml/src/ggml-backend-impl.h): llama.cpp-omni's graph
+// executor (ggml_backend_sched), GGUF loader and omni pipeline stay untouched C++.  This file is HOST code only: every ggml op is
+// mapped onto one entry point of the thin C-ABI of hand-written sm_100a kernels (include/b200_ops.h, libb200ops.so).
+//
+// Reference interface being filled in (what ggml-cuda.cu fills at :655-665, :724-731, :3191-3206, :3739-3755, :3847-3852):
+//   ggml_backend_reg_i          ggml-backend-impl.h:194-204     -> b200_reg_*
+//   ggml_backend_device_i       ggml-backend-impl.h:140-182     -> b200_dev_*
+//   ggml_backend_buffer_type_i  ggml-backend-impl.h:17-29       -> b200_buft_*
+//   ggml_backend_buffer_i       ggml-backend-impl.h:41-58       -> b200_buf_*
+//   ggml_backend_i              ggml-backend-impl.h:87-120      -> b200_backend_*
+// Entry points looked up with dlsym (ggml-backend-reg.cpp:257-273): ggml_backend_init, ggml_backend_score.
+//
+// Compiled against the reference's PUBLIC headers where they lie (-I$REF/ggml/include -I$REF/ggml/src); nothing is copied.
+#include "ggml.h"
+#include "ggml-backend.h"
+#include "ggml-backend-impl.h"
+#include "../../../include/ggml-b200.h"
+#include "../../../include/b200_ops.h"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#define B200_LOG(...) do { fprintf(stderr, "ggml-b200: " __VA_ARGS__); fputc('\n', stderr); } while (0)
+// void interface functions cannot report errors: abort like the reference's CUDA_CHECK does (ggml-cuda/common.cuh)
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "ggml-b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorString(e_), __FILE__, __LINE__, #expr); abort(); } } while (0)
+
+namespace {
+
+constexpr int MAX_DEVICES = 16;
+
+struct DeviceCtx {
+    int index = 0;
+    std::string name, description, pci_id;
+    ggml_backend_buffer_type buft = {};
+    ggml_backend_device dev = {};
+};
+
+struct BufferCtx {
+    int device = 0;
+    void * base = nullptr;
+    void * staging = nullptr; size_t staging_size = 0;      // repack staging (weights only)
+    std::mutex mu;
+};
+
+struct BackendCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    void * scratch = nullptr; size_t scratch_size = 0;      // activation records / split-KV partials
+    std::string name;
+    // decode-step CUDA graph (one per backend): re-captured whenever the node list or any tensor address / shape / parameter changes
+    std::vector<uint64_t> graph_key, pending_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graphs_enabled = true;
+};
+
+DeviceCtx g_devices[MAX_DEVICES];
+int g_n_devices = -1;
+ggml_backend_reg g_reg = {};
+
+// ---------------------------------------------------------------------------------------------------------------- tensor views
+bool type_known(enum ggml_type t) {
+    switch (t) {
+        case GGML_TYPE_F32: case GGML_TYPE_F16: case GGML_TYPE_BF16: case GGML_TYPE_Q4_0: case GGML_TYPE_Q8_0: case GGML_TYPE_Q4_K:
+        case GGML_TYPE_Q5_K: case GGML_TYPE_Q6_K: case GGML_TYPE_I32: case GGML_TYPE_I64: return true;
+        default: return false;
+    }
+}
+
+// Weights whose native block is not a 16-byte multiple live in the PLANAR layout (include/b200_ops.h) when they sit, whole and
+// 2-D, in a USAGE_WEIGHTS buffer: set_tensor scatters them, get_tensor gathers them back, MUL_MAT reads them planar.  The same
+// predicate is evaluated on every path, so no per-tensor state is needed.  (Layout freedom: consumers only touch weight bytes
+// through set/get_tensor — SURVEY.md §8b.)
+bool is_planar(const ggml_tensor * t) {
+    if (!t || !t->buffer || t->buffer->usage != GGML_BACKEND_BUFFER_USAGE_WEIGHTS) return false;
+    if (!b200_repack_supported((int) t->type)) return false;
+    return t->view_src == nullptr && t->ne[2] == 1 && t->ne[3] == 1 && ggml_is_contiguous(t);
+}
+
+b200_tensor view_of(const ggml_tensor * t) {
+    b200_tensor v;
+    v.data = t->data; v.type = (int32_t) t->type; v.layout = is_planar(t) ? B200_LAYOUT_PLANAR : B200_LAYOUT_NATIVE;
+    for (int i = 0; i < 4; ++i) { v.ne[i] = t->ne[i]; v.nb[i] = (int64_t) t->nb[i]; }
+    return v;
+}
+
+float fparam(const ggml_tensor * t, int i) { float f; memcpy(&f, (const int32_t *) t->op_params + i, sizeof(f)); return f; }
+int32_t iparam(const ggml_tensor * t, int i) { return ((const int32_t *) t->op_params)[i]; }
+
+// ---------------------------------------------------------------------------------------------------------------- buffers
+void b200_buf_free(ggml_backend_buffer_t buffer) {
+    BufferCtx * c = (BufferCtx *) buffer->context;
+    cudaSetDevice(c->device);
+    if (c->base) cudaFree(c->base);
+    if (c->staging) cudaFree(c->staging);
+    delete c;
+}
+void * b200_buf_get_base(ggml_backend_buffer_t buffer) { return ((BufferCtx *) buffer->context)->base; }
+
+enum ggml_status b200_buf_init_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor) {
+    (void) buffer; (void) tensor;                                  // no per-tensor extras: layouts are derived (is_planar)
+    return GGML_STATUS_SUCCESS;
+}
+
+void b200_buf_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, uint8_t value, size_t offset, size_t size) {
+    BufferCtx * c = (BufferCtx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemset((char *) tensor->data + offset, value, size));
+    CUDA_OK(cudaDeviceSynchronize());
+}
+
+void * staging_for(BufferCtx * c, size_t size) {
+    if (c->staging_size < size) {
+        if (c->staging) CUDA_OK(cudaFree(c->staging));
+        c->staging_size = size < ((size_t) 4 << 20) ? ((size_t) 4 << 20) : size;
+        CUDA_OK(cudaMalloc(&c->staging, c->staging_size));
+    }
+    return c->staging;
+}
+
+// uploads arrive in arbitrary (offset, size) chunks (llama-model-loader.cpp:1077-1093): planar weights are scattered chunk by chunk
+void b200_buf_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
+    BufferCtx * c = (BufferCtx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    if (size == 0) return;
+    if (is_planar(tensor)) {
+        std::lock_guard<std::mutex> lock(c->mu);
+        void * st = staging_for(c, size);
+        CUDA_OK(cudaMemcpy(st, data, size, cudaMemcpyHostToDevice));
+        const int64_t nblocks = ggml_nelements(tensor) / ggml_blck_size(tensor->type);
+        const int rc = b200_repack_scatter((int) tensor->type, st, tensor->data, nblocks, (int64_t) offset, (int64_t) size, nullptr);
+        if (rc) { B200_LOG("repack_scatter failed: %s", b200_error_string(rc)); abort(); }
+        CUDA_OK(cudaStreamSynchronize(nullptr));
+        return;
+    }
+    CUDA_OK(cudaMemcpy((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice));
+}
+
+void b200_buf_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
+    BufferCtx * c = (BufferCtx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    if (size == 0) return;
+    if (is_planar(tensor)) {
+        std::lock_guard<std::mutex> lock(c->mu);
+        void * st = staging_for(c, size);
+        const int64_t nblocks = ggml_nelements(tensor) / ggml_blck_size(tensor->type);
+        const int rc = b200_repack_gather((int) tensor->type, tensor->data, st, nblocks, (int64_t) offset, (int64_t) size, nullptr);
+        if (rc) { B200_LOG("repack_gather failed: %s", b200_error_string(rc)); abort(); }
+        CUDA_OK(cudaMemcpy(data, st, size, cudaMemcpyDeviceToHost));
+        return;
+    }
+    CUDA_OK(cudaMemcpy(data, (const char *) tensor->data + offset, size, cudaMemcpyDeviceToHost));
+}
+
+bool buffer_is_b200(ggml_backend_buffer_t buffer);
+
+bool b200_buf_cpy_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * src, ggml_tensor * dst) {
+    (void) buffer;
+    if (!src->buffer || !buffer_is_b200(src->buffer)) return false;                     // host sources go through set_tensor
+    if (is_planar(src) != is_planar(dst) || ggml_nbytes(src) != ggml_nbytes(dst)) return false;
+    BufferCtx * sc = (BufferCtx *) src->buffer->context, * dc = (BufferCtx *) dst->buffer->context;
+    if (sc->device == dc->device) { CUDA_OK(cudaSetDevice(dc->device)); CUDA_OK(cudaMemcpy(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice)); }
+    else CUDA_OK(cudaMemcpyPeer(dst->data, dc->device, src->data, sc->device, ggml_nbytes(src)));
+    return true;
+}
+
+void b200_buf_clear(ggml_backend_buffer_t buffer, uint8_t value) {
+    BufferCtx * c = (BufferCtx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemset(c->base, value, buffer->size));
+    CUDA_OK(cudaDeviceSynchronize());
+}
+
+const ggml_backend_buffer_i b200_buffer_iface = {
+    /* free_buffer   */ b200_buf_free,
+    /* get_base      */ b200_buf_get_base,
+    /* init_tensor   */ b200_buf_init_tensor,
+    /* memset_tensor */ b200_buf_memset_tensor,
+    /* set_tensor    */ b200_buf_set_tensor,
+    /* get_tensor    */ b200_buf_get_tensor,
+    /* cpy_tensor    */ b200_buf_cpy_tensor,
+    /* clear         */ b200_buf_clear,
+    /* reset         */ nullptr,
+};
+bool buffer_is_b200(ggml_backend_buffer_t buffer) { return buffer->iface.free_buffer == b200_buf_free; }
+
+// ---------------------------------------------------------------------------------------------------------------- buffer type
+const char * b200_buft_get_name(ggml_backend_buffer_type_t buft) { return ((DeviceCtx *) buft->context)->name.c_str(); }
+
+ggml_backend_buffer_t b200_buft_alloc(ggml_backend_buffer_type_t buft, size_t size) {
+    DeviceCtx * d = (DeviceCtx *) buft->context;
+    if (cudaSetDevice(d->index) != cudaSuccess) return nullptr;
+    BufferCtx * c = new BufferCtx(); c->device = d->index;
+    const size_t bytes = size ? size : 1;
+    cudaError_t e = cudaMalloc(&c->base, bytes);
+    if (e != cudaSuccess) {                                          // NULL on OOM: the allocator propagates it (ggml-cuda.cu:690-695)
+        (void) cudaGetLastError();
+        B200_LOG("allocating %.2f MiB on device %d failed: %s", size / 1024.0 / 1024.0, d->index, cudaGetErrorString(e));
+        delete c; return nullptr;
+    }
+    return ggml_backend_buffer_init(buft, b200_buffer_iface, c, size);
+}
+size_t b200_buft_alignment(ggml_backend_buffer_type_t) { return 256; }
+size_t b200_buft_max_size(ggml_backend_buffer_type_t) { return SIZE_MAX; }
+size_t b200_buft_alloc_size(ggml_backend_buffer_type_t, const ggml_tensor * t) { return (ggml_nbytes(t) + 255) & ~(size_t) 255; }   // planar == native in bytes
+bool   b200_buft_is_host(ggml_backend_buffer_type_t) { return false; }
+
+// ---------------------------------------------------------------------------------------------------------------- supports_op
+bool f32c(const ggml_tensor * t) { return t && t->type == GGML_TYPE_F32 && t->nb[0] == sizeof(float); }
+bool floaty(const ggml_tensor * t) { return t && (t->type == GGML_TYPE_F32 || t->type == GGML_TYPE_F16 || t->type == GGML_TYPE_BF16); }
+bool broadcastable(const ggml_tensor * a, const ggml_tensor * b) {
+    for (int i = 0; i < 4; ++i) if (b->ne[i] == 0 || a->ne[i] % b->ne[i]) return false;
+    return true;
+}
+
+int unary_map(enum ggml_unary_op u) {
+    switch (u) {
+        case GGML_UNARY_OP_SILU: return B200_SILU;       case GGML_UNARY_OP_GELU: return B200_GELU;         case GGML_UNARY_OP_RELU: return B200_RELU;
+        case GGML_UNARY_OP_GELU_QUICK: return B200_GELU_QUICK; case GGML_UNARY_OP_TANH: return B200_TANH;   case GGML_UNARY_OP_SIGMOID: return B200_SIGMOID;
+        case GGML_UNARY_OP_GELU_ERF: return B200_GELU_ERF; case GGML_UNARY_OP_NEG: return B200_NEG;         case GGML_UNARY_OP_EXP: return B200_EXP;
+        case GGML_UNARY_OP_ABS: return B200_ABS;
+        default: return -1;
+    }
+}
+
+// Must depend on types / shapes / strides only: llama probes with dummy tensors whose buffer has size 0 (llama-model.cpp:286-291).
+// debugging aid: GGML_B200_DISABLE_OPS=ROPE,FLASH_ATTN_EXT hands those ops back to the scheduler's CPU fallback (bisecting parity)
+bool op_disabled(const ggml_tensor * op) {
+    static const std::string list = [] { const char * e = getenv("GGML_B200_DISABLE_OPS"); return std::string(e ? e : ""); }();
+    if (list.empty()) return false;
+    const std::string name = ggml_op_name(op->op);
+    size_t pos = 0;
+    while (pos <= list.size()) {
+        const size_t end = list.find(',', pos) == std::string::npos ? list.size() : list.find(',', pos);
+        if (list.compare(pos, end - pos, name) == 0) return true;
+        pos = end + 1;
+    }
+    return false;
+}
+
+bool b200_dev_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
+    const ggml_tensor * s0 = op->src[0], * s1 = op->src[1];
+    if (op_disabled(op)) return false;
+    for (int i = 0; i < GGML_MAX_SRC; ++i) if (op->src[i] && !type_known(op->src[i]->type)) return false;
+    if (!type_known(op->type)) return false;
+    switch (op->op) {
+        case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
+            return true;
+        case GGML_OP_MUL_MAT: {
+            if (!s0 || !s1 || ggml_is_transposed(s0) || ggml_is_transposed(s1)) return false;
+            if (s0->view_src && b200_repack_supported((int) s0->type) && s0->buffer && s0->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS) return false;   // a view into a planar weight
+            b200_tensor w = view_of(s0), x = view_of(s1), d = view_of(op);
+            return b200_mul_mat_supported(&w, &x, &d) != 0;
+        }
+        case GGML_OP_ADD: case GGML_OP_SUB: case GGML_OP_MUL: case GGML_OP_DIV:
+            return floaty(s0) && floaty(s1) && floaty(op) && ggml_are_same_shape(s0, op) && broadcastable(s0, s1);
+        case GGML_OP_RMS_NORM:
+            return f32c(s0) && f32c(op) && ggml_are_same_shape(s0, op);
+        case GGML_OP_ROPE: {
+            const int mode = iparam(op, 2), n_dims = iparam(op, 1);
+            if (mode != 0 && mode != GGML_ROPE_TYPE_NEOX) return false;
+            if (!f32c(s0) || !f32c(op) || !s1 || s1->type != GGML_TYPE_I32 || !ggml_is_contiguous(s1)) return false;
+            if (op->src[2] && (op->src[2]->type != GGML_TYPE_F32 || !ggml_is_contiguous(op->src[2]))) return false;
+            return n_dims > 0 && n_dims % 2 == 0 && n_dims <= s0->ne[0] && s0->ne[0] % 2 == 0;
+        }
+        case GGML_OP_SET_ROWS:
+            if (!s0 || !s1 || s0->type != GGML_TYPE_F32 || !floaty(op) || (s1->type != GGML_TYPE_I64 && s1->type != GGML_TYPE_I32)) return false;
+            return s0->ne[0] == op->ne[0] && s0->ne[2] == op->ne[2] && s0->ne[3] == op->ne[3] && s1->ne[0] == s0->ne[1] &&
+                   s1->ne[1] != 0 && s1->ne[2] != 0 && s0->ne[2] % s1->ne[1] == 0 && s0->ne[3] % s1->ne[2] == 0 && op->nb[0] == ggml_type_size(op->type);
+        case GGML_OP_GET_ROWS:
+            return floaty(s0) && floaty(op) && s1 && s1->type == GGML_TYPE_I32 && s0->ne[0] == op->ne[0] && op->ne[1] == s1->ne[0] &&
+                   op->ne[2] == s1->ne[1] && op->ne[3] == s1->ne[2];
+        case GGML_OP_CPY: case GGML_OP_CONT: case GGML_OP_DUP: {
+            if (!s0) return false;
+            const bool ints = s0->type == GGML_TYPE_I32 && op->type == GGML_TYPE_I32;
+            return (ints || (floaty(s0) && floaty(op))) && ggml_nelements(s0) == ggml_nelements(op);
+        }
+        case GGML_OP_SCALE:
+            return floaty(s0) && floaty(op) && ggml_are_same_shape(s0, op);
+        case GGML_OP_UNARY:
+            return floaty(s0) && floaty(op) && ggml_are_same_shape(s0, op) && unary_map(ggml_get_unary_op(op)) >= 0;
+        case GGML_OP_SQR: case GGML_OP_SQRT:
+            return floaty(s0) && floaty(op) && ggml_are_same_shape(s0, op);
+        case GGML_OP_GLU: {
+            const enum ggml_glu_op g = ggml_get_glu_op(op);
+            if (g == GGML_GLU_OP_SWIGLU_OAI || !floaty(s0) || !floaty(op)) return false;
+            if (s1) return floaty(s1) && ggml_are_same_shape(s0, s1) && ggml_are_same_shape(s1, op);
+            return s0->ne[0] == 2 * op->ne[0] && s0->ne[1] == op->ne[1] && s0->ne[2] == op->ne[2] && s0->ne[3] == op->ne[3];
+        }
+        case GGML_OP_SOFT_MAX: {
+            if (!f32c(s0) || !f32c(op) || op->src[2] || fparam(op, 1) != 0.0f || s0->ne[0] > 24576) return false;
+            if (s1 && ((s1->type != GGML_TYPE_F32 && s1->type != GGML_TYPE_F16) || s1->ne[0] != s0->ne[0] || s1->ne[1] < s0->ne[1] ||
+                       s1->ne[2] == 0 || s1->ne[3] == 0 || s0->ne[2] % s1->ne[2] || s0->ne[3] % s1->ne[3] || s1->nb[0] != ggml_type_size(s1->type))) return false;
+            return true;
+        }
+        case GGML_OP_FLASH_ATTN_EXT: {
+            if (op->src[4] || fparam(op, 1) != 0.0f || fparam(op, 2) != 0.0f) return false;          // sinks / ALiBi / softcap: not on this path
+            if (!s0 || !s1 || !op->src[2] || s0->ne[1] * s0->ne[3] > 65535) return false;
+            b200_tensor q = view_of(s0), k = view_of(s1), v = view_of(op->src[2]), d = view_of(op), m;
+            if (op->src[3]) m = view_of(op->src[3]);
+            return b200_flash_attn_supported(&q, &k, &v, op->src[3] ? &m : nullptr, &d) != 0;
+        }
+        default:
+            return false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- graph compute
+void * scratch_for(BackendCtx * c, size_t bytes) {
+    if (bytes <= c->scratch_size) return c->scratch;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (c->scratch) CUDA_OK(cudaFree(c->scratch));
+    c->scratch_size = (bytes + ((size_t) 8 << 20)) & ~(((size_t) 1 << 20) - 1);
+    CUDA_OK(cudaMalloc(&c->scratch, c->scratch_size));
+    return c->scratch;
+}
+
+// scratch a node needs (so that it can be sized BEFORE a stream capture starts)
+size_t node_scratch_bytes(const ggml_tensor * n) {
+    if (n->op == GGML_OP_MUL_MAT) { b200_tensor w = view_of(n->src[0]), x = view_of(n->src[1]); return b200_mul_mat_scratch_bytes(&w, &x); }
+    if (n->op == GGML_OP_FLASH_ATTN_EXT) { b200_tensor q = view_of(n->src[0]), k = view_of(n->src[1]); return b200_flash_attn_scratch_bytes(&q, &k); }
+    return 0;
+}
+
+bool is_noop(const ggml_tensor * n) {
+    return n->op == GGML_OP_NONE || n->op == GGML_OP_RESHAPE || n->op == GGML_OP_VIEW || n->op == GGML_OP_PERMUTE || n->op == GGML_OP_TRANSPOSE || ggml_is_empty(n);
+}
+
+// number of times `t` is read by nodes of the graph (views of t count as reads of t's consumers, conservatively as uses)
+int n_uses(const ggml_cgraph * g, const ggml_tensor * t) {
+    int n = 0;
+    const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+    for (int i = 0; i < nn; ++i) {
+        const ggml_tensor * c = ggml_graph_node((ggml_cgraph *) g, i);
+        for (int s = 0; s < GGML_MAX_SRC; ++s) if (c->src[s] == t) ++n;
+        if (c->view_src == t) ++n;
+    }
+    return n;
+}
+
+// One node -> one C-ABI call.  `next` (may be null) lets RMS_NORM absorb the MUL by the norm weight that follows it in every llama-family
+// graph (the reference fuses the same pair, ggml-cuda.cu ggml_cuda_can_fuse / norm.cu:510-660).  Returns the number of nodes consumed.
+int run_node(BackendCtx * c, const ggml_cgraph * g, ggml_tensor * n, ggml_tensor * next, int & rc) {
+    void * st = c->stream;
+    const ggml_tensor * s0 = n->src[0], * s1 = n->src[1];
+    rc = B200_OK;
+    switch (n->op) {
+        case GGML_OP_MUL_MAT: {
+            b200_tensor w = view_of(s0), x = view_of(s1), d = view_of(n);
+            const size_t sb = b200_mul_mat_scratch_bytes(&w, &x);
+            rc = b200_mul_mat(&w, &x, &d, sb ? scratch_for(c, sb) : nullptr, sb, st);
+            return 1;
+        }
+        case GGML_OP_ADD: case GGML_OP_SUB: case GGML_OP_MUL: case GGML_OP_DIV: {
+            b200_tensor a = view_of(s0), b = view_of(s1), d = view_of(n);
+            const int op = n->op == GGML_OP_ADD ? B200_ADD : n->op == GGML_OP_SUB ? B200_SUB : n->op == GGML_OP_MUL ? B200_MUL : B200_DIV;
+            rc = b200_binary(op, &a, &b, &d, st);
+            return 1;
+        }
+        case GGML_OP_RMS_NORM: {
+            b200_tensor x = view_of(s0), d = view_of(n);
+            if (next && next->op == GGML_OP_MUL && (next->src[0] == n || next->src[1] == n) && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) && n_uses(g, n) == 1) {
+                const ggml_tensor * wt = next->src[0] == n ? next->src[1] : next->src[0];
+                if (f32c(wt) && ggml_are_same_shape(next, n) && broadcastable(n, wt)) {
+                    b200_tensor w = view_of(wt), dm = view_of(next);
+                    rc = b200_rms_norm(&x, &w, nullptr, &dm, fparam(n, 0), st);
+                    if (rc == B200_OK) return 2;
+                }
+            }
+            rc = b200_rms_norm(&x, nullptr, nullptr, &d, fparam(n, 0), st);
+            return 1;
+        }
+        case GGML_OP_ROPE: {
+            b200_tensor x = view_of(s0), d = view_of(n);
+            b200_rope_params p;
+            p.n_dims = iparam(n, 1); p.mode = iparam(n, 2); p.n_ctx_orig = iparam(n, 4);
+            p.freq_base = fparam(n, 5); p.freq_scale = fparam(n, 6); p.ext_factor = fparam(n, 7); p.attn_factor = fparam(n, 8);
+            p.beta_fast = fparam(n, 9); p.beta_slow = fparam(n, 10);
+            rc = b200_rope(&x, (const int32_t *) s1->data, n->src[2] ? (const float *) n->src[2]->data : nullptr, &d, &p, st);
+            return 1;
+        }
+        case GGML_OP_SET_ROWS: { b200_tensor a = view_of(s0), i = view_of(s1), d = view_of(n); rc = b200_set_rows(&a, &i, &d, st); return 1; }
+        case GGML_OP_GET_ROWS: { b200_tensor a = view_of(s0), i = view_of(s1), d = view_of(n); rc = b200_get_rows(&a, &i, &d, st); return 1; }
+        case GGML_OP_CPY: case GGML_OP_CONT: case GGML_OP_DUP: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_cpy(&a, &d, st); return 1; }
+        case GGML_OP_SCALE: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_scale(&a, &d, fparam(n, 0), fparam(n, 1), st); return 1; }
+        case GGML_OP_UNARY: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary(unary_map(ggml_get_unary_op(n)), &a, &d, st); return 1; }
+        case GGML_OP_SQR:  { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary(B200_SQR, &a, &d, st); return 1; }
+        case GGML_OP_SQRT: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary(B200_SQRT, &a, &d, st); return 1; }
+        case GGML_OP_GLU: {
+            b200_tensor a = view_of(s0), d = view_of(n), u;
+            if (s1) u = view_of(s1);
+            rc = b200_glu((int) ggml_get_glu_op(n), &a, s1 ? &u : nullptr, &d, iparam(n, 1), st);
+            return 1;
+        }
+        case GGML_OP_SOFT_MAX: {
+            b200_tensor a = view_of(s0), d = view_of(n), m;
+            if (s1) m = view_of(s1);
+            rc = b200_soft_max(&a, s1 ? &m : nullptr, &d, fparam(n, 0), fparam(n, 1), st);
+            return 1;
+        }
+        case GGML_OP_FLASH_ATTN_EXT: {
+            b200_tensor q = view_of(s0), k = view_of(s1), v = view_of(n->src[2]), d = view_of(n), m;
+            if (n->src[3]) m = view_of(n->src[3]);
+            const size_t sb = b200_flash_attn_scratch_bytes(&q, &k);
+            rc = b200_flash_attn(&q, &k, &v, n->src[3] ? &m : nullptr, &d, fparam(n, 0), fparam(n, 1), fparam(n, 2), sb ? scratch_for(c, sb) : nullptr, sb, st);
+            return 1;
+        }
+        default:
+            rc = B200_ERR_UNSUPPORTED;
+            return 1;
+    }
+}
+
+enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
+    const int nn = ggml_graph_n_nodes(g);
+    for (int i = 0; i < nn; ) {
+        ggml_tensor * n = ggml_graph_node(g, i);
+        if (is_noop(n)) { ++i; continue; }
+        ggml_tensor * next = nullptr;
+        for (int j = i + 1; j < nn; ++j) { ggml_tensor * t = ggml_graph_node(g, j); if (!is_noop(t)) { next = (j == i + 1) ? t : nullptr; break; } }
+        int rc = 0;
+        const int used = run_node(c, g, n, next, rc);
+        if (rc != B200_OK) {
+            // graph_compute on an op supports_op rejected is a caller bug (the reference asserts, ggml-cuda.cu:3043-3047)
+            B200_LOG("op %s (%s) failed: %s", ggml_op_name(n->op), n->name, b200_error_string(rc));
+            return GGML_STATUS_FAILED;
+        }
+        i += used;
+    }
+    return GGML_STATUS_SUCCESS;
+}
+
+// The properties that decide whether a captured graph can be replayed (what the reference compares in
+// ggml_cuda_graph_update_required / is_cuda_graph_update_required, ggml-cuda.cu:2800-2900): op, addresses, shapes, strides, op params.
+void graph_key_of(const ggml_cgraph * g, std::vector<uint64_t> & key) {
+    key.clear();
+    const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+    key.reserve((size_t) nn * 24);
+    for (int i = 0; i < nn; ++i) {
+        const ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, i);
+        key.push_back((uint64_t) n->op | ((uint64_t) n->type << 32)); key.push_back((uint64_t) (uintptr_t) n->data);
+        for (int d = 0; d < 4; ++d) { key.push_back((uint64_t) n->ne[d]); key.push_back((uint64_t) n->nb[d]); }
+        for (int s = 0; s < GGML_MAX_SRC; ++s) if (n->src[s]) {
+            key.push_back((uint64_t) (uintptr_t) n->src[s]->data ^ ((uint64_t) s << 56));
+            for (int d = 0; d < 4; ++d) { key.push_back((uint64_t) n->src[s]->ne[d]); key.push_back((uint64_t) n->src[s]->nb[d]); }
+            key.push_back((uint64_t) n->src[s]->type);
+        }
+        const uint64_t * op64 = (const uint64_t *) n->op_params;
+        for (size_t w = 0; w < GGML_MAX_OP_PARAMS / sizeof(uint64_t); ++w) key.push_back(op64[w]);
+    }
+}
+
+enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph * g) {
+    BackendCtx * c = (BackendCtx *) backend->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    const int nn = ggml_graph_n_nodes(g);
+    // Decode-sized graphs (every MUL_MAT has <= 8 columns) are launch-bound: capture them once into a CUDA graph and replay while the
+    // node list is unchanged (pointers, shapes and parameters; tensor CONTENTS may change) — like the reference's CUDA-graph path,
+    // which is also limited to batch-1 graphs (ggml-cuda.cu:2725-2790).
+    bool small = c->graphs_enabled && nn >= 8;
+    size_t need = 0;
+    for (int i = 0; i < nn && small; ++i) {
+        const ggml_tensor * n = ggml_graph_node(g, i);
+        if (n->op == GGML_OP_MUL_MAT && n->src[1]->ne[1] > 8) small = false;
+        const size_t sb = is_noop(n) ? 0 : node_scratch_bytes(n);
+        if (sb > need) need = sb;
+    }
+    if (!small) return run_nodes(c, g);
+    scratch_for(c, need);                                            // no allocation may happen while capturing
+    std::vector<uint64_t> key;
+    graph_key_of(g, key);
+    if (c->graph_exec && key == c->graph_key) {
+        CUDA_OK(cudaGraphLaunch(c->graph_exec, c->stream));
+        return GGML_STATUS_SUCCESS;
+    }
+    // a node list seen for the first time runs eagerly (module loading, one-time attribute setup); it is captured when it comes back
+    if (key != c->pending_key) { c->pending_key.swap(key); return run_nodes(c, g); }
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear(); }
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const enum ggml_status status = run_nodes(c, g);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (status != GGML_STATUS_SUCCESS || e != cudaSuccess || !graph) {
+        (void) cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        c->graphs_enabled = false;                                    // something on this path is not capturable: plain launches from now on
+        return status != GGML_STATUS_SUCCESS ? status : run_nodes(c, g);
+    }
+    e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { (void) cudaGetLastError(); c->graph_exec = nullptr; c->graphs_enabled = false; return run_nodes(c, g); }
+    c->graph_key.swap(key);
+    CUDA_OK(cudaGraphLaunch(c->graph_exec, c->stream));
+    return GGML_STATUS_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- backend (stream)
+const char * b200_backend_get_name(ggml_backend_t backend) { return ((BackendCtx *) backend->context)->name.c_str(); }
+
+void b200_backend_free(ggml_backend_t backend) {
+    BackendCtx * c = (BackendCtx *) backend->context;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->scratch) cudaFree(c->scratch);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    delete backend;
+}
+
+void b200_backend_set_tensor_async(ggml_backend_t backend, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
+    BackendCtx * c = (BackendCtx *) backend->context;
+    if (is_planar(tensor)) { cudaStreamSynchronize(c->stream); b200_buf_set_tensor(tensor->buffer, tensor, data, offset, size); return; }
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemcpyAsync((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice, c->stream));
+}
+void b200_backend_get_tensor_async(ggml_backend_t backend, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
+    BackendCtx * c = (BackendCtx *) backend->context;
+    if (is_planar(tensor)) { cudaStreamSynchronize(c->stream); b200_buf_get_tensor(tensor->buffer, tensor, data, offset, size); return; }
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemcpyAsync(data, (const char *) tensor->data + offset, size, cudaMemcpyDeviceToHost, c->stream));
+}
+
+bool backend_is_b200(ggml_backend_t b) { return b && b->iface.get_name == b200_backend_get_name; }
+
+// layer-split pipeline hop: the hidden state crosses a device boundary as ONE peer copy ordered on both streams.
+// (bench.py --gpus N uses NCCL send/recv for the same hop between its one-process-per-GPU ranks; inside ONE process — which is how the
+// reference's scheduler drives several devices, ggml-backend.cpp:1539 — a peer copy over NVLink is the native primitive.)
+bool b200_backend_cpy_tensor_async(ggml_backend_t src_backend, ggml_backend_t dst_backend, const ggml_tensor * src, ggml_tensor * dst) {
+    if (!backend_is_b200(src_backend) || !backend_is_b200(dst_backend)) return false;
+    if (!src->buffer || !dst->buffer || !buffer_is_b200(src->buffer) || !buffer_is_b200(dst->buffer)) return false;
+    if (is_planar(src) || is_planar(dst) || ggml_nbytes(src) != ggml_nbytes(dst) || !ggml_is_contiguous(src) || !ggml_is_contiguous(dst)) return false;
+    BackendCtx * sc = (BackendCtx *) src_backend->context, * dc = (BackendCtx *) dst_backend->context;
+    if (sc == dc) {
+        CUDA_OK(cudaSetDevice(sc->device));
+        CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice, sc->stream));
+        return true;
+    }
+    // copy on the SOURCE stream (after the producer), then make the destination stream wait for it
+    CUDA_OK(cudaSetDevice(sc->device));
+    if (sc->device == dc->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice, sc->stream));
+    else CUDA_OK(cudaMemcpyPeerAsync(dst->data, dc->device, src->data, sc->device, ggml_nbytes(src), sc->stream));
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(ev, sc->stream));
+    CUDA_OK(cudaSetDevice(dc->device));
+    CUDA_OK(cudaStreamWaitEvent(dc->stream, ev, 0));
+    CUDA_OK(cudaEventDestroy(ev));                                   // destruction is deferred until the event completes
+    return true;
+}
+
+void b200_backend_synchronize(ggml_backend_t backend) {
+    BackendCtx * c = (BackendCtx *) backend->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+void b200_backend_event_record(ggml_backend_t backend, ggml_backend_event_t event) {
+    BackendCtx * c = (BackendCtx *) backend->context;
+    CUDA_OK(cudaEventRecord((cudaEvent_t) event->context, c->stream));
+}
+void b200_backend_event_wait(ggml_backend_t backend, ggml_backend_event_t event) {
+    BackendCtx * c = (BackendCtx *) backend->context;
+    CUDA_OK(cudaStreamWaitEvent(c->stream, (cudaEvent_t) event->context, 0));
+}
+
+const ggml_backend_i b200_backend_iface = {
+    /* get_name           */ b200_backend_get_name,
+    /* free               */ b200_backend_free,
+    /* set_tensor_async   */ b200_backend_set_tensor_async,
+    /* get_tensor_async   */ b200_backend_get_tensor_async,
+    /* cpy_tensor_async   */ b200_backend_cpy_tensor_async,
+    /* synchronize        */ b200_backend_synchronize,
+    /* graph_plan_create  */ nullptr,
+    /* graph_plan_free    */ nullptr,
+    /* graph_plan_update  */ nullptr,
+    /* graph_plan_compute */ nullptr,
+    /* graph_compute      */ b200_backend_graph_compute,
+    /* event_record       */ b200_backend_event_record,
+    /* event_wait         */ b200_backend_event_wait,
+    /* graph_optimize     */ nullptr,
+};
+
+ggml_guid_t b200_guid() {
+    static ggml_guid guid = { 0xb2, 0x00, 0x5a, 0x10, 0x0a, 0x67, 0x67, 0x6d, 0x6c, 0x2d, 0x62, 0x32, 0x30, 0x30, 0x00, 0x01 };
+    return &guid;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- device
+const char * b200_dev_get_name(ggml_backend_dev_t dev) { return ((DeviceCtx *) dev->context)->name.c_str(); }
+const char * b200_dev_get_description(ggml_backend_dev_t dev) { return ((DeviceCtx *) dev->context)->description.c_str(); }
+void b200_dev_get_memory(ggml_backend_dev_t dev, size_t * free, size_t * total) {
+    CUDA_OK(cudaSetDevice(((DeviceCtx *) dev->context)->index));
+    CUDA_OK(cudaMemGetInfo(free, total));
+}
+enum ggml_backend_dev_type b200_dev_get_type(ggml_backend_dev_t) { return GGML_BACKEND_DEVICE_TYPE_GPU; }
+void b200_dev_get_props(ggml_backend_dev_t dev, ggml_backend_dev_props * props) {
+    DeviceCtx * d = (DeviceCtx *) dev->context;
+    memset(props, 0, sizeof(*props));
+    props->name = d->name.c_str(); props->description = d->description.c_str(); props->type = GGML_BACKEND_DEVICE_TYPE_GPU;
+    props->device_id = d->pci_id.empty() ? nullptr : d->pci_id.c_str();      // used by llama.cpp to de-duplicate devices (llama.cpp:208-229)
+    b200_dev_get_memory(dev, &props->memory_free, &props->memory_total);
+    props->caps.async = true; props->caps.host_buffer = false; props->caps.buffer_from_host_ptr = false; props->caps.events = true;
+}
+
+ggml_backend_t b200_dev_init_backend(ggml_backend_dev_t dev, const char *) {
+    DeviceCtx * d = (DeviceCtx *) dev->context;
+    if (cudaSetDevice(d->index) != cudaSuccess) return nullptr;
+    BackendCtx * c = new BackendCtx(); c->device = d->index; c->name = d->name;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+    if (const char * e = getenv("GGML_B200_DISABLE_GRAPHS")) c->graphs_enabled = atoi(e) == 0;
+    ggml_backend * b = new ggml_backend;
+    b->guid = b200_guid(); b->iface = b200_backend_iface; b->device = dev; b->context = c;
+    return b;
+}
+ggml_backend_buffer_type_t b200_dev_get_buffer_type(ggml_backend_dev_t dev) { return &((DeviceCtx *) dev->context)->buft; }
+bool b200_dev_supports_buft(ggml_backend_dev_t dev, ggml_backend_buffer_type_t buft) {
+    return buft->iface.get_name == b200_buft_get_name && buft->device == dev;
+}
+bool b200_dev_offload_op(ggml_backend_dev_t, const ggml_tensor * op) {
+    // weights left on the host: worth shipping to the GPU only for real batches (same threshold as ggml-cuda.cu:3724-3731)
+    const int min_batch = 32;
+    return (op->ne[1] >= min_batch && op->op != GGML_OP_GET_ROWS) || (op->ne[2] >= min_batch && op->op == GGML_OP_MUL_MAT_ID);
+}
+ggml_backend_event_t b200_dev_event_new(ggml_backend_dev_t dev) {
+    CUDA_OK(cudaSetDevice(((DeviceCtx *) dev->context)->index));
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    return new ggml_backend_event{ dev, ev };
+}
+void b200_dev_event_free(ggml_backend_dev_t, ggml_backend_event_t event) { cudaEventDestroy((cudaEvent_t) event->context); delete event; }
+void b200_dev_event_synchronize(ggml_backend_dev_t, ggml_backend_event_t event) { CUDA_OK(cudaEventSynchronize((cudaEvent_t) event->context)); }
+
+const ggml_backend_device_i b200_device_iface = {
+    /* get_name             */ b200_dev_get_name,
+    /* get_description      */ b200_dev_get_description,
+    /* get_memory           */ b200_dev_get_memory,
+    /* get_type             */ b200_dev_get_type,
+    /* get_props            */ b200_dev_get_props,
+    /* init_backend         */ b200_dev_init_backend,
+    /* get_buffer_type      */ b200_dev_get_buffer_type,
+    /* get_host_buffer_type */ nullptr,
+    /* buffer_from_host_ptr */ nullptr,
+    /* supports_op          */ b200_dev_supports_op,
+    /* supports_buft        */ b200_dev_supports_buft,
+    /* offload_op           */ b200_dev_offload_op,
+    /* event_new            */ b200_dev_event_new,
+    /* event_free           */ b200_dev_event_free,
+    /* event_synchronize    */ b200_dev_event_synchronize,
+};
+
+// ---------------------------------------------------------------------------------------------------------------- registry
+int probe_devices() {
+    if (g_n_devices >= 0) return g_n_devices;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void) cudaGetLastError(); n = 0; }
+    int kept = 0;
+    for (int i = 0; i < n && kept < MAX_DEVICES; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) != cudaSuccess) continue;
+        if (p.major != 10) { B200_LOG("device %d (%s, sm_%d%d) skipped: kernels are built for sm_100a only", i, p.name, p.major, p.minor); continue; }
+        DeviceCtx & d = g_devices[kept];
+        d.index = i; d.name = "B200:" + std::to_string(kept); d.description = p.name;
+        char pci[32]; snprintf(pci, sizeof(pci), "%04x:%02x:%02x.0", p.pciDomainID, p.pciBusID, p.pciDeviceID); d.pci_id = pci;
+        d.buft.iface = { b200_buft_get_name, b200_buft_alloc, b200_buft_alignment, b200_buft_max_size, b200_buft_alloc_size, b200_buft_is_host };
+        d.buft.device = &d.dev; d.buft.context = &d;
+        d.dev.iface = b200_device_iface; d.dev.reg = &g_reg; d.dev.context = &d;
+        ++kept;
+    }
+    // peers: the layer-split hop is a direct NVLink copy
+    for (int a = 0; a < kept; ++a) for (int b = 0; b < kept; ++b) if (a != b) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, g_devices[a].index, g_devices[b].index) == cudaSuccess && can) {
+            cudaSetDevice(g_devices[a].index);
+            cudaError_t e = cudaDeviceEnablePeerAccess(g_devices[b].index, 0);
+            if (e != cudaSuccess) (void) cudaGetLastError();
+        }
+    }
+    g_n_devices = kept;
+    return kept;
+}
+
+const char * b200_reg_get_name(ggml_backend_reg_t) { return "B200"; }
+size_t b200_reg_get_device_count(ggml_backend_reg_t) { return (size_t) probe_devices(); }
+ggml_backend_dev_t b200_reg_get_device(ggml_backend_reg_t, size_t index) {
+    return index < (size_t) probe_devices() ? &g_devices[index].dev : nullptr;
+}
+void * b200_reg_get_proc_address(ggml_backend_reg_t, const char * name) {
+    (void) name;        // optional hooks consumers ask for (split buffer type, set_n_threads, features, host-buffer registration): none
+    return nullptr;
+}
+
+} // namespace
+
+extern "C" {
+
+ggml_backend_reg_t ggml_backend_b200_reg(void) {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        g_reg.api_version = GGML_BACKEND_API_VERSION;
+        g_reg.iface = { b200_reg_get_name, b200_reg_get_device_count, b200_reg_get_device, b200_reg_get_proc_address };
+        g_reg.context = nullptr;
+        probe_devices();
+    });
+    return &g_reg;
+}
+
+ggml_backend_reg_t ggml_backend_init(void) { return ggml_backend_b200_reg(); }
+
+// 0 = cannot run here (no sm_100 device): the loader then skips the library (ggml-backend-reg.cpp:257-273)
+int ggml_backend_score(void) { ggml_backend_b200_reg(); return g_n_devices > 0 ? 100 : 0; }
+
+ggml_backend_t ggml_backend_b200_init(int device) {
+    ggml_backend_b200_reg();
+    if (device < 0 || device >= g_n_devices) return nullptr;
+    return b200_dev_init_backend(&g_devices[device].dev, nullptr);
+}
+
+int ggml_backend_b200_abi(void) { return b200_abi_version(); }
+
+} // extern "C"

@@ -1,0 +1,91 @@
+// llama_parity.cpp — end-to-end parity THROUGH THE REFERENCE: the unmodified libllama (oracle/_ref, built from /root/reference by
+// oracle/Makefile) decodes the same synthetic Qwen3 GGUF once on its own ggml CPU backend (n_gpu_layers = 0) and once with every layer
+// offloaded to the backend loaded from GGML_BACKEND_PATH (libggml-b200.so), greedy sampling, same prompt.  north_star bar: bit-exact
+// token ids for greedy decode, logits within 1e-3 relative.  TEST INFRASTRUCTURE (uses only the reference's public API, include/llama.h).
+//
+//   llama_parity model.gguf [n_prompt=32] [n_gen=32] [n_threads=8] [flash_attn=1] [cpu_self=0]
+// prints one JSON line: {"tokens_equal": bool, "n_gen": N, "first_mismatch": i, "max_rel_logit_err": x, "prefill_rel_err": y, ...}
+#include "llama.h"
+#include "ggml-backend.h"
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+struct Run { std::vector<llama_token> toks; std::vector<std::vector<float>> logits; double tg_ms = 0, pp_ms = 0; bool ok = false; };
+
+static Run run(const char * path, int ngl, int n_prompt, int n_gen, int n_threads, int fa, const std::vector<llama_token> * force, bool repack, bool incremental = false) {
+    Run r;
+    llama_model_params mp = llama_model_default_params();
+    static ggml_backend_dev_t no_devices[1] = { nullptr };
+    if (ngl == 0) mp.devices = no_devices;         // a true CPU run: otherwise batches >= 32 tokens are offloaded to the GPU backend op by op (offload_op)
+    mp.n_gpu_layers = ngl; mp.use_mmap = true; mp.use_extra_bufts = repack;      // repack = the CPU backend's interleaved q4_K_8x8 weights (different f32 summation order)
+    llama_model * model = llama_model_load_from_file(path, mp);
+    if (!model) { fprintf(stderr, "load failed\n"); return r; }
+    llama_context_params cp = llama_context_default_params();
+    cp.n_ctx = 1024; cp.n_batch = 512; cp.n_ubatch = 512; cp.n_threads = n_threads; cp.n_threads_batch = n_threads;
+    cp.flash_attn_type = fa ? LLAMA_FLASH_ATTN_TYPE_ENABLED : LLAMA_FLASH_ATTN_TYPE_DISABLED; cp.no_perf = true;
+    llama_context * ctx = llama_init_from_model(model, cp);
+    if (!ctx) { fprintf(stderr, "context failed\n"); llama_model_free(model); return r; }
+    const int n_vocab = llama_vocab_n_tokens(llama_model_get_vocab(model));
+    std::vector<llama_token> prompt(n_prompt);
+    uint32_t s = 12345;
+    for (auto & t : prompt) { s = s * 1664525u + 1013904223u; t = (llama_token) ((s >> 8) % (uint32_t) n_vocab); }
+    auto t0 = std::chrono::steady_clock::now();
+    if (incremental) {                                                  // the same prompt one token at a time (n = 1 graphs only)
+        for (int i = 0; i < n_prompt; ++i) if (llama_decode(ctx, llama_batch_get_one(&prompt[i], 1))) { fprintf(stderr, "prefill failed\n"); return r; }
+    } else if (llama_decode(ctx, llama_batch_get_one(prompt.data(), n_prompt))) { fprintf(stderr, "prefill failed\n"); return r; }
+    const float * lg = llama_get_logits_ith(ctx, -1);
+    r.logits.emplace_back(lg, lg + n_vocab);
+    auto t1 = std::chrono::steady_clock::now();
+    r.pp_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    for (int i = 0; i < n_gen; ++i) {
+        const std::vector<float> & l = r.logits.back();
+        llama_token best = 0;
+        for (int v = 1; v < n_vocab; ++v) if (l[v] > l[best]) best = v;
+        r.toks.push_back(best);
+        // teacher forcing on the second run keeps the two runs on the same sequence even after a (reported) mismatch
+        llama_token feed = force && i < (int) force->size() ? (*force)[i] : best;
+        if (llama_decode(ctx, llama_batch_get_one(&feed, 1))) { fprintf(stderr, "decode failed\n"); return r; }
+        lg = llama_get_logits_ith(ctx, -1);
+        r.logits.emplace_back(lg, lg + n_vocab);
+    }
+    r.tg_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    r.ok = true;
+    llama_free(ctx); llama_model_free(model);
+    return r;
+}
+
+int main(int argc, char ** argv) {
+    if (argc < 2) { fprintf(stderr, "usage: %s model.gguf [n_prompt] [n_gen] [threads] [fa]\n", argv[0]); return 2; }
+    const int n_prompt = argc > 2 ? atoi(argv[2]) : 32, n_gen = argc > 3 ? atoi(argv[3]) : 32, nt = argc > 4 ? atoi(argv[4]) : 8, fa = argc > 5 ? atoi(argv[5]) : 1;
+    llama_log_set([](ggml_log_level lvl, const char * txt, void *) { if (lvl >= GGML_LOG_LEVEL_ERROR) fputs(txt, stderr); }, nullptr);
+    ggml_backend_load_all();
+    llama_backend_init();
+    size_t n_gpu = 0;
+    for (size_t i = 0; i < ggml_backend_dev_count(); ++i) if (ggml_backend_dev_type(ggml_backend_dev_get(i)) == GGML_BACKEND_DEVICE_TYPE_GPU) ++n_gpu;
+    // mode "cpu-self": the CPU backend against itself (plain vs repacked weights) — how far two correct implementations drift on this model
+    const bool cpu_self = argc > 6 && atoi(argv[6]) == 1;
+    if (!n_gpu && !cpu_self && !(argc > 6 && (atoi(argv[6]) == 2 || atoi(argv[6]) == 3))) { printf("{\"error\": \"no GPU backend registered (GGML_BACKEND_PATH?)\"}\n"); return 3; }
+    Run cpu = run(argv[1], 0, n_prompt, n_gen, nt, fa, nullptr, false);
+    const int self_mode = argc > 6 ? atoi(argv[6]) : 0;                 // 1: repacked weights; 2: plain weights, 3 threads (must be bit-identical)
+    // 3: CPU batched prompt vs CPU one-token-at-a-time prompt; 4: B200 batched vs B200 one-at-a-time (baseline run also on the GPU)
+    if (self_mode == 4) cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false);
+    Run gpu = run(argv[1], cpu_self || self_mode == 2 || self_mode == 3 ? 0 : 999, n_prompt, n_gen, self_mode == 2 ? 3 : nt, fa, &cpu.toks, cpu_self, self_mode >= 3);
+    if (!cpu.ok || !gpu.ok) { printf("{\"error\": \"run failed\"}\n"); return 4; }
+    int first = -1; double max_rel = 0, pre_rel = 0; double step_rel[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n_gen; ++i) if (cpu.toks[i] != gpu.toks[i] && first < 0) first = i;
+    for (size_t i = 0; i < cpu.logits.size(); ++i) {
+        double mx = 0, err = 0;
+        for (size_t v = 0; v < cpu.logits[i].size(); ++v) { mx = std::fmax(mx, std::fabs(cpu.logits[i][v])); err = std::fmax(err, std::fabs(cpu.logits[i][v] - gpu.logits[i][v])); }
+        const double rel = err / (mx > 0 ? mx : 1);
+        if (i == 0) pre_rel = rel; else max_rel = std::fmax(max_rel, rel);
+        if (i >= 1 && i <= 6) step_rel[i - 1] = rel;
+    }
+    printf("{\"tokens_equal\": %s, \"n_prompt\": %d, \"n_gen\": %d, \"first_mismatch\": %d, \"max_rel_logit_err\": %.3g, \"prefill_rel_err\": %.3g, "
+           "\"decode_step_rel_err\": [%.2g, %.2g, %.2g, %.2g, %.2g, %.2g], \"cpu_tg_tok_s\": %.2f, \"gpu_tg_tok_s\": %.2f, \"cpu_pp_tok_s\": %.1f, \"gpu_pp_tok_s\": %.1f, \"threads\": %d, \"flash_attn\": %d}\n",
+           first < 0 ? "true" : "false", n_prompt, n_gen, first, max_rel, pre_rel, step_rel[0], step_rel[1], step_rel[2], step_rel[3], step_rel[4], step_rel[5], n_gen * 1e3 / cpu.tg_ms, n_gen * 1e3 / gpu.tg_ms,
+           n_prompt * 1e3 / cpu.pp_ms, n_prompt * 1e3 / gpu.pp_ms, nt, fa);
+    return first < 0 && max_rel <= 1e-3 ? 0 : 1;
+}
