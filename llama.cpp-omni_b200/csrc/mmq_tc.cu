@@ -1,0 +1,342 @@
+// mmq_tc.cu — prefill / batched GEMM  Y[m, n] = W[m, k] . X[n, k]^T  for quantised W (q4_K native, q6_K planar) and n > 8 columns,
+// on the 5th-generation tensor cores: tcgen05.mma (kind::f16, M = 128, N <= 256, K = 16) with the accumulator in TMEM.
+//
+// Replaces ggml_cuda_mul_mat_q (ggml-cuda/mmq.cu:205, kernel mul_mat_q mmq.cuh:3136 with the q4_K / q6_K tile loaders :1741, :2043, and
+// quantize_mmq_q8_1 quantize.cu:50-146) — int8 mma.sync tiles in the reference; here the quant blocks are dequantised to F16 in shared
+// memory and the contraction runs as F16 x F16 -> F32 UMMA.  K-quant sub-block scales (6-bit scale/min per 32 weights, int8 scale per 16)
+// do not map onto the hardware block-scaled formats, so the dequant has to materialise F16 (SURVEY.md §7 "tcgen05 prefill").
+//
+// One persistent CTA per SM, 14 warps, warp-specialised (the canonical Blackwell GEMM anatomy, hand-written in PTX):
+//   warps 0-7   A producers: read raw quant blocks with 16-byte loads (every weight byte once per (m, n) tile), dequantise with half2 math
+//               (byte -> 1024+q via PRMT with 0x64, HSUB2, HFMA2 by d*sc / -dmin*m) and store the 128 x 64 F16 tile in the canonical K-major
+//               no-swizzle UMMA layout (8 x 16-byte core matrices; row groups 128 B apart -> conflict-free 16-byte stores);
+//               fence.proxy.async + mbarrier arrive hands the stage to the tensor core
+//   warp  8     B producer: the activations were converted F32 -> F16 ONCE by k_x_to_f16_tiles into the same canonical layout, tile by tile,
+//               so a 256 x 64 B tile is plain contiguous memory: 4 x 8 KB cp.async.bulk (TMA) per stage, complete_tx on the stage barrier
+//   warp  9     MMA issuer: one lane issues 4 tcgen05.mma per stage (D in TMEM, 2 x 256 columns double-buffered) and tcgen05.commit's the stage
+//               back to the producers / the accumulator to the epilogue
+//   warps 10-13 epilogue: tcgen05.ld 32 lanes x 32 columns, coalesced F32 stores (lane = weight row = contiguous dst index)
+// FLOPs per launch = 2 m n k.  Tensor-bound for n >= ~64.
+//
+// Numerics: weights are rounded to F16 after dequantisation (relative 2^-11 per factor), activations to F16, products accumulate in F32.
+// The CPU oracle instead quantises activations to q8_K (~3e-3 relative per element): this path is closer to the exact product than the
+// oracle is; parity bar = the reference's own MUL_MAT bar, NMSE <= 5e-4 (tests/test-backend-ops.cpp:3300).
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int TC_M = 128, TC_N = 256, TC_K = 64, TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_M * TC_K * 2, TC_B_BYTES = TC_N * TC_K * 2;                 // 16 KB, 32 KB
+constexpr int TC_A_LBO = (TC_M / 8) * 128, TC_B_LBO = (TC_N / 8) * 128, TC_SBO = 128;        // core matrices: K direction / row-group direction
+constexpr int TC_DEQ_THREADS = 256, TC_THREADS = 448;
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256;
+
+struct TcArgs {
+    const uint8_t * w; const uint8_t * wd;          // payload plane, f16 d plane (q6_K planar) or null
+    const uint8_t * x16;                            // activations, F16, pre-tiled: [n_tiles][k/64][TC_B_BYTES]
+    float * dst; int64_t dst_ld;                    // dst[n * dst_ld + m]
+    int64_t m, k, n, row_bytes;                     // n = real columns; row_bytes of the payload plane
+    int type, tiles_m, tiles_n;
+};
+
+// ---------------------------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t tc_smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp): start address, leading
+// (K direction) and stride (M/N direction) byte offsets in 16-byte units, descriptor version 1 (Blackwell), layout type 0
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t) ((saddr & 0x3ffff) >> 4) | ((uint64_t) (lbo >> 4) << 16) | ((uint64_t) (sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t tc_idesc(int n) { return (1u << 4) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (TC_M >> 4) << 24); }
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+                 "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------- dequant -> F16
+// 4 bytes (values 0..255 each) -> two half2 holding 1024 + byte: PRMT interleaves the bytes with 0x64 (f16 0x64xx = 1024 + xx)
+__device__ __forceinline__ void bytes_to_h2(uint32_t b, __half2 & lo, __half2 & hi) {
+    const uint32_t x = __byte_perm(b, 0x64646464u, 0x4140), y = __byte_perm(b, 0x64646464u, 0x4342);
+    lo = *(const __half2 *) &x; hi = *(const __half2 *) &y;
+}
+__device__ __forceinline__ uint4 ldg16(const uint8_t * p) { return __ldg((const uint4 *) p); }
+
+// 8 consecutive weights w = (q - off) * s + c from two words of byte codes -> one 16-byte core-matrix row
+__device__ __forceinline__ uint4 deq8(uint32_t b0, uint32_t b1, __half2 off, __half2 s, __half2 c) {
+    __half2 h[4];
+    bytes_to_h2(b0, h[0], h[1]); bytes_to_h2(b1, h[2], h[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __hfma2(__hsub2(h[i], off), s, c);
+    return *(const uint4 *) h;
+}
+
+// Raw bytes of one 256-weight block that thread (row, hf) needs for its four K-chunks, loaded one block AHEAD of their use so that the
+// L2 round trip overlaps the dequantisation of the current block.
+struct RawQ4K { uint4 hdr, q[8]; };                       // d|dmin + 12 scale bytes; qs[128]
+struct RawQ6K { uint4 l[4], h[4], sc; float d; };         // ql[64h' + 32hf ..+32) and qh[32h' ..+32) for h' = 0, 1; 16 int8 scales; d
+
+__device__ __forceinline__ void raw_load(RawQ4K & R, const uint8_t * blk) {
+    R.hdr = ldg16(blk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) R.q[i] = ldg16(blk + 16 + 16 * i);
+}
+__device__ __forceinline__ void raw_load(RawQ6K & R, const uint8_t * pay, const uint8_t * dptr, int hf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        R.l[2 * h] = ldg16(pay + 64 * h + 32 * hf); R.l[2 * h + 1] = ldg16(pay + 64 * h + 32 * hf + 16);
+        R.h[2 * h] = ldg16(pay + 128 + 32 * h);     R.h[2 * h + 1] = ldg16(pay + 128 + 32 * h + 16);
+    }
+    R.sc = ldg16(pay + 192);
+    R.d = h2f(__ldg((const uint16_t *) dptr));
+}
+
+__device__ __forceinline__ void st_row(uint32_t addr, const uint4 & v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// thread (row, hf) writes its 32 weights of K-chunk c (64 weights) of the block into stage memory (a_row = shared address of its row)
+template <int c> __device__ __forceinline__ void deq_chunk(const RawQ4K & R, int hf, uint32_t a_row) {
+    // scales / mins of sub-block j = 2c + hf (get_scale_min_k4, ggml-quants.c:703-711)
+    const uint4 & hdr = R.hdr;
+    const int j = 2 * c + hf;
+    const uint32_t scw = c < 2 ? (hdr.y & 0x3f3f3f3fu) : ((hdr.w & 0x0f0f0f0fu) | (((hdr.y >> 6) & 0x03030303u) << 4));
+    const uint32_t mnw = c < 2 ? (hdr.z & 0x3f3f3f3fu) : (((hdr.w >> 4) & 0x0f0f0f0fu) | (((hdr.z >> 6) & 0x03030303u) << 4));
+    const int sh = (j & 3) * 8;
+    const float sc = (float) ((scw >> sh) & 0xff), mn = (float) ((mnw >> sh) & 0xff);
+    const float d = h2f(hdr.x & 0xffff), dmin = h2f(hdr.x >> 16);
+    const __half2 s = __float2half2_rn(d * sc), cm = __float2half2_rn(-(dmin * mn)), off = __float2half2_rn(1024.0f);
+    const uint32_t w[8] = { R.q[2 * c].x, R.q[2 * c].y, R.q[2 * c].z, R.q[2 * c].w, R.q[2 * c + 1].x, R.q[2 * c + 1].y, R.q[2 * c + 1].z, R.q[2 * c + 1].w };
+    const int shq = 4 * hf;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8((w[2 * i] >> shq) & 0x0f0f0f0fu, (w[2 * i + 1] >> shq) & 0x0f0f0f0fu, off, s, cm));
+}
+
+template <int c> __device__ __forceinline__ void deq_chunk(const RawQ6K & R, int hf, uint32_t a_row) {
+    // chunk c = elements 64c..64c+63 of the block = half h, quads 2(c&1) and 2(c&1)+1 (dequantize_row_q6_K, ggml-quants.c:1762-1791);
+    // quad = 2(c&1) + hf reads ql[64h + 32(quad&1) + l] (low nibble for quads 0/1, high for 2/3) and bits 2quad.. of qh[32h + l]
+    constexpr int h = c >> 1;
+    const int quad = 2 * (c & 1) + hf;
+    const uint32_t lw[8] = { R.l[2 * h].x, R.l[2 * h].y, R.l[2 * h].z, R.l[2 * h].w, R.l[2 * h + 1].x, R.l[2 * h + 1].y, R.l[2 * h + 1].z, R.l[2 * h + 1].w };
+    const uint32_t hw[8] = { R.h[2 * h].x, R.h[2 * h].y, R.h[2 * h].z, R.h[2 * h].w, R.h[2 * h + 1].x, R.h[2 * h + 1].y, R.h[2 * h + 1].z, R.h[2 * h + 1].w };
+    const uint32_t scw = h ? ((c & 1) ? R.sc.w : R.sc.z) : ((c & 1) ? R.sc.y : R.sc.x);      // scales[8h + 4(c&1) .. +3]; this quad: bytes 2hf, 2hf+1
+    const float sc0 = (float) (int) (int8_t) (scw >> (16 * hf)), sc1 = (float) (int) (int8_t) (scw >> (16 * hf + 8));
+    const __half2 s0 = __float2half2_rn(R.d * sc0), s1 = __float2half2_rn(R.d * sc1);
+    const __half2 off = __float2half2_rn(1056.0f), zero = __float2half2_rn(0.0f);        // 1024 (PRMT bias) + 32 (q6_K code offset)
+    constexpr int shl = (c & 1) ? 4 : 0;
+    const int shh = 2 * quad;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t b0 = ((lw[2 * i] >> shl) & 0x0f0f0f0fu) | (((hw[2 * i] >> shh) & 0x03030303u) << 4);
+        const uint32_t b1 = ((lw[2 * i + 1] >> shl) & 0x0f0f0f0fu) | (((hw[2 * i + 1] >> shh) & 0x03030303u) << 4);
+        st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8(b0, b1, off, i < 2 ? s0 : s1, zero));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- activations -> F16 tiles
+// X F32 [n, k] (row stride x_ld elements) -> x16 tiles in the canonical UMMA layout; rows n .. n_pad-1 are zero.  8 consecutive threads
+// write one 128-byte core matrix.
+__global__ void __launch_bounds__(256) k_x_to_f16_tiles(const float * __restrict__ x, int64_t x_ld, uint8_t * __restrict__ x16, int64_t n, int64_t n_pad, int64_t k) {
+    const int64_t id = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k8n = k >> 3;
+    if (id >= n_pad * k8n) return;
+    const int r = (int) (id & 7);
+    const int64_t k8 = (id >> 3) % k8n, ng = (id >> 3) / k8n;
+    const int64_t row = ng * 8 + r;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (row < n) {
+        const float4 a = __ldg((const float4 *) (x + row * x_ld + k8 * 8)), b = __ldg((const float4 *) (x + row * x_ld + k8 * 8 + 4));
+        __half2 h[4] = { __floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w) };
+        out = *(const uint4 *) h;
+    }
+    const int64_t nt = row / TC_N, nl = row % TC_N, kc64 = k8 >> 3, kc = k8 & 7;
+    uint8_t * tile = x16 + (nt * (k >> 6) + kc64) * TC_B_BYTES;
+    *(uint4 *) (tile + kc * TC_B_LBO + (nl >> 3) * TC_SBO + (nl & 7) * 16) = out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- the GEMM kernel
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant__ TcArgs A) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = tc_smem_u32(smem);
+    const uint32_t bars = sbase + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);       // a_full[S], b_full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr
+    const uint32_t a_full = bars, b_full = bars + 8 * TC_STAGES, empty = bars + 16 * TC_STAGES, t_full = bars + 24 * TC_STAGES, t_empty = t_full + 16;
+    volatile uint32_t * tmem_slot = (volatile uint32_t *) (smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 24 * TC_STAGES + 32);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(a_full + 8 * s, TC_DEQ_THREADS); tc_mbar_init(b_full + 8 * s, 1); tc_mbar_init(empty + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { tc_mbar_init(t_full + 8 * i, 1); tc_mbar_init(t_empty + 8 * i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32((const void *) tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int n_tiles = A.tiles_m * A.tiles_n, nkc = (int) (A.k >> 6);        // K chunks of 64 per tile
+    uint32_t it = 0;                                                          // stage uses so far (same sequence in every role)
+
+    if (warp < 8) {
+        // ================================================================== A producers (dequant)
+        const int row = threadIdx.x & 127, hf = threadIdx.x >> 7;
+        const uint32_t a_row_off = (row >> 3) * TC_SBO + (row & 7) * 16;
+        const int64_t nkb = A.k >> 8;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int mt = t % A.tiles_m;
+            int64_t gr = (int64_t) mt * TC_M + row; if (gr >= A.m) gr = A.m - 1;        // tail rows: recompute a valid row, never stored
+            const uint8_t * wrow = A.w + gr * A.row_bytes;
+#define TC_STAGE_STEP(C, RAW) do { \
+                const uint32_t s = it % TC_STAGES; \
+                tc_mbar_wait(empty + 8 * s, ((it / TC_STAGES) & 1) ^ 1); \
+                deq_chunk<C>(RAW, hf, sbase + s * (TC_A_BYTES + TC_B_BYTES) + a_row_off); \
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
+                tc_mbar_arrive(a_full + 8 * s); ++it; } while (0)
+            if (A.type == B200_Q4_K) {
+                RawQ4K cur, nxt;
+                raw_load(cur, wrow);
+                for (int64_t kb = 0; kb < nkb; ++kb) {
+                    if (kb + 1 < nkb) raw_load(nxt, wrow + (kb + 1) * 144);
+                    TC_STAGE_STEP(0, cur); TC_STAGE_STEP(1, cur); TC_STAGE_STEP(2, cur); TC_STAGE_STEP(3, cur);
+                    cur = nxt;
+                }
+            } else {
+                const uint8_t * drow = A.wd + gr * nkb * 2;
+                RawQ6K cur, nxt;
+                raw_load(cur, wrow, drow, hf);
+                for (int64_t kb = 0; kb < nkb; ++kb) {
+                    if (kb + 1 < nkb) raw_load(nxt, wrow + (kb + 1) * 208, drow + (kb + 1) * 2, hf);
+                    TC_STAGE_STEP(0, cur); TC_STAGE_STEP(1, cur); TC_STAGE_STEP(2, cur); TC_STAGE_STEP(3, cur);
+                    cur = nxt;
+                }
+            }
+#undef TC_STAGE_STEP
+        }
+    } else if (warp == 8) {
+        // ================================================================== B producer (TMA bulk copies of pre-tiled F16 activations)
+        if (lane == 0) {
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int nt = t / A.tiles_m;
+                const uint8_t * src = A.x16 + (int64_t) nt * nkc * TC_B_BYTES;
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const uint32_t s = it % TC_STAGES;
+                    tc_mbar_wait(empty + 8 * s, ((it / TC_STAGES) & 1) ^ 1);
+                    tc_mbar_expect_tx(b_full + 8 * s, TC_B_BYTES);
+                    const uint32_t dst = sbase + s * (TC_A_BYTES + TC_B_BYTES) + TC_A_BYTES;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tc_bulk_g2s(dst + q * (TC_B_BYTES / 4), src + (int64_t) kc * TC_B_BYTES + q * (TC_B_BYTES / 4), TC_B_BYTES / 4, b_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            uint32_t tcount = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+                const int nt = t / A.tiles_m;
+                int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
+                const uint32_t idesc = tc_idesc((int) ((ncols + 15) & ~15));
+                const uint32_t acc = tcount & 1, d_tmem = tmem + acc * TC_N;
+                tc_mbar_wait(t_empty + 8 * acc, ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const uint32_t s = it % TC_STAGES, par = (it / TC_STAGES) & 1;
+                    tc_mbar_wait(a_full + 8 * s, par);
+                    tc_mbar_wait(b_full + 8 * s, par);
+                    tc_fence_after();
+                    const uint32_t a_s = sbase + s * (TC_A_BYTES + TC_B_BYTES), b_s = a_s + TC_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < TC_K / 16; ++j)
+                        tc_mma(d_tmem, tc_desc(a_s + j * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), tc_desc(b_s + j * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), idesc, (kc | j) != 0);
+                    tc_commit(empty + 8 * s);                                 // frees the stage when these MMAs have read it
+                }
+                tc_commit(t_full + 8 * acc);                                  // accumulator complete
+            }
+        }
+    } else {
+        // ================================================================== epilogue (warps 10..13 -> TMEM lane quarters 2, 3, 0, 1)
+        const int quarter = warp & 3;
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+            const int mt = t % A.tiles_m, nt = t / A.tiles_m;
+            const uint32_t acc = tcount & 1;
+            tc_mbar_wait(t_full + 8 * acc, (tcount >> 1) & 1);
+            tc_fence_after();
+            const int64_t mrow = (int64_t) mt * TC_M + quarter * 32 + lane;
+            int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
+            float * out = A.dst + ((int64_t) nt * TC_N) * A.dst_ld + mrow;
+            for (int cc = 0; cc * 32 < ncols; ++cc) {
+                uint32_t v[32];
+                tc_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + acc * TC_N + cc * 32, v);
+                if (mrow < A.m) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            tc_mbar_arrive(t_empty + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------- host side
+bool mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w, int64_t row_stride) {
+    if (n <= 8 || k % 256) return false;
+    if (type == B200_Q4_K) return (uintptr_t) w % 16 == 0 && row_stride == k / 256 * 144;
+    if (type == B200_Q6_K) return layout == B200_LAYOUT_PLANAR && (uintptr_t) w % 16 == 0;
+    return false;
+}
+size_t mmq_tc_scratch_bytes(int64_t k, int64_t n) { return (size_t) ((n + TC_N - 1) / TC_N * TC_N) * (size_t) k * 2; }
+
+int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, cudaStream_t st) {
+    static int once = 0;
+    if (!once) { B200_CUDA_TRY(cudaFuncSetAttribute(k_mmq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); once = 1; }
+    const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
+    k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
+    B200_LAUNCH_CHECK();
+    TcArgs A = {};
+    const int64_t nkb = k / 256;
+    A.w = (const uint8_t *) w; A.type = type; A.m = m; A.k = k; A.n = n; A.dst = dst; A.dst_ld = dst_ld; A.x16 = (const uint8_t *) scratch;
+    if (type == B200_Q4_K) { A.row_bytes = nkb * 144; A.wd = nullptr; }
+    else                   { A.row_bytes = nkb * 208; A.wd = (const uint8_t *) w + m * nkb * 208; }
+    A.tiles_m = (int) ((m + TC_M - 1) / TC_M); A.tiles_n = (int) (n_pad / TC_N);
+    int grid = A.tiles_m * A.tiles_n; if (grid > sm_count()) grid = sm_count();
+    k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+} // namespace b200

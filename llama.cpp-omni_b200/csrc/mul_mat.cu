@@ -4,11 +4,17 @@
 //                   the weight type first exactly like the CPU oracle does (vec_dot_type, ggml-cpu.c:196-350)
 // Batch dims follow ggml broadcast rules: w.ne[2] divides x.ne[2], w.ne[3] divides x.ne[3].
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 
 int matvec_q_cols(const void * w, int type, int layout, int64_t m, int64_t row_stride, const void * act, int64_t k, int ncols,
                   float * y, int64_t y_col_stride, cudaStream_t st);
+// mmq_tc.cu: tcgen05 dequant-GEMM for n > 8 columns
+bool   mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w, int64_t row_stride);
+size_t mmq_tc_scratch_bytes(int64_t k, int64_t n);
+int    mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, cudaStream_t st);
+static bool tc_disabled() { static const bool off = getenv("B200_DISABLE_TC") && atoi(getenv("B200_DISABLE_TC")) != 0; return off; }
 
 template <typename WT> __device__ __forceinline__ float w2f(WT v);
 template <> __device__ __forceinline__ float w2f<float>(float v) { return v; }
@@ -112,7 +118,10 @@ extern "C" int b200_mul_mat_supported(const b200_tensor * w, const b200_tensor *
 
 extern "C" size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x) {
     if (!is_quant(w->type)) return 0;
-    return (size_t) act_layout(w->type, w->ne[0]).bytes * (size_t) (x->ne[1] * x->ne[2] * x->ne[3]);
+    const size_t act = (size_t) act_layout(w->type, w->ne[0]).bytes * (size_t) (x->ne[1] * x->ne[2] * x->ne[3]);
+    // the tensor-core path keeps ONE batch slice of F16 activation tiles in the same scratch
+    const size_t tc = mmq_tc_supported(w->type, w->layout, w->ne[0], x->ne[1], w->data, w->nb[1]) ? mmq_tc_scratch_bytes(w->ne[0], x->ne[1]) : 0;
+    return act > tc ? act : tc;
 }
 
 extern "C" int b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
@@ -133,8 +142,16 @@ extern "C" int b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const 
     }
     if (scratch_bytes < b200_mul_mat_scratch_bytes(w, x) || ((uintptr_t) scratch % 16)) return B200_ERR_ARG;
     const int64_t act_b = act_layout(t, k).bytes;
+    const bool tc = !tc_disabled() && mmq_tc_supported(t, w->layout, k, n, w->data, w->nb[1]);
     for (int64_t i3 = 0; i3 < x->ne[3]; ++i3) for (int64_t i2 = 0; i2 < x->ne[2]; ++i2) {
         const float * xs = (const float *) ((const char *) x->data + i2 * x->nb[2] + i3 * x->nb[3]);
+        if (tc) {       // prefill / batched: dequant tiles -> tcgen05.mma (mmq_tc.cu)
+            const char * wb = (const char *) w->data + (i2 / r2) * w->nb[2] + (i3 / r3) * w->nb[3];
+            float * yb = (float *) ((char *) dst->data + i2 * dst->nb[2] + i3 * dst->nb[3]);
+            const int rc = mmq_tc(wb, t, m, k, xs, x->nb[1] / 4, n, yb, dst->nb[1] / 4, scratch, st);
+            if (rc) return rc;
+            continue;
+        }
         uint8_t * act = (uint8_t *) scratch + (i3 * x->ne[2] + i2) * n * act_b;
         int rc = b200_quantize_act(t, xs, x->nb[1] / 4, act, k, n, stream);
         if (rc) return rc;

@@ -57,6 +57,25 @@ def mm_check(got, ref, w_deq, x, factor=2e-6):
     assert np.all(err <= factor * mag + 1e-12), (err.max(), (err / (mag + 1e-30)).max())
 
 
+def nmse(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300))
+
+
+def tc_routed(ops, t, planar, n, k):
+    """n > 8 columns of q4_K (native) / q6_K (planar) go to the tcgen05 dequant-GEMM (csrc/mmq_tc.cu): F16 operands, F32 accumulation."""
+    return n > 8 and k % 256 == 0 and (t == ops.Q4_K or (t == ops.Q6_K and planar))
+
+
+def tc_check(got, oracle_ref, w_deq, x):
+    """Bars of the tensor-core path: the reference's own MUL_MAT bar against the CPU oracle (NMSE <= 5e-4, tests/test-backend-ops.cpp:3300)
+    and, since the oracle's q8_K activations are the larger error, a much tighter one against the exact product of the dequantised weights."""
+    exact = x.astype(np.float64) @ w_deq.astype(np.float64).T
+    assert nmse(got, exact) <= 2e-6, nmse(got, exact)
+    if oracle_ref is not None:
+        assert nmse(got, oracle_ref) <= 5e-4, nmse(got, oracle_ref)
+
+
 # ---------------------------------------------------------------------------------------------------------------- quantisers
 def _canon_q8K(rec, k):
     return rec
@@ -135,10 +154,36 @@ def test_mul_mat_vs_oracle(ops, name, m, k, n):
     wf = O.dequant(t, blocks, k)
     wd = dev(blocks)
     got = ops.mul_mat(wd, t, m, k, dev(x)).cpu().numpy()
-    mm_check(got, ref, wf, x)
+    (tc_check(got, ref, wf, x) if tc_routed(ops, t, False, n, k) else mm_check(got, ref, wf, x))
     if t in ops.PAYLOAD:
         got = ops.mul_mat(ops.to_planar(t, wd), t, m, k, dev(x), layout=ops.LAYOUT_PLANAR).cpu().numpy()
-        mm_check(got, ref, wf, x)
+        (tc_check(got, ref, wf, x) if tc_routed(ops, t, True, n, k) else mm_check(got, ref, wf, x))
+
+
+@pytest.mark.parametrize("name,m,k,n", [("q4_K", 4096, 4096, 512), ("q6_K", 1024, 4096, 300), ("q4_K", 200, 512, 17), ("q6_K", 129, 256, 9),
+                                        ("q4_K", 12288, 4096, 2048), ("q4_K", 4096, 12288, 257), ("q6_K", 4096, 12288, 64)])
+def test_mul_mat_prefill_tensor_core(ops, name, m, k, n):
+    """Prefill GEMM (BASELINE.json configs[2] shapes and ragged ones) through b200_mul_mat -> k_mmq_tc.  Exact product of the dequantised
+    weights in f64 on the GPU for the whole output; the CPU oracle (q8_K activations) on a sample of rows and columns."""
+    t = QT[name]
+    rng = np.random.default_rng(hash((name, m, k, n)) & 0xffff)
+    blocks = rand_blocks(rng, t, m * k // 256)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    wd = dev(blocks)
+    planar = t == O.Q6_K
+    if planar:
+        wd = ops.to_planar(t, wd)
+    got = ops.mul_mat(wd, t, m, k, dev(x), layout=ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NATIVE)
+    torch.cuda.synchronize()
+    wf = O.dequant(t, blocks, k)
+    exact = (dev(x).double() @ dev(wf).double().T)
+    err = nmse(got.cpu().numpy(), exact.cpu().numpy())
+    assert err <= 2e-6, err
+    rows = np.unique(np.concatenate([np.arange(min(m, 40)), np.arange(max(0, m - 40), m), rng.integers(0, m, 48)]))
+    cols = np.unique(np.concatenate([np.arange(min(n, 4)), np.arange(max(0, n - 4), n), rng.integers(0, n, 4)]))
+    sub = blocks.reshape(m, -1)[rows]
+    ref = O.mul_mat(t, sub, x[cols], len(rows), k)
+    assert nmse(got.cpu().numpy()[np.ix_(cols, rows)], ref) <= 5e-4
 
 
 def test_mul_mat_lm_head_shape(ops):

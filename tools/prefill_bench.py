@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Prefill GEMM (k_mmq_tc, tcgen05) timing through the C-ABI at the Qwen3-8B layer shapes: python tools/prefill_bench.py [n_tokens]
+Prints TFLOP/s per shape and the linear-layer time of a whole 36-layer prompt vs MEASURED_PEAKS.json bf16_tflops (sustained)."""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from __graft_entry__ import load_package  # noqa: E402
+
+pkg = load_package()
+ops, dec = pkg.ops, pkg.decode
+dev = torch.device("cuda:0")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+pk = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+PEAK = pk.get("bf16_tflops_sustained", 1400.0)
+E, F = 4096, 12288
+shapes = [("wq/wo q4_K", ops.Q4_K, 4096, E, 2), ("wk q4_K", ops.Q4_K, 1024, E, 1), ("wv q6_K", ops.Q6_K, 1024, E, 1),
+          ("gate/up q4_K", ops.Q4_K, F, E, 2), ("down q6_K", ops.Q6_K, E, F, 0.5), ("down q4_K", ops.Q4_K, E, F, 0.5)]
+gen = torch.Generator(device=dev)
+gen.manual_seed(0)
+total_us, total_flop = 0.0, 0.0
+out = {}
+for name, wt, m, k, per_layer in shapes:
+    w = dec._rand_weight(wt, m, k, gen, dev)
+    x = torch.randn(n, k, device=dev)
+    y = torch.empty(n, m, device=dev)
+    layout = ops.LAYOUT_PLANAR if wt == ops.Q6_K else ops.LAYOUT_NATIVE
+    for _ in range(3):
+        ops.mul_mat(w, wt, m, k, x, layout=layout, out=y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        ops.mul_mat(w, wt, m, k, x, layout=layout, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / iters * 1e3
+    fl = 2.0 * m * k * n
+    out[name] = {"us": round(us, 1), "tflops": round(fl / us / 1e6, 1)}
+    print(f"{name:14s} m={m:6d} k={k:6d} n={n:5d}: {us:9.1f} us  {fl / us / 1e6:8.1f} TFLOP/s  ({fl / us / 1e6 / PEAK:.1%} of measured sustained {PEAK})")
+    total_us += us * per_layer
+    total_flop += fl * per_layer
+layer_ms = total_us / 1e3
+print(json.dumps({"n_tokens": n, "linear_ms_per_layer": round(layer_ms, 3), "linear_tok_per_s_36_layers": round(n / (36 * layer_ms / 1e3), 1),
+                  "linear_tflops": round(total_flop / total_us / 1e6, 1), "frac_of_measured_sustained": round(total_flop / total_us / 1e6 / PEAK, 4),
+                  "shapes": out}))
