@@ -6,8 +6,9 @@
 // memory and the contraction runs as F16 x F16 -> F32 UMMA.  K-quant sub-block scales (6-bit scale/min per 32 weights, int8 scale per 16)
 // do not map onto the hardware block-scaled formats, so the dequant has to materialise F16 (SURVEY.md §7 "tcgen05 prefill").
 //
-// One persistent CTA per SM, 14 warps, warp-specialised (the canonical Blackwell GEMM anatomy, hand-written in PTX):
-//   warps 0-7   A producers: read raw quant blocks with 16-byte loads (every weight byte once per (m, n) tile), dequantise with half2 math
+// One persistent CTA per SM, 15 warps, warp-specialised (the canonical Blackwell GEMM anatomy, hand-written in PTX):
+//   warps 0-7   A producers: copy their half of a raw quant block from the raw ring to registers (thread group g = warps 4g..4g+3 owns half g of
+//               every 256-weight block = K-chunks 2g, 2g+1, so the groups fill alternate pairs of stages), dequantise with half2 math
 //               (byte -> 1024+q via PRMT with 0x64, HSUB2, HFMA2 by d*sc / -dmin*m) and store the 128 x 64 F16 tile in the canonical K-major
 //               no-swizzle UMMA layout (8 x 16-byte core matrices; row groups 128 B apart -> conflict-free 16-byte stores);
 //               fence.proxy.async + mbarrier arrive hands the stage to the tensor core
@@ -15,6 +16,8 @@
 //               so a 256 x 64 B tile is plain contiguous memory: 4 x 8 KB cp.async.bulk (TMA) per stage, complete_tx on the stage barrier
 //   warp  9     MMA issuer: one lane issues 4 tcgen05.mma per stage (D in TMEM, 2 x 256 columns double-buffered) and tcgen05.commit's the stage
 //               back to the producers / the accumulator to the epilogue
+//   warp  14    raw weight producer: ONE 2-D tiled TMA (cp.async.bulk.tensor, box = 128 rows x one 144 / 208-byte quant block) per 4 stages
+//               into a 3-slot raw ring, up to 3 blocks ahead of the dequantisers -> no register scoreboard ever waits on L2 / HBM
 //   warps 10-13 epilogue: tcgen05.ld 32 lanes x 32 columns, coalesced F32 stores (lane = weight row = contiguous dst index)
 // FLOPs per launch = 2 m n k.  Tensor-bound for n >= ~64.
 //
@@ -22,14 +25,18 @@
 // The CPU oracle instead quantises activations to q8_K (~3e-3 relative per element): this path is closer to the exact product than the
 // oracle is; parity bar = the reference's own MUL_MAT bar, NMSE <= 5e-4 (tests/test-backend-ops.cpp:3300).
 #include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
 
 namespace b200 {
 
-constexpr int TC_M = 128, TC_N = 256, TC_K = 64, TC_STAGES = 4;
+constexpr int TC_M = 128, TC_N = 256, TC_K = 64, TC_STAGES = 3;
+constexpr int TC_RAW = 3, TC_RAW_BYTES = TC_M * 208;                                        // raw quant-block ring: 128 rows x one block (q6_K payload = 208 B)
 constexpr int TC_A_BYTES = TC_M * TC_K * 2, TC_B_BYTES = TC_N * TC_K * 2;                 // 16 KB, 32 KB
 constexpr int TC_A_LBO = (TC_M / 8) * 128, TC_B_LBO = (TC_N / 8) * 128, TC_SBO = 128;        // core matrices: K direction / row-group direction
-constexpr int TC_DEQ_THREADS = 256, TC_THREADS = 448;
-constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256;
+constexpr int TC_DEQ_THREADS = 256, TC_THREADS = 480;
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_RAW * TC_RAW_BYTES + 256;
+static_assert(TC_SMEM <= 227 * 1024, "k_mmq_tc shared memory");
 
 struct TcArgs {
     const uint8_t * w; const uint8_t * wd;          // payload plane, f16 d plane (q6_K planar) or null
@@ -37,6 +44,7 @@ struct TcArgs {
     float * dst; int64_t dst_ld;                    // dst[n * dst_ld + m]
     int64_t m, k, n, row_bytes;                     // n = real columns; row_bytes of the payload plane
     int type, tiles_m, tiles_n;
+    int flags;                                      // experiment switches (B200_TC_FLAGS): 1 no dequant, 2 no MMA, 4 no B copies
 };
 
 // ---------------------------------------------------------------------------------------------------------------- PTX helpers
@@ -54,6 +62,13 @@ __device__ __forceinline__ void tc_bulk_g2s(uint32_t dst, const void * src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 2-D tiled TMA: box {block bytes, 128 rows} of the weight payload plane -> dense [128][block bytes] in shared memory (rows past m read as 0)
+__device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap * map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 tc_lds16(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
+__device__ __forceinline__ uint2 tc_lds8(uint32_t a) { uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a)); return r; }
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp): start address, leading
 // (K direction) and stride (M/N direction) byte offsets in 16-byte units, descriptor version 1 (Blackwell), layout type 0
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -97,66 +112,102 @@ __device__ __forceinline__ uint4 deq8(uint32_t b0, uint32_t b1, __half2 off, __h
     return *(const uint4 *) h;
 }
 
-// Raw bytes of one 256-weight block that thread (row, hf) needs for its four K-chunks, loaded one block AHEAD of their use so that the
-// L2 round trip overlaps the dequantisation of the current block.
-struct RawQ4K { uint4 hdr, q[8]; };                       // d|dmin + 12 scale bytes; qs[128]
-struct RawQ6K { uint4 l[4], h[4], sc; float d; };         // ql[64h' + 32hf ..+32) and qh[32h' ..+32) for h' = 0, 1; 16 int8 scales; d
+// Producer mapping: thread (row, g) owns HALF g of every 256-weight block of its row = K-chunks 2g and 2g+1 (64 weights each), so the two
+// thread groups fill alternate PAIRS of stages and no byte is loaded twice.  The raw bytes of a half block (80 B q4_K, 116 B q6_K) are
+// loaded into registers TWO blocks (8 stages, ~3.5 us of MMA time) ahead of their use: the L2/HBM round trip never stalls the pipeline.
+struct RawQ4K { uint4 hdr, q[4]; };                       // d|dmin + 12 scale bytes; qs[64g .. 64g+64)
+struct RawQ6K { uint4 l[4], h[2]; uint2 sc; float d; };   // ql[64g ..+64), qh[32g ..+32), int8 scales[8g ..+8), d
 
-__device__ __forceinline__ void raw_load(RawQ4K & R, const uint8_t * blk) {
-    R.hdr = ldg16(blk);
+// blk = shared address of this row's block in the raw ring slot (row stride 144 / 208 B: 16-byte reads of 8 consecutive rows hit 8 distinct
+// 16-byte bank groups -> conflict-free)
+__device__ __forceinline__ void raw_load(RawQ4K & R, uint32_t blk, int g) {
+    R.hdr = tc_lds16(blk);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) R.q[i] = ldg16(blk + 16 + 16 * i);
+    for (int i = 0; i < 4; ++i) R.q[i] = tc_lds16(blk + 16 + 64 * g + 16 * i);
 }
-__device__ __forceinline__ void raw_load(RawQ6K & R, const uint8_t * pay, const uint8_t * dptr, int hf) {
+__device__ __forceinline__ void raw_load(RawQ6K & R, uint32_t pay, int g) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        R.l[2 * h] = ldg16(pay + 64 * h + 32 * hf); R.l[2 * h + 1] = ldg16(pay + 64 * h + 32 * hf + 16);
-        R.h[2 * h] = ldg16(pay + 128 + 32 * h);     R.h[2 * h + 1] = ldg16(pay + 128 + 32 * h + 16);
-    }
-    R.sc = ldg16(pay + 192);
-    R.d = h2f(__ldg((const uint16_t *) dptr));
+    for (int i = 0; i < 4; ++i) R.l[i] = tc_lds16(pay + 64 * g + 16 * i);
+    R.h[0] = tc_lds16(pay + 128 + 32 * g); R.h[1] = tc_lds16(pay + 128 + 32 * g + 16);
+    R.sc = tc_lds8(pay + 192 + 8 * g);
 }
 
 __device__ __forceinline__ void st_row(uint32_t addr, const uint4 & v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// thread (row, hf) writes its 32 weights of K-chunk c (64 weights) of the block into stage memory (a_row = shared address of its row)
-template <int c> __device__ __forceinline__ void deq_chunk(const RawQ4K & R, int hf, uint32_t a_row) {
-    // scales / mins of sub-block j = 2c + hf (get_scale_min_k4, ggml-quants.c:703-711)
+// thread (row, g) writes the 64 weights of its cc-th chunk (block chunk c = 2g + cc) into stage memory (a_row = shared address of its row)
+template <int cc> __device__ __forceinline__ void deq_chunk(const RawQ4K & R, int g, uint32_t a_row) {
+    // chunk c: low nibbles of qs[32c ..+32) = sub-block 2c (k 0..31 of the chunk), high nibbles = sub-block 2c+1 (k 32..63);
+    // their 6-bit scales / mins (get_scale_min_k4, ggml-quants.c:703-711) are bytes 2cc, 2cc+1 of the group's packed word
     const uint4 & hdr = R.hdr;
-    const int j = 2 * c + hf;
-    const uint32_t scw = c < 2 ? (hdr.y & 0x3f3f3f3fu) : ((hdr.w & 0x0f0f0f0fu) | (((hdr.y >> 6) & 0x03030303u) << 4));
-    const uint32_t mnw = c < 2 ? (hdr.z & 0x3f3f3f3fu) : (((hdr.w >> 4) & 0x0f0f0f0fu) | (((hdr.z >> 6) & 0x03030303u) << 4));
-    const int sh = (j & 3) * 8;
-    const float sc = (float) ((scw >> sh) & 0xff), mn = (float) ((mnw >> sh) & 0xff);
+    const uint32_t scw = g ? ((hdr.w & 0x0f0f0f0fu) | (((hdr.y >> 6) & 0x03030303u) << 4)) : (hdr.y & 0x3f3f3f3fu);
+    const uint32_t mnw = g ? (((hdr.w >> 4) & 0x0f0f0f0fu) | (((hdr.z >> 6) & 0x03030303u) << 4)) : (hdr.z & 0x3f3f3f3fu);
     const float d = h2f(hdr.x & 0xffff), dmin = h2f(hdr.x >> 16);
-    const __half2 s = __float2half2_rn(d * sc), cm = __float2half2_rn(-(dmin * mn)), off = __float2half2_rn(1024.0f);
-    const uint32_t w[8] = { R.q[2 * c].x, R.q[2 * c].y, R.q[2 * c].z, R.q[2 * c].w, R.q[2 * c + 1].x, R.q[2 * c + 1].y, R.q[2 * c + 1].z, R.q[2 * c + 1].w };
-    const int shq = 4 * hf;
+    const __half2 off = __float2half2_rn(1024.0f);
+    const uint32_t w[8] = { R.q[2 * cc].x, R.q[2 * cc].y, R.q[2 * cc].z, R.q[2 * cc].w, R.q[2 * cc + 1].x, R.q[2 * cc + 1].y, R.q[2 * cc + 1].z, R.q[2 * cc + 1].w };
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8((w[2 * i] >> shq) & 0x0f0f0f0fu, (w[2 * i + 1] >> shq) & 0x0f0f0f0fu, off, s, cm));
+    for (int hf = 0; hf < 2; ++hf) {
+        const float sc = (float) ((scw >> (16 * cc + 8 * hf)) & 0xff), mn = (float) ((mnw >> (16 * cc + 8 * hf)) & 0xff);
+        const __half2 s = __float2half2_rn(d * sc), cm = __float2half2_rn(-(dmin * mn));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8((w[2 * i] >> (4 * hf)) & 0x0f0f0f0fu, (w[2 * i + 1] >> (4 * hf)) & 0x0f0f0f0fu, off, s, cm));
+    }
 }
 
-template <int c> __device__ __forceinline__ void deq_chunk(const RawQ6K & R, int hf, uint32_t a_row) {
-    // chunk c = elements 64c..64c+63 of the block = half h, quads 2(c&1) and 2(c&1)+1 (dequantize_row_q6_K, ggml-quants.c:1762-1791);
-    // quad = 2(c&1) + hf reads ql[64h + 32(quad&1) + l] (low nibble for quads 0/1, high for 2/3) and bits 2quad.. of qh[32h + l]
-    constexpr int h = c >> 1;
-    const int quad = 2 * (c & 1) + hf;
-    const uint32_t lw[8] = { R.l[2 * h].x, R.l[2 * h].y, R.l[2 * h].z, R.l[2 * h].w, R.l[2 * h + 1].x, R.l[2 * h + 1].y, R.l[2 * h + 1].z, R.l[2 * h + 1].w };
-    const uint32_t hw[8] = { R.h[2 * h].x, R.h[2 * h].y, R.h[2 * h].z, R.h[2 * h].w, R.h[2 * h + 1].x, R.h[2 * h + 1].y, R.h[2 * h + 1].z, R.h[2 * h + 1].w };
-    const uint32_t scw = h ? ((c & 1) ? R.sc.w : R.sc.z) : ((c & 1) ? R.sc.y : R.sc.x);      // scales[8h + 4(c&1) .. +3]; this quad: bytes 2hf, 2hf+1
-    const float sc0 = (float) (int) (int8_t) (scw >> (16 * hf)), sc1 = (float) (int) (int8_t) (scw >> (16 * hf + 8));
-    const __half2 s0 = __float2half2_rn(R.d * sc0), s1 = __float2half2_rn(R.d * sc1);
+template <int cc> __device__ __forceinline__ void deq_chunk(const RawQ6K & R, int g, uint32_t a_row) {
+    // half g of the block, chunk cc = quads 2cc and 2cc+1 (dequantize_row_q6_K, ggml-quants.c:1762-1791): quad q reads ql[64g + 32(q&1) + l]
+    // (low nibble for quads 0/1, high for 2/3) and bits 2q, 2q+1 of qh[32g + l]; int8 scale index 8g + 2q + (l >> 4)
+    const uint32_t hw[8] = { R.h[0].x, R.h[0].y, R.h[0].z, R.h[0].w, R.h[1].x, R.h[1].y, R.h[1].z, R.h[1].w };
+    const uint32_t scw = cc ? R.sc.y : R.sc.x;            // scales[8g + 4cc .. +3]: quad 2cc -> bytes 0, 1; quad 2cc+1 -> bytes 2, 3
     const __half2 off = __float2half2_rn(1056.0f), zero = __float2half2_rn(0.0f);        // 1024 (PRMT bias) + 32 (q6_K code offset)
-    constexpr int shl = (c & 1) ? 4 : 0;
-    const int shh = 2 * quad;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t b0 = ((lw[2 * i] >> shl) & 0x0f0f0f0fu) | (((hw[2 * i] >> shh) & 0x03030303u) << 4);
-        const uint32_t b1 = ((lw[2 * i + 1] >> shl) & 0x0f0f0f0fu) | (((hw[2 * i + 1] >> shh) & 0x03030303u) << 4);
-        st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8(b0, b1, off, i < 2 ? s0 : s1, zero));
+    for (int hf = 0; hf < 2; ++hf) {                     // quad = 2cc + hf -> k 32hf .. 32hf+31 of the chunk; ql bytes 32hf ..+32 of the half
+        const float sc0 = (float) (int) (int8_t) (scw >> (16 * hf)), sc1 = (float) (int) (int8_t) (scw >> (16 * hf + 8));
+        const __half2 s0 = __float2half2_rn(R.d * sc0), s1 = __float2half2_rn(R.d * sc1);
+        const uint32_t lw[8] = { R.l[2 * hf].x, R.l[2 * hf].y, R.l[2 * hf].z, R.l[2 * hf].w, R.l[2 * hf + 1].x, R.l[2 * hf + 1].y, R.l[2 * hf + 1].z, R.l[2 * hf + 1].w };
+        constexpr int shl = 4 * cc;
+        const int shh = 2 * (2 * cc + hf);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t b0 = ((lw[2 * i] >> shl) & 0x0f0f0f0fu) | (((hw[2 * i] >> shh) & 0x03030303u) << 4);
+            const uint32_t b1 = ((lw[2 * i + 1] >> shl) & 0x0f0f0f0fu) | (((hw[2 * i + 1] >> shh) & 0x03030303u) << 4);
+            st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8(b0, b1, off, i < 2 ? s0 : s1, zero));
+        }
+    }
+}
+
+// one tile's worth of A stages for thread (row, g): block kb of the row arrives in raw-ring slot (rit + kb) % TC_RAW (TMA, issued by the raw
+// producer warp up to TC_RAW blocks ahead); the thread copies its half block to registers, hands the slot back, and fills stage uses
+// it0 + 4kb + 2g and + 2g + 1
+template <class Raw, int BLK>
+__device__ __forceinline__ void tc_produce_tile(uint32_t raw0, const uint8_t * drow, int64_t nkb, int g, int lane, uint32_t it0, uint32_t rit0, uint32_t stage0,
+                                                uint32_t a_full, uint32_t empty, uint32_t raw_full, uint32_t raw_empty, int flags) {
+    float dn = 0.0f;
+    if (drow) dn = h2f(__ldg((const uint16_t *) drow));                         // q6_K: the block's f16 d comes from the planar d plane, one block ahead
+    for (int64_t kb = 0; kb < nkb; ++kb) {
+        const uint32_t ru = rit0 + (uint32_t) kb, r = ru % TC_RAW;
+        Raw R;
+        tc_mbar_wait(raw_full + 8 * r, (ru / TC_RAW) & 1);
+        raw_load(R, raw0 + r * TC_RAW_BYTES, g);
+        if constexpr (BLK == 208) { R.d = dn; if (kb + 1 < nkb) dn = h2f(__ldg((const uint16_t *) (drow + (kb + 1) * 2))); }
+        // The slot may be overwritten by the next TMA (async proxy) as soon as all 8 warps have arrived, so the generic-proxy ld.shared above must
+        // have been PERFORMED, not just issued — their values are not consumed before the arrive, and ptxas schedules SYNCS.ARRIVE right behind
+        // the LDS (observed: rows of the next block leaking into this one).  The cross-proxy fence orders them before the TMA write.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(raw_empty + 8 * r);
+        const uint32_t it = it0 + (uint32_t) kb * 4 + 2 * g;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const uint32_t u = it + cc, s = u % TC_STAGES;
+            tc_mbar_wait(empty + 8 * s, ((u / TC_STAGES) & 1) ^ 1);
+            if (!(flags & 1)) { if (cc == 0) deq_chunk<0>(R, g, stage0 + s * (TC_A_BYTES + TC_B_BYTES)); else deq_chunk<1>(R, g, stage0 + s * (TC_A_BYTES + TC_B_BYTES)); }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(a_full + 8 * s);                       // one arrival per warp
+        }
     }
 }
 
@@ -182,17 +233,20 @@ __global__ void __launch_bounds__(256) k_x_to_f16_tiles(const float * __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------- the GEMM kernel
-__global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant__ TcArgs A) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant__ TcArgs A, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = tc_smem_u32(smem);
-    const uint32_t bars = sbase + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);       // a_full[S], b_full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr
+    const uint32_t raw0 = sbase + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);       // raw quant-block ring
+    const uint32_t bars = raw0 + TC_RAW * TC_RAW_BYTES;                         // a_full[S], b_full[S], empty[S], tmem_full[2], tmem_empty[2], raw_full[R], raw_empty[R], tmem ptr
     const uint32_t a_full = bars, b_full = bars + 8 * TC_STAGES, empty = bars + 16 * TC_STAGES, t_full = bars + 24 * TC_STAGES, t_empty = t_full + 16;
-    volatile uint32_t * tmem_slot = (volatile uint32_t *) (smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 24 * TC_STAGES + 32);
+    const uint32_t raw_full = t_empty + 16, raw_empty = raw_full + 8 * TC_RAW;
+    volatile uint32_t * tmem_slot = (volatile uint32_t *) (smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_RAW * TC_RAW_BYTES + 24 * TC_STAGES + 32 + 16 * TC_RAW);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(a_full + 8 * s, TC_DEQ_THREADS); tc_mbar_init(b_full + 8 * s, 1); tc_mbar_init(empty + 8 * s, 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(a_full + 8 * s, TC_DEQ_THREADS / 64); tc_mbar_init(b_full + 8 * s, 1); tc_mbar_init(empty + 8 * s, 1); }
         for (int i = 0; i < 2; ++i) { tc_mbar_init(t_full + 8 * i, 1); tc_mbar_init(t_empty + 8 * i, 128); }
+        for (int r = 0; r < TC_RAW; ++r) { tc_mbar_init(raw_full + 8 * r, 1); tc_mbar_init(raw_empty + 8 * r, TC_DEQ_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -209,38 +263,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
 
     if (warp < 8) {
         // ================================================================== A producers (dequant)
-        const int row = threadIdx.x & 127, hf = threadIdx.x >> 7;
-        const uint32_t a_row_off = (row >> 3) * TC_SBO + (row & 7) * 16;
+        const int row = threadIdx.x & 127, g = threadIdx.x >> 7;
+        const uint32_t stage0 = sbase + row * 16;                              // row group (row >> 3) * TC_SBO + (row & 7) * 16
         const int64_t nkb = A.k >> 8;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint32_t rit = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it += (uint32_t) nkc, rit += (uint32_t) nkb) {
             const int mt = t % A.tiles_m;
-            int64_t gr = (int64_t) mt * TC_M + row; if (gr >= A.m) gr = A.m - 1;        // tail rows: recompute a valid row, never stored
-            const uint8_t * wrow = A.w + gr * A.row_bytes;
-#define TC_STAGE_STEP(C, RAW) do { \
-                const uint32_t s = it % TC_STAGES; \
-                tc_mbar_wait(empty + 8 * s, ((it / TC_STAGES) & 1) ^ 1); \
-                deq_chunk<C>(RAW, hf, sbase + s * (TC_A_BYTES + TC_B_BYTES) + a_row_off); \
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
-                tc_mbar_arrive(a_full + 8 * s); ++it; } while (0)
-            if (A.type == B200_Q4_K) {
-                RawQ4K cur, nxt;
-                raw_load(cur, wrow);
-                for (int64_t kb = 0; kb < nkb; ++kb) {
-                    if (kb + 1 < nkb) raw_load(nxt, wrow + (kb + 1) * 144);
-                    TC_STAGE_STEP(0, cur); TC_STAGE_STEP(1, cur); TC_STAGE_STEP(2, cur); TC_STAGE_STEP(3, cur);
-                    cur = nxt;
-                }
-            } else {
-                const uint8_t * drow = A.wd + gr * nkb * 2;
-                RawQ6K cur, nxt;
-                raw_load(cur, wrow, drow, hf);
-                for (int64_t kb = 0; kb < nkb; ++kb) {
-                    if (kb + 1 < nkb) raw_load(nxt, wrow + (kb + 1) * 208, drow + (kb + 1) * 2, hf);
-                    TC_STAGE_STEP(0, cur); TC_STAGE_STEP(1, cur); TC_STAGE_STEP(2, cur); TC_STAGE_STEP(3, cur);
-                    cur = nxt;
-                }
-            }
-#undef TC_STAGE_STEP
+            int64_t gr = (int64_t) mt * TC_M + row; if (gr >= A.m) gr = A.m - 1;        // tail rows (zero-filled by TMA): any valid d, never stored
+            if (A.type == B200_Q4_K) tc_produce_tile<RawQ4K, 144>(raw0 + row * 144, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags);
+            else                     tc_produce_tile<RawQ6K, 208>(raw0 + row * 208, A.wd + gr * nkb * 2, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags);
         }
     } else if (warp == 8) {
         // ================================================================== B producer (TMA bulk copies of pre-tiled F16 activations)
@@ -251,6 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const uint32_t s = it % TC_STAGES;
                     tc_mbar_wait(empty + 8 * s, ((it / TC_STAGES) & 1) ^ 1);
+                    if (A.flags & 4) { tc_mbar_arrive(b_full + 8 * s); continue; }
                     tc_mbar_expect_tx(b_full + 8 * s, TC_B_BYTES);
                     const uint32_t dst = sbase + s * (TC_A_BYTES + TC_B_BYTES) + TC_A_BYTES;
 #pragma unroll
@@ -277,10 +309,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
                     const uint32_t a_s = sbase + s * (TC_A_BYTES + TC_B_BYTES), b_s = a_s + TC_A_BYTES;
 #pragma unroll
                     for (int j = 0; j < TC_K / 16; ++j)
-                        tc_mma(d_tmem, tc_desc(a_s + j * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), tc_desc(b_s + j * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), idesc, (kc | j) != 0);
+                        if (!(A.flags & 2)) tc_mma(d_tmem, tc_desc(a_s + j * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), tc_desc(b_s + j * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), idesc, (kc | j) != 0);
                     tc_commit(empty + 8 * s);                                 // frees the stage when these MMAs have read it
                 }
                 tc_commit(t_full + 8 * acc);                                  // accumulator complete
+            }
+        }
+    } else if (warp == 14) {
+        // ================================================================== raw weight producer: one 2-D TMA (128 rows x one quant block) per 4 stages
+        if (lane == 0) {
+            const int blk = A.type == B200_Q4_K ? 144 : 208;
+            const int nkb = (int) (A.k >> 8);
+            uint32_t ru = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int mt = t % A.tiles_m;
+                for (int kb = 0; kb < nkb; ++kb, ++ru) {
+                    const uint32_t r = ru % TC_RAW;
+                    tc_mbar_wait(raw_empty + 8 * r, ((ru / TC_RAW) & 1) ^ 1);
+                    tc_mbar_expect_tx(raw_full + 8 * r, (uint32_t) (TC_M * blk));
+                    tc_tma_2d(raw0 + r * TC_RAW_BYTES, &wmap, kb * blk, mt * TC_M, raw_full + 8 * r);
+                }
             }
         }
     } else {
@@ -321,20 +369,44 @@ bool mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w
 }
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n) { return (size_t) ((n + TC_N - 1) / TC_N * TC_N) * (size_t) k * 2; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*tc_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tc_encode_fn tc_encoder() {
+    static tc_encode_fn fn = [] {
+        void * p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (tc_encode_fn) p;
+    }();
+    return fn;
+}
+
 int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, cudaStream_t st) {
     static int once = 0;
     if (!once) { B200_CUDA_TRY(cudaFuncSetAttribute(k_mmq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); once = 1; }
+    if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
+    // the payload plane as a 2-D byte tensor [m rows][row bytes]; box = one quant block x 128 rows
+    CUtensorMap wmap;
+    {
+        const cuuint64_t blk = type == B200_Q4_K ? 144 : 208, rowb = (cuuint64_t) (k / 256) * blk;
+        const cuuint64_t gdim[2] = { rowb, (cuuint64_t) m }, gstr[1] = { rowb };
+        const cuuint32_t box[2] = { (cuuint32_t) blk, TC_M }, estr[2] = { 1, 1 };
+        if (tc_encoder()(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *) w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         (getenv("B200_TC_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B200_ERR_UNSUPPORTED;
+    }
     const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
     k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
     B200_LAUNCH_CHECK();
     TcArgs A = {};
+    static const int env_flags = getenv("B200_TC_FLAGS") ? atoi(getenv("B200_TC_FLAGS")) : 0;
+    A.flags = env_flags;
     const int64_t nkb = k / 256;
     A.w = (const uint8_t *) w; A.type = type; A.m = m; A.k = k; A.n = n; A.dst = dst; A.dst_ld = dst_ld; A.x16 = (const uint8_t *) scratch;
     if (type == B200_Q4_K) { A.row_bytes = nkb * 144; A.wd = nullptr; }
     else                   { A.row_bytes = nkb * 208; A.wd = (const uint8_t *) w + m * nkb * 208; }
     A.tiles_m = (int) ((m + TC_M - 1) / TC_M); A.tiles_n = (int) (n_pad / TC_N);
     int grid = A.tiles_m * A.tiles_n; if (grid > sm_count()) grid = sm_count();
-    k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A);
+    k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A, wmap);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
