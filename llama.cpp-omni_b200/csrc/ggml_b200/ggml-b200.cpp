@@ -60,6 +60,11 @@ struct BackendCtx {
     std::vector<uint64_t> graph_key, pending_key;
     cudaGraphExec_t graph_exec = nullptr;
     bool graphs_enabled = true;
+    // whole-token decode engine (b200_decoder_*): built when a batch-1 graph matches the llama-family decoder pattern (match_decoder)
+    void * engine = nullptr; int32_t engine_n_kv = 0;
+    std::vector<uint64_t> engine_key, engine_reject_key;
+    std::vector<ggml_tensor *> engine_pre;                   // nodes still run per-op before the engine step (the KQ-mask cast)
+    bool engine_enabled = true;
 };
 
 DeviceCtx g_devices[MAX_DEVICES];
@@ -438,6 +443,166 @@ enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
     return GGML_STATUS_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------------------------------------------- decode-engine matcher
+// Recognise the batch-1 graph llm_build_qwen3 / llm_build_llama emit (src/llama-model.cpp:9287-9406, build_attn src/llama-graph.cpp:1546-1597,
+// build_ffn :713-819, cpy_k / cpy_v src/llama-kv-cache.cpp:1021-1110) by DATAFLOW, walking back from the last node, and describe it as a
+// b200_decode_desc: the whole split then runs as ONE persistent kernel (csrc/stream_decode.cu) instead of ~24 launches per layer.  Every
+// compute node of the graph must be accounted for, otherwise the graph keeps the per-op path (LoRA, biases, control vectors, other archs).
+bool is_view_op(const ggml_tensor * t) {
+    return t->op == GGML_OP_RESHAPE || t->op == GGML_OP_VIEW || t->op == GGML_OP_PERMUTE || t->op == GGML_OP_TRANSPOSE;
+}
+const ggml_tensor * strip_views(const ggml_tensor * t) {       // the compute node behind a chain of whole-tensor views
+    while (t && is_view_op(t)) { if (ggml_nelements(t) != ggml_nelements(t->src[0])) return nullptr; t = t->src[0]; }
+    return t;
+}
+bool is_weight(const ggml_tensor * t) { return t && t->buffer && t->buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS && t->op == GGML_OP_NONE; }
+
+struct DecoderMatch {
+    std::vector<b200_decode_layer> layers;                    // filled back to front, reversed at the end
+    b200_decode_desc d = {};
+    std::vector<ggml_tensor *> pre;
+    int n_matched = 0; int32_t n_kv = 0;
+    float eps = -1.0f; bool have_rope = false;
+    const ggml_tensor * pos = nullptr, * idx = nullptr, * mask = nullptr;
+};
+
+b200_weight weight_of(const ggml_tensor * w) { b200_weight r; r.data = w->data; r.type = (int32_t) w->type; r.layout = is_planar(w) ? B200_LAYOUT_PLANAR : B200_LAYOUT_NATIVE; return r; }
+
+// y = MUL_MAT(w, x) with a 2-D weight and ONE activation column
+bool m_mul_mat(const ggml_tensor * y, const ggml_tensor *& w, const ggml_tensor *& x, DecoderMatch & M) {
+    if (!y || y->op != GGML_OP_MUL_MAT || !is_weight(y->src[0]) || y->src[0]->ne[2] != 1 || y->src[0]->ne[3] != 1 || ggml_nelements(y->src[1]) != y->src[0]->ne[0]) return false;
+    if (y->flags & GGML_TENSOR_FLAG_OUTPUT) { /* only the logits may be an output; checked by the caller */ }
+    w = y->src[0]; x = y->src[1]; ++M.n_matched;
+    return true;
+}
+// y = MUL(RMS_NORM(x), w): build_norm (src/llama-graph.cpp:660-695)
+bool m_norm(const ggml_tensor * y, const ggml_tensor *& x, const ggml_tensor *& w, DecoderMatch & M) {
+    if (!y || y->op != GGML_OP_MUL) return false;
+    const ggml_tensor * n = y->src[0], * wt = y->src[1];
+    if (!n || n->op != GGML_OP_RMS_NORM || !is_weight(wt) || wt->type != GGML_TYPE_F32 || !ggml_is_contiguous(wt) || wt->ne[0] != n->ne[0] || ggml_nelements(wt) != wt->ne[0]) return false;
+    const float eps = fparam(n, 0);
+    if (M.eps >= 0.0f && eps != M.eps) return false;
+    M.eps = eps; x = n->src[0]; w = wt; M.n_matched += 2;
+    return true;
+}
+// t = ROPE([MUL(RMS_NORM(.), nw)] reshape(MUL_MAT(w, a)), pos): one of Qcur / Kcur
+bool m_qk(const ggml_tensor * t, const ggml_tensor *& w, const ggml_tensor *& a, const ggml_tensor *& nw, DecoderMatch & M) {
+    t = strip_views(t);
+    if (!t || t->op != GGML_OP_ROPE || t->src[2] != nullptr || !t->src[1] || t->src[1]->type != GGML_TYPE_I32 || ggml_nelements(t->src[1]) != 1) return false;
+    b200_rope_params p;
+    p.n_dims = iparam(t, 1); p.mode = iparam(t, 2); p.n_ctx_orig = iparam(t, 4);
+    p.freq_base = fparam(t, 5); p.freq_scale = fparam(t, 6); p.ext_factor = fparam(t, 7); p.attn_factor = fparam(t, 8); p.beta_fast = fparam(t, 9); p.beta_slow = fparam(t, 10);
+    if (M.have_rope && memcmp(&p, &M.d.rope, sizeof(p)) != 0) return false;
+    if (M.pos && M.pos != t->src[1]) return false;
+    M.d.rope = p; M.have_rope = true; M.pos = t->src[1]; ++M.n_matched;
+    const ggml_tensor * in = strip_views(t->src[0]);
+    nw = nullptr;
+    if (in && in->op == GGML_OP_MUL) { const ggml_tensor * x = nullptr; if (!m_norm(in, x, nw, M)) return false; in = strip_views(x); }
+    return m_mul_mat(in, w, a, M);
+}
+
+bool match_decoder(const ggml_cgraph * g, DecoderMatch & M) {
+    const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+    if (nn < 8) return false;
+    int n_real = 0;
+    std::unordered_map<const void *, const ggml_tensor *> set_rows;                 // cache tensor data -> SET_ROWS node writing it
+    for (int i = 0; i < nn; ++i) {
+        const ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, i);
+        if (is_noop(n)) continue;
+        ++n_real;
+        if (n->op == GGML_OP_SET_ROWS) { if (!n->src[0] || !n->view_src) return false; set_rows[n->view_src->data] = n; }
+    }
+    const ggml_tensor * last = ggml_graph_node((ggml_cgraph *) g, nn - 1);
+    const ggml_tensor * x = nullptr;                                                 // residual stream, walking backwards
+    if (last->op == GGML_OP_MUL_MAT) {                                               // result_output = output . (RMS_NORM(x) * output_norm)
+        const ggml_tensor * w = nullptr, * h = nullptr, * nw = nullptr;
+        if (!m_mul_mat(last, w, h, M) || !m_norm(h, x, nw, M)) return false;
+        M.d.lm_head = weight_of(w); M.d.out_norm = (const float *) nw->data; M.d.logits = (float *) last->data; M.d.hidden_out = (float *) h->data;
+        M.d.n_vocab = (int32_t) w->ne[1];
+    } else if (last->op == GGML_OP_ADD) { x = last; M.d.x_out = (float *) last->data; }
+    else return false;
+
+    while (x && x->op == GGML_OP_ADD) {
+        b200_decode_layer L = {};
+        // ---- l_out = ffn_out + ffn_inp;  ffn_out = down . swiglu(gate . f, up . f);  f = RMS_NORM(ffn_inp) * ffn_norm
+        ++M.n_matched;
+        const ggml_tensor * ffn_inp = x->src[1], * w = nullptr, * h = nullptr, * f = nullptr, * f2 = nullptr, * nw = nullptr, * nx = nullptr;
+        if (!m_mul_mat(x->src[0], w, h, M)) return false;
+        L.down = weight_of(w); M.d.n_ff = (int32_t) w->ne[0];
+        if (!h || h->op != GGML_OP_GLU || ggml_get_glu_op(h) != GGML_GLU_OP_SWIGLU || !h->src[1] || iparam(h, 1) != 0) return false;
+        ++M.n_matched;
+        if (!m_mul_mat(h->src[0], w, f, M)) return false;
+        L.gate = weight_of(w);
+        if (!m_mul_mat(h->src[1], w, f2, M) || f2 != f) return false;
+        L.up = weight_of(w);
+        if (!m_norm(f, nx, nw, M) || nx != ffn_inp) return false;
+        L.ffn_norm = (const float *) nw->data;
+        // ---- ffn_inp = wo . attn + inpL   (last layer of a full model: both through an identity GET_ROWS of the single output row)
+        if (!ffn_inp || ffn_inp->op != GGML_OP_ADD) return false;
+        ++M.n_matched;
+        const ggml_tensor * proj = ffn_inp->src[0], * inpL = ffn_inp->src[1];
+        if (proj && proj->op == GGML_OP_GET_ROWS && inpL && inpL->op == GGML_OP_GET_ROWS) {
+            if (proj->src[0]->ne[1] != 1 || inpL->src[0]->ne[1] != 1 || ggml_nelements(proj->src[1]) != 1 || proj->src[1] != inpL->src[1]) return false;
+            proj = proj->src[0]; inpL = inpL->src[0]; M.n_matched += 2;
+        }
+        const ggml_tensor * kqv = nullptr;
+        if (!m_mul_mat(proj, w, kqv, M)) return false;
+        L.wo = weight_of(w); M.d.n_embd = (int32_t) w->ne[1];
+        const ggml_tensor * fa = strip_views(kqv);
+        if (!fa || fa->op != GGML_OP_FLASH_ATTN_EXT || fa->src[4] || fparam(fa, 1) != 0.0f || fparam(fa, 2) != 0.0f) return false;
+        ++M.n_matched;
+        const ggml_tensor * q = fa->src[0], * k = fa->src[1], * v = fa->src[2], * mask = fa->src[3];
+        if (!q || !k || !v || !mask || mask->type != GGML_TYPE_F16 || k->type != GGML_TYPE_F16 || v->type != GGML_TYPE_F16) return false;
+        if (q->ne[1] != 1 || q->ne[3] != 1 || k->ne[3] != 1) return false;
+        const int64_t D = q->ne[0], H = q->ne[2], HK = k->ne[2];
+        if (k->nb[2] != D * 2 || v->nb[2] != D * 2 || k->ne[1] != v->ne[1] || mask->ne[0] != k->ne[1]) return false;        // heads side by side inside a cache row
+        if (M.mask && M.mask != mask) return false;
+        if (M.n_kv && M.n_kv != (int32_t) k->ne[1]) return false;
+        M.mask = mask; M.n_kv = (int32_t) k->ne[1];
+        M.d.head_dim = (int32_t) D; M.d.n_head = (int32_t) H; M.d.n_head_kv = (int32_t) HK; M.d.attn_scale = fparam(fa, 0);
+        L.k_cache = k->data; L.v_cache = v->data; L.k_row_bytes = (int64_t) k->nb[1]; L.v_row_bytes = (int64_t) v->nb[1];
+        const ggml_tensor * a = nullptr, * a2 = nullptr, * qn = nullptr, * kn = nullptr;
+        if (!m_qk(q, w, a, qn, M)) return false;
+        L.wq = weight_of(w);
+        // ---- KV-cache writes of this layer: SET_ROWS into the tensors the attention reads
+        auto ik = set_rows.find(k->data), iv = set_rows.find(v->data);
+        if (ik == set_rows.end() || iv == set_rows.end()) return false;
+        const ggml_tensor * sk = ik->second, * sv = iv->second;
+        if (sk->type != GGML_TYPE_F16 || sv->type != GGML_TYPE_F16 || (int64_t) sk->nb[1] != L.k_row_bytes || (int64_t) sv->nb[1] != L.v_row_bytes) return false;
+        if (sk->src[1]->type != GGML_TYPE_I64 || ggml_nelements(sk->src[1]) != 1 || ggml_nelements(sv->src[1]) != 1 || sv->src[1]->type != GGML_TYPE_I64) return false;
+        if (M.idx && M.idx != sk->src[1]) return false;
+        M.idx = sk->src[1];                                                          // v_idxs holds the same cell index when V is not transposed
+        M.n_matched += 2;
+        if (!m_qk(sk->src[0], w, a2, kn, M) || a2 != a) return false;
+        L.wk = weight_of(w);
+        if (!m_mul_mat(strip_views(sv->src[0]), w, a2, M) || a2 != a) return false;
+        L.wv = weight_of(w);
+        if ((qn == nullptr) != (kn == nullptr)) return false;
+        L.q_norm = qn ? (const float *) qn->data : nullptr; L.k_norm = kn ? (const float *) kn->data : nullptr;
+        // ---- a = RMS_NORM(inpL) * attn_norm
+        if (!m_norm(a, nx, nw, M) || nx != inpL) return false;
+        L.attn_norm = (const float *) nw->data;
+        M.layers.push_back(L);
+        x = inpL;
+    }
+    if (!x || M.layers.empty() || !M.pos || !M.idx || !M.mask) return false;
+    if (x->op != GGML_OP_NONE && !is_view_op(x)) return false;                      // the split's input: token embedding row or the previous stage's l_out
+    if (x->type != GGML_TYPE_F32 || ggml_nelements(x) != M.d.n_embd || !ggml_is_contiguous(x)) return false;
+    M.d.x_in = (const float *) x->data;
+    if (M.mask->op == GGML_OP_CPY) { M.pre.push_back((ggml_tensor *) M.mask); ++M.n_matched; }       // the F32 -> F16 cast of the KQ mask stays a per-op launch
+    else if (M.mask->op != GGML_OP_NONE) return false;
+    if (M.n_matched != n_real) return false;                                        // something in the graph is not part of the pattern
+    for (int i = 0; i < nn; ++i) {                                                   // only the logits / result_norm may be graph outputs
+        const ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, i);
+        if ((n->flags & GGML_TENSOR_FLAG_OUTPUT) && n != last && (void *) n->data != (void *) M.d.hidden_out) return false;
+    }
+    std::vector<b200_decode_layer> fwd(M.layers.rbegin(), M.layers.rend());
+    M.layers.swap(fwd);
+    M.d.n_layer = (int32_t) M.layers.size(); M.d.layers = M.layers.data(); M.d.rms_eps = M.eps;
+    M.d.pos = (const int32_t *) M.pos->data; M.d.kv_idx = (const int64_t *) M.idx->data; M.d.mask = M.mask->data;
+    return true;
+}
+
 // The properties that decide whether a captured graph can be replayed (what the reference compares in
 // ggml_cuda_graph_update_required / is_cuda_graph_update_required, ggml-cuda.cu:2800-2900): op, addresses, shapes, strides, op params.
 void graph_key_of(const ggml_cgraph * g, std::vector<uint64_t> & key) {
@@ -477,6 +642,28 @@ enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph 
     scratch_for(c, need);                                            // no allocation may happen while capturing
     std::vector<uint64_t> key;
     graph_key_of(g, key);
+    // ---- whole-token decode engine: one persistent kernel for the split when it is the llama-family batch-1 decoder pattern
+    if (c->engine_enabled) {
+        if (c->engine && key == c->engine_key) {
+            for (ggml_tensor * n : c->engine_pre) { int rc = 0; run_node(c, g, n, nullptr, rc); if (rc != B200_OK) return GGML_STATUS_FAILED; }
+            const int rc = b200_decoder_step(c->engine, c->engine_n_kv, c->stream);
+            if (rc != B200_OK) { B200_LOG("decoder step failed: %s", b200_error_string(rc)); return GGML_STATUS_FAILED; }
+            return GGML_STATUS_SUCCESS;
+        }
+        if (key != c->engine_reject_key) {
+            DecoderMatch M;
+            void * h = nullptr;
+            if (match_decoder(g, M) && b200_decoder_create(&M.d, &h) == B200_OK) {
+                if (c->engine) { CUDA_OK(cudaStreamSynchronize(c->stream)); b200_decoder_destroy(c->engine); }
+                c->engine = h; c->engine_n_kv = M.n_kv; c->engine_pre = M.pre; c->engine_key = key;
+                for (ggml_tensor * n : c->engine_pre) { int rc = 0; run_node(c, g, n, nullptr, rc); if (rc != B200_OK) return GGML_STATUS_FAILED; }
+                const int rc = b200_decoder_step(c->engine, c->engine_n_kv, c->stream);
+                if (rc != B200_OK) { B200_LOG("decoder step failed: %s", b200_error_string(rc)); return GGML_STATUS_FAILED; }
+                return GGML_STATUS_SUCCESS;
+            }
+            c->engine_reject_key = key;                              // not the pattern (or unsupported types): remember, use the per-op path
+        }
+    }
     if (c->graph_exec && key == c->graph_key) {
         CUDA_OK(cudaGraphLaunch(c->graph_exec, c->stream));
         return GGML_STATUS_SUCCESS;
@@ -510,6 +697,7 @@ void b200_backend_free(ggml_backend_t backend) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->engine) b200_decoder_destroy(c->engine);
     if (c->scratch) cudaFree(c->scratch);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -617,6 +805,7 @@ ggml_backend_t b200_dev_init_backend(ggml_backend_dev_t dev, const char *) {
     BackendCtx * c = new BackendCtx(); c->device = d->index; c->name = d->name;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
     if (const char * e = getenv("GGML_B200_DISABLE_GRAPHS")) c->graphs_enabled = atoi(e) == 0;
+    if (const char * e = getenv("GGML_B200_DISABLE_ENGINE")) c->engine_enabled = atoi(e) == 0;
     ggml_backend * b = new ggml_backend;
     b->guid = b200_guid(); b->iface = b200_backend_iface; b->device = dev; b->context = c;
     return b;

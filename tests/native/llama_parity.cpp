@@ -72,7 +72,9 @@ int main(int argc, char ** argv) {
     const int self_mode = argc > 6 ? atoi(argv[6]) : 0;                 // 1: repacked weights; 2: plain weights, 3 threads (must be bit-identical)
     // 3: CPU batched prompt vs CPU one-token-at-a-time prompt; 4: B200 batched vs B200 one-at-a-time (baseline run also on the GPU)
     if (self_mode == 4) cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false);
-    Run gpu = run(argv[1], cpu_self || self_mode == 2 || self_mode == 3 ? 0 : 999, n_prompt, n_gen, self_mode == 2 ? 3 : nt, fa, &cpu.toks, cpu_self, self_mode >= 3);
+    // 5: B200 per-op launches (baseline) vs B200 whole-token decode engine — the plugin reads GGML_B200_DISABLE_ENGINE when a backend is created
+    if (self_mode == 5) { setenv("GGML_B200_DISABLE_ENGINE", "1", 1); cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false); setenv("GGML_B200_DISABLE_ENGINE", "0", 1); }
+    Run gpu = run(argv[1], cpu_self || self_mode == 2 || self_mode == 3 ? 0 : 999, n_prompt, n_gen, self_mode == 2 ? 3 : nt, fa, &cpu.toks, cpu_self, self_mode == 3 || self_mode == 4);
     if (!cpu.ok || !gpu.ok) { printf("{\"error\": \"run failed\"}\n"); return 4; }
     int first = -1; double max_rel = 0, pre_rel = 0; double step_rel[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n_gen; ++i) if (cpu.toks[i] != gpu.toks[i] && first < 0) first = i;
