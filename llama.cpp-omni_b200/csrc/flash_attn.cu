@@ -218,6 +218,12 @@ static int fa_launch(const FaArgs & A, int G, int64_t nz, cudaStream_t st) {
     return B200_OK;
 }
 
+// fa_prefill.cu: tensor-core tiles for >= 16 query tokens
+bool   fa_prefill_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst);
+size_t fa_prefill_scratch_bytes(const b200_tensor * q, const b200_tensor * mask_or_null, int64_t m_ne3);
+int    fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
+                  void * scratch, cudaStream_t st);
+
 } // namespace b200
 
 using namespace b200;
@@ -244,6 +250,7 @@ extern "C" int b200_flash_attn_supported(const b200_tensor * q, const b200_tenso
 extern "C" size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b200_tensor * k) {
     const int64_t nz = q->ne[1] * q->ne[3];
     if (nz == 0 || k->ne[1] == 0 || k->ne[2] == 0) return 0;
+    if (q->ne[1] >= 16) return fa_prefill_scratch_bytes(q, nullptr, q->ne[3]);     // upper bound for the KV-tile counts (mask batch <= q batch)
     const FaPlan P = fa_plan(nz, k->ne[1], q->ne[2], k->ne[2]);
     if (P.splits <= 1) return 0;
     const size_t slots = (size_t) nz * q->ne[2] * P.splits;
@@ -256,6 +263,10 @@ extern "C" int b200_flash_attn(const b200_tensor * q, const b200_tensor * k, con
     if (!b200_flash_attn_supported(q, k, v, mask, dst) || max_bias != 0.0f || logit_softcap != 0.0f) return B200_ERR_UNSUPPORTED;
     const int64_t nz = q->ne[1] * q->ne[3];
     if (nz == 0 || q->ne[2] == 0) return B200_OK;
+    if (k->ne[1] > 0 && fa_prefill_supported(q, k, v, mask, dst)) {
+        const bool have = scratch && scratch_bytes >= fa_prefill_scratch_bytes(q, mask, mask ? mask->ne[3] : 1) && (uintptr_t) scratch % 4 == 0;
+        return fa_prefill(q, k, v, mask, dst, scale, have ? scratch : nullptr, (cudaStream_t) stream);
+    }
     if (nz > 65535) return B200_ERR_UNSUPPORTED;
     const FaPlan P = fa_plan(nz, k->ne[1], q->ne[2], k->ne[2]);
     FaArgs A = {};

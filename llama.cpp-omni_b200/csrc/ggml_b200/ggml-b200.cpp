@@ -218,6 +218,35 @@ size_t b200_buft_max_size(ggml_backend_buffer_type_t) { return SIZE_MAX; }
 size_t b200_buft_alloc_size(ggml_backend_buffer_type_t, const ggml_tensor * t) { return (ggml_nbytes(t) + 255) & ~(size_t) 255; }   // planar == native in bytes
 bool   b200_buft_is_host(ggml_backend_buffer_type_t) { return false; }
 
+// ---------------------------------------------------------------------------------------------------------------- pinned host buffer type
+// What ggml_backend_cuda_host_buffer_type gives the reference (ggml-cuda.cu:1100-1156): llama allocates its output (logits) buffer and the CPU
+// backend's compute buffer in the device's host buffer type, so that the per-token H2D input copies and the logits D2H are DMA transfers from
+// page-locked memory.  The buffer behaves like a plain CPU buffer (ggml_backend_cpu_buffer_from_ptr); only allocation and free differ.
+const char * b200_host_buft_get_name(ggml_backend_buffer_type_t) { return "B200_Host"; }
+void b200_host_buf_free(ggml_backend_buffer_t buffer) { cudaFreeHost(buffer->context); }
+ggml_backend_buffer_t b200_host_buft_alloc(ggml_backend_buffer_type_t buft, size_t size) {
+    void * ptr = nullptr;
+    if (getenv("GGML_B200_NO_PINNED") || cudaMallocHost(&ptr, size ? size : 1) != cudaSuccess) {
+        (void) cudaGetLastError();
+        return ggml_backend_buft_alloc_buffer(ggml_backend_cpu_buffer_type(), size);      // pageable fallback, still correct
+    }
+    ggml_backend_buffer_t buffer = ggml_backend_cpu_buffer_from_ptr(ptr, size);
+    buffer->buft = buft;
+    buffer->iface.free_buffer = b200_host_buf_free;
+    return buffer;
+}
+size_t b200_host_buft_alignment(ggml_backend_buffer_type_t) { return 64; }
+bool   b200_host_buft_is_host(ggml_backend_buffer_type_t) { return true; }
+ggml_backend_buffer_type g_host_buft = {};
+ggml_backend_buffer_type_t b200_dev_get_host_buffer_type(ggml_backend_dev_t dev) {
+    static std::once_flag once;
+    std::call_once(once, [dev] {
+        g_host_buft.iface = { b200_host_buft_get_name, b200_host_buft_alloc, b200_host_buft_alignment, nullptr, nullptr, b200_host_buft_is_host };
+        g_host_buft.device = dev; g_host_buft.context = nullptr;
+    });
+    return &g_host_buft;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- supports_op
 bool f32c(const ggml_tensor * t) { return t && t->type == GGML_TYPE_F32 && t->nb[0] == sizeof(float); }
 bool floaty(const ggml_tensor * t) { return t && (t->type == GGML_TYPE_F32 || t->type == GGML_TYPE_F16 || t->type == GGML_TYPE_BF16); }
@@ -796,7 +825,7 @@ void b200_dev_get_props(ggml_backend_dev_t dev, ggml_backend_dev_props * props) 
     props->name = d->name.c_str(); props->description = d->description.c_str(); props->type = GGML_BACKEND_DEVICE_TYPE_GPU;
     props->device_id = d->pci_id.empty() ? nullptr : d->pci_id.c_str();      // used by llama.cpp to de-duplicate devices (llama.cpp:208-229)
     b200_dev_get_memory(dev, &props->memory_free, &props->memory_total);
-    props->caps.async = true; props->caps.host_buffer = false; props->caps.buffer_from_host_ptr = false; props->caps.events = true;
+    props->caps.async = true; props->caps.host_buffer = true; props->caps.buffer_from_host_ptr = false; props->caps.events = true;
 }
 
 ggml_backend_t b200_dev_init_backend(ggml_backend_dev_t dev, const char *) {
@@ -812,6 +841,7 @@ ggml_backend_t b200_dev_init_backend(ggml_backend_dev_t dev, const char *) {
 }
 ggml_backend_buffer_type_t b200_dev_get_buffer_type(ggml_backend_dev_t dev) { return &((DeviceCtx *) dev->context)->buft; }
 bool b200_dev_supports_buft(ggml_backend_dev_t dev, ggml_backend_buffer_type_t buft) {
+    // (the pinned host type is for the CPU backend's tensors: our kernels take device pointers only, so it is NOT a buffer type we compute from)
     return buft->iface.get_name == b200_buft_get_name && buft->device == dev;
 }
 bool b200_dev_offload_op(ggml_backend_dev_t, const ggml_tensor * op) {
@@ -836,7 +866,7 @@ const ggml_backend_device_i b200_device_iface = {
     /* get_props            */ b200_dev_get_props,
     /* init_backend         */ b200_dev_init_backend,
     /* get_buffer_type      */ b200_dev_get_buffer_type,
-    /* get_host_buffer_type */ nullptr,
+    /* get_host_buffer_type */ b200_dev_get_host_buffer_type,
     /* buffer_from_host_ptr */ nullptr,
     /* supports_op          */ b200_dev_supports_op,
     /* supports_buft        */ b200_dev_supports_buft,

@@ -447,6 +447,38 @@ def test_flash_attn_small_batch_causal(ops):
     assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-6
 
 
+@pytest.mark.parametrize("n_q,n_kv,past,D,n_head,n_head_kv", [(512, 512, 0, 128, 8, 2), (300, 768, 411, 128, 8, 2), (64, 256, 150, 64, 6, 6),
+                                                             (17, 100, 83, 128, 4, 1), (2048, 2048, 0, 128, 4, 1)])
+def test_flash_attn_prefill_tensor_core(ops, n_q, n_kv, past, D, n_head, n_head_kv):
+    """>= 16 query tokens -> k_fa_prefill (mma.sync tiles, csrc/fa_prefill.cu): causal mask over a cache with `past` earlier positions, ragged
+    sizes, GQA.  P is rounded to f16 for the P.V product (as in the reference's fattn-mma-f16), so the bar is the reference's own
+    FLASH_ATTN_EXT bar, NMSE <= 5e-4 (tests/test-backend-ops.cpp:5085), plus a tighter elementwise bound against the f32 oracle."""
+    rng = np.random.default_rng(n_q + n_kv + D)
+    q = rng.standard_normal((n_q, n_head, D)).astype(np.float32)
+    k = (rng.standard_normal((n_head_kv, n_kv, D)) * 0.5).astype(np.float16)
+    v = rng.standard_normal((n_head_kv, n_kv, D)).astype(np.float16)
+    n_q_pad = (n_q + 63) // 64 * 64
+    mask = np.zeros((n_q_pad, n_kv), np.float16)
+    for i in range(n_q):
+        mask[i, past + i + 1:] = -np.inf
+    mask[n_q:] = -np.inf
+    scale = 1.0 / np.sqrt(D)
+    got = ops.flash_attn(dev(q).permute(1, 0, 2), dev(k), dev(v), dev(mask), scale).cpu().numpy()
+    assert np.isfinite(got).all()
+    if n_q * n_kv * n_head <= 2 ** 23:
+        ref = O.flash_attn(q, k, v, mask, scale, f16_acc=False)
+    else:                                     # the C oracle is O(n_q n_kv): use it on a sample of query rows, f64 torch for all of them
+        rows = np.unique(np.concatenate([np.arange(4), np.arange(n_q - 4, n_q), rng.integers(0, n_q, 24)]))
+        sub = O.flash_attn(q[rows], k, v, mask[rows], scale, f16_acc=False)
+        assert nmse(got[rows], sub) <= 5e-4 and np.abs(got[rows] - sub).max() <= 4e-3 * np.abs(sub).max()
+        qt = dev(q).half().double().permute(1, 0, 2)                                     # the oracle rounds Q to f16
+        kt, vt = dev(k).double().repeat_interleave(n_head // n_head_kv, 0), dev(v).double().repeat_interleave(n_head // n_head_kv, 0)
+        sc = qt @ kt.transpose(1, 2) * scale + dev(mask[:n_q]).double()[None]
+        ref = (torch.softmax(sc, -1) @ vt).permute(1, 0, 2).cpu().numpy()
+    assert nmse(got, ref) <= 5e-4, nmse(got, ref)
+    assert np.abs(got - ref).max() <= 4e-3 * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
+
+
 def test_qkv_post_matches_separate_ops(ops):
     """b200_qkv_post == rms_norm*w -> rope -> set_rows run as separate C-ABI calls (Qwen3 shapes; 2 tokens)."""
     rng = np.random.default_rng(13)
