@@ -264,6 +264,12 @@ def run_b200(args) -> None:
     kv_bytes = dec.kv_bytes_per_token(cfg, n_kv, layers)
     step_bytes = (w_bytes + kv_bytes) * n_streams
     achieved = step_bytes / (ms_step / 1e3) / 1e9
+    traffic = None                                          # dram bytes of one k_stream launch from the committed ncu capture of this workload
+    tf = ROOT / "profiles" / "k_stream_traffic.json"
+    if engine and world == 1 and tf.exists():
+        t = json.loads(tf.read_text())
+        if t.get("n_kv") == n_kv and not args.tiny:
+            traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
     line = {"metric": "decode_tok_per_s", "value": round(value, 2), "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations), f16 KV", "data": "synthetic",
@@ -274,10 +280,12 @@ def run_b200(args) -> None:
             "gpu_launches": launches * args.steps * n_streams,
             "e2e": {"value": round(e2e_value, 2), "unit": "tok/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "peak_source": peak_src, "bytes_per_step": int(step_bytes),
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_step": int(step_bytes),
                          "kernel": ("k_stream (persistent decode engine: all weight matvecs + attention of the token in one launch)" if engine else
                                     "k_stream / k_mmvq per-op launches + k_fa_decode") + ": algorithmic weight+KV bytes of one token / graph-replay time"},
             "clocks": clk}
+    if rank == 0 and world == 1 and not args.no_prefill and not args.tiny:
+        line["prefill"] = prefill_leg(D, cfg, dec, torch, dev, args.prefill_tokens)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = reference_layer_sample(cfg, 1, os.cpu_count() or 1, 3, 1)
@@ -286,6 +294,39 @@ def run_b200(args) -> None:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def prefill_leg(D, cfg, dec, torch, dev, n_tokens: int) -> dict:
+    """Second half of BASELINE.json's metric ("prefill tok/s"): ONE ubatch of n_tokens (configs[2]: 2048) through every layer + the last token's
+    lm_head, per-op C-ABI launches exactly as the ggml plugin issues them for an n-token graph; CUDA-event timed, 3 warm-up passes.  The tensor
+    roofline: linear-layer FLOPs (2 x tokens x weight elements) + causal attention FLOPs over the whole pass vs MEASURED_PEAKS bf16_tflops_sustained."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    peak = float(json.loads(p.read_text()).get("bf16_tflops_sustained", 1400.0)) if p.exists() else 1400.0
+    n = min(n_tokens, cfg.n_ctx)
+    n_kv = (n + 255) // 256 * 256
+    x = torch.randn(n, cfg.n_embd, device=dev) * 0.05
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            _, launches = D.prefill(x, 0, n_kv)
+        st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record(st)
+        for _ in range(reps):
+            D.prefill(x, 0, n_kv)
+        e1.record(st)
+        st.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    per_layer = 2 * cfg.n_embd * (cfg.n_head + cfg.n_head_kv) * cfg.head_dim + 3 * cfg.n_embd * cfg.n_ff
+    flops = 2.0 * n * cfg.n_layer * per_layer + cfg.n_layer * 4.0 * cfg.n_head * cfg.head_dim * n * n / 2
+    for lw in D.L:                                   # leave the KV cache as the decode legs expect it
+        lw["k_cache"][:n].normal_(0, 0.5)
+        lw["v_cache"][:n].normal_(0, 1.0)
+    return {"metric": "prefill_tok_per_s", "value": round(n / (ms / 1e3), 1), "unit": "tok/s", "n_tokens": n, "ms": round(ms, 2), "gpu_launches_per_pass": launches,
+            "roofline": {"bound": "tensor", "achieved": round(flops / (ms / 1e3) / 1e12, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(flops / (ms / 1e3) / 1e12 / peak, 4),
+                         "kernel": "whole pass: k_mmq_tc (tcgen05 dequant-GEMM) + k_fa_prefill + elementwise; algorithmic FLOPs = linear + causal attention (SURVEY.md 8d)"},
+            "config": {"workload": f"{cfg.name} prefill n_tokens={n} (one ubatch), empty KV cache"}}
 
 
 def main() -> None:
@@ -297,6 +338,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tiny", action="store_true", help="tiny model (plumbing checks only; not a bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the prefill leg (the extra `prefill` object of the JSON line)")
+    ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--per-op", action="store_true", help="one launch per (fused) op instead of the persistent decode engine")
     args = ap.parse_args()
     if args.impl == "reference":

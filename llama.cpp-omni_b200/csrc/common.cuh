@@ -81,6 +81,16 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// cudaFuncSetAttribute is PER DEVICE: a process that drives several GPUs (the ggml scheduler's layer split) must raise the dynamic
+// shared-memory limit of a kernel on each of them.  `mask` is a per-kernel static bit set of devices already done.
+template <class K> inline cudaError_t ensure_dyn_smem(K kernel, int bytes, unsigned long long & mask) {
+    int dev = 0; cudaGetDevice(&dev);
+    if (mask >> (dev & 63) & 1ull) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) mask |= 1ull << (dev & 63);
+    return e;
+}
+
 inline int sm_count() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }

@@ -223,12 +223,9 @@ size_t fa_prefill_scratch_bytes(const b200_tensor * q, const b200_tensor * mask_
 
 int fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
                void * scratch, cudaStream_t st) {
-    static int once = 0;
-    if (!once) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(k_fa_prefill<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * FP_BN * 128 * 2));
-        B200_CUDA_TRY(cudaFuncSetAttribute(k_fa_prefill<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * FP_BN * 64 * 2));
-        once = 1;
-    }
+    static unsigned long long done128 = 0, done64 = 0;
+    B200_CUDA_TRY(ensure_dyn_smem(k_fa_prefill<128>, 4 * FP_BN * 128 * 2, done128));
+    B200_CUDA_TRY(ensure_dyn_smem(k_fa_prefill<64>, 4 * FP_BN * 64 * 2, done64));
     FaPArgs A = {};
     A.q = (const char *) q->data; A.k = (const char *) k->data; A.v = (const char *) v->data; A.mask = mask ? (const char *) mask->data : nullptr; A.dst = (char *) dst->data;
     A.q_nb1 = q->nb[1]; A.q_nb2 = q->nb[2]; A.q_nb3 = q->nb[3]; A.k_nb1 = k->nb[1]; A.k_nb2 = k->nb[2]; A.k_nb3 = k->nb[3];

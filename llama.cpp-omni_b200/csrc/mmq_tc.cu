@@ -382,8 +382,8 @@ static tc_encode_fn tc_encoder() {
 }
 
 int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, cudaStream_t st) {
-    static int once = 0;
-    if (!once) { B200_CUDA_TRY(cudaFuncSetAttribute(k_mmq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); once = 1; }
+    static unsigned long long done = 0;
+    B200_CUDA_TRY(ensure_dyn_smem(k_mmq_tc, TC_SMEM, done));
     if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
     // the payload plane as a 2-D byte tensor [m rows][row bytes]; box = one quant block x 128 rows
     CUtensorMap wmap;

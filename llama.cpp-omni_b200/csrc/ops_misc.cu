@@ -486,8 +486,8 @@ extern "C" int b200_soft_max(const b200_tensor * x, const b200_tensor * mask, co
     if (mask && ((mask->type != B200_F32 && mask->type != B200_F16) || mask->ne[0] != x->ne[0] || mask->ne[1] < x->ne[1] ||
                  mask->ne[2] == 0 || mask->ne[3] == 0 || x->ne[2] % mask->ne[2] || x->ne[3] % mask->ne[3])) return B200_ERR_UNSUPPORTED;
     if (x->ne[0] > 24576) return B200_ERR_UNSUPPORTED;
-    static bool sm_attr = false;
-    if (!sm_attr) { B200_CUDA_TRY(cudaFuncSetAttribute(k_soft_max, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 * 4)); sm_attr = true; }
+    static unsigned long long sm_attr = 0;
+    B200_CUDA_TRY(ensure_dyn_smem(k_soft_max, 24576 * 4, sm_attr));
     const int64_t rows = nrows(x);
     if (rows == 0 || x->ne[0] == 0) return B200_OK;
     SmArgs A; A.x = t4(x); A.dst = t4(dst); A.has_mask = mask != nullptr; A.mask = mask ? t4(mask) : A.x; A.scale = scale; A.rows = rows;

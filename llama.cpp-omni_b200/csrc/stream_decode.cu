@@ -511,12 +511,9 @@ bool sd_phase_ok(const SdPhase & P) {
 }
 
 static int sd_setup() {
-    static std::once_flag once; static int rc = B200_OK;
-    std::call_once(once, [] {
-        cudaError_t e = cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM_BYTES);
-        if (e != cudaSuccess) rc = -(int) e;
-    });
-    return rc;
+    static unsigned long long done = 0;
+    const cudaError_t e = ensure_dyn_smem(k_stream, SD_SMEM_BYTES, done);
+    return e == cudaSuccess ? B200_OK : -(int) e;
 }
 
 // one launch of the persistent kernel.  phases_dev == nullptr: run `single` (no grid barrier needed -> ordinary launch);

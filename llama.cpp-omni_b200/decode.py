@@ -232,6 +232,57 @@ class Qwen3Decoder:
         self.x_out = self.engine_x_out
         return 2
 
+    # ---- prefill: one ubatch of n tokens through the same C-ABI entry points the ggml plugin calls node by node for an n-token graph -------
+    def prefill(self, x: torch.Tensor, pos0: int, n_kv: int) -> tuple[torch.Tensor, int]:
+        """x [n, n_embd] F32 (embedding rows) at positions pos0 .. pos0+n-1 -> (logits of the LAST token, #launches).  Quantised MUL_MATs with
+        n > 8 columns run on the tcgen05 dequant-GEMM (csrc/mmq_tc.cu), attention on k_fa_prefill (csrc/fa_prefill.cu); KV rows are written."""
+        cfg, L = self.cfg, ops.lib()
+        n, E, F, D = x.shape[0], cfg.n_embd, cfg.n_ff, cfg.head_dim
+        q, kv = cfg.n_head * D, cfg.n_head_kv * D
+        st = ops.stream()
+        dev = self.dev
+        pos = torch.arange(pos0, pos0 + n, dtype=torch.int32, device=dev)
+        idx = pos.to(torch.int64)
+        n_pad = (n + 63) // 64 * 64
+        ar = torch.arange(n_kv, device=dev)[None, :]
+        mask = torch.full((n_pad, n_kv), float("-inf"), device=dev)
+        mask[:n] = torch.where(ar <= pos[:, None].to(torch.int64), 0.0, float("-inf"))
+        mask16 = torch.empty((n_pad, n_kv), dtype=torch.float16, device=dev)
+        ops.cpy(mask, mask16)
+        nl = 1
+        bufs = {k: torch.empty((n, m), device=dev) for k, m in (("a", E), ("q", q), ("k", kv), ("v", kv), ("attn", q), ("x1", E), ("g", F), ("u", F), ("h", F), ("x2", E))}
+        fa_scratch = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+
+        def mm(w, wtype, m, k, xin, out):
+            ops.mul_mat(w, wtype, m, k, xin, layout=ops.LAYOUT_PLANAR if wtype == ops.Q6_K else ops.LAYOUT_NATIVE, out=out)
+        for lw in self.L:
+            ty = lw["types"]
+            ops.rms_norm(x, cfg.rms_eps, w=lw["attn_norm"], out=bufs["a"])
+            mm(lw["wq"], ty["wq"], q, E, bufs["a"], bufs["q"]); mm(lw["wk"], ty["wk"], kv, E, bufs["a"], bufs["k"]); mm(lw["wv"], ty["wv"], kv, E, bufs["a"], bufs["v"])
+            ops.check(L.b200_qkv_post(P(bufs["q"].data_ptr()), P(bufs["k"].data_ptr()), P(bufs["v"].data_ptr()), P(lw["q_norm"].data_ptr()),
+                                      P(lw["k_norm"].data_ptr()), P(pos.data_ptr()), P(idx.data_ptr()), ops.I64,
+                                      P(lw["k_cache"].data_ptr()), P(lw["v_cache"].data_ptr()), C.c_int64(kv * 2), C.c_int64(kv * 2),
+                                      D, cfg.n_head, cfg.n_head_kv, C.c_int64(n), C.c_int64(q), C.c_int64(kv), C.c_int64(kv),
+                                      C.byref(self.rope), C.c_float(cfg.rms_eps), st))
+            kview = lw["k_cache"][:n_kv].view(n_kv, cfg.n_head_kv, D).permute(1, 0, 2)
+            vview = lw["v_cache"][:n_kv].view(n_kv, cfg.n_head_kv, D).permute(1, 0, 2)
+            ops.flash_attn(bufs["q"].view(n, cfg.n_head, D).permute(1, 0, 2), kview, vview, mask16, 1.0 / D ** 0.5,
+                           out=bufs["attn"].view(n, cfg.n_head, D), scratch=fa_scratch)
+            mm(lw["wo"], ty["wo"], E, q, bufs["attn"], bufs["x1"])
+            ops.binary(ops.ADD, bufs["x1"], x, out=bufs["x1"])
+            ops.rms_norm(bufs["x1"], cfg.rms_eps, w=lw["ffn_norm"], out=bufs["a"])
+            mm(lw["gate"], ty["gate"], F, E, bufs["a"], bufs["g"]); mm(lw["up"], ty["up"], F, E, bufs["a"], bufs["u"])
+            ops.check(L.b200_glu(ops.GLU_SWIGLU, ops._ref(ops.T(bufs["g"])), ops._ref(ops.T(bufs["u"])), ops._ref(ops.T(bufs["h"])), 0, st))
+            mm(lw["down"], ty["down"], E, F, bufs["h"], bufs["x2"])              # the layer input (x) is dead once x1 exists: x2 may be the same buffer
+            x = ops.binary(ops.ADD, bufs["x2"], bufs["x1"], out=bufs["x2"])
+            nl += 2 * 7 + 8                           # 7 GEMMs (+ their activation tiling), norm x2, qkv_post, kvmax + fa, add x2, glu
+        logits = None
+        if self.has_head:
+            last = ops.rms_norm(x[n - 1:n], cfg.rms_eps, w=self.out_norm)
+            logits = ops.mul_mat(self.lm_head, ops.Q6_K, cfg.n_vocab, E, last, layout=ops.LAYOUT_PLANAR)
+            nl += 3
+        return logits, nl
+
     def _matvec(self, jobs, act, k) -> int:
         """One launch per run of equal weight type (a Q4_K_M layer mixes Q4_K and Q6_K in q/k/v)."""
         n, i = 0, 0
