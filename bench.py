@@ -155,9 +155,12 @@ def run_b200(args) -> None:
         dist.init_process_group("nccl", device_id=dev)
     ops.lib()
     cfg = dec.LLMConfig.tiny() if args.tiny else dec.LLMConfig()
-    per = (cfg.n_layer + world - 1) // world
-    layers = range(rank * per, min(cfg.n_layer, (rank + 1) * per))
-    last = rank == world - 1
+    # contiguous layer ranges balanced by the bytes a token streams per stage, lm_head with the last stage (llama.cpp-omni_b200/pipeline.py)
+    layer_bytes = [dec.weight_bytes_per_token(cfg, range(i, i + 1), with_head=False) for i in range(cfg.n_layer)]
+    ranges = pkg.pipeline.partition_layers(layer_bytes, dec.weight_bytes_per_token(cfg, range(0), with_head=True), world)
+    pipe = pkg.pipeline.Pipeline(rank, world, ranges, dist)
+    layers = ranges[rank]
+    last = rank == pipe.last
     D = dec.Qwen3Decoder(cfg, dev, layers=layers, has_head=last, seed=rank)
     depth = min(args.depth, cfg.n_ctx - args.steps - args.warmup - 2)
     n_kv = min(cfg.n_ctx, (depth + args.steps + args.warmup + 1 + 255) // 256 * 256)
@@ -197,16 +200,11 @@ def run_b200(args) -> None:
         for _s in range(n_streams):
             if e2e or world > 1:
                 h2d += set_inputs(i)
-            if rank == 0:
-                if e2e:
-                    D.x_in.copy_(host_embd[i], non_blocking=True)
-                    h2d += E * 4
-            else:
-                dist.recv(hidden, src=rank - 1)
-            graph.replay()
-            if not last:
-                dist.send(D.x_out, dst=rank + 1)
-            elif e2e:
+            if rank == pipe.first and e2e:
+                D.x_in.copy_(host_embd[i], non_blocking=True)
+                h2d += E * 4
+            pipe.stage_step(hidden, D.x_out, graph.replay)          # recv from the previous stage -> one graph replay -> send to the next
+            if last and e2e:
                 host_logits.copy_(D.logits, non_blocking=True)
                 d2h += cfg.n_vocab * 4
         if e2e and last:
@@ -274,7 +272,7 @@ def run_b200(args) -> None:
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations), f16 KV", "data": "synthetic",
             "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}, KV depth {depth}..{depth + args.steps + args.warmup} (n_kv={n_kv})",
-                       "streams_in_flight": n_streams, "parallelism": "single GPU" if world == 1 else f"layer-split pipeline pp{world}",
+                       "streams_in_flight": n_streams, "parallelism": "single GPU" if world == 1 else f"layer-split pipeline pp{world}, layers per stage {[len(r) for r in ranges]} (+lm_head on the last)",
                        "engine": "persistent (1 kernel/token)" if engine else "per-op launches",
                        "timing": f"one CUDA graph per token; weights {w_bytes / 1e9:.2f} GB/rank exceed the 126 MB L2, so no flush is needed"},
             "gpu_launches": launches * args.steps * n_streams,

@@ -8,4 +8,4 @@ supplies device memory and streams.  There is NO CPU fallback: importing `ops` w
 
 The directory name is not a valid Python identifier; load it with `__graft_entry__.load_package()`.
 """
-from . import ops, decode  # noqa: F401
+from . import ops, decode, pipeline  # noqa: F401
