@@ -87,6 +87,13 @@ B200_API int    b200_mul_mat_supported(const b200_tensor * w, const b200_tensor 
 B200_API size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x);
 B200_API int    b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
                              size_t scratch_bytes, void * stream);
+/* Same, with flags.  B200_MM_REUSE_ACT: `scratch` still holds the prepared activations (F16 tiles of the tensor-core path, or q8 records) of
+ * the SAME x from the immediately preceding b200_mul_mat[_ex] call on this scratch, with a weight type of the same preparation class — the
+ * q/k/v and gate/up projections of a layer share their input, so only the first of them pays for the conversion.  The caller guarantees
+ * that neither x nor scratch changed in between; when the flag cannot be honoured (different path) it is ignored. */
+enum { B200_MM_REUSE_ACT = 1 };
+B200_API int    b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
+                                size_t scratch_bytes, int flags, void * stream);
 
 /* Decode fast path: y[m] (+= residual) = W[m, k] . act, activations already quantised by b200_quantize_act /
  * a fused producer.  Up to 4 weight matrices that share the same activation run in ONE launch (q/k/v, gate/up).

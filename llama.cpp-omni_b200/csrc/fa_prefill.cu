@@ -24,6 +24,7 @@ struct FaPArgs {
     int64_t n_q, n_kv, n_head, n_head_kv, k_ne3, m_ne3;
     float scale;
     const int32_t * kv_tiles;      // [n_batch_mask][n_q_tiles] KV tiles to visit, or null = all
+    const int32_t * kv_plain;      // [n_batch_mask][n_q_tiles] leading KV tiles whose mask is all 0 for the tile's rows (no mask loads needed), or null
 };
 
 __device__ __forceinline__ uint32_t fp_smem(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -45,26 +46,36 @@ __device__ __forceinline__ void fp_mma(float (&c)[4], const uint32_t (&a)[4], ui
 }
 __device__ __forceinline__ uint32_t fp_pack(float lo, float hi) { const __half2 h = __floats2half2_rn(lo, hi); return *(const uint32_t *) &h; }
 
-// per query tile: how many KV tiles must be visited = 1 + the last tile that holds an unmasked (> -inf) position for any of its rows.
-// One CTA per (query tile, KV tile) pair, 16-byte mask loads, atomicMax into out[] (zeroed by the launcher): the 8 MB mask of a 2048-token
-// prompt is read once, in parallel.
-__global__ void __launch_bounds__(128) k_fa_kvmax(const char * mask, int64_t m_nb1, int64_t m_nb3, int64_t n_q, int64_t n_kv, int32_t * out, int n_q_tiles) {
+// per query tile: (1) how many KV tiles must be visited = 1 + the last tile that holds an unmasked (> -inf) position for any of its rows;
+// (2) how many LEADING tiles have an all-zero mask for every row (for a causal mask: everything left of the diagonal tile) — those need no
+// mask loads at all.  One CTA per (query tile, KV tile) pair, 16-byte mask loads, atomicMax / atomicMin into out[] (initialised by the
+// launcher): the 8 MB mask of a 2048-token prompt is read once, in parallel.
+__global__ void __launch_bounds__(128) k_fa_kvmax(const char * mask, int64_t m_nb1, int64_t m_nb3, int64_t n_q, int64_t n_kv, int32_t * out_max, int32_t * out_plain, int n_q_tiles) {
     const int qt = blockIdx.x, kt = blockIdx.y, ib = blockIdx.z;
-    bool any = false;
+    bool any = false, nonzero = false;
     for (int i = threadIdx.x; i < FP_BM * (FP_BN / 8); i += blockDim.x) {            // 64 rows x 8 chunks of 8 halves
         const int64_t row = (int64_t) qt * FP_BM + i / (FP_BN / 8), col = (int64_t) kt * FP_BN + (i % (FP_BN / 8)) * 8;
         if (row >= n_q || col >= n_kv) continue;
         const char * p = mask + row * m_nb1 + ib * m_nb3 + col * 2;
         if (col + 8 <= n_kv && ((uintptr_t) p % 16) == 0) {
-            const uint4 w = __ldg((const uint4 *) p);                                   // -inf is 0xfc00
+            const uint4 w = __ldg((const uint4 *) p);                                   // -inf is 0xfc00, +0 is 0x0000
             const uint32_t v[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
-            for (int c = 0; c < 4; ++c) any |= (v[c] & 0xffffu) != 0xfc00u || (v[c] >> 16) != 0xfc00u;
+            for (int c = 0; c < 4; ++c) { any |= (v[c] & 0xffffu) != 0xfc00u || (v[c] >> 16) != 0xfc00u; nonzero |= v[c] != 0u; }
         } else {
-            for (int c = 0; c < 8 && col + c < n_kv; ++c) any |= ((const uint16_t *) p)[c] != 0xfc00u;
+            for (int c = 0; c < 8 && col + c < n_kv; ++c) { const uint16_t h = ((const uint16_t *) p)[c]; any |= h != 0xfc00u; nonzero |= h != 0u; }
+            nonzero |= col + 8 > n_kv;                                                  // a ragged last tile needs the bounds handling of the masked path
         }
     }
-    if (__syncthreads_or(any) && threadIdx.x == 0) atomicMax(out + ib * n_q_tiles + qt, kt + 1);
+    const int r_any = __syncthreads_or(any), r_nz = __syncthreads_or(nonzero);
+    if (threadIdx.x == 0) {
+        if (r_any) atomicMax(out_max + ib * n_q_tiles + qt, kt + 1);
+        if (r_nz) atomicMin(out_plain + ib * n_q_tiles + qt, kt);
+    }
+}
+__global__ void k_fa_kvmax_init(int32_t * out_max, int32_t * out_plain, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out_max[i] = 0; out_plain[i] = 0x7fffffff; }
 }
 
 template <int D>
@@ -96,6 +107,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fa_prefill(const FaPArgs A) {
     const char * vb = A.v + (int64_t) kvh * A.v_nb2 + (ib % A.k_ne3) * A.v_nb3;
     const int n_kv_tiles_all = (int) ((A.n_kv + FP_BN - 1) / FP_BN);
     const int n_tiles = A.kv_tiles ? min(A.kv_tiles[(ib % A.m_ne3) * gridDim.x + qt], n_kv_tiles_all) : n_kv_tiles_all;
+    const int n_plain = A.kv_plain ? A.kv_plain[(ib % A.m_ne3) * gridDim.x + qt] : 0;          // tiles j < n_plain: mask is all zero
 
     // swizzled tile fill: row r, chunk c -> chunk c ^ (r & 7)
     auto load_tile = [&](int j, int buf) {
@@ -144,6 +156,13 @@ __global__ void __launch_bounds__(FP_THREADS) k_fa_prefill(const FaPArgs A) {
         }
         // ---- scale + mask, online softmax (rows g and g+8; 4 lanes share a row)
         float mx[2] = { -INFINITY, -INFINITY };
+        if (j < n_plain) {
+#pragma unroll
+            for (int nb = 0; nb < FP_BN / 8; ++nb) {
+                s[nb][0] *= A.scale; s[nb][1] *= A.scale; s[nb][2] *= A.scale; s[nb][3] *= A.scale;
+                mx[0] = fmaxf(mx[0], fmaxf(s[nb][0], s[nb][1])); mx[1] = fmaxf(mx[1], fmaxf(s[nb][2], s[nb][3]));
+            }
+        } else
 #pragma unroll
         for (int nb = 0; nb < FP_BN / 8; ++nb) {
             const int64_t col = (int64_t) j * FP_BN + nb * 8 + 2 * t4;
@@ -163,14 +182,14 @@ __global__ void __launch_bounds__(FP_THREADS) k_fa_prefill(const FaPArgs A) {
         for (int h = 0; h < 2; ++h) {
             mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1)); mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
             const float m_new = fmaxf(m_run[h], mx[h]);
-            corr[h] = m_new == -INFINITY ? 1.0f : expf(m_run[h] - m_new);
+            corr[h] = m_new == -INFINITY ? 1.0f : __expf(m_run[h] - m_new);
             m_run[h] = m_new;
         }
         float sum[2] = { 0.0f, 0.0f };
         const float mb0 = m_run[0] == -INFINITY ? 0.0f : m_run[0], mb1 = m_run[1] == -INFINITY ? 0.0f : m_run[1];
 #pragma unroll
         for (int nb = 0; nb < FP_BN / 8; ++nb) {
-            s[nb][0] = expf(s[nb][0] - mb0); s[nb][1] = expf(s[nb][1] - mb0); s[nb][2] = expf(s[nb][2] - mb1); s[nb][3] = expf(s[nb][3] - mb1);
+            s[nb][0] = __expf(s[nb][0] - mb0); s[nb][1] = __expf(s[nb][1] - mb0); s[nb][2] = __expf(s[nb][2] - mb1); s[nb][3] = __expf(s[nb][3] - mb1);
             sum[0] += s[nb][0] + s[nb][1]; sum[1] += s[nb][2] + s[nb][3];
         }
         l_run[0] = l_run[0] * corr[0] + sum[0]; l_run[1] = l_run[1] * corr[1] + sum[1];       // per-lane partial sums; reduced over the 4 lanes at the end
@@ -218,7 +237,7 @@ bool fa_prefill_supported(const b200_tensor * q, const b200_tensor * k, const b2
 }
 size_t fa_prefill_scratch_bytes(const b200_tensor * q, const b200_tensor * mask_or_null, int64_t m_ne3) {
     (void) mask_or_null;
-    return (size_t) ((q->ne[1] + FP_BM - 1) / FP_BM) * (size_t) (m_ne3 > 0 ? m_ne3 : 1) * 4 + 16;
+    return (size_t) ((q->ne[1] + FP_BM - 1) / FP_BM) * (size_t) (m_ne3 > 0 ? m_ne3 : 1) * 8 + 16;       // kv_tiles + kv_plain
 }
 
 int fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
@@ -236,10 +255,12 @@ int fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor *
         A.m_nb1 = mask->nb[1]; A.m_nb3 = mask->nb[3]; A.m_ne3 = mask->ne[3];
         if (scratch) {
             const int n_kv_tiles = (int) ((A.n_kv + FP_BN - 1) / FP_BN);
-            B200_CUDA_TRY(cudaMemsetAsync(scratch, 0, (size_t) n_q_tiles * A.m_ne3 * 4, st));
-            k_fa_kvmax<<<dim3((unsigned) n_q_tiles, (unsigned) n_kv_tiles, (unsigned) A.m_ne3), 128, 0, st>>>(A.mask, A.m_nb1, A.m_nb3, A.n_q, A.n_kv, (int32_t *) scratch, n_q_tiles);
+            const int n_ent = n_q_tiles * (int) A.m_ne3;
+            int32_t * kmax = (int32_t *) scratch, * kplain = kmax + n_ent;
+            k_fa_kvmax_init<<<(n_ent + 127) / 128, 128, 0, st>>>(kmax, kplain, n_ent);
+            k_fa_kvmax<<<dim3((unsigned) n_q_tiles, (unsigned) n_kv_tiles, (unsigned) A.m_ne3), 128, 0, st>>>(A.mask, A.m_nb1, A.m_nb3, A.n_q, A.n_kv, kmax, kplain, n_q_tiles);
             B200_LAUNCH_CHECK();
-            A.kv_tiles = (const int32_t *) scratch;
+            A.kv_tiles = kmax; A.kv_plain = kplain;
         }
     }
     const dim3 grid((unsigned) n_q_tiles, (unsigned) A.n_head, (unsigned) q->ne[3]);

@@ -65,6 +65,8 @@ struct BackendCtx {
     std::vector<uint64_t> engine_key, engine_reject_key;
     std::vector<ggml_tensor *> engine_pre;                   // nodes still run per-op before the engine step (the KQ-mask cast)
     bool engine_enabled = true;
+    // activation-tile reuse (B200_MM_REUSE_ACT): the tensor whose prepared activations the scratch currently holds, reset per graph_compute
+    const ggml_tensor * scratch_act = nullptr; const void * scratch_act_data = nullptr; int scratch_act_type = -1;
 };
 
 DeviceCtx g_devices[MAX_DEVICES];
@@ -390,7 +392,14 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, ggml_tensor * n, ggml_tensor
         case GGML_OP_MUL_MAT: {
             b200_tensor w = view_of(s0), x = view_of(s1), d = view_of(n);
             const size_t sb = b200_mul_mat_scratch_bytes(&w, &x);
-            rc = b200_mul_mat(&w, &x, &d, sb ? scratch_for(c, sb) : nullptr, sb, st);
+            void * scratch_before = c->scratch;
+            void * sc = sb ? scratch_for(c, sb) : nullptr;
+            // q/k/v and gate/up share their input: the second and third projection reuse the F16 activation tiles the first one left in scratch
+            // (only for the tensor-core path: > 8 columns of q4_K / planar q6_K; the preparation does not depend on which of the two types)
+            const bool tc_class = (s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q6_K) && s1->ne[1] > 8 && s1->ne[2] * s1->ne[3] == 1;
+            const bool reuse = tc_class && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == 1;
+            rc = b200_mul_mat_ex(&w, &x, &d, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
+            c->scratch_act = tc_class ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = tc_class ? 1 : 0;
             return 1;
         }
         case GGML_OP_ADD: case GGML_OP_SUB: case GGML_OP_MUL: case GGML_OP_DIV: {
@@ -444,6 +453,7 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, ggml_tensor * n, ggml_tensor
             b200_tensor q = view_of(s0), k = view_of(s1), v = view_of(n->src[2]), d = view_of(n), m;
             if (n->src[3]) m = view_of(n->src[3]);
             const size_t sb = b200_flash_attn_scratch_bytes(&q, &k);
+            c->scratch_act = nullptr;                                    // the attention kernels use the same scratch
             rc = b200_flash_attn(&q, &k, &v, n->src[3] ? &m : nullptr, &d, fparam(n, 0), fparam(n, 1), fparam(n, 2), sb ? scratch_for(c, sb) : nullptr, sb, st);
             return 1;
         }
@@ -455,9 +465,11 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, ggml_tensor * n, ggml_tensor
 
 enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
     const int nn = ggml_graph_n_nodes(g);
+    c->scratch_act = nullptr;
     for (int i = 0; i < nn; ) {
         ggml_tensor * n = ggml_graph_node(g, i);
         if (is_noop(n)) { ++i; continue; }
+        if (c->scratch_act && n->data == c->scratch_act_data) c->scratch_act = nullptr;     // an in-place op rewrites the tensor the tiles were made from
         ggml_tensor * next = nullptr;
         for (int j = i + 1; j < nn; ++j) { ggml_tensor * t = ggml_graph_node(g, j); if (!is_noop(t)) { next = (j == i + 1) ? t : nullptr; break; } }
         int rc = 0;

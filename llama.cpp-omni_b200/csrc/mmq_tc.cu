@@ -381,7 +381,7 @@ static tc_encode_fn tc_encoder() {
     return fn;
 }
 
-int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, cudaStream_t st) {
+int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st) {
     static unsigned long long done = 0;
     B200_CUDA_TRY(ensure_dyn_smem(k_mmq_tc, TC_SMEM, done));
     if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
@@ -395,8 +395,10 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
                          (getenv("B200_TC_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B200_ERR_UNSUPPORTED;
     }
     const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
-    k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
-    B200_LAUNCH_CHECK();
+    if (!reuse_tiles) {
+        k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
+        B200_LAUNCH_CHECK();
+    }
     TcArgs A = {};
     static const int env_flags = getenv("B200_TC_FLAGS") ? atoi(getenv("B200_TC_FLAGS")) : 0;
     A.flags = env_flags;

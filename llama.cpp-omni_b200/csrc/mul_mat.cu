@@ -13,7 +13,7 @@ int matvec_q_cols(const void * w, int type, int layout, int64_t m, int64_t row_s
 // mmq_tc.cu: tcgen05 dequant-GEMM for n > 8 columns
 bool   mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w, int64_t row_stride);
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n);
-int    mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, cudaStream_t st);
+int    mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st);
 static bool tc_disabled() { static const bool off = getenv("B200_DISABLE_TC") && atoi(getenv("B200_DISABLE_TC")) != 0; return off; }
 
 template <typename WT> __device__ __forceinline__ float w2f(WT v);
@@ -126,6 +126,11 @@ extern "C" size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_t
 
 extern "C" int b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
                             size_t scratch_bytes, void * stream) {
+    return b200_mul_mat_ex(w, x, dst, scratch, scratch_bytes, 0, stream);
+}
+
+extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
+                               size_t scratch_bytes, int flags, void * stream) {
     if (!b200_mul_mat_supported(w, x, dst)) return B200_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t) stream;
     const int t = w->type;
@@ -148,7 +153,7 @@ extern "C" int b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const 
         if (tc) {       // prefill / batched: dequant tiles -> tcgen05.mma (mmq_tc.cu)
             const char * wb = (const char *) w->data + (i2 / r2) * w->nb[2] + (i3 / r3) * w->nb[3];
             float * yb = (float *) ((char *) dst->data + i2 * dst->nb[2] + i3 * dst->nb[3]);
-            const int rc = mmq_tc(wb, t, m, k, xs, x->nb[1] / 4, n, yb, dst->nb[1] / 4, scratch, st);
+            const int rc = mmq_tc(wb, t, m, k, xs, x->nb[1] / 4, n, yb, dst->nb[1] / 4, scratch, (flags & B200_MM_REUSE_ACT) && x->ne[2] * x->ne[3] == 1, st);
             if (rc) return rc;
             continue;
         }

@@ -20,7 +20,7 @@ _TORCH2B = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.
 
 EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b200_repack_supported", "b200_repack_scatter",
            "b200_repack_gather", "b200_act_bytes", "b200_quantize_act", "b200_mul_mat_supported", "b200_mul_mat_scratch_bytes",
-           "b200_mul_mat", "b200_matvec_q", "b200_matvec_q_swiglu", "b200_rms_norm", "b200_rms_norm_quantize", "b200_rope",
+           "b200_mul_mat", "b200_mul_mat_ex", "b200_matvec_q", "b200_matvec_q_swiglu", "b200_rms_norm", "b200_rms_norm_quantize", "b200_rope",
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
            "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
            "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy"]
