@@ -396,7 +396,10 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, ggml_tensor * n, ggml_tensor
             void * sc = sb ? scratch_for(c, sb) : nullptr;
             // q/k/v and gate/up share their input: the second and third projection reuse the F16 activation tiles the first one left in scratch
             // (only for the tensor-core path: > 8 columns of q4_K / planar q6_K; the preparation does not depend on which of the two types)
-            const bool tc_class = (s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q6_K) && s1->ne[1] > 8 && s1->ne[2] * s1->ne[3] == 1;
+            // (same routing conditions as mmq_tc_supported in csrc/mmq_tc.cu: native 16-byte-multiple blocks with back-to-back rows, or planar planes)
+            const bool tc_native = (s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q5_K) && s0->nb[1] == ggml_row_size(s0->type, s0->ne[0]);
+            const bool tc_planar = (s0->type == GGML_TYPE_Q6_K || s0->type == GGML_TYPE_Q8_0 || s0->type == GGML_TYPE_Q4_0) && is_planar(s0);
+            const bool tc_class = (tc_native || tc_planar) && (uintptr_t) s0->data % 16 == 0 && s1->ne[1] > 8 && s1->ne[2] * s1->ne[3] == 1 && s0->ne[0] % 256 == 0;
             const bool reuse = tc_class && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == 1;
             rc = b200_mul_mat_ex(&w, &x, &d, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
             c->scratch_act = tc_class ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = tc_class ? 1 : 0;

@@ -1,4 +1,5 @@
-// mmq_tc.cu — prefill / batched GEMM  Y[m, n] = W[m, k] . X[n, k]^T  for quantised W (q4_K native, q6_K planar) and n > 8 columns,
+// mmq_tc.cu — prefill / batched GEMM  Y[m, n] = W[m, k] . X[n, k]^T  for quantised W (q4_K / q5_K native, q6_K / q8_0 / q4_0 planar) and n > 8
+// columns,
 // on the 5th-generation tensor cores: tcgen05.mma (kind::f16, M = 128, N <= 256, K = 16) with the accumulator in TMEM.
 //
 // Replaces ggml_cuda_mul_mat_q (ggml-cuda/mmq.cu:205, kernel mul_mat_q mmq.cuh:3136 with the q4_K / q6_K tile loaders :1741, :2043, and
@@ -31,11 +32,12 @@
 namespace b200 {
 
 constexpr int TC_M = 128, TC_N = 256, TC_K = 64, TC_STAGES = 3;
-constexpr int TC_RAW = 3, TC_RAW_BYTES = TC_M * 208;                                        // raw quant-block ring: 128 rows x one block (q6_K payload = 208 B)
+constexpr int TC_RAW_REGION = 3 * TC_M * 208;                                               // raw quant-block ring: 128 rows x the bytes of 256 weights per slot
+constexpr int TC_RAW_MAX = 3;                                                               // slots: 3 (2 for q8_0, whose 256-weight span is 256 B per row)
 constexpr int TC_A_BYTES = TC_M * TC_K * 2, TC_B_BYTES = TC_N * TC_K * 2;                 // 16 KB, 32 KB
 constexpr int TC_A_LBO = (TC_M / 8) * 128, TC_B_LBO = (TC_N / 8) * 128, TC_SBO = 128;        // core matrices: K direction / row-group direction
 constexpr int TC_DEQ_THREADS = 256, TC_THREADS = 480;
-constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_RAW * TC_RAW_BYTES + 256;
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_RAW_REGION + 256;
 static_assert(TC_SMEM <= 227 * 1024, "k_mmq_tc shared memory");
 
 struct TcArgs {
@@ -44,6 +46,7 @@ struct TcArgs {
     float * dst; int64_t dst_ld;                    // dst[n * dst_ld + m]
     int64_t m, k, n, row_bytes;                     // n = real columns; row_bytes of the payload plane
     int type, tiles_m, tiles_n;
+    int span_bytes, n_raw;                          // payload bytes of 256 weights of one row (= TMA box width); raw ring slots
     int flags;                                      // experiment switches (B200_TC_FLAGS): 1 no dequant, 2 no MMA, 4 no B copies
 };
 
@@ -132,6 +135,23 @@ __device__ __forceinline__ void raw_load(RawQ6K & R, uint32_t pay, int g) {
     R.sc = tc_lds8(pay + 192 + 8 * g);
 }
 
+struct RawQ5K { uint4 hdr, h[2], q[4]; };                 // d|dmin + scales; qh[32]; qs[64g ..+64)
+struct RawQ80 { uint4 q[8]; float d[4]; };                // int8 of blocks 4g .. 4g+3 (planar payload); their f16 d (d plane)
+struct RawQ40 { uint4 q[4]; float d[4]; };                // nibbles of blocks 4g .. 4g+3; their d
+__device__ __forceinline__ void raw_load(RawQ5K & R, uint32_t blk, int g) {
+    R.hdr = tc_lds16(blk); R.h[0] = tc_lds16(blk + 16); R.h[1] = tc_lds16(blk + 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) R.q[i] = tc_lds16(blk + 48 + 64 * g + 16 * i);
+}
+__device__ __forceinline__ void raw_load(RawQ80 & R, uint32_t pay, int g) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) R.q[i] = tc_lds16(pay + 128 * g + 16 * i);
+}
+__device__ __forceinline__ void raw_load(RawQ40 & R, uint32_t pay, int g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) R.q[i] = tc_lds16(pay + 64 * g + 16 * i);
+}
+
 __device__ __forceinline__ void st_row(uint32_t addr, const uint4 & v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -178,20 +198,87 @@ template <int cc> __device__ __forceinline__ void deq_chunk(const RawQ6K & R, in
     }
 }
 
+template <int cc> __device__ __forceinline__ void deq_chunk(const RawQ5K & R, int g, uint32_t a_row) {
+    // q4_K plus one high bit per weight: group j = 2g + cc uses bit 2j of qh[l] for its low-nibble sub-block and bit 2j+1 for the high one
+    // (dequantize_row_q5_K, ggml-quants.c:1554-1578)
+    const uint4 & hdr = R.hdr;
+    const uint32_t scw = g ? ((hdr.w & 0x0f0f0f0fu) | (((hdr.y >> 6) & 0x03030303u) << 4)) : (hdr.y & 0x3f3f3f3fu);
+    const uint32_t mnw = g ? (((hdr.w >> 4) & 0x0f0f0f0fu) | (((hdr.z >> 6) & 0x03030303u) << 4)) : (hdr.z & 0x3f3f3f3fu);
+    const float d = h2f(hdr.x & 0xffff), dmin = h2f(hdr.x >> 16);
+    const __half2 off = __float2half2_rn(1024.0f);
+    const uint32_t w[8] = { R.q[2 * cc].x, R.q[2 * cc].y, R.q[2 * cc].z, R.q[2 * cc].w, R.q[2 * cc + 1].x, R.q[2 * cc + 1].y, R.q[2 * cc + 1].z, R.q[2 * cc + 1].w };
+    const uint32_t hw[8] = { R.h[0].x, R.h[0].y, R.h[0].z, R.h[0].w, R.h[1].x, R.h[1].y, R.h[1].z, R.h[1].w };
+    const int j = 2 * g + cc;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        const float sc = (float) ((scw >> (16 * cc + 8 * hf)) & 0xff), mn = (float) ((mnw >> (16 * cc + 8 * hf)) & 0xff);
+        const __half2 s = __float2half2_rn(d * sc), cm = __float2half2_rn(-(dmin * mn));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t b0 = ((w[2 * i] >> (4 * hf)) & 0x0f0f0f0fu) | (((hw[2 * i] >> (2 * j + hf)) & 0x01010101u) << 4);
+            const uint32_t b1 = ((w[2 * i + 1] >> (4 * hf)) & 0x0f0f0f0fu) | (((hw[2 * i + 1] >> (2 * j + hf)) & 0x01010101u) << 4);
+            st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8(b0, b1, off, s, cm));
+        }
+    }
+}
+
+template <int cc> __device__ __forceinline__ void deq_chunk(const RawQ80 & R, int, uint32_t a_row) {
+    // blocks 2cc, 2cc+1 of the thread's four: w = d * int8 (ggml-quants.c:390-402); int8 -> half through the biased byte b ^ 0x80 = q + 128
+    const __half2 off = __float2half2_rn(1024.0f + 128.0f), zero = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        const __half2 s = __float2half2_rn(R.d[2 * cc + hf]);
+        const uint4 & a = R.q[4 * cc + 2 * hf], & b = R.q[4 * cc + 2 * hf + 1];
+        const uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8(w[2 * i] ^ 0x80808080u, w[2 * i + 1] ^ 0x80808080u, off, s, zero));
+    }
+}
+
+template <int cc> __device__ __forceinline__ void deq_chunk(const RawQ40 & R, int, uint32_t a_row) {
+    // block = 16 bytes: low nibbles are weights 0..15, high nibbles 16..31, w = d * (q - 8) (ggml-quants.c:307-325)
+    const __half2 off = __float2half2_rn(1024.0f + 8.0f), zero = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        const __half2 s = __float2half2_rn(R.d[2 * cc + hf]);
+        const uint4 & a = R.q[2 * cc + hf];
+        const uint32_t w[4] = { a.x, a.y, a.z, a.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i)                                              // i = 0, 1: low nibbles of words 0-1, 2-3; i = 2, 3: high nibbles
+            st_row(a_row + (4 * hf + i) * TC_A_LBO, deq8((w[2 * (i & 1)] >> (4 * (i >> 1))) & 0x0f0f0f0fu, (w[2 * (i & 1) + 1] >> (4 * (i >> 1))) & 0x0f0f0f0fu, off, s, zero));
+    }
+}
+
 // one tile's worth of A stages for thread (row, g): block kb of the row arrives in raw-ring slot (rit + kb) % TC_RAW (TMA, issued by the raw
 // producer warp up to TC_RAW blocks ahead); the thread copies its half block to registers, hands the slot back, and fills stage uses
 // it0 + 4kb + 2g and + 2g + 1
-template <class Raw, int BLK>
-__device__ __forceinline__ void tc_produce_tile(uint32_t raw0, const uint8_t * drow, int64_t nkb, int g, int lane, uint32_t it0, uint32_t rit0, uint32_t stage0,
-                                                uint32_t a_full, uint32_t empty, uint32_t raw_full, uint32_t raw_empty, int flags) {
-    float dn = 0.0f;
-    if (drow) dn = h2f(__ldg((const uint16_t *) drow));                         // q6_K: the block's f16 d comes from the planar d plane, one block ahead
+// d-plane prefetch of the planar types: q6_K one f16 per 256 weights, q8_0 / q4_0 four (this thread's blocks 4g .. 4g+3 of the span's eight)
+template <class Raw> struct DAhead { __device__ static void load(const uint8_t *, int64_t, int, float (&)[4]) {} __device__ static void put(Raw &, const float (&)[4]) {} };
+template <> struct DAhead<RawQ6K> {
+    __device__ static void load(const uint8_t * drow, int64_t kb, int, float (&d)[4]) { d[0] = h2f(__ldg((const uint16_t *) (drow + kb * 2))); }
+    __device__ static void put(RawQ6K & R, const float (&d)[4]) { R.d = d[0]; }
+};
+template <class Raw> struct DAhead4 {
+    __device__ static void load(const uint8_t * drow, int64_t kb, int g, float (&d)[4]) {
+        const uint2 v = __ldg((const uint2 *) (drow + kb * 16 + g * 8));
+        d[0] = h2f(v.x & 0xffff); d[1] = h2f(v.x >> 16); d[2] = h2f(v.y & 0xffff); d[3] = h2f(v.y >> 16);
+    }
+    __device__ static void put(Raw & R, const float (&d)[4]) { R.d[0] = d[0]; R.d[1] = d[1]; R.d[2] = d[2]; R.d[3] = d[3]; }
+};
+template <> struct DAhead<RawQ80> : DAhead4<RawQ80> {};
+template <> struct DAhead<RawQ40> : DAhead4<RawQ40> {};
+
+template <class Raw>
+__device__ __forceinline__ void tc_produce_tile(uint32_t raw_row, uint32_t raw_stride, uint32_t n_raw, const uint8_t * drow, int64_t nkb, int g, int lane, uint32_t it0, uint32_t rit0,
+                                                uint32_t stage0, uint32_t a_full, uint32_t empty, uint32_t raw_full, uint32_t raw_empty, int flags) {
+    float dn[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    if (drow) DAhead<Raw>::load(drow, 0, g, dn);                                 // planar types: the f16 d of the span, one span ahead of its use
     for (int64_t kb = 0; kb < nkb; ++kb) {
-        const uint32_t ru = rit0 + (uint32_t) kb, r = ru % TC_RAW;
+        const uint32_t ru = rit0 + (uint32_t) kb, r = ru % n_raw;
         Raw R;
-        tc_mbar_wait(raw_full + 8 * r, (ru / TC_RAW) & 1);
-        raw_load(R, raw0 + r * TC_RAW_BYTES, g);
-        if constexpr (BLK == 208) { R.d = dn; if (kb + 1 < nkb) dn = h2f(__ldg((const uint16_t *) (drow + (kb + 1) * 2))); }
+        tc_mbar_wait(raw_full + 8 * r, (ru / n_raw) & 1);
+        raw_load(R, raw_row + r * raw_stride, g);
+        if (drow) { DAhead<Raw>::put(R, dn); if (kb + 1 < nkb) DAhead<Raw>::load(drow, kb + 1, g, dn); }
         // The slot may be overwritten by the next TMA (async proxy) as soon as all 8 warps have arrived, so the generic-proxy ld.shared above must
         // have been PERFORMED, not just issued — their values are not consumed before the arrive, and ptxas schedules SYNCS.ARRIVE right behind
         // the LDS (observed: rows of the next block leaking into this one).  The cross-proxy fence orders them before the TMA write.
@@ -237,16 +324,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = tc_smem_u32(smem);
     const uint32_t raw0 = sbase + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);       // raw quant-block ring
-    const uint32_t bars = raw0 + TC_RAW * TC_RAW_BYTES;                         // a_full[S], b_full[S], empty[S], tmem_full[2], tmem_empty[2], raw_full[R], raw_empty[R], tmem ptr
+    const uint32_t bars = raw0 + TC_RAW_REGION;                         // a_full[S], b_full[S], empty[S], tmem_full[2], tmem_empty[2], raw_full[R], raw_empty[R], tmem ptr
     const uint32_t a_full = bars, b_full = bars + 8 * TC_STAGES, empty = bars + 16 * TC_STAGES, t_full = bars + 24 * TC_STAGES, t_empty = t_full + 16;
-    const uint32_t raw_full = t_empty + 16, raw_empty = raw_full + 8 * TC_RAW;
-    volatile uint32_t * tmem_slot = (volatile uint32_t *) (smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_RAW * TC_RAW_BYTES + 24 * TC_STAGES + 32 + 16 * TC_RAW);
+    const uint32_t raw_full = t_empty + 16, raw_empty = raw_full + 8 * TC_RAW_MAX;
+    volatile uint32_t * tmem_slot = (volatile uint32_t *) (smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_RAW_REGION + 24 * TC_STAGES + 32 + 16 * TC_RAW_MAX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(a_full + 8 * s, TC_DEQ_THREADS / 64); tc_mbar_init(b_full + 8 * s, 1); tc_mbar_init(empty + 8 * s, 1); }
         for (int i = 0; i < 2; ++i) { tc_mbar_init(t_full + 8 * i, 1); tc_mbar_init(t_empty + 8 * i, 128); }
-        for (int r = 0; r < TC_RAW; ++r) { tc_mbar_init(raw_full + 8 * r, 1); tc_mbar_init(raw_empty + 8 * r, TC_DEQ_THREADS / 32); }
+        for (int r = 0; r < TC_RAW_MAX; ++r) { tc_mbar_init(raw_full + 8 * r, 1); tc_mbar_init(raw_empty + 8 * r, TC_DEQ_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -270,8 +357,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it += (uint32_t) nkc, rit += (uint32_t) nkb) {
             const int mt = t % A.tiles_m;
             int64_t gr = (int64_t) mt * TC_M + row; if (gr >= A.m) gr = A.m - 1;        // tail rows (zero-filled by TMA): any valid d, never stored
-            if (A.type == B200_Q4_K) tc_produce_tile<RawQ4K, 144>(raw0 + row * 144, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags);
-            else                     tc_produce_tile<RawQ6K, 208>(raw0 + row * 208, A.wd + gr * nkb * 2, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags);
+            const uint32_t rrow = raw0 + row * A.span_bytes, rstride = (uint32_t) (TC_M * A.span_bytes), nr = (uint32_t) A.n_raw;
+            switch (A.type) {
+                case B200_Q4_K: tc_produce_tile<RawQ4K>(rrow, rstride, nr, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                case B200_Q5_K: tc_produce_tile<RawQ5K>(rrow, rstride, nr, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                case B200_Q6_K: tc_produce_tile<RawQ6K>(rrow, rstride, nr, A.wd + gr * nkb * 2, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                case B200_Q8_0: tc_produce_tile<RawQ80>(rrow, rstride, nr, A.wd + gr * nkb * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                default:        tc_produce_tile<RawQ40>(rrow, rstride, nr, A.wd + gr * nkb * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+            }
         }
     } else if (warp == 8) {
         // ================================================================== B producer (TMA bulk copies of pre-tiled F16 activations)
@@ -318,16 +411,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
     } else if (warp == 14) {
         // ================================================================== raw weight producer: one 2-D TMA (128 rows x one quant block) per 4 stages
         if (lane == 0) {
-            const int blk = A.type == B200_Q4_K ? 144 : 208;
+            const int blk = A.span_bytes;
             const int nkb = (int) (A.k >> 8);
+            const uint32_t n_raw = (uint32_t) A.n_raw, rstride = (uint32_t) (TC_M * A.span_bytes);
             uint32_t ru = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int mt = t % A.tiles_m;
                 for (int kb = 0; kb < nkb; ++kb, ++ru) {
-                    const uint32_t r = ru % TC_RAW;
-                    tc_mbar_wait(raw_empty + 8 * r, ((ru / TC_RAW) & 1) ^ 1);
-                    tc_mbar_expect_tx(raw_full + 8 * r, (uint32_t) (TC_M * blk));
-                    tc_tma_2d(raw0 + r * TC_RAW_BYTES, &wmap, kb * blk, mt * TC_M, raw_full + 8 * r);
+                    const uint32_t r = ru % n_raw;
+                    tc_mbar_wait(raw_empty + 8 * r, ((ru / n_raw) & 1) ^ 1);
+                    tc_mbar_expect_tx(raw_full + 8 * r, rstride);
+                    tc_tma_2d(raw0 + r * rstride, &wmap, kb * blk, mt * TC_M, raw_full + 8 * r);
                 }
             }
         }
@@ -363,8 +457,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
 // ---------------------------------------------------------------------------------------------------------------- host side
 bool mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w, int64_t row_stride) {
     if (n <= 8 || k % 256) return false;
-    if (type == B200_Q4_K) return (uintptr_t) w % 16 == 0 && row_stride == k / 256 * 144;
-    if (type == B200_Q6_K) return layout == B200_LAYOUT_PLANAR && (uintptr_t) w % 16 == 0;
+    if ((uintptr_t) w % 16) return false;
+    if (type == B200_Q4_K || type == B200_Q5_K) return row_stride == k / 256 * type_size(type);             // native 16-byte-multiple blocks
+    if (type == B200_Q6_K || type == B200_Q8_0 || type == B200_Q4_0) return layout == B200_LAYOUT_PLANAR;   // payload plane + f16 d plane
     return false;
 }
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n) { return (size_t) ((n + TC_N - 1) / TC_N * TC_N) * (size_t) k * 2; }
@@ -388,7 +483,7 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
     // the payload plane as a 2-D byte tensor [m rows][row bytes]; box = one quant block x 128 rows
     CUtensorMap wmap;
     {
-        const cuuint64_t blk = type == B200_Q4_K ? 144 : 208, rowb = (cuuint64_t) (k / 256) * blk;
+        const cuuint64_t blk = (cuuint64_t) (256 / blck_size(type)) * payload_size(type), rowb = (cuuint64_t) (k / 256) * blk;
         const cuuint64_t gdim[2] = { rowb, (cuuint64_t) m }, gstr[1] = { rowb };
         const cuuint32_t box[2] = { (cuuint32_t) blk, TC_M }, estr[2] = { 1, 1 };
         if (tc_encoder()(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *) w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -404,8 +499,10 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
     A.flags = env_flags;
     const int64_t nkb = k / 256;
     A.w = (const uint8_t *) w; A.type = type; A.m = m; A.k = k; A.n = n; A.dst = dst; A.dst_ld = dst_ld; A.x16 = (const uint8_t *) scratch;
-    if (type == B200_Q4_K) { A.row_bytes = nkb * 144; A.wd = nullptr; }
-    else                   { A.row_bytes = nkb * 208; A.wd = (const uint8_t *) w + m * nkb * 208; }
+    A.span_bytes = (256 / blck_size(type)) * payload_size(type);                // 144, 176, 208, 256 (q8_0), 128 (q4_0)
+    A.n_raw = TC_RAW_REGION / (TC_M * A.span_bytes) >= TC_RAW_MAX ? TC_RAW_MAX : TC_RAW_REGION / (TC_M * A.span_bytes);
+    A.row_bytes = nkb * A.span_bytes;
+    A.wd = payload_size(type) != type_size(type) ? (const uint8_t *) w + m * A.row_bytes : nullptr;          // planar: f16 d plane behind the payload plane
     A.tiles_m = (int) ((m + TC_M - 1) / TC_M); A.tiles_n = (int) (n_pad / TC_N);
     int grid = A.tiles_m * A.tiles_n; if (grid > sm_count()) grid = sm_count();
     k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A, wmap);

@@ -63,8 +63,8 @@ def nmse(a, b):
 
 
 def tc_routed(ops, t, planar, n, k):
-    """n > 8 columns of q4_K (native) / q6_K (planar) go to the tcgen05 dequant-GEMM (csrc/mmq_tc.cu): F16 operands, F32 accumulation."""
-    return n > 8 and k % 256 == 0 and (t == ops.Q4_K or (t == ops.Q6_K and planar))
+    """n > 8 columns of q4_K / q5_K (native) and q6_K / q8_0 / q4_0 (planar) go to the tcgen05 dequant-GEMM (csrc/mmq_tc.cu): F16 operands, F32 accumulation."""
+    return n > 8 and k % 256 == 0 and (t in (ops.Q4_K, ops.Q5_K) or (t in (ops.Q6_K, ops.Q8_0, ops.Q4_0) and planar))
 
 
 def tc_check(got, oracle_ref, w_deq, x):
@@ -161,16 +161,18 @@ def test_mul_mat_vs_oracle(ops, name, m, k, n):
 
 
 @pytest.mark.parametrize("name,m,k,n", [("q4_K", 4096, 4096, 512), ("q6_K", 1024, 4096, 300), ("q4_K", 200, 512, 17), ("q6_K", 129, 256, 9),
-                                        ("q4_K", 12288, 4096, 2048), ("q4_K", 4096, 12288, 257), ("q6_K", 4096, 12288, 64)])
+                                        ("q4_K", 12288, 4096, 2048), ("q4_K", 4096, 12288, 257), ("q6_K", 4096, 12288, 64),
+                                        ("q5_K", 1024, 4096, 300), ("q8_0", 1024, 4096, 300), ("q4_0", 1024, 4096, 300), ("q5_K", 130, 512, 40),
+                                        ("q8_0", 200, 768, 33), ("q4_0", 129, 256, 9)])
 def test_mul_mat_prefill_tensor_core(ops, name, m, k, n):
     """Prefill GEMM (BASELINE.json configs[2] shapes and ragged ones) through b200_mul_mat -> k_mmq_tc.  Exact product of the dequantised
     weights in f64 on the GPU for the whole output; the CPU oracle (q8_K activations) on a sample of rows and columns."""
     t = QT[name]
     rng = np.random.default_rng(hash((name, m, k, n)) & 0xffff)
-    blocks = rand_blocks(rng, t, m * k // 256)
+    blocks = rand_blocks(rng, t, m * k // O.BLOCK[t][0])
     x = rng.standard_normal((n, k)).astype(np.float32)
     wd = dev(blocks)
-    planar = t == O.Q6_K
+    planar = t in ops.PAYLOAD
     if planar:
         wd = ops.to_planar(t, wd)
     got = ops.mul_mat(wd, t, m, k, dev(x), layout=ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NATIVE)
