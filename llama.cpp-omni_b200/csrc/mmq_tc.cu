@@ -454,6 +454,110 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
     if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
 }
 
+
+// ================================================================================================================ F16 weights
+// Y[m, n] = W[m, k] . X[n, k]^T for F16 W (the F16 model of BASELINE.json configs[4]; the VPM / APM / TTS graphs of SURVEY.md 8f): no dequantisation,
+// so the weight tile goes from global memory straight into the tensor core's operand layout — one 2-D TMA per stage with the 128-byte swizzle
+// (box = 64 halves x 128 rows = the canonical K-major SWIZZLE_128B UMMA tile, 8-row groups 1024 B apart), activations as above.  6 warps:
+// TMA producer, MMA issuer, 4 epilogue warps.  Replaces the cuBLAS branch of ggml_cuda_mul_mat (ggml-cuda.cu:1983, 2001-2084) and mmvf for n > 8;
+// arithmetic = the CPU oracle's (activations rounded to F16 = vec_dot_type of F16 weights, ggml-cpu.c:196-350; F32 accumulation).
+constexpr int TF_STAGES = 4, TF_THREADS = 192;
+constexpr int TF_SMEM = TF_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
+
+struct TcF16Args { const uint8_t * x16; float * dst; int64_t dst_ld, m, k, n; int tiles_m, tiles_n; };
+
+__device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t saddr) {      // K-major SWIZZLE_128B: SBO = 1024 B (8 rows x 128 B), LBO unused, layout type 2
+    return (uint64_t) ((saddr & 0x3ffff) >> 4) | ((uint64_t) 1 << 16) | ((uint64_t) (1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(TF_THREADS, 1) k_mm_f16_tc(const __grid_constant__ TcF16Args A, const __grid_constant__ CUtensorMap wmap) {
+    extern __shared__ __align__(1024) uint8_t smem_f[];
+    const uint32_t sbase = (tc_smem_u32(smem_f) + 1023u) & ~1023u;              // SWIZZLE_128B tiles must sit on 1024-byte boundaries
+    const uint32_t bars = sbase + TF_STAGES * (TC_A_BYTES + TC_B_BYTES);
+    const uint32_t full = bars, empty = bars + 8 * TF_STAGES, t_full = bars + 16 * TF_STAGES, t_empty = t_full + 16, tmem_slot_a = t_empty + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TF_STAGES; ++s) { tc_mbar_init(full + 8 * s, 1); tc_mbar_init(empty + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { tc_mbar_init(t_full + 8 * i, 1); tc_mbar_init(t_empty + 8 * i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot_a), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_a));
+    const int n_tiles = A.tiles_m * A.tiles_n, nkc = (int) (A.k >> 6);
+    uint32_t it = 0;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int mt = t % A.tiles_m, nt = t / A.tiles_m;
+                const uint8_t * src = A.x16 + (int64_t) nt * nkc * TC_B_BYTES;
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const uint32_t s = it % TF_STAGES;
+                    tc_mbar_wait(empty + 8 * s, ((it / TF_STAGES) & 1) ^ 1);
+                    tc_mbar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES);
+                    const uint32_t a_s = sbase + s * (TC_A_BYTES + TC_B_BYTES);
+                    tc_tma_2d(a_s, &wmap, kc * TC_K, mt * TC_M, full + 8 * s);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tc_bulk_g2s(a_s + TC_A_BYTES + q * (TC_B_BYTES / 4), src + (int64_t) kc * TC_B_BYTES + q * (TC_B_BYTES / 4), TC_B_BYTES / 4, full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t tcount = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+                const int nt = t / A.tiles_m;
+                int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
+                const uint32_t idesc = tc_idesc((int) ((ncols + 15) & ~15));
+                const uint32_t acc = tcount & 1, d_tmem = tmem + acc * TC_N;
+                tc_mbar_wait(t_empty + 8 * acc, ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < nkc; ++kc, ++it) {
+                    const uint32_t s = it % TF_STAGES;
+                    tc_mbar_wait(full + 8 * s, (it / TF_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_s = sbase + s * (TC_A_BYTES + TC_B_BYTES), b_s = a_s + TC_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < TC_K / 16; ++j)
+                        tc_mma(d_tmem, tc_desc_sw128(a_s + j * 32), tc_desc(b_s + j * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), idesc, (kc | j) != 0);
+                    tc_commit(empty + 8 * s);
+                }
+                tc_commit(t_full + 8 * acc);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+            const int mt = t % A.tiles_m, nt = t / A.tiles_m;
+            const uint32_t acc = tcount & 1;
+            tc_mbar_wait(t_full + 8 * acc, (tcount >> 1) & 1);
+            tc_fence_after();
+            const int64_t mrow = (int64_t) mt * TC_M + quarter * 32 + lane;
+            int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
+            float * out = A.dst + ((int64_t) nt * TC_N) * A.dst_ld + mrow;
+            for (int cc = 0; cc * 32 < ncols; ++cc) {
+                uint32_t v[32];
+                tc_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + acc * TC_N + cc * 32, v);
+                if (mrow < A.m) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            tc_mbar_arrive(t_empty + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------------- host side
 bool mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w, int64_t row_stride) {
     if (n <= 8 || k % 256) return false;
@@ -506,6 +610,35 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
     A.tiles_m = (int) ((m + TC_M - 1) / TC_M); A.tiles_n = (int) (n_pad / TC_N);
     int grid = A.tiles_m * A.tiles_n; if (grid > sm_count()) grid = sm_count();
     k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A, wmap);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+bool mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t row_stride) {
+    return type == B200_F16 && n > 8 && k % 64 == 0 && (uintptr_t) w % 16 == 0 && row_stride == k * 2;
+}
+
+int mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st) {
+    static unsigned long long done = 0;
+    B200_CUDA_TRY(ensure_dyn_smem(k_mm_f16_tc, TF_SMEM, done));
+    if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
+    CUtensorMap wmap;
+    {
+        const cuuint64_t gdim[2] = { (cuuint64_t) k, (cuuint64_t) m }, gstr[1] = { (cuuint64_t) k * 2 };
+        const cuuint32_t box[2] = { TC_K, TC_M }, estr[2] = { 1, 1 };
+        if (tc_encoder()(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B200_ERR_UNSUPPORTED;
+    }
+    const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
+    if (!reuse_tiles) {
+        k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
+        B200_LAUNCH_CHECK();
+    }
+    TcF16Args A = {};
+    A.x16 = (const uint8_t *) scratch; A.dst = dst; A.dst_ld = dst_ld; A.m = m; A.k = k; A.n = n;
+    A.tiles_m = (int) ((m + TC_M - 1) / TC_M); A.tiles_n = (int) (n_pad / TC_N);
+    int grid = A.tiles_m * A.tiles_n; if (grid > sm_count()) grid = sm_count();
+    k_mm_f16_tc<<<grid, TF_THREADS, TF_SMEM, st>>>(A, wmap);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -14,6 +14,8 @@ int matvec_q_cols(const void * w, int type, int layout, int64_t m, int64_t row_s
 bool   mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w, int64_t row_stride);
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n);
 int    mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st);
+bool   mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t row_stride);
+int    mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st);
 static bool tc_disabled() { static const bool off = getenv("B200_DISABLE_TC") && atoi(getenv("B200_DISABLE_TC")) != 0; return off; }
 
 template <typename WT> __device__ __forceinline__ float w2f(WT v);
@@ -117,7 +119,8 @@ extern "C" int b200_mul_mat_supported(const b200_tensor * w, const b200_tensor *
 }
 
 extern "C" size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x) {
-    if (!is_quant(w->type)) return 0;
+    if (!is_quant(w->type)) return mm_f16_tc_supported(w->type, w->ne[0], x->ne[1], w->data, w->nb[1]) && (uintptr_t) x->data % 16 == 0 && x->nb[1] % 16 == 0 ?
+                                   mmq_tc_scratch_bytes(w->ne[0], x->ne[1]) : 0;
     const size_t act = (size_t) act_layout(w->type, w->ne[0]).bytes * (size_t) (x->ne[1] * x->ne[2] * x->ne[3]);
     // the tensor-core path keeps ONE batch slice of F16 activation tiles in the same scratch
     const size_t tc = mmq_tc_supported(w->type, w->layout, w->ne[0], x->ne[1], w->data, w->nb[1]) ? mmq_tc_scratch_bytes(w->ne[0], x->ne[1]) : 0;
@@ -138,6 +141,19 @@ extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, con
     if (m == 0 || n == 0 || dst->ne[2] * dst->ne[3] == 0) return B200_OK;
     const int64_t r2 = x->ne[2] / w->ne[2], r3 = x->ne[3] / w->ne[3];
     if (!is_quant(t)) {
+        // F16 weights, more than 8 columns: TMA-fed tcgen05 GEMM (mmq_tc.cu k_mm_f16_tc), one launch per batch slice
+        if (!tc_disabled() && mm_f16_tc_supported(t, k, n, w->data, w->nb[1]) && scratch && (uintptr_t) scratch % 16 == 0 &&
+            scratch_bytes >= mmq_tc_scratch_bytes(k, n) && (uintptr_t) x->data % 16 == 0 && x->nb[1] % 16 == 0 && x->nb[2] % 16 == 0 && x->nb[3] % 16 == 0 &&
+            w->nb[2] % 16 == 0 && w->nb[3] % 16 == 0 && dst->nb[1] % 4 == 0) {
+            for (int64_t i3 = 0; i3 < x->ne[3]; ++i3) for (int64_t i2 = 0; i2 < x->ne[2]; ++i2) {
+                const float * xs = (const float *) ((const char *) x->data + i2 * x->nb[2] + i3 * x->nb[3]);
+                const char * wb = (const char *) w->data + (i2 / r2) * w->nb[2] + (i3 / r3) * w->nb[3];
+                float * yb = (float *) ((char *) dst->data + i2 * dst->nb[2] + i3 * dst->nb[3]);
+                const int rc = mm_f16_tc(wb, m, k, xs, x->nb[1] / 4, n, yb, dst->nb[1] / 4, scratch, (flags & B200_MM_REUSE_ACT) && x->ne[2] * x->ne[3] == 1, st);
+                if (rc) return rc;
+            }
+            return B200_OK;
+        }
         MmvfArgs A = { (const char *) w->data, (const char *) x->data, (char *) dst->data, m, k, n,
                        w->nb[1], w->nb[2], w->nb[3], x->nb[1], x->nb[2], x->nb[3], dst->nb[1], dst->nb[2], dst->nb[3],
                        dst->ne[2], dst->ne[3], r2, r3 };

@@ -232,6 +232,24 @@ def test_mul_mat_float_weights(ops, dt):
     assert np.abs(got - ref).max() <= 1e-5 * (np.abs(x) @ np.abs(w).T).max()
 
 
+@pytest.mark.parametrize("m,k,n,batch", [(4096, 4096, 512, None), (300, 1024, 77, None), (129, 64, 9, None), (1152, 4304 // 16 * 16 - 4304 % 64, 200, None),
+                                          (256, 256, 33, (2, 3))])
+def test_mul_mat_f16_weights_tensor_core(ops, m, k, n, batch):
+    """F16 weights with more than 8 columns -> k_mm_f16_tc (2-D TMA with the 128-byte swizzle straight into the UMMA operand layout).  Same
+    arithmetic as the CPU oracle: activations rounded to F16 (vec_dot_type of F16 weights), products accumulated in F32."""
+    k = k // 64 * 64
+    rng = np.random.default_rng(m + k + n)
+    w = (rng.standard_normal((m, k)) * 0.05).astype(np.float16)
+    xs = (n, k) if batch is None else batch + (n, k)
+    x = rng.standard_normal(xs).astype(np.float32)
+    wt = torch.from_numpy(w).cuda()
+    got = ops.mul_mat(wt, ops.F16, m, k, dev(x), w_ne=[k, m]).cpu().numpy()
+    xr = torch.from_numpy(x).cuda().half().double()
+    ref = (xr @ wt.double().T).cpu().numpy()
+    mag = (np.abs(x.reshape(-1, k)) @ np.abs(w.astype(np.float32)).T).reshape(ref.shape)
+    assert np.all(np.abs(got - ref) <= 2e-6 * mag + 1e-9), (np.abs(got - ref) / (mag + 1e-30)).max()
+
+
 def test_matvec_jobs_residual_swiglu(ops):
     rng = np.random.default_rng(5)
     k = 1024

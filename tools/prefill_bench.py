@@ -14,18 +14,20 @@ from __graft_entry__ import load_package  # noqa: E402
 pkg = load_package()
 ops, dec = pkg.ops, pkg.decode
 dev = torch.device("cuda:0")
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2048
 pk = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
 PEAK = pk.get("bf16_tflops_sustained", 1400.0)
 E, F = 4096, 12288
 shapes = [("wq/wo q4_K", ops.Q4_K, 4096, E, 2), ("wk q4_K", ops.Q4_K, 1024, E, 1), ("wv q6_K", ops.Q6_K, 1024, E, 1),
           ("gate/up q4_K", ops.Q4_K, F, E, 2), ("down q6_K", ops.Q6_K, E, F, 0.5), ("down q4_K", ops.Q4_K, E, F, 0.5)]
+if "--f16" in sys.argv:                                   # the F16 model of BASELINE.json configs[4]: k_mm_f16_tc
+    shapes = [("wq/wo f16", ops.F16, 4096, E, 2), ("wk/wv f16", ops.F16, 1024, E, 2), ("gate/up f16", ops.F16, F, E, 2), ("down f16", ops.F16, E, F, 1)]
 gen = torch.Generator(device=dev)
 gen.manual_seed(0)
 total_us, total_flop = 0.0, 0.0
 out = {}
 for name, wt, m, k, per_layer in shapes:
-    w = dec._rand_weight(wt, m, k, gen, dev)
+    w = dec._rand_weight(wt, m, k, gen, dev) if wt != ops.F16 else (torch.randn(m, k, device=dev) * 0.02).half()
     x = torch.randn(n, k, device=dev)
     y = torch.empty(n, m, device=dev)
     layout = ops.LAYOUT_PLANAR if wt == ops.Q6_K else ops.LAYOUT_NATIVE
