@@ -4,19 +4,19 @@
 // flash_attn_mask_to_KV_max (fattn-common.cuh).  Oracle: ggml-cpu/ops.cpp:7912-8148 (Q rounded to f16, f32 softmax; the CPU accumulates V in
 // f16, we accumulate in f32 — the reference's own bar for this op is NMSE <= 5e-4, tests/test-backend-ops.cpp:5085).
 //
-// One CTA = 64 query tokens of one head (4 warps x 16 rows); K/V tiles of 64 positions stream through a double-buffered, XOR-swizzled
+// One CTA = 128 query tokens of one head (8 warps x 16 rows); K/V tiles of 64 positions stream through a double-buffered, XOR-swizzled
 // shared-memory ring with cp.async (16 B per thread, rows of the F16 cache are 256 B = 16 chunks); S = Q.K^T and O += P.V run as
 // mma.sync.m16n8k16 f16 -> f32 with ldmatrix(.trans) operand fetch, the online softmax lives in the accumulator registers (FlashAttention-2
 // layout: S accumulators of two 8-wide n-blocks ARE the A fragment of the P.V product).  Attention is ~4 % of the prefill FLOPs (SURVEY §8d:
 // 1.24 of 29.7 TFLOP at 2048 tokens), the tcgen05 budget of round 1 went to the 96 % in k_mmq_tc; a TMEM-resident FA is the next step.
-//   * k_fa_kvmax: per 64-row query tile, the number of KV tiles that contain any unmasked position (causal masks: everything right of the
+//   * k_fa_kvmax: per query tile (FP_BM rows), the number of KV tiles that contain any unmasked position (causal masks: everything right of the
 //     diagonal is skipped, which halves the work) — the mask is shared by all heads, so this runs once per launch, not per head.
 #include "common.cuh"
 #include <math.h>
 
 namespace b200 {
 
-constexpr int FP_BM = 64, FP_BN = 64, FP_THREADS = 128;
+constexpr int FP_BM = 128, FP_BN = 64, FP_THREADS = 256;     // 8 warps x 16 query rows share every K/V tile
 
 struct FaPArgs {
     const char * q; const char * k; const char * v; const char * mask; char * dst;
@@ -53,7 +53,7 @@ __device__ __forceinline__ uint32_t fp_pack(float lo, float hi) { const __half2 
 __global__ void __launch_bounds__(128) k_fa_kvmax(const char * mask, int64_t m_nb1, int64_t m_nb3, int64_t n_q, int64_t n_kv, int32_t * out_max, int32_t * out_plain, int n_q_tiles) {
     const int qt = blockIdx.x, kt = blockIdx.y, ib = blockIdx.z;
     bool any = false, nonzero = false;
-    for (int i = threadIdx.x; i < FP_BM * (FP_BN / 8); i += blockDim.x) {            // 64 rows x 8 chunks of 8 halves
+    for (int i = threadIdx.x; i < FP_BM * (FP_BN / 8); i += blockDim.x) {            // FP_BM rows x 8 chunks of 8 halves
         const int64_t row = (int64_t) qt * FP_BM + i / (FP_BN / 8), col = (int64_t) kt * FP_BN + (i % (FP_BN / 8)) * 8;
         if (row >= n_q || col >= n_kv) continue;
         const char * p = mask + row * m_nb1 + ib * m_nb3 + col * 2;

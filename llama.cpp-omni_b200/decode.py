@@ -253,12 +253,14 @@ class Qwen3Decoder:
         bufs = {k: torch.empty((n, m), device=dev) for k, m in (("a", E), ("q", q), ("k", kv), ("v", kv), ("attn", q), ("x1", E), ("g", F), ("u", F), ("h", F), ("x2", E))}
         fa_scratch = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
 
-        def mm(w, wtype, m, k, xin, out):
-            ops.mul_mat(w, wtype, m, k, xin, layout=ops.LAYOUT_PLANAR if wtype == ops.Q6_K else ops.LAYOUT_NATIVE, out=out)
+        mm_scratch = torch.empty((n + 255) // 256 * 256 * max(E, F, q) * 2, dtype=torch.uint8, device=dev)      # F16 activation tiles of one MUL_MAT
+
+        def mm(w, wtype, m, k, xin, out, reuse=False):
+            ops.mul_mat(w, wtype, m, k, xin, layout=ops.LAYOUT_PLANAR if wtype == ops.Q6_K else ops.LAYOUT_NATIVE, out=out, scratch=mm_scratch, reuse_act=reuse)
         for lw in self.L:
             ty = lw["types"]
             ops.rms_norm(x, cfg.rms_eps, w=lw["attn_norm"], out=bufs["a"])
-            mm(lw["wq"], ty["wq"], q, E, bufs["a"], bufs["q"]); mm(lw["wk"], ty["wk"], kv, E, bufs["a"], bufs["k"]); mm(lw["wv"], ty["wv"], kv, E, bufs["a"], bufs["v"])
+            mm(lw["wq"], ty["wq"], q, E, bufs["a"], bufs["q"]); mm(lw["wk"], ty["wk"], kv, E, bufs["a"], bufs["k"], n > 8); mm(lw["wv"], ty["wv"], kv, E, bufs["a"], bufs["v"], n > 8)
             ops.check(L.b200_qkv_post(P(bufs["q"].data_ptr()), P(bufs["k"].data_ptr()), P(bufs["v"].data_ptr()), P(lw["q_norm"].data_ptr()),
                                       P(lw["k_norm"].data_ptr()), P(pos.data_ptr()), P(idx.data_ptr()), ops.I64,
                                       P(lw["k_cache"].data_ptr()), P(lw["v_cache"].data_ptr()), C.c_int64(kv * 2), C.c_int64(kv * 2),
@@ -271,7 +273,7 @@ class Qwen3Decoder:
             mm(lw["wo"], ty["wo"], E, q, bufs["attn"], bufs["x1"])
             ops.binary(ops.ADD, bufs["x1"], x, out=bufs["x1"])
             ops.rms_norm(bufs["x1"], cfg.rms_eps, w=lw["ffn_norm"], out=bufs["a"])
-            mm(lw["gate"], ty["gate"], F, E, bufs["a"], bufs["g"]); mm(lw["up"], ty["up"], F, E, bufs["a"], bufs["u"])
+            mm(lw["gate"], ty["gate"], F, E, bufs["a"], bufs["g"]); mm(lw["up"], ty["up"], F, E, bufs["a"], bufs["u"], n > 8)
             ops.check(L.b200_glu(ops.GLU_SWIGLU, ops._ref(ops.T(bufs["g"])), ops._ref(ops.T(bufs["u"])), ops._ref(ops.T(bufs["h"])), 0, st))
             mm(lw["down"], ty["down"], E, F, bufs["h"], bufs["x2"])              # the layer input (x) is dead once x1 exists: x2 may be the same buffer
             x = ops.binary(ops.ADD, bufs["x2"], bufs["x1"], out=bufs["x2"])

@@ -178,8 +178,9 @@ def quantize_act(wtype: int, x: torch.Tensor) -> torch.Tensor:
 
 
 def mul_mat(w: torch.Tensor, wtype: int, m: int, k: int, x: torch.Tensor, layout: int = LAYOUT_NATIVE, w_ne=None, w_nb=None,
-            out: torch.Tensor | None = None) -> torch.Tensor:
-    """dst[..., n, m] = x[..., n, k] . W[m, k]^T   (GGML_OP_MUL_MAT)."""
+            out: torch.Tensor | None = None, scratch: torch.Tensor | None = None, reuse_act: bool = False) -> torch.Tensor:
+    """dst[..., n, m] = x[..., n, k] . W[m, k]^T   (GGML_OP_MUL_MAT).  `scratch` + `reuse_act`: b200_mul_mat_ex with B200_MM_REUSE_ACT — the caller
+    passes the SAME scratch as for the previous call on the same x (q/k/v, gate/up), whose prepared activations are then not rebuilt."""
     L = lib()
     wd = T(w, wtype, ne=w_ne or [k, m], nb=w_nb, layout=layout)
     xd = T(x)
@@ -189,8 +190,11 @@ def mul_mat(w: torch.Tensor, wtype: int, m: int, k: int, x: torch.Tensor, layout
     if not L.b200_mul_mat_supported(C.byref(wd), C.byref(xd), C.byref(od)):
         raise B200Error("mul_mat: unsupported")
     sb = L.b200_mul_mat_scratch_bytes(C.byref(wd), C.byref(xd))
-    scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
-    check(L.b200_mul_mat(C.byref(wd), C.byref(xd), C.byref(od), C.c_void_p(scratch.data_ptr()), C.c_size_t(sb), stream()))
+    if scratch is None or scratch.numel() < sb:
+        if reuse_act:
+            raise B200Error("mul_mat: reuse_act needs the scratch of the previous call")
+        scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
+    check(L.b200_mul_mat_ex(C.byref(wd), C.byref(xd), C.byref(od), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), int(reuse_act), stream()))
     return out
 
 
