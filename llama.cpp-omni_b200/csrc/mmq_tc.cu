@@ -47,6 +47,9 @@ struct TcArgs {
     int64_t m, k, n, row_bytes;                     // n = real columns; row_bytes of the payload plane
     int type, tiles_m, tiles_n;
     int span_bytes, n_raw;                          // payload bytes of 256 weights of one row (= TMA box width); raw ring slots
+    int splitk;                                     // 1, or 2: two CTAs share a tile, each reduces half of K and adds its partial to dst with red.global.add (dst zeroed by the launcher;
+                                                    // two addends commute, so the result is still deterministic)
+    int nsub;                                       // 1: tiles are 256 columns wide; 2: 128 (twice the tiles when 256-wide ones cannot fill the SMs)
     int flags;                                      // experiment switches (B200_TC_FLAGS): 1 no dequant, 2 no MMA, 4 no B copies
 };
 
@@ -72,6 +75,18 @@ __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap * map,
 }
 __device__ __forceinline__ uint4 tc_lds16(uint32_t a) { uint4 r; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
 __device__ __forceinline__ uint2 tc_lds8(uint32_t a) { uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a)); return r; }
+// one stage of activations: the 256-column tile is [8 K-chunks][32 row groups][128 B]; a 128-column half tile is 8 pieces of 2 KB
+__device__ __forceinline__ void tc_load_b(uint32_t dst, const uint8_t * tile, int nsub, int half, uint32_t bar, bool expect) {
+    if (nsub == 1) {
+        if (expect) tc_mbar_expect_tx(bar, 32768);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tc_bulk_g2s(dst + q * 8192, tile + q * 8192, 8192, bar);
+    } else {
+        if (expect) tc_mbar_expect_tx(bar, 16384);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tc_bulk_g2s(dst + q * 2048, tile + q * 4096 + half * 2048, 2048, bar);
+    }
+}
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp): start address, leading
 // (K direction) and stride (M/N direction) byte offsets in 16-byte units, descriptor version 1 (Blackwell), layout type 0
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -345,41 +360,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int n_tiles = A.tiles_m * A.tiles_n, nkc = (int) (A.k >> 6);        // K chunks of 64 per tile
+    const int n_tiles = A.tiles_m * A.tiles_n * A.splitk, nkc = (int) (A.k >> 6) / A.splitk;        // work items; K chunks of 64 per work item
     uint32_t it = 0;                                                          // stage uses so far (same sequence in every role)
 
     if (warp < 8) {
         // ================================================================== A producers (dequant)
         const int row = threadIdx.x & 127, g = threadIdx.x >> 7;
         const uint32_t stage0 = sbase + row * 16;                              // row group (row >> 3) * TC_SBO + (row & 7) * 16
-        const int64_t nkb = A.k >> 8;
+        const int64_t nkb = (A.k >> 8) / A.splitk;                            // 256-weight spans per work item
         uint32_t rit = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it += (uint32_t) nkc, rit += (uint32_t) nkb) {
-            const int mt = t % A.tiles_m;
+            const int mt = (t / A.splitk) % A.tiles_m;
             int64_t gr = (int64_t) mt * TC_M + row; if (gr >= A.m) gr = A.m - 1;        // tail rows (zero-filled by TMA): any valid d, never stored
             const uint32_t rrow = raw0 + row * A.span_bytes, rstride = (uint32_t) (TC_M * A.span_bytes), nr = (uint32_t) A.n_raw;
             switch (A.type) {
                 case B200_Q4_K: tc_produce_tile<RawQ4K>(rrow, rstride, nr, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
                 case B200_Q5_K: tc_produce_tile<RawQ5K>(rrow, rstride, nr, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
-                case B200_Q6_K: tc_produce_tile<RawQ6K>(rrow, rstride, nr, A.wd + gr * nkb * 2, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
-                case B200_Q8_0: tc_produce_tile<RawQ80>(rrow, rstride, nr, A.wd + gr * nkb * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
-                default:        tc_produce_tile<RawQ40>(rrow, rstride, nr, A.wd + gr * nkb * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                case B200_Q6_K: tc_produce_tile<RawQ6K>(rrow, rstride, nr, A.wd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 2, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                case B200_Q8_0: tc_produce_tile<RawQ80>(rrow, rstride, nr, A.wd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                default:        tc_produce_tile<RawQ40>(rrow, rstride, nr, A.wd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
             }
         }
     } else if (warp == 8) {
         // ================================================================== B producer (TMA bulk copies of pre-tiled F16 activations)
         if (lane == 0) {
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int nt = t / A.tiles_m;
-                const uint8_t * src = A.x16 + (int64_t) nt * nkc * TC_B_BYTES;
+                const int ntx = (t / A.splitk) / A.tiles_m, nt = ntx / A.nsub, half = ntx % A.nsub;
+                const uint8_t * src = A.x16 + ((int64_t) nt * nkc * A.splitk + (int64_t) (t % A.splitk) * nkc) * TC_B_BYTES;
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const uint32_t s = it % TC_STAGES;
                     tc_mbar_wait(empty + 8 * s, ((it / TC_STAGES) & 1) ^ 1);
                     if (A.flags & 4) { tc_mbar_arrive(b_full + 8 * s); continue; }
-                    tc_mbar_expect_tx(b_full + 8 * s, TC_B_BYTES);
                     const uint32_t dst = sbase + s * (TC_A_BYTES + TC_B_BYTES) + TC_A_BYTES;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tc_bulk_g2s(dst + q * (TC_B_BYTES / 4), src + (int64_t) kc * TC_B_BYTES + q * (TC_B_BYTES / 4), TC_B_BYTES / 4, b_full + 8 * s);
+                    tc_load_b(dst, src + (int64_t) kc * TC_B_BYTES, A.nsub, half, b_full + 8 * s, true);
                 }
             }
         }
@@ -388,9 +401,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
         if (lane == 0) {
             uint32_t tcount = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-                const int nt = t / A.tiles_m;
-                int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
+                const int ntx = (t / A.splitk) / A.tiles_m, wn = TC_N / A.nsub;
+                int64_t ncols = A.n - (int64_t) ntx * wn; if (ncols > wn) ncols = wn;
                 const uint32_t idesc = tc_idesc((int) ((ncols + 15) & ~15));
+                const uint32_t b_lbo = (uint32_t) (wn / 8) * 128;
+                const uint64_t b_hi = tc_desc(0, b_lbo, TC_SBO);              // everything but the start address; the K-step advances the address by 2 LBO
                 const uint32_t acc = tcount & 1, d_tmem = tmem + acc * TC_N;
                 tc_mbar_wait(t_empty + 8 * acc, ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
                     const uint32_t a_s = sbase + s * (TC_A_BYTES + TC_B_BYTES), b_s = a_s + TC_A_BYTES;
 #pragma unroll
                     for (int j = 0; j < TC_K / 16; ++j)
-                        if (!(A.flags & 2)) tc_mma(d_tmem, tc_desc(a_s + j * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), tc_desc(b_s + j * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), idesc, (kc | j) != 0);
+                        if (!(A.flags & 2)) tc_mma(d_tmem, tc_desc(a_s + j * 2 * TC_A_LBO, TC_A_LBO, TC_SBO), b_hi | (uint64_t) ((b_s + j * 2 * b_lbo) >> 4), idesc, (kc | j) != 0);
                     tc_commit(empty + 8 * s);                                 // frees the stage when these MMAs have read it
                 }
                 tc_commit(t_full + 8 * acc);                                  // accumulator complete
@@ -412,16 +427,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
         // ================================================================== raw weight producer: one 2-D TMA (128 rows x one quant block) per 4 stages
         if (lane == 0) {
             const int blk = A.span_bytes;
-            const int nkb = (int) (A.k >> 8);
+            const int nkb = (int) (A.k >> 8) / A.splitk;
             const uint32_t n_raw = (uint32_t) A.n_raw, rstride = (uint32_t) (TC_M * A.span_bytes);
             uint32_t ru = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int mt = t % A.tiles_m;
+                const int mt = (t / A.splitk) % A.tiles_m;
                 for (int kb = 0; kb < nkb; ++kb, ++ru) {
                     const uint32_t r = ru % n_raw;
                     tc_mbar_wait(raw_empty + 8 * r, ((ru / n_raw) & 1) ^ 1);
                     tc_mbar_expect_tx(raw_full + 8 * r, rstride);
-                    tc_tma_2d(raw0 + r * rstride, &wmap, kb * blk, mt * TC_M, raw_full + 8 * r);
+                    tc_tma_2d(raw0 + r * rstride, &wmap, ((t % A.splitk) * nkb + kb) * blk, mt * TC_M, raw_full + 8 * r);
                 }
             }
         }
@@ -430,19 +445,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
         const int quarter = warp & 3;
         uint32_t tcount = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-            const int mt = t % A.tiles_m, nt = t / A.tiles_m;
+            const int mt = (t / A.splitk) % A.tiles_m, ntx = (t / A.splitk) / A.tiles_m, wn = TC_N / A.nsub;
             const uint32_t acc = tcount & 1;
             tc_mbar_wait(t_full + 8 * acc, (tcount >> 1) & 1);
             tc_fence_after();
             const int64_t mrow = (int64_t) mt * TC_M + quarter * 32 + lane;
-            int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
-            float * out = A.dst + ((int64_t) nt * TC_N) * A.dst_ld + mrow;
+            int64_t ncols = A.n - (int64_t) ntx * wn; if (ncols > wn) ncols = wn;
+            float * out = A.dst + ((int64_t) ntx * wn) * A.dst_ld + mrow;
             for (int cc = 0; cc * 32 < ncols; ++cc) {
                 uint32_t v[32];
                 tc_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + acc * TC_N + cc * 32, v);
-                if (mrow < A.m) {
+                if (mrow < A.m && A.splitk == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __uint_as_float(v[j]);
+                } else if (mrow < A.m) {
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) atomicAdd(out + (int64_t) (cc * 32 + j) * A.dst_ld, __uint_as_float(v[j]));
                 }
             }
             tc_fence_before();
@@ -464,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
 constexpr int TF_STAGES = 4, TF_THREADS = 192;
 constexpr int TF_SMEM = TF_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 + 256;
 
-struct TcF16Args { const uint8_t * x16; float * dst; int64_t dst_ld, m, k, n; int tiles_m, tiles_n; };
+struct TcF16Args { const uint8_t * x16; float * dst; int64_t dst_ld, m, k, n; int tiles_m, tiles_n, nsub, splitk; };
 
 __device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t saddr) {      // K-major SWIZZLE_128B: SBO = 1024 B (8 rows x 128 B), LBO unused, layout type 2
     return (uint64_t) ((saddr & 0x3ffff) >> 4) | ((uint64_t) 1 << 16) | ((uint64_t) (1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -489,21 +506,20 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_mm_f16_tc(const __grid_consta
     __syncthreads();
     tc_fence_after();
     uint32_t tmem; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot_a));
-    const int n_tiles = A.tiles_m * A.tiles_n, nkc = (int) (A.k >> 6);
+    const int n_tiles = A.tiles_m * A.tiles_n * A.splitk, nkc = (int) (A.k >> 6) / A.splitk;
     uint32_t it = 0;
     if (warp == 0) {
         if (lane == 0) {
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int mt = t % A.tiles_m, nt = t / A.tiles_m;
-                const uint8_t * src = A.x16 + (int64_t) nt * nkc * TC_B_BYTES;
+                const int mt = (t / A.splitk) % A.tiles_m, ntx = (t / A.splitk) / A.tiles_m, nt = ntx / A.nsub, half = ntx % A.nsub;
+                const uint8_t * src = A.x16 + ((int64_t) nt * nkc * A.splitk + (int64_t) (t % A.splitk) * nkc) * TC_B_BYTES;
                 for (int kc = 0; kc < nkc; ++kc, ++it) {
                     const uint32_t s = it % TF_STAGES;
                     tc_mbar_wait(empty + 8 * s, ((it / TF_STAGES) & 1) ^ 1);
-                    tc_mbar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES);
+                    tc_mbar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES / A.nsub);
                     const uint32_t a_s = sbase + s * (TC_A_BYTES + TC_B_BYTES);
-                    tc_tma_2d(a_s, &wmap, kc * TC_K, mt * TC_M, full + 8 * s);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tc_bulk_g2s(a_s + TC_A_BYTES + q * (TC_B_BYTES / 4), src + (int64_t) kc * TC_B_BYTES + q * (TC_B_BYTES / 4), TC_B_BYTES / 4, full + 8 * s);
+                    tc_tma_2d(a_s, &wmap, ((t % A.splitk) * nkc + kc) * TC_K, mt * TC_M, full + 8 * s);
+                    tc_load_b(a_s + TC_A_BYTES, src + (int64_t) kc * TC_B_BYTES, A.nsub, half, full + 8 * s, false);
                 }
             }
         }
@@ -511,9 +527,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_mm_f16_tc(const __grid_consta
         if (lane == 0) {
             uint32_t tcount = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-                const int nt = t / A.tiles_m;
-                int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
+                const int ntx = (t / A.splitk) / A.tiles_m, wn = TC_N / A.nsub;
+                int64_t ncols = A.n - (int64_t) ntx * wn; if (ncols > wn) ncols = wn;
                 const uint32_t idesc = tc_idesc((int) ((ncols + 15) & ~15));
+                const uint32_t b_lbo = (uint32_t) (wn / 8) * 128;
+                const uint64_t b_hi = tc_desc(0, b_lbo, TC_SBO);              // everything but the start address; the K-step advances the address by 2 LBO
                 const uint32_t acc = tcount & 1, d_tmem = tmem + acc * TC_N;
                 tc_mbar_wait(t_empty + 8 * acc, ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -524,7 +542,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_mm_f16_tc(const __grid_consta
                     const uint32_t a_s = sbase + s * (TC_A_BYTES + TC_B_BYTES), b_s = a_s + TC_A_BYTES;
 #pragma unroll
                     for (int j = 0; j < TC_K / 16; ++j)
-                        tc_mma(d_tmem, tc_desc_sw128(a_s + j * 32), tc_desc(b_s + j * 2 * TC_B_LBO, TC_B_LBO, TC_SBO), idesc, (kc | j) != 0);
+                        tc_mma(d_tmem, tc_desc_sw128(a_s + j * 32), b_hi | (uint64_t) ((b_s + j * 2 * b_lbo) >> 4), idesc, (kc | j) != 0);
                     tc_commit(empty + 8 * s);
                 }
                 tc_commit(t_full + 8 * acc);
@@ -534,19 +552,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_mm_f16_tc(const __grid_consta
         const int quarter = warp & 3;
         uint32_t tcount = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-            const int mt = t % A.tiles_m, nt = t / A.tiles_m;
+            const int mt = (t / A.splitk) % A.tiles_m, ntx = (t / A.splitk) / A.tiles_m, wn = TC_N / A.nsub;
             const uint32_t acc = tcount & 1;
             tc_mbar_wait(t_full + 8 * acc, (tcount >> 1) & 1);
             tc_fence_after();
             const int64_t mrow = (int64_t) mt * TC_M + quarter * 32 + lane;
-            int64_t ncols = A.n - (int64_t) nt * TC_N; if (ncols > TC_N) ncols = TC_N;
-            float * out = A.dst + ((int64_t) nt * TC_N) * A.dst_ld + mrow;
+            int64_t ncols = A.n - (int64_t) ntx * wn; if (ncols > wn) ncols = wn;
+            float * out = A.dst + ((int64_t) ntx * wn) * A.dst_ld + mrow;
             for (int cc = 0; cc * 32 < ncols; ++cc) {
                 uint32_t v[32];
                 tc_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + acc * TC_N + cc * 32, v);
-                if (mrow < A.m) {
+                if (mrow < A.m && A.splitk == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __uint_as_float(v[j]);
+                } else if (mrow < A.m) {
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) atomicAdd(out + (int64_t) (cc * 32 + j) * A.dst_ld, __uint_as_float(v[j]));
                 }
             }
             tc_fence_before();
@@ -565,6 +585,19 @@ bool mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w
     if (type == B200_Q4_K || type == B200_Q5_K) return row_stride == k / 256 * type_size(type);             // native 16-byte-multiple blocks
     if (type == B200_Q6_K || type == B200_Q8_0 || type == B200_Q4_0) return layout == B200_LAYOUT_PLANAR;   // payload plane + f16 d plane
     return false;
+}
+// 128-column tiles when the work items (tiles x split-K) cannot give even half of the SMs something to do (small m, small ubatches)
+static int tc_nsub(int tiles_m, int64_t n) {
+    static const int thr = getenv("B200_TC_N128_MAX") ? atoi(getenv("B200_TC_N128_MAX")) : 0;
+    const int64_t tiles256 = (int64_t) tiles_m * ((n + TC_N - 1) / TC_N);
+    return n > TC_N / 2 && tiles256 * 2 <= (thr > 0 ? thr : sm_count()) ? 2 : 1;        // only while the doubled tile count still fits one wave
+}
+// two CTAs per tile, half of K each, when even the 256-column tiling leaves more than half of the SMs without work (`units` = K in units that
+// must stay whole per CTA: 256-weight spans for quantised weights, 128 for F16)
+static int tc_splitk(int tiles_m, int64_t n, int64_t units) {
+    static const int off = getenv("B200_TC_NO_SPLITK") ? atoi(getenv("B200_TC_NO_SPLITK")) : 0;
+    const int64_t tiles256 = (int64_t) tiles_m * ((n + TC_N - 1) / TC_N);
+    return !off && units % 2 == 0 && units >= 4 && tiles256 * 2 <= sm_count() ? 2 : 1;
 }
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n) { return (size_t) ((n + TC_N - 1) / TC_N * TC_N) * (size_t) k * 2; }
 
@@ -607,8 +640,11 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
     A.n_raw = TC_RAW_REGION / (TC_M * A.span_bytes) >= TC_RAW_MAX ? TC_RAW_MAX : TC_RAW_REGION / (TC_M * A.span_bytes);
     A.row_bytes = nkb * A.span_bytes;
     A.wd = payload_size(type) != type_size(type) ? (const uint8_t *) w + m * A.row_bytes : nullptr;          // planar: f16 d plane behind the payload plane
-    A.tiles_m = (int) ((m + TC_M - 1) / TC_M); A.tiles_n = (int) (n_pad / TC_N);
-    int grid = A.tiles_m * A.tiles_n; if (grid > sm_count()) grid = sm_count();
+    A.tiles_m = (int) ((m + TC_M - 1) / TC_M);
+    A.splitk = tc_splitk(A.tiles_m, n, k / 256);
+    A.nsub = tc_nsub(A.tiles_m * A.splitk, n); A.tiles_n = (int) ((n + TC_N / A.nsub - 1) / (TC_N / A.nsub));
+    if (A.splitk > 1) B200_CUDA_TRY(cudaMemset2DAsync(dst, (size_t) dst_ld * 4, 0, (size_t) m * 4, (size_t) n, st));
+    int grid = A.tiles_m * A.tiles_n * A.splitk; if (grid > sm_count()) grid = sm_count();
     k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A, wmap);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -636,8 +672,11 @@ int mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_l
     }
     TcF16Args A = {};
     A.x16 = (const uint8_t *) scratch; A.dst = dst; A.dst_ld = dst_ld; A.m = m; A.k = k; A.n = n;
-    A.tiles_m = (int) ((m + TC_M - 1) / TC_M); A.tiles_n = (int) (n_pad / TC_N);
-    int grid = A.tiles_m * A.tiles_n; if (grid > sm_count()) grid = sm_count();
+    A.tiles_m = (int) ((m + TC_M - 1) / TC_M);
+    A.splitk = tc_splitk(A.tiles_m, n, k / 128);
+    A.nsub = tc_nsub(A.tiles_m * A.splitk, n); A.tiles_n = (int) ((n + TC_N / A.nsub - 1) / (TC_N / A.nsub));
+    if (A.splitk > 1) B200_CUDA_TRY(cudaMemset2DAsync(dst, (size_t) dst_ld * 4, 0, (size_t) m * 4, (size_t) n, st));
+    int grid = A.tiles_m * A.tiles_n * A.splitk; if (grid > sm_count()) grid = sm_count();
     k_mm_f16_tc<<<grid, TF_THREADS, TF_SMEM, st>>>(A, wmap);
     B200_LAUNCH_CHECK();
     return B200_OK;
