@@ -129,6 +129,69 @@ __device__ __forceinline__ ActLayout sd_act_layout(int act_group, int kl) {
     return L;
 }
 
+// fast path of sd_prologue (every phase of the decode program): ONE pass over the inputs — each warp keeps its <= 2 super-blocks in registers
+// between the sum of squares and the quantisation.  A round trip to L2 costs ~1 us while the weight stream saturates HBM, so ALL loads of the
+// prologue (NX summands x 2 blocks, and the norm weights) are issued back to back, branch-free, before any use.  NX is a template parameter:
+// the single-input phases (wo, gate/up, down) must not carry the register pressure of the 4-summand layer-entry phase.
+template <int NX>
+__device__ __forceinline__ void sd_prologue_fast(const SdPhase & P, uint8_t * act, float * red, unsigned long long * pf, const ActLayout & L, int k, int kl, int k0,
+                                                 bool norm, bool writer) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float scale = 1.0f;
+
+    const int nb = kl >> 8, n_x = P.n_x;
+    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 a[2][NX][2], w[2][2];
+    if (pf) pf[6] = globaltimer();
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const bool live = warp + SD_WARPS * t < nb;
+        const int e = k0 + (live ? warp + SD_WARPS * t : warp) * 256 + lane * 8;
+#pragma unroll
+        for (int sx = 0; sx < NX; ++sx) {
+            const bool on = live && sx < n_x;
+            const float * px = P.x[on ? sx : 0] + e;
+            a[t][sx][0] = on ? __ldcg((const float4 *) px) : z4; a[t][sx][1] = on ? __ldcg((const float4 *) (px + 4)) : z4;
+        }
+        w[t][0] = norm && live ? __ldg((const float4 *) (P.norm_w + e)) : z4; w[t][1] = norm && live ? __ldg((const float4 *) (P.norm_w + e + 4)) : z4;
+    }
+    float v[2][8];
+    float ss = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        v[t][0] = a[t][0][0].x; v[t][1] = a[t][0][0].y; v[t][2] = a[t][0][0].z; v[t][3] = a[t][0][0].w;
+        v[t][4] = a[t][0][1].x; v[t][5] = a[t][0][1].y; v[t][6] = a[t][0][1].z; v[t][7] = a[t][0][1].w;
+#pragma unroll
+        for (int sx = 1; sx < NX; ++sx) if (sx < n_x) {                 // fixed order x[0] + x[1] + ...: deterministic
+            v[t][0] += a[t][sx][0].x; v[t][1] += a[t][sx][0].y; v[t][2] += a[t][sx][0].z; v[t][3] += a[t][sx][0].w;
+            v[t][4] += a[t][sx][1].x; v[t][5] += a[t][sx][1].y; v[t][6] += a[t][sx][1].z; v[t][7] += a[t][sx][1].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
+    }
+    if (pf) pf[4] = globaltimer();
+    if (norm) scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
+    if (pf) pf[5] = globaltimer();
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int blk = warp + SD_WARPS * t;
+        if (blk < nb) {
+            const int e = k0 + blk * 256 + lane * 8;
+            if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
+            if (norm) {
+                const float wv[8] = { w[t][0].x, w[t][0].y, w[t][0].z, w[t][0].w, w[t][1].x, w[t][1].y, w[t][1].z, w[t][1].w };
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[t][i] = __fmul_rn(__fmul_rn(v[t][i], scale), wv[i]);
+                if (writer && P.norm_out) {
+                    *(float4 *) (P.norm_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]);
+                }
+            }
+            quant_block_q8K<true>(v[t], act, blk, L.d_off, L.bsum_off);
+        }
+    }
+    cons_sync();
+    }
+
 __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_t * act, float * red, unsigned long long * pf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = P.k, kl = k / P.ksplit, k0 = kpart * kl;                 // this CTA quantises [k0, k0 + kl)
@@ -147,60 +210,8 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
     float scale = 1.0f;
     const bool norm = P.prologue == SD_PRO_RMSNORM_QUANT;
     if (P.act_group == 256 && (kl >> 8) <= 2 * SD_WARPS && (P.ksplit == 1 || !norm)) {
-        // fast path (every phase of the decode program): ONE pass over the inputs — each warp keeps its <= 2 super-blocks in registers
-        // between the sum of squares and the quantisation.  A round trip to L2 costs ~1 us while the weight stream saturates HBM, so ALL
-        // loads of the prologue (up to 4 summands x 2 blocks, and the norm weights) are issued back to back, branch-free, before any use.
-        const int nb = kl >> 8, n_x = P.n_x;
-        const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        float4 a[2][4][2], w[2][2];
-        if (pf) pf[6] = globaltimer();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const bool live = warp + SD_WARPS * t < nb;
-            const int e = k0 + (live ? warp + SD_WARPS * t : warp) * 256 + lane * 8;
-#pragma unroll
-            for (int sx = 0; sx < 4; ++sx) {
-                const bool on = live && sx < n_x;
-                const float * px = P.x[on ? sx : 0] + e;
-                a[t][sx][0] = on ? __ldcg((const float4 *) px) : z4; a[t][sx][1] = on ? __ldcg((const float4 *) (px + 4)) : z4;
-            }
-            w[t][0] = norm && live ? __ldg((const float4 *) (P.norm_w + e)) : z4; w[t][1] = norm && live ? __ldg((const float4 *) (P.norm_w + e + 4)) : z4;
-        }
-        float v[2][8];
-        float ss = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            v[t][0] = a[t][0][0].x; v[t][1] = a[t][0][0].y; v[t][2] = a[t][0][0].z; v[t][3] = a[t][0][0].w;
-            v[t][4] = a[t][0][1].x; v[t][5] = a[t][0][1].y; v[t][6] = a[t][0][1].z; v[t][7] = a[t][0][1].w;
-#pragma unroll
-            for (int sx = 1; sx < 4; ++sx) if (sx < n_x) {                 // fixed order x[0] + x[1] + ...: deterministic
-                v[t][0] += a[t][sx][0].x; v[t][1] += a[t][sx][0].y; v[t][2] += a[t][sx][0].z; v[t][3] += a[t][sx][0].w;
-                v[t][4] += a[t][sx][1].x; v[t][5] += a[t][sx][1].y; v[t][6] += a[t][sx][1].z; v[t][7] += a[t][sx][1].w;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
-        }
-        if (pf) pf[4] = globaltimer();
-        if (norm) scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
-        if (pf) pf[5] = globaltimer();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int blk = warp + SD_WARPS * t;
-            if (blk < nb) {
-                const int e = k0 + blk * 256 + lane * 8;
-                if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
-                if (norm) {
-                    const float wv[8] = { w[t][0].x, w[t][0].y, w[t][0].z, w[t][0].w, w[t][1].x, w[t][1].y, w[t][1].z, w[t][1].w };
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[t][i] = __fmul_rn(__fmul_rn(v[t][i], scale), wv[i]);
-                    if (writer && P.norm_out) {
-                        *(float4 *) (P.norm_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]);
-                    }
-                }
-                quant_block_q8K<true>(v[t], act, blk, L.d_off, L.bsum_off);
-            }
-        }
-        cons_sync();
+        if (P.n_x == 1) sd_prologue_fast<1>(P, act, red, pf, L, k, kl, k0, norm, writer);
+        else            sd_prologue_fast<4>(P, act, red, pf, L, k, kl, k0, norm, writer);
         return;
     }
     if (norm) {                                                           // generic path: separate sum-of-squares pass over the FULL row
@@ -402,8 +413,14 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const 
     if (pf) pf[7] = (unsigned long long) waited;                           // cycles warp 0 spent waiting for weights in this phase
 }
 
+// PROF = false is the production instantiation: `pf` is a compile-time null in every inlined helper and the experiment switches are a compile-time
+// 0, so neither the %globaltimer stamps nor their branches and registers exist in it (the kernel is far larger than the instruction caches
+// and its speed moves by several per cent with the position of the hot loops).
+template <bool PROF>
 __global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * __restrict__ phases_g, int n_phases, unsigned * gbar,
-                                                               const __grid_constant__ SdPhase single, const SdRuntime rt) {
+                                                               const __grid_constant__ SdPhase single, const SdRuntime rt_in) {
+    SdRuntime rt = rt_in;
+    if (!PROF) { rt.flags = 0; rt.prof = nullptr; }
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t  * ring = smem;
     uint8_t  * act  = smem + SD_RING_BYTES;
@@ -443,7 +460,7 @@ __global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * 
     uint32_t consumed = 0;
     unsigned bar_base = 0;                                                // value of the arrival counter when this launch began
     if (threadIdx.x == 0 && n_phases > 1) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bar_base) : "l"(gbar + 32) : "memory");
-    const bool prof = rt.prof != nullptr && threadIdx.x == 0;
+    const bool prof = PROF && rt.prof != nullptr && threadIdx.x == 0;
     unsigned long long * const pbase = prof ? rt.prof + (size_t) blockIdx.x * 8 : nullptr;      // [phase][cta][8]
     const size_t pstr = (size_t) gridDim.x * 8;
 
@@ -454,18 +471,18 @@ __global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * 
         const StagedPhase & E = ring_ph[p % SD_NPH];
         const SdPhase & P = E.P;
         if (P.kind == SD_MATVEC) {
-            sd_prologue(P, E.S.kpart, act, red, prof ? pbase + p * pstr : nullptr);
+            sd_prologue(P, E.S.kpart, act, red, PROF && prof ? pbase + p * pstr : nullptr);
             if (prof) pbase[p * pstr + 1] = globaltimer();
             const int kl = P.k / P.ksplit;
             const ActLayout L = sd_act_layout(P.act_group, kl);
             ActS A; A.qs = smem_u32(act); A.d = A.qs + (uint32_t) L.d_off; A.bsum = A.qs + (uint32_t) L.bsum_off;
             bool regs = P.act_group == 256 && kl <= 4096;                 // q8_K fragments of a 4096-wide record fit in registers
             for (int m = 0; m < P.n_mat; ++m) regs = regs && (P.mat[m].type == B200_Q4_K || P.mat[m].type == B200_Q6_K);
-            if (regs) sd_consume<true >(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, prof ? pbase + p * pstr : nullptr, rt.flags);
-            else      sd_consume<false>(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, prof ? pbase + p * pstr : nullptr, rt.flags);
+            if (regs) sd_consume<true >(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, PROF && prof ? pbase + p * pstr : nullptr, rt.flags);
+            else      sd_consume<false>(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, PROF && prof ? pbase + p * pstr : nullptr, rt.flags);
         } else {
             if (prof) pbase[p * pstr + 1] = globaltimer();
-            sd_attention(P, rt, attn_scratch, rope_tab, prof ? pbase + p * pstr : nullptr);
+            sd_attention(P, rt, attn_scratch, rope_tab, PROF && prof ? pbase + p * pstr : nullptr);
         }
         if (prof) pbase[p * pstr + 2] = globaltimer();
         sd_grid_barrier(gbar, bar_base + (unsigned) (p + 1) * gridDim.x, done, p + 1, p + 1 < n_phases);
@@ -510,27 +527,29 @@ bool sd_phase_ok(const SdPhase & P) {
     return true;
 }
 
-static int sd_setup() {
-    static unsigned long long done = 0;
-    const cudaError_t e = ensure_dyn_smem(k_stream, SD_SMEM_BYTES, done);
+static int sd_setup(bool prof) {
+    static unsigned long long done[2] = { 0, 0 };
+    const cudaError_t e = prof ? ensure_dyn_smem(k_stream<true>, SD_SMEM_BYTES, done[1]) : ensure_dyn_smem(k_stream<false>, SD_SMEM_BYTES, done[0]);
     return e == cudaSuccess ? B200_OK : -(int) e;
 }
 
 // one launch of the persistent kernel.  phases_dev == nullptr: run `single` (no grid barrier needed -> ordinary launch);
 // otherwise a cooperative launch guarantees the one-CTA-per-SM grid is co-resident for the grid barriers.
 int sd_launch(const SdPhase * phases_dev, int n_phases, const SdPhase * single, unsigned * gbar, const SdRuntime & rt, cudaStream_t st) {
-    int rc = sd_setup();
+    static const int env_flags = getenv("B200_SD_FLAGS") ? atoi(getenv("B200_SD_FLAGS")) : 0;     // experiment switches (bit 0: no evict_first hint)
+    const bool prof = rt.prof != nullptr || env_flags != 0;
+    int rc = sd_setup(prof);
     if (rc) return rc;
     static const SdPhase zero = {};
     const SdPhase & S = single ? *single : zero;
-    static const int env_flags = getenv("B200_SD_FLAGS") ? atoi(getenv("B200_SD_FLAGS")) : 0;     // experiment switches (bit 0: no evict_first hint)
     SdRuntime rt2 = rt; rt2.flags = env_flags;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) sm_count()); cfg.blockDim = dim3(SD_THREADS + 128); cfg.dynamicSmemBytes = SD_SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = (phases_dev && n_phases > 1) ? 1 : 0;
-    B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stream, phases_dev, n_phases, gbar, S, rt2));
+    if (prof) B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stream<true>, phases_dev, n_phases, gbar, S, rt2));
+    else      B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stream<false>, phases_dev, n_phases, gbar, S, rt2));
     return B200_OK;
 }
 
