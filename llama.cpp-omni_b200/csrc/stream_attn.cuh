@@ -186,10 +186,10 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
 #pragma unroll
             for (int u = 1; u < U; ++u) mx = fmaxf(mx, s[u][g]);
             const float m_new = fmaxf(m[g], mx);
-            const float corr = m_new == -INFINITY ? 1.0f : expf(m[g] - m_new);
+            const float corr = m_new == -INFINITY ? 1.0f : __expf(m[g] - m_new);
             float sum = 0.0f;
 #pragma unroll
-            for (int u = 0; u < U; ++u) { pr[u][g] = s[u][g] == -INFINITY ? 0.0f : expf(s[u][g] - m_new); sum += pr[u][g]; }
+            for (int u = 0; u < U; ++u) { pr[u][g] = s[u][g] == -INFINITY ? 0.0f : __expf(s[u][g] - m_new); sum += pr[u][g]; }
             m[g] = m_new; l[g] = l[g] * corr + sum;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[g][i] *= corr;
@@ -216,7 +216,7 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
     for (int g = 0; g < SA_G; ++g) {
         const float mo = __shfl_xor_sync(0xffffffffu, m[g], 16), lo = __shfl_xor_sync(0xffffffffu, l[g], 16);
         const float M = fmaxf(m[g], mo);
-        const float ws = m[g] == -INFINITY ? 0.0f : expf(m[g] - M), wo = mo == -INFINITY ? 0.0f : expf(mo - M);
+        const float ws = m[g] == -INFINITY ? 0.0f : __expf(m[g] - M), wo = mo == -INFINITY ? 0.0f : __expf(mo - M);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float v = acc[g][i] * ws + __shfl_xor_sync(0xffffffffu, acc[g][i], 16) * wo;
@@ -234,7 +234,7 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
 #pragma unroll
         for (int r = 0; r < SD_WARPS; ++r) {
             const float2 ml = sm.red_ml[r][g];
-            const float w = ml.x == -INFINITY ? 0.0f : expf(ml.x - M);
+            const float w = ml.x == -INFINITY ? 0.0f : __expf(ml.x - M);
             v = fmaf(sm.red[r][o], w, v); L = fmaf(ml.y, w, L);
         }
         if (splits == 1) {
@@ -273,10 +273,10 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
             float Mn = M;
 #pragma unroll
             for (int i = 0; i < NP; ++i) Mn = fmaxf(Mn, ml[i].x);
-            const float c = Mn == -INFINITY ? 1.0f : expf(M - Mn);          // M == -inf: v = L = 0 anyway
+            const float c = Mn == -INFINITY ? 1.0f : __expf(M - Mn);          // M == -inf: v = L = 0 anyway
             v *= c; L *= c; M = Mn;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) { const float w = ml[i].x == -INFINITY ? 0.0f : expf(ml[i].x - M); v = fmaf(t[i], w, v); L = fmaf(ml[i].y, w, L); }
+            for (int i = 0; i < NP; ++i) { const float w = ml[i].x == -INFINITY ? 0.0f : __expf(ml[i].x - M); v = fmaf(t[i], w, v); L = fmaf(ml[i].y, w, L); }
         }
         A.out[head * D + d] = L == 0.0f ? 0.0f : v / L;
     }
