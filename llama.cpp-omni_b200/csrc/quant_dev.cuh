@@ -6,9 +6,16 @@
 
 namespace b200 {
 
-// Shared-memory copies of the record (stream_decode.cu) store the int8 plane with a 16-byte-segment swizzle so that the matvec's
-// fragment loads are bank-conflict free: segment bit 3 is XORed into segment bits 1 and 2.  SWZ = false: linear (global records).
-template <bool SWZ> __device__ __forceinline__ int64_t act_qs_off(int64_t off) { return SWZ ? (off ^ (((off >> 7) & 1) * 0x60)) : off; }
+// Shared-memory copies of the record (stream_decode.cu) store the int8 plane with a 16-byte-segment ROTATION: segment i (0..7) of the r-th
+// 128-byte region lives at position (i + r) & 7 of that region.  The register-resident fragment fill of the decode engine (hfrag_fill: lane l
+// reads the 8 segments of region l, one per LDS.128) then touches 8 different 16-byte bank groups per quarter-warp instead of one — with the
+// previous XOR swizzle that fill was 4-way bank-conflicted and cost ~1 us per matvec phase (measured with the in-kernel marks).
+// SWZ = false: linear (global records).
+template <bool SWZ> __device__ __forceinline__ int64_t act_qs_off(int64_t off) {
+    if (!SWZ) return off;
+    const int64_t seg = off >> 4, r = seg >> 3;
+    return (off & 15) | ((r * 8 + ((seg + r) & 7)) << 4);
+}
 
 // One warp quantises one 256-element super-block held in `v` (lane owns elements [8*lane, 8*lane+8)) into the planar record.
 template <bool SWZ = false>

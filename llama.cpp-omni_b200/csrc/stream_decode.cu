@@ -381,14 +381,19 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const 
     const bool swiglu = P.epilogue == SD_EPI_SWIGLU;
     HFrag fr;
     if (REGS) hfrag_fill(A, nblk, fr);
+    if (pf && (flags & 512)) pf[4] = globaltimer();                        // finer marks of warp 0's first unit (B200_SD_FLAGS=512)
+    bool first = true;
     for (int u = warp; u < nunits; u += SD_WARPS) {
         const uint32_t slot = consumed % SD_DEPTH, par = (consumed / SD_DEPTH) & 1;
         const uint32_t base = ring_w + slot * SD_SLOT_BYTES;
         const long long tw = pf ? clock64() : 0;
         mbar_wait(full_w + 8 * slot, par);
         if (pf) waited += clock64() - tw;
+        if (pf && (flags & 512) && first) pf[5] = globaltimer();
         const SlotDesc d = descs_w[slot];
         const int type = d.type_n & 0xff, n = d.type_n >> 8;
+        float rz = 0.0f;                                                   // the residual's L2 round trip overlaps the dot products
+        if (d.resid && lane < n) rz = __ldcg(d.resid + lane);
         const uint32_t rbp = d.sub_p, rbd = d.sub_d;
         const uint32_t bp = (uint32_t) n * rbp, bd = (uint32_t) n * rbd;     // slot: [payload rows][d rows] (+ the same again for `up`)
         float2 g2 = make_float2(0.0f, 0.0f), v = make_float2(0.0f, 0.0f);
@@ -400,12 +405,13 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const 
             v = unit_dots_lds(type, n, base, rbp, base + bp, rbd, A, kl);
             if (swiglu) { g2 = v; v = unit_dots_lds(type, n, base + bp + bd, rbp, base + 2 * bp + bd, rbd, A, kl); }
         }
+        if (pf && (flags & 512) && first) { pf[6] = globaltimer(); first = false; }
         __syncwarp();                                                      // every lane's reads of the slot are done
         if (lane == 0) mbar_arrive(empty_w + 8 * slot);                    // hand it back to the producer before the epilogue's global traffic
         if (lane < n) {
             float o = lane == 0 ? v.x : v.y;
             if (swiglu) { const float gg = lane == 0 ? g2.x : g2.y; o = (gg / (1.0f + expf(-gg))) * o; }
-            if (d.resid) o += __ldcg(d.resid + lane);
+            o += rz;
             d.y[lane] = o;
         }
         ++consumed;
