@@ -51,6 +51,57 @@ __device__ __forceinline__ void quant_block_q8K(const float (&v)[8], uint8_t * r
     if (lane == 0) ((float *) (rec + d_off))[blk] = d;
 }
 
+// NB super-blocks in LOCKSTEP (same arithmetic as quant_block_q8K): the shuffle / divide chains of the blocks are independent, so the warp's
+// second block costs almost nothing extra — in the decode engine's prologue 4 of the 12 warps own two blocks and were the critical path.
+// live[t] = false: block t is a dummy (nothing is stored).
+template <bool SWZ, int NB>
+__device__ __forceinline__ void quant_blocks_q8K(const float (&v)[NB][8], const int (&blk)[NB], const bool (&live)[NB], uint8_t * rec, int64_t d_off, int64_t bsum_off) {
+    const int lane = threadIdx.x & 31;
+    float amax[NB]; int imax[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+        amax[t] = 0.0f; imax[t] = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float a = fabsf(v[t][i]); if (a > amax[t]) { amax[t] = a; imax[t] = lane * 8 + i; } }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int t = 0; t < NB; ++t) {
+            const float oa = __shfl_xor_sync(0xffffffffu, amax[t], o); const int oi = __shfl_xor_sync(0xffffffffu, imax[t], o);
+            if (oa > amax[t] || (oa == amax[t] && oi < imax[t])) { amax[t] = oa; imax[t] = oi; }
+        }
+    }
+    float vmax[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+        float mine = 0.0f;                                             // the SIGNED value at imax
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if ((imax[t] & 7) == i) mine = v[t][i];
+        vmax[t] = __shfl_sync(0xffffffffu, mine, (imax[t] >> 3) & 31);
+    }
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+        int8_t q[8]; int s = 0;
+        float d = 0.0f;
+        if (amax[t] != 0.0f) {
+            const float iscale = __fdiv_rn(-127.0f, vmax[t]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { int x = __float2int_rn(__fmul_rn(iscale, v[t][i])); x = x > 127 ? 127 : x; q[i] = (int8_t) x; s += x; }
+            d = __fdiv_rn(1.0f, iscale);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = 0;
+        }
+        const int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);        // 16-wide partial sums
+        if (live[t]) {
+            *(uint2 *) (rec + act_qs_off<SWZ>((int64_t) blk[t] * 256 + lane * 8)) = *(const uint2 *) q;
+            if ((lane & 1) == 0) ((int16_t *) (rec + bsum_off))[blk[t] * 16 + (lane >> 1)] = (int16_t) s2;
+            if (lane == 0) ((float *) (rec + d_off))[blk[t]] = d;
+        }
+    }
+}
+
 // 8 lanes quantise one 32-element block (lane part = lane & 7 owns 4 elements); `live` = block index in range.
 template <bool SWZ = false>
 __device__ __forceinline__ void quant_block_q8_0(const float4 v, bool live, uint8_t * rec, int64_t blk, int64_t d_off, int64_t bsum_off) {

@@ -172,11 +172,12 @@ __device__ __forceinline__ void sd_prologue_fast(const SdPhase & P, uint8_t * ac
     if (pf) pf[4] = globaltimer();
     if (norm) scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
     if (pf) pf[5] = globaltimer();
+const int blks[2] = { warp, warp + SD_WARPS };
+    const bool lives[2] = { warp < nb, warp + SD_WARPS < nb };
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-        const int blk = warp + SD_WARPS * t;
-        if (blk < nb) {
-            const int e = k0 + blk * 256 + lane * 8;
+        if (lives[t]) {
+            const int e = k0 + blks[t] * 256 + lane * 8;
             if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
             if (norm) {
                 const float wv[8] = { w[t][0].x, w[t][0].y, w[t][0].z, w[t][0].w, w[t][1].x, w[t][1].y, w[t][1].z, w[t][1].w };
@@ -186,9 +187,9 @@ __device__ __forceinline__ void sd_prologue_fast(const SdPhase & P, uint8_t * ac
                     *(float4 *) (P.norm_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]);
                 }
             }
-            quant_block_q8K<true>(v[t], act, blk, L.d_off, L.bsum_off);
         }
     }
+    quant_blocks_q8K<true, 2>(v, blks, lives, act, L.d_off, L.bsum_off);     // both blocks of the warp in lockstep (dummy second block for warps 4..11)
     cons_sync();
     }
 
