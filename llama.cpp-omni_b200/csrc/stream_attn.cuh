@@ -211,37 +211,42 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
         load_tile(t0);
     }
     if (pf) pf[5] = globaltimer();
-    // ---- merge the 24 row groups: the two groups of a warp by shuffle, the 12 warps through shared memory -----------------------------------
+    // ---- merge the 24 row groups: the two groups of a warp by shuffle, the 12 warps through shared memory (16-byte stores and loads) ---------
 #pragma unroll
     for (int g = 0; g < SA_G; ++g) {
         const float mo = __shfl_xor_sync(0xffffffffu, m[g], 16), lo = __shfl_xor_sync(0xffffffffu, l[g], 16);
         const float M = fmaxf(m[g], mo);
         const float ws = m[g] == -INFINITY ? 0.0f : __expf(m[g] - M), wo = mo == -INFINITY ? 0.0f : __expf(mo - M);
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float v = acc[g][i] * ws + __shfl_xor_sync(0xffffffffu, acc[g][i], 16) * wo;
-            if (lane < 16) sm.red[warp][g * D + hl * 8 + i] = v;
+        for (int i = 0; i < 8; ++i) v[i] = acc[g][i] * ws + __shfl_xor_sync(0xffffffffu, acc[g][i], 16) * wo;
+        if (lane < 16) {
+            *(float4 *) &sm.red[warp][g * D + hl * 8]     = make_float4(v[0], v[1], v[2], v[3]);
+            *(float4 *) &sm.red[warp][g * D + hl * 8 + 4] = make_float4(v[4], v[5], v[6], v[7]);
         }
         if (lane == 0) sm.red_ml[warp][g] = make_float2(M, l[g] * ws + lo * wo);
     }
     cons_sync();
-    for (int o = tid; o < SA_G * D; o += SD_THREADS) {
-        const int g = o / D, d = o % D, head = head0 + g;
+    if (tid < SA_G * D / 4) {                                               // 128 threads x 4 consecutive outputs of one head
+        const int o = tid * 4, g = o / D, d = o % D, head = head0 + g;
         float M = -INFINITY;
 #pragma unroll
         for (int r = 0; r < SD_WARPS; ++r) M = fmaxf(M, sm.red_ml[r][g].x);
-        float v = 0.0f, L = 0.0f;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f); float L = 0.0f;
 #pragma unroll
         for (int r = 0; r < SD_WARPS; ++r) {
             const float2 ml = sm.red_ml[r][g];
             const float w = ml.x == -INFINITY ? 0.0f : __expf(ml.x - M);
-            v = fmaf(sm.red[r][o], w, v); L = fmaf(ml.y, w, L);
+            const float4 a = *(const float4 *) &sm.red[r][o];
+            v.x = fmaf(a.x, w, v.x); v.y = fmaf(a.y, w, v.y); v.z = fmaf(a.z, w, v.z); v.w = fmaf(a.w, w, v.w); L = fmaf(ml.y, w, L);
         }
         if (splits == 1) {
-            A.out[head * D + d] = L == 0.0f ? 0.0f : v / L;
+            const float inv = L == 0.0f ? 0.0f : 1.0f / L;
+            *(float4 *) &A.out[head * D + d] = L == 0.0f ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(v.x / L, v.y / L, v.z / L, v.w / L);
+            (void) inv;
         } else {
             const int64_t ps = (int64_t) head * splits + split;
-            A.part_acc[ps * D + d] = v;
+            *(float4 *) &A.part_acc[ps * D + d] = v;
             if (d == 0) A.part_ml[ps] = make_float2(M, L);
         }
     }
