@@ -5,8 +5,9 @@ last one; KV cache of layer il lives with layer il, src/llama-context.cpp:313) f
 exchange on the decode path is the residual stream `l_out` ([n_embd] F32 per token, 16 KiB) between consecutive stages: a point-to-point
 send/recv (NCCL over NVLink on GPUs, gloo in the CPU tests).  There is no all-reduce on this path and none is invented.
 
-Unlike the reference (equal layer counts scaled by free memory), stages are balanced by the BYTES a decoded token must stream from HBM in each
-stage, lm_head included — at batch 1 a stage's time is its bytes, and lm_head (0.51 GB of Q6_K) weighs as much as 4.4 transformer layers.
+Unlike the reference (equal layer counts scaled by free memory), stages are balanced by a per-layer COST the caller supplies, lm_head
+included.  bench.py uses streamed bytes + the fixed latency of a layer's dependent phase transitions (in bytes of streaming time): by bytes
+alone lm_head (0.51 GB of Q6_K) weighs 4.4 transformer layers, by measured time 1.5 — balancing by the latter took 2 GPUs from 771 to 877 tok/s.
 """
 from __future__ import annotations
 
