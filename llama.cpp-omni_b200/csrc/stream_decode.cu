@@ -52,6 +52,11 @@ __device__ __forceinline__ int lds_s16(uint32_t a) { int r; asm volatile("ld.sha
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t r; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float r; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a)); return r; }
 __device__ __forceinline__ unsigned long long globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// 32 bytes in one request (LDG.E.256, sm_100): p must be 32-byte aligned; through L2 (.cg) — the data was just written by other SMs
+__device__ __forceinline__ void ld256_cg(const float * p, float4 & lo, float4 & hi) {
+    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned * p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // ---------------------------------------------------------------------------------------------------------------- geometry
@@ -151,9 +156,11 @@ __device__ __forceinline__ void sd_prologue_fast(const SdPhase & P, uint8_t * ac
         for (int sx = 0; sx < NX; ++sx) {
             const bool on = live && sx < n_x;
             const float * px = P.x[on ? sx : 0] + e;
-            a[t][sx][0] = on ? __ldcg((const float4 *) px) : z4; a[t][sx][1] = on ? __ldcg((const float4 *) (px + 4)) : z4;
+            a[t][sx][0] = z4; a[t][sx][1] = z4;
+            if (on) ld256_cg(px, a[t][sx][0], a[t][sx][1]);              // ONE 256-bit request per summand and block: the prologue is bound by outstanding requests
         }
-        w[t][0] = norm && live ? __ldg((const float4 *) (P.norm_w + e)) : z4; w[t][1] = norm && live ? __ldg((const float4 *) (P.norm_w + e + 4)) : z4;
+        w[t][0] = z4; w[t][1] = z4;
+        if (norm && live) ld256_cg(P.norm_w + e, w[t][0], w[t][1]);
     }
     float v[2][8];
     float ss = 0.0f;
