@@ -263,26 +263,34 @@ __device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * 
     cons_sync();
     if (pf) pf[7] = globaltimer();
     if (!sm.is_last) return;
-    // merge: thread o owns one output element; it loads its column of partials AND the head's (m, l) pairs in one round trip, then turns
-    // them into w_s = exp(m_s - M) / sum_s l_s w_s itself (cheaper than a second round trip through shared memory)
-    for (int o = tid; o < SA_G * D; o += SD_THREADS) {
-        const int g = o / D, d = o % D, head = head0 + g;
+    // merge: 128 threads x 4 consecutive output elements; a thread loads its float4 column of partials AND the head's (m, l) pairs in one
+    // round trip (18 + 18 requests instead of 36 scalar ones per element: the phase's tail is bound by outstanding requests), then turns them
+    // into w_s = exp(m_s - M) / sum_s l_s w_s itself (cheaper than a second round trip through shared memory)
+    if (tid < SA_G * D / 4) {
+        const int o = tid * 4, g = o / D, d = o % D, head = head0 + g;
         const float * pa = A.part_acc + (int64_t) head * splits * D + d;
         const float2 * pm = A.part_ml + (int64_t) head * splits;
-        float v = 0.0f, L = 0.0f, M = -INFINITY;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f); float L = 0.0f, M = -INFINITY;
         constexpr int NP = 18;                                              // chunks per pass = 148 SMs / 8 kv heads: the whole merge is ONE round trip
         for (int s0 = 0; s0 < splits; s0 += NP) {
-            float t[NP]; float2 ml[NP];
+            float4 t[NP]; float2 ml[NP];
 #pragma unroll
-            for (int i = 0; i < NP; ++i) { const bool in = s0 + i < splits; t[i] = in ? __ldcg(pa + (int64_t) (s0 + i) * D) : 0.0f; ml[i] = in ? __ldcg(pm + s0 + i) : make_float2(-INFINITY, 0.0f); }
+            for (int i = 0; i < NP; ++i) {
+                const bool in = s0 + i < splits;
+                t[i] = in ? __ldcg((const float4 *) (pa + (int64_t) (s0 + i) * D)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                ml[i] = in ? __ldcg(pm + s0 + i) : make_float2(-INFINITY, 0.0f);
+            }
             float Mn = M;
 #pragma unroll
             for (int i = 0; i < NP; ++i) Mn = fmaxf(Mn, ml[i].x);
             const float c = Mn == -INFINITY ? 1.0f : __expf(M - Mn);          // M == -inf: v = L = 0 anyway
-            v *= c; L *= c; M = Mn;
+            v.x *= c; v.y *= c; v.z *= c; v.w *= c; L *= c; M = Mn;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) { const float w = ml[i].x == -INFINITY ? 0.0f : __expf(ml[i].x - M); v = fmaf(t[i], w, v); L = fmaf(ml[i].y, w, L); }
+            for (int i = 0; i < NP; ++i) {
+                const float w = ml[i].x == -INFINITY ? 0.0f : __expf(ml[i].x - M);
+                v.x = fmaf(t[i].x, w, v.x); v.y = fmaf(t[i].y, w, v.y); v.z = fmaf(t[i].z, w, v.z); v.w = fmaf(t[i].w, w, v.w); L = fmaf(ml[i].y, w, L);
+            }
         }
-        A.out[head * D + d] = L == 0.0f ? 0.0f : v / L;
+        *(float4 *) &A.out[head * D + d] = L == 0.0f ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(v.x / L, v.y / L, v.z / L, v.w / L);
     }
 }
