@@ -11,74 +11,42 @@ namespace b200 {
 // reads the 8 segments of region l, one per LDS.128) then touches 8 different 16-byte bank groups per quarter-warp instead of one — with the
 // previous XOR swizzle that fill was 4-way bank-conflicted and cost ~1 us per matvec phase (measured with the in-kernel marks).
 // SWZ = false: linear (global records).
+// round-to-nearest-even of |x| < 2^22 exactly as the reference does it (nearest_int, ggml-quants.c: add 1.5 * 2^23, read the mantissa): an FADD
+// and an integer subtract on the full-rate pipes instead of F2I on the quarter-rate conversion unit — bit-identical to __float2int_rn here
+__device__ __forceinline__ int nearest_int_magic(float x) { return __float_as_int(__fadd_rn(x, 12582912.0f)) - 0x4B400000; }
+
 template <bool SWZ> __device__ __forceinline__ int64_t act_qs_off(int64_t off) {
     if (!SWZ) return off;
     const int64_t seg = off >> 4, r = seg >> 3;
     return (off & 15) | ((r * 8 + ((seg + r) & 7)) << 4);
 }
 
-// One warp quantises one 256-element super-block held in `v` (lane owns elements [8*lane, 8*lane+8)) into the planar record.
-template <bool SWZ = false>
-__device__ __forceinline__ void quant_block_q8K(const float (&v)[8], uint8_t * rec, int64_t blk, int64_t d_off, int64_t bsum_off) {
-    const int lane = threadIdx.x & 31;
-    // (amax, first index attaining it): strict '>' in the reference keeps the FIRST maximum
-    float amax = 0.0f; int imax = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const float a = fabsf(v[i]); if (a > amax) { amax = a; imax = lane * 8 + i; } }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float oa = __shfl_xor_sync(0xffffffffu, amax, o); const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
-        if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }
-    }
-    int8_t q[8]; int s = 0;
-    float d = 0.0f;
-    if (amax != 0.0f) {
-        float mine = 0.0f;                                             // the SIGNED value at imax
-#pragma unroll
-        for (int i = 0; i < 8; ++i) if ((imax & 7) == i) mine = v[i];
-        const float vmax = __shfl_sync(0xffffffffu, mine, (imax >> 3) & 31);
-        const float iscale = __fdiv_rn(-127.0f, vmax);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { int t = __float2int_rn(__fmul_rn(iscale, v[i])); t = t > 127 ? 127 : t; q[i] = (int8_t) t; s += t; }
-        d = __fdiv_rn(1.0f, iscale);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = 0;
-    }
-    *(uint2 *) (rec + act_qs_off<SWZ>(blk * 256 + lane * 8)) = *(const uint2 *) q;
-    const int s2 = s + __shfl_xor_sync(0xffffffffu, s, 1);            // 16-wide partial sums
-    if ((lane & 1) == 0) ((int16_t *) (rec + bsum_off))[blk * 16 + (lane >> 1)] = (int16_t) s2;
-    if (lane == 0) ((float *) (rec + d_off))[blk] = d;
-}
-
-// NB super-blocks in LOCKSTEP (same arithmetic as quant_block_q8K): the shuffle / divide chains of the blocks are independent, so the warp's
+// NB super-blocks in LOCKSTEP (arithmetic of quantize_row_q8_K_ref, ggml-quants.c:2555-2592, bit for bit): the shuffle / divide chains of the blocks are independent, so the warp's
 // second block costs almost nothing extra — in the decode engine's prologue 4 of the 12 warps own two blocks and were the critical path.
 // live[t] = false: block t is a dummy (nothing is stored).
 template <bool SWZ, int NB>
 __device__ __forceinline__ void quant_blocks_q8K(const float (&v)[NB][8], const int (&blk)[NB], const bool (&live)[NB], uint8_t * rec, int64_t d_off, int64_t bsum_off) {
     const int lane = threadIdx.x & 31;
-    float amax[NB]; int imax[NB];
+    // amax by a plain max tree (one shuffle per step and block); the FIRST element attaining it (the reference keeps the first maximum, whose
+    // SIGN enters iscale) = first such element of the lowest lane that holds one (ballot)
+    float amax[NB], lmax[NB], first[NB];
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
-        amax[t] = 0.0f; imax[t] = 0x7fffffff;
+        lmax[t] = 0.0f; first[t] = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float a = fabsf(v[t][i]); if (a > amax[t]) { amax[t] = a; imax[t] = lane * 8 + i; } }
+        for (int i = 0; i < 8; ++i) { const float a = fabsf(v[t][i]); if (a > lmax[t]) { lmax[t] = a; first[t] = v[t][i]; } }   // strict '>': first of the lane
+        amax[t] = lmax[t];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int t = 0; t < NB; ++t) {
-            const float oa = __shfl_xor_sync(0xffffffffu, amax[t], o); const int oi = __shfl_xor_sync(0xffffffffu, imax[t], o);
-            if (oa > amax[t] || (oa == amax[t] && oi < imax[t])) { amax[t] = oa; imax[t] = oi; }
-        }
+        for (int t = 0; t < NB; ++t) amax[t] = fmaxf(amax[t], __shfl_xor_sync(0xffffffffu, amax[t], o));
     }
     float vmax[NB];
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
-        float mine = 0.0f;                                             // the SIGNED value at imax
-#pragma unroll
-        for (int i = 0; i < 8; ++i) if ((imax[t] & 7) == i) mine = v[t][i];
-        vmax[t] = __shfl_sync(0xffffffffu, mine, (imax[t] >> 3) & 31);
+        const unsigned holders = __ballot_sync(0xffffffffu, lmax[t] == amax[t]);
+        vmax[t] = __shfl_sync(0xffffffffu, first[t], __ffs(holders) - 1);
     }
 #pragma unroll
     for (int t = 0; t < NB; ++t) {
@@ -87,7 +55,7 @@ __device__ __forceinline__ void quant_blocks_q8K(const float (&v)[NB][8], const 
         if (amax[t] != 0.0f) {
             const float iscale = __fdiv_rn(-127.0f, vmax[t]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { int x = __float2int_rn(__fmul_rn(iscale, v[t][i])); x = x > 127 ? 127 : x; q[i] = (int8_t) x; s += x; }
+            for (int i = 0; i < 8; ++i) { int x = nearest_int_magic(__fmul_rn(iscale, v[t][i])); x = x > 127 ? 127 : x; q[i] = (int8_t) x; s += x; }
             d = __fdiv_rn(1.0f, iscale);
         } else {
 #pragma unroll
@@ -100,6 +68,17 @@ __device__ __forceinline__ void quant_blocks_q8K(const float (&v)[NB][8], const 
             if (lane == 0) ((float *) (rec + d_off))[blk[t]] = d;
         }
     }
+}
+
+// One warp quantises one 256-element super-block held in `v` (lane owns elements [8*lane, 8*lane+8)) into the planar record: the NB = 1 case
+// of quant_blocks_q8K, so that the bit-exactness tests of the stand-alone quantiser (tests/test_gpu_parity.py) cover the engine's code too.
+template <bool SWZ = false>
+__device__ __forceinline__ void quant_block_q8K(const float (&v)[8], uint8_t * rec, int64_t blk, int64_t d_off, int64_t bsum_off) {
+    float vv[1][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vv[0][i] = v[i];
+    const int blks[1] = { (int) blk }; const bool lives[1] = { true };
+    quant_blocks_q8K<SWZ, 1>(vv, blks, lives, rec, d_off, bsum_off);
 }
 
 // 8 lanes quantise one 32-element block (lane part = lane & 7 owns 4 elements); `live` = block index in range.

@@ -112,9 +112,11 @@ __device__ __forceinline__ float cta_sum(float v, float * red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) red[warp] = v;
     cons_sync();
-    float t = lane < SD_WARPS ? red[lane] : 0.0f;
-    t = warp_sum(t);
-    cons_sync();
+    // every thread adds the 12 warp sums itself, in warp order (broadcast LDS: no second shuffle tree, no trailing barrier — `red` is not
+    // written again before the consumers have passed at least one more cons_sync)
+    float t = red[0];
+#pragma unroll
+    for (int r = 1; r < SD_WARPS; ++r) t += red[r];
     return t;
 }
 
