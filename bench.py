@@ -157,9 +157,9 @@ def run_b200(args) -> None:
     cfg = dec.LLMConfig.tiny() if args.tiny else dec.LLMConfig()
     # contiguous layer ranges balanced by the bytes a token streams per stage, lm_head with the last stage (llama.cpp-omni_b200/pipeline.py)
     # stage cost = streamed bytes + the fixed latency of the layer's 5 dependent phase transitions, expressed in bytes of streaming time
-    # (measured, profiles/README.md: a layer takes ~60 us of which ~18 us is its bytes at the HBM peak; lm_head 87 us of which 79 us is bytes)
+    # (measured, profiles/README.md: a layer takes ~54 us of which ~18 us is its bytes at the HBM peak; lm_head 87 us of which 79 us is bytes)
     peak_bps = peaks()[0] * 1e9
-    layer_cost = [dec.weight_bytes_per_token(cfg, range(i, i + 1), with_head=False) + int(42e-6 * peak_bps) for i in range(cfg.n_layer)]
+    layer_cost = [dec.weight_bytes_per_token(cfg, range(i, i + 1), with_head=False) + int(36e-6 * peak_bps) for i in range(cfg.n_layer)]
     head_cost = dec.weight_bytes_per_token(cfg, range(0), with_head=True) + int(8e-6 * peak_bps)
     ranges = pkg.pipeline.partition_layers(layer_cost, head_cost, world)
     pipe = pkg.pipeline.Pipeline(rank, world, ranges, dist)
