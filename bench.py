@@ -166,20 +166,23 @@ def run_b200(args) -> None:
     layers = ranges[rank]
     last = rank == pipe.last
     D = dec.Qwen3Decoder(cfg, dev, layers=layers, has_head=last, seed=rank)
-    depth = min(args.depth, cfg.n_ctx - args.steps - args.warmup - 2)
-    n_kv = min(cfg.n_ctx, (depth + args.steps + args.warmup + 1 + 255) // 256 * 256)
+    # decode positions depth, depth+1, ...; a run longer than the context wraps back to `depth` (same n_kv, same bytes per step)
+    depth = max(0, min(args.depth, cfg.n_ctx - 2))
+    span = max(1, min(args.steps + args.warmup + 1, cfg.n_ctx - depth - 1))
+    n_kv = min(cfg.n_ctx, (depth + span + 255) // 256 * 256)
     # pre-fill the KV cache up to `depth` so attention reads real (finite) rows
     for lw in D.L:
         lw["k_cache"][:depth].normal_(0, 0.5)
         lw["v_cache"][:depth].normal_(0, 1.0)
     E = cfg.n_embd
-    host_embd = (torch.randn(args.steps + args.warmup + 1, E) * 0.05).pin_memory()     # rows of token_embd gathered on the host
+    n_rows = min(args.steps + args.warmup + 1, 4096)
+    host_embd = (torch.randn(n_rows, E) * 0.05).pin_memory()     # rows of token_embd gathered on the host
     host_logits = torch.empty(cfg.n_vocab).pin_memory()
     stream = torch.cuda.Stream(device=dev)
     n_streams = world                                      # decode streams in flight across the pipeline
 
     def set_inputs(i: int):
-        hi = dec.Qwen3Decoder.host_inputs(cfg, depth + i, n_kv)
+        hi = dec.Qwen3Decoder.host_inputs(cfg, depth + i % span, n_kv)
         D.pos.copy_(hi["pos"], non_blocking=True)
         D.kv_idx.copy_(hi["kv_idx"], non_blocking=True)
         D.mask_f32[:, :n_kv].copy_(hi["mask"], non_blocking=True)
@@ -205,7 +208,7 @@ def run_b200(args) -> None:
             if e2e or world > 1:
                 h2d += set_inputs(i)
             if rank == pipe.first and e2e:
-                D.x_in.copy_(host_embd[i], non_blocking=True)
+                D.x_in.copy_(host_embd[i % n_rows], non_blocking=True)
                 h2d += E * 4
             pipe.stage_step(hidden, D.x_out, graph.replay)          # recv from the previous stage -> one graph replay -> send to the next
             if last and e2e:
@@ -275,7 +278,7 @@ def run_b200(args) -> None:
     line = {"metric": "decode_tok_per_s", "value": round(value, 2), "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations), f16 KV", "data": "synthetic",
-            "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}, KV depth {depth}..{depth + args.steps + args.warmup} (n_kv={n_kv})",
+            "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}, KV depth {depth}..{depth + span - 1} (n_kv={n_kv})",
                        "streams_in_flight": n_streams, "parallelism": "single GPU" if world == 1 else f"layer-split pipeline pp{world}, layers per stage {[len(r) for r in ranges]} (+lm_head on the last)",
                        "engine": "persistent (1 kernel/token)" if engine else "per-op launches",
                        "timing": f"one CUDA graph per token; weights {w_bytes / 1e9:.2f} GB/rank exceed the 126 MB L2, so no flush is needed"},
