@@ -82,7 +82,11 @@ B200_API int    b200_quantize_act(int weight_type, const float * x, int64_t x_co
 /* ---- MUL_MAT (replaces ggml_cuda_mul_mat ggml-cuda.cu:2001-2084: mmvq.cu mul_mat_vec_q for n <= 8, mmq.cu mul_mat_q
  *      beyond; oracle: ggml_compute_forward_mul_mat ggml-cpu.c:1210-1402) ------------------------------------------------
  * dst[m, n] (F32) = W[m, k] (any supported type) . X[n, k]^T (F32), batched over ne[2], ne[3] with ggml broadcast rules.
- * `scratch` must hold b200_mul_mat_scratch_bytes(...) bytes (activation records / tile buffers). */
+ * `scratch` must hold b200_mul_mat_scratch_bytes(...) bytes (activation records / tile buffers).
+ * Routing: n <= 8 columns -> dequant-in-register matvec on q8_K / q8_0 activation records (the CPU oracle's integer arithmetic);
+ *          n >  8 columns, q4_K / q5_K native or q6_K / q8_0 / q4_0 planar, k % 256 == 0 -> tcgen05 dequant-GEMM k_mmq_tc (csrc/mmq_tc.cu:
+ *          F16 operands, F32 accumulation in TMEM); F16 weights, n > 8, k % 64 == 0 -> k_mm_f16_tc (TMA-fed tcgen05 GEMM);
+ *          everything else -> column-chunked matvec / warp-per-row float kernel. */
 B200_API int    b200_mul_mat_supported(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst);
 B200_API size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x);
 B200_API int    b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
@@ -160,7 +164,9 @@ B200_API int b200_soft_max(const b200_tensor * x, const b200_tensor * mask, cons
 
 /* ---- FLASH_ATTN_EXT (replaces fattn.cu:195-341 -> fattn-vec.cuh / fattn-mma-f16.cuh; oracle ops.cpp:7912-8148) ----------
  * q F32 [D, n_q, n_head, n_b], k/v F16 [D, n_kv, n_head_kv, n_b], mask F16 [n_kv, >= n_q, ...] or NULL,
- * dst F32 [D, n_head, n_q, n_b].  `scratch`: b200_flash_attn_scratch_bytes (split-KV partials). */
+ * dst F32 [D, n_head, n_q, n_b].  `scratch`: b200_flash_attn_scratch_bytes (split-KV partials / KV-tile counts).
+ * n_q < 16: split-KV decode kernel (csrc/flash_attn.cu); n_q >= 16: tiled tensor-core kernel with a mask pre-scan (csrc/fa_prefill.cu,
+ * replaces fattn-mma-f16.cuh:1246 + flash_attn_mask_to_KV_max). */
 B200_API int    b200_flash_attn_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v,
                                           const b200_tensor * mask, const b200_tensor * dst);
 B200_API size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b200_tensor * k);
