@@ -144,6 +144,10 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
     dec->rt.theta_scale = powf(d->rope.freq_base, -2.0f / D); dec->rt.freq_scale = d->rope.freq_scale; dec->rt.ext_factor = d->rope.ext_factor;
     dec->rt.attn_factor = d->rope.attn_factor; dec->rt.corr0 = lo < 0 ? 0 : lo; dec->rt.corr1 = hi > D - 1 ? D - 1 : hi;
     dec->rt.rope_mode = d->rope.mode; dec->rt.has_rope = d->n_layer > 0;
+    // the memset / upload above ran on the legacy stream; k_stream is launched on the caller's (possibly non-blocking) stream, which has no
+    // implicit ordering with it: the barrier counters and the phase table must have landed before this function returns
+    e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) { delete dec; return -(int) e; }
     *handle = dec;
     return B200_OK;
 }

@@ -247,14 +247,23 @@ extern "C" int b200_flash_attn_supported(const b200_tensor * q, const b200_tenso
     return 1;
 }
 
-extern "C" size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b200_tensor * k) {
+// split-KV decode kernel: part_acc + part_ml of every (query, head, split)
+static size_t fa_decode_scratch_bytes(const b200_tensor * q, const b200_tensor * k) {
     const int64_t nz = q->ne[1] * q->ne[3];
-    if (nz == 0 || k->ne[1] == 0 || k->ne[2] == 0) return 0;
-    if (q->ne[1] >= 16) return fa_prefill_scratch_bytes(q, nullptr, q->ne[3]);     // upper bound for the KV-tile counts (mask batch <= q batch)
     const FaPlan P = fa_plan(nz, k->ne[1], q->ne[2], k->ne[2]);
     if (P.splits <= 1) return 0;
     const size_t slots = (size_t) nz * q->ne[2] * P.splits;
     return slots * q->ne[0] * 4 + slots * 8 + 16;
+}
+
+// Which kernel runs is decided in b200_flash_attn from alignment as well (fa_prefill_supported), which this function cannot see: it
+// returns the LARGER of the two requirements, so the buffer fits whichever path is taken.
+extern "C" size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b200_tensor * k) {
+    const int64_t nz = q->ne[1] * q->ne[3];
+    if (nz == 0 || k->ne[1] == 0 || k->ne[2] == 0) return 0;
+    const size_t dec = nz <= 65535 ? fa_decode_scratch_bytes(q, k) : 0;
+    if (q->ne[1] >= 16) { const size_t pre = fa_prefill_scratch_bytes(q, nullptr, q->ne[3]); return pre > dec ? pre : dec; }   // upper bound for the KV-tile counts (mask batch <= q batch)
+    return dec;
 }
 
 extern "C" int b200_flash_attn(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask,
@@ -281,7 +290,7 @@ extern "C" int b200_flash_attn(const b200_tensor * q, const b200_tensor * k, con
     A.ratio = (int) (q->ne[2] / k->ne[2]); A.groups = P.groups; A.splits = P.splits; A.chunk = P.chunk; A.scale = scale;
     if (k->ne[1] == 0) { A.splits = 1; A.chunk = 32; }
     if (A.splits > 1) {
-        if (!scratch || scratch_bytes < b200_flash_attn_scratch_bytes(q, k) || (uintptr_t) scratch % 16) return B200_ERR_ARG;
+        if (!scratch || scratch_bytes < fa_decode_scratch_bytes(q, k) || (uintptr_t) scratch % 16) return B200_ERR_ARG;
         const size_t slots = (size_t) nz * q->ne[2] * P.splits;
         A.part_acc = (float *) scratch;
         A.part_ml  = (float2 *) ((char *) scratch + ((slots * q->ne[0] * 4 + 15) & ~(size_t) 15));

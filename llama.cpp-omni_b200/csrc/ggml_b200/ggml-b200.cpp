@@ -16,6 +16,7 @@
 #include "ggml.h"
 #include "ggml-backend.h"
 #include "ggml-backend-impl.h"
+#include "ggml-impl.h"                 // struct ggml_cgraph, ggml_node_has_n_uses (what the reference's own fusion checks use)
 #include "../../../include/ggml-b200.h"
 #include "../../../include/b200_ops.h"
 
@@ -51,19 +52,28 @@ struct BufferCtx {
     std::mutex mu;
 };
 
+// 128-bit fingerprint of everything that decides whether a captured graph / a built engine can be replayed (see graph_key_of)
+struct GraphKey {
+    uint64_t h1 = 0, h2 = 0; int n = -1;
+    bool operator==(const GraphKey & o) const { return h1 == o.h1 && h2 == o.h2 && n == o.n; }
+    bool operator!=(const GraphKey & o) const { return !(*this == o); }
+    void clear() { h1 = h2 = 0; n = -1; }
+};
+
 struct BackendCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
     void * scratch = nullptr; size_t scratch_size = 0;      // activation records / split-KV partials
     std::string name;
     // decode-step CUDA graph (one per backend): re-captured whenever the node list or any tensor address / shape / parameter changes
-    std::vector<uint64_t> graph_key, pending_key;
+    GraphKey graph_key, pending_key;
     cudaGraphExec_t graph_exec = nullptr;
     bool graphs_enabled = true;
     // whole-token decode engine (b200_decoder_*): built when a batch-1 graph matches the llama-family decoder pattern (match_decoder)
     void * engine = nullptr; int32_t engine_n_kv = 0;
-    std::vector<uint64_t> engine_key, engine_reject_key;
-    std::vector<ggml_tensor *> engine_pre;                   // nodes still run per-op before the engine step (the KQ-mask cast)
+    GraphKey engine_key, engine_reject_key;
+    std::vector<int> engine_pre;                             // node INDICES still run per-op before the engine step (the KQ-mask cast); re-resolved from each graph
+    cudaEvent_t hop_event = nullptr;                         // cpy_tensor_async: source-stream -> destination-stream ordering (re-recorded per hop)
     bool engine_enabled = true;
     // activation-tile reuse (B200_MM_REUSE_ACT): the tensor whose prepared activations the scratch currently holds, reset per graph_compute
     const ggml_tensor * scratch_act = nullptr; const void * scratch_act_data = nullptr; int scratch_act_type = -1;
@@ -148,7 +158,10 @@ void b200_buf_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, con
         CUDA_OK(cudaStreamSynchronize(nullptr));
         return;
     }
+    // the compute streams are cudaStreamNonBlocking (no implicit ordering with the legacy stream this copy runs on), and a copy from
+    // pageable memory may return before the DMA has landed: finish it here (the reference: cudaMemcpyAsync + cudaStreamSynchronize(cudaStreamPerThread))
     CUDA_OK(cudaMemcpy((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaStreamSynchronize(nullptr));
 }
 
 void b200_buf_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
@@ -176,6 +189,7 @@ bool b200_buf_cpy_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * src, 
     BufferCtx * sc = (BufferCtx *) src->buffer->context, * dc = (BufferCtx *) dst->buffer->context;
     if (sc->device == dc->device) { CUDA_OK(cudaSetDevice(dc->device)); CUDA_OK(cudaMemcpy(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice)); }
     else CUDA_OK(cudaMemcpyPeer(dst->data, dc->device, src->data, sc->device, ggml_nbytes(src)));
+    CUDA_OK(cudaStreamSynchronize(nullptr));                          // D2D copies are asynchronous to the host: the caller's next graph_compute runs on a non-blocking stream
     return true;
 }
 
@@ -353,6 +367,9 @@ bool b200_dev_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
 void * scratch_for(BackendCtx * c, size_t bytes) {
     if (bytes <= c->scratch_size) return c->scratch;
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    // the captured decode graph has the old scratch address baked into its kernel arguments: it must not be replayed after the free
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    c->graph_key.clear(); c->pending_key.clear();
     if (c->scratch) CUDA_OK(cudaFree(c->scratch));
     c->scratch_size = (bytes + ((size_t) 8 << 20)) & ~(((size_t) 1 << 20) - 1);
     CUDA_OK(cudaMalloc(&c->scratch, c->scratch_size));
@@ -384,7 +401,17 @@ int n_uses(const ggml_cgraph * g, const ggml_tensor * t) {
 
 // One node -> one C-ABI call.  `next` (may be null) lets RMS_NORM absorb the MUL by the norm weight that follows it in every llama-family
 // graph (the reference fuses the same pair, ggml-cuda.cu ggml_cuda_can_fuse / norm.cu:510-660).  Returns the number of nodes consumed.
-int run_node(BackendCtx * c, const ggml_cgraph * g, ggml_tensor * n, ggml_tensor * next, int & rc) {
+// true when `n` (node i of g) is read exactly once in the WHOLE graph the scheduler split this view from: a graph view shares its parent's
+// use counts (ggml_graph_view), which is what the reference's own fusion test reads (ggml_node_has_n_uses, ggml-impl.h:570); a count taken
+// over the split alone would miss a consumer in another split / on another backend
+bool single_use(const ggml_cgraph * g, int i, const ggml_tensor * n) {
+    if (g->use_counts && g->visited_hash_set.keys) return ggml_node_has_n_uses(g, i, 1);
+    return n_uses(g, n) == 1 && !n->view_src;
+}
+
+int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool allow_fuse = false) {
+    ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, node_idx);
+    ggml_tensor * next = allow_fuse && node_idx + 1 < ggml_graph_n_nodes((ggml_cgraph *) g) ? ggml_graph_node((ggml_cgraph *) g, node_idx + 1) : nullptr;
     void * st = c->stream;
     const ggml_tensor * s0 = n->src[0], * s1 = n->src[1];
     rc = B200_OK;
@@ -413,7 +440,7 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, ggml_tensor * n, ggml_tensor
         }
         case GGML_OP_RMS_NORM: {
             b200_tensor x = view_of(s0), d = view_of(n);
-            if (next && next->op == GGML_OP_MUL && (next->src[0] == n || next->src[1] == n) && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) && n_uses(g, n) == 1) {
+            if (next && next->op == GGML_OP_MUL && (next->src[0] == n || next->src[1] == n) && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) && single_use(g, node_idx, n)) {
                 const ggml_tensor * wt = next->src[0] == n ? next->src[1] : next->src[0];
                 if (f32c(wt) && ggml_are_same_shape(next, n) && broadcastable(n, wt)) {
                     b200_tensor w = view_of(wt), dm = view_of(next);
@@ -473,10 +500,8 @@ enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
         ggml_tensor * n = ggml_graph_node(g, i);
         if (is_noop(n)) { ++i; continue; }
         if (c->scratch_act && n->data == c->scratch_act_data) c->scratch_act = nullptr;     // an in-place op rewrites the tensor the tiles were made from
-        ggml_tensor * next = nullptr;
-        for (int j = i + 1; j < nn; ++j) { ggml_tensor * t = ggml_graph_node(g, j); if (!is_noop(t)) { next = (j == i + 1) ? t : nullptr; break; } }
         int rc = 0;
-        const int used = run_node(c, g, n, next, rc);
+        const int used = run_node(c, g, i, rc, true);                    // RMS_NORM may absorb the MUL right behind it
         if (rc != B200_OK) {
             // graph_compute on an op supports_op rejected is a caller bug (the reference asserts, ggml-cuda.cu:3043-3047)
             B200_LOG("op %s (%s) failed: %s", ggml_op_name(n->op), n->name, b200_error_string(rc));
@@ -504,7 +529,7 @@ bool is_weight(const ggml_tensor * t) { return t && t->buffer && t->buffer->usag
 struct DecoderMatch {
     std::vector<b200_decode_layer> layers;                    // filled back to front, reversed at the end
     b200_decode_desc d = {};
-    std::vector<ggml_tensor *> pre;
+    std::vector<int> pre;                                      // node indices
     int n_matched = 0; int32_t n_kv = 0;
     float eps = -1.0f; bool have_rope = false;
     const ggml_tensor * pos = nullptr, * idx = nullptr, * mask = nullptr;
@@ -633,7 +658,12 @@ bool match_decoder(const ggml_cgraph * g, DecoderMatch & M) {
     if (x->op != GGML_OP_NONE && !is_view_op(x)) return false;                      // the split's input: token embedding row or the previous stage's l_out
     if (x->type != GGML_TYPE_F32 || ggml_nelements(x) != M.d.n_embd || !ggml_is_contiguous(x)) return false;
     M.d.x_in = (const float *) x->data;
-    if (M.mask->op == GGML_OP_CPY) { M.pre.push_back((ggml_tensor *) M.mask); ++M.n_matched; }       // the F32 -> F16 cast of the KQ mask stays a per-op launch
+    if (M.mask->op == GGML_OP_CPY) {                                                 // the F32 -> F16 cast of the KQ mask stays a per-op launch
+        int idx = -1;
+        for (int i = 0; i < nn; ++i) if (ggml_graph_node((ggml_cgraph *) g, i) == M.mask) { idx = i; break; }
+        if (idx < 0) return false;
+        M.pre.push_back(idx); ++M.n_matched;
+    }
     else if (M.mask->op != GGML_OP_NONE) return false;
     if (M.n_matched != n_real) return false;                                        // something in the graph is not part of the pattern
     for (int i = 0; i < nn; ++i) {                                                   // only the logits / result_norm may be graph outputs
@@ -648,23 +678,31 @@ bool match_decoder(const ggml_cgraph * g, DecoderMatch & M) {
 }
 
 // The properties that decide whether a captured graph can be replayed (what the reference compares in
-// ggml_cuda_graph_update_required / is_cuda_graph_update_required, ggml-cuda.cu:2800-2900): op, addresses, shapes, strides, op params.
-void graph_key_of(const ggml_cgraph * g, std::vector<uint64_t> & key) {
-    key.clear();
+// ggml_cuda_graph_update_required / is_cuda_graph_update_required, ggml-cuda.cu:2800-2900): op, addresses, shapes, strides, op params —
+// folded on the fly into two independent 64-bit multiply-xor hashes (no per-token allocation; ~900 nodes x ~50 words per decode graph).
+struct KeyHasher {
+    uint64_t a = 0x9e3779b97f4a7c15ull, b = 0xc2b2ae3d27d4eb4full;
+    inline void add(uint64_t v) {
+        a = (a ^ v) * 0x100000001b3ull; a ^= a >> 29;
+        b = (b + v) * 0xff51afd7ed558ccdull; b ^= b >> 32;
+    }
+};
+void graph_key_of(const ggml_cgraph * g, GraphKey & key) {
+    KeyHasher H;
     const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
-    key.reserve((size_t) nn * 24);
     for (int i = 0; i < nn; ++i) {
         const ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, i);
-        key.push_back((uint64_t) n->op | ((uint64_t) n->type << 32)); key.push_back((uint64_t) (uintptr_t) n->data);
-        for (int d = 0; d < 4; ++d) { key.push_back((uint64_t) n->ne[d]); key.push_back((uint64_t) n->nb[d]); }
+        H.add((uint64_t) n->op | ((uint64_t) n->type << 32)); H.add((uint64_t) (uintptr_t) n->data); H.add((uint64_t) n->flags);
+        for (int d = 0; d < 4; ++d) { H.add((uint64_t) n->ne[d]); H.add((uint64_t) n->nb[d]); }
         for (int s = 0; s < GGML_MAX_SRC; ++s) if (n->src[s]) {
-            key.push_back((uint64_t) (uintptr_t) n->src[s]->data ^ ((uint64_t) s << 56));
-            for (int d = 0; d < 4; ++d) { key.push_back((uint64_t) n->src[s]->ne[d]); key.push_back((uint64_t) n->src[s]->nb[d]); }
-            key.push_back((uint64_t) n->src[s]->type);
+            H.add((uint64_t) (uintptr_t) n->src[s]->data ^ ((uint64_t) s << 56));
+            for (int d = 0; d < 4; ++d) { H.add((uint64_t) n->src[s]->ne[d]); H.add((uint64_t) n->src[s]->nb[d]); }
+            H.add((uint64_t) n->src[s]->type);
         }
         const uint64_t * op64 = (const uint64_t *) n->op_params;
-        for (size_t w = 0; w < GGML_MAX_OP_PARAMS / sizeof(uint64_t); ++w) key.push_back(op64[w]);
+        for (size_t w = 0; w < GGML_MAX_OP_PARAMS / sizeof(uint64_t); ++w) H.add(op64[w]);
     }
+    key.h1 = H.a; key.h2 = H.b; key.n = nn;
 }
 
 enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph * g) {
@@ -684,12 +722,16 @@ enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph 
     }
     if (!small) return run_nodes(c, g);
     scratch_for(c, need);                                            // no allocation may happen while capturing
-    std::vector<uint64_t> key;
+    GraphKey key;
     graph_key_of(g, key);
+    auto run_pre = [&](const std::vector<int> & pre) {                // the engine's per-op prefix, re-resolved from THIS graph by node index
+        for (int idx : pre) { int rc = 0; run_node(c, g, idx, rc); if (rc != B200_OK) return false; }
+        return true;
+    };
     // ---- whole-token decode engine: one persistent kernel for the split when it is the llama-family batch-1 decoder pattern
     if (c->engine_enabled) {
         if (c->engine && key == c->engine_key) {
-            for (ggml_tensor * n : c->engine_pre) { int rc = 0; run_node(c, g, n, nullptr, rc); if (rc != B200_OK) return GGML_STATUS_FAILED; }
+            if (!run_pre(c->engine_pre)) return GGML_STATUS_FAILED;
             const int rc = b200_decoder_step(c->engine, c->engine_n_kv, c->stream);
             if (rc != B200_OK) { B200_LOG("decoder step failed: %s", b200_error_string(rc)); return GGML_STATUS_FAILED; }
             return GGML_STATUS_SUCCESS;
@@ -700,7 +742,7 @@ enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph 
             if (match_decoder(g, M) && b200_decoder_create(&M.d, &h) == B200_OK) {
                 if (c->engine) { CUDA_OK(cudaStreamSynchronize(c->stream)); b200_decoder_destroy(c->engine); }
                 c->engine = h; c->engine_n_kv = M.n_kv; c->engine_pre = M.pre; c->engine_key = key;
-                for (ggml_tensor * n : c->engine_pre) { int rc = 0; run_node(c, g, n, nullptr, rc); if (rc != B200_OK) return GGML_STATUS_FAILED; }
+                if (!run_pre(c->engine_pre)) return GGML_STATUS_FAILED;
                 const int rc = b200_decoder_step(c->engine, c->engine_n_kv, c->stream);
                 if (rc != B200_OK) { B200_LOG("decoder step failed: %s", b200_error_string(rc)); return GGML_STATUS_FAILED; }
                 return GGML_STATUS_SUCCESS;
@@ -713,7 +755,7 @@ enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph 
         return GGML_STATUS_SUCCESS;
     }
     // a node list seen for the first time runs eagerly (module loading, one-time attribute setup); it is captured when it comes back
-    if (key != c->pending_key) { c->pending_key.swap(key); return run_nodes(c, g); }
+    if (key != c->pending_key) { c->pending_key = key; return run_nodes(c, g); }
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_key.clear(); }
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -728,7 +770,7 @@ enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph 
     e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { (void) cudaGetLastError(); c->graph_exec = nullptr; c->graphs_enabled = false; return run_nodes(c, g); }
-    c->graph_key.swap(key);
+    c->graph_key = key;
     CUDA_OK(cudaGraphLaunch(c->graph_exec, c->stream));
     return GGML_STATUS_SUCCESS;
 }
@@ -743,6 +785,7 @@ void b200_backend_free(ggml_backend_t backend) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->engine) b200_decoder_destroy(c->engine);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->hop_event) cudaEventDestroy(c->hop_event);
     cudaStreamDestroy(c->stream);
     delete c;
     delete backend;
@@ -780,12 +823,10 @@ bool b200_backend_cpy_tensor_async(ggml_backend_t src_backend, ggml_backend_t ds
     CUDA_OK(cudaSetDevice(sc->device));
     if (sc->device == dc->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice, sc->stream));
     else CUDA_OK(cudaMemcpyPeerAsync(dst->data, dc->device, src->data, sc->device, ggml_nbytes(src), sc->stream));
-    cudaEvent_t ev;
-    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CUDA_OK(cudaEventRecord(ev, sc->stream));
+    if (!sc->hop_event) CUDA_OK(cudaEventCreateWithFlags(&sc->hop_event, cudaEventDisableTiming));      // one event per source backend, re-recorded per hop
+    CUDA_OK(cudaEventRecord(sc->hop_event, sc->stream));
     CUDA_OK(cudaSetDevice(dc->device));
-    CUDA_OK(cudaStreamWaitEvent(dc->stream, ev, 0));
-    CUDA_OK(cudaEventDestroy(ev));                                   // destruction is deferred until the event completes
+    CUDA_OK(cudaStreamWaitEvent(dc->stream, sc->hop_event, 0));      // the wait captures the record above; a later re-record does not move it
     return true;
 }
 

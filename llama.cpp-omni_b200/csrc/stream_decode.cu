@@ -329,6 +329,38 @@ __device__ __forceinline__ void sd_issue(const SegTab & S, int u, uint32_t dst, 
     }
 }
 
+// L2 prefetch of this CTA's whole share of a staged matvec phase (all 32 lanes of the staging warp, fire-and-forget bulk prefetches): weights
+// depend on nothing, so HBM can run `ahead` phases in front of the shared-memory rings — through the consumers' grid barriers, prologues and the
+// attention phase, when the rings are full and the demand stream would otherwise stall.  The later demand copy (L2::evict_first) then hits L2.
+__device__ __forceinline__ void l2_prefetch(const uint8_t * p, uint32_t bytes, uint64_t pol, bool hint) {
+    if (hint) asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" :: "l"(p), "r"(bytes), "l"(pol) : "memory");
+    else      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_span(const uint8_t * base, int64_t bytes, int lane, uint64_t pol, bool hint) {
+    constexpr int CH = 4096;
+    for (int64_t off = (int64_t) lane * CH; off < bytes; off += 32 * CH) l2_prefetch(base + off, (uint32_t) (bytes - off < CH ? bytes - off : CH), pol, hint);
+}
+__device__ __forceinline__ void sd_prefetch_l2(const SegTab & S, int lane, int shift, uint64_t pol, bool hint) {
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+        const int nr = S.nrows[j] >> shift;                               // shift > 0: only the first 1/2^shift of the rows (byte budget)
+        if (nr <= 0) continue;
+        if (S.ksplit == 1) {
+            l2_prefetch_span(S.pay[j], (int64_t) nr * S.rbp[j], lane, pol, hint);
+            if (S.sub_d[j]) l2_prefetch_span(S.dpl[j], (int64_t) nr * S.rbd[j], lane, pol, hint);
+            if (S.nm == 2) {
+                l2_prefetch_span(S.pay2, (int64_t) nr * S.rbp[j], lane, pol, hint);
+                if (S.sub_d[j]) l2_prefetch_span(S.dpl2, (int64_t) nr * S.rbd[j], lane, pol, hint);
+            }
+        } else {
+            for (int r = lane; r < nr; r += 32) {
+                l2_prefetch(S.pay[j] + (int64_t) r * S.rbp[j], (uint32_t) S.sub_p[j], pol, hint);
+                if (S.sub_d[j]) l2_prefetch(S.dpl[j] + (int64_t) r * S.rbd[j], (uint32_t) S.sub_d[j], pol, hint);
+            }
+        }
+    }
+}
+
 // The producer warp group (4 warps): warp 0 of the group stages phase descriptors + this CTA's segment tables two phases ahead of the one
 // being issued; every producer warp keeps the rings of 3 consumer warps full (lanes 0..2, one ring each — bulk copies are issued from
 // uniform registers, i.e. serially per lane, so the rings are spread over four warps rather than twelve lanes of one).  Producers never
@@ -341,9 +373,16 @@ __device__ __forceinline__ void sd_producer(const SdPhase * src, int n_phases, S
     const int cw = pw * RPW + lane;                                        // the consumer warp this lane feeds (lanes < RPW)
     int staged_n = 0;
     uint32_t issued = 0;
+    // experiment switches (profiling instantiation only; rt.flags == 0 in production): bit 10 = L2-prefetch every staged matvec phase,
+    // bit 11 = with an evict_last hint, bits 13-14 = stage (and prefetch) this many phases ahead instead of SD_STAGE_AHEAD, bits 15-16 = only
+    // the first 1/2, 1/4, 1/8 of each phase's rows
+    const bool l2pf = (rt.flags & 1024) != 0, l2hint = (rt.flags & 2048) != 0;
+    const int ahead = ((rt.flags >> 13) & 3) ? ((rt.flags >> 13) & 3) : SD_STAGE_AHEAD, l2shift = (rt.flags >> 15) & 3;
+    uint64_t pol_last = 0;
+    if (l2hint) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
     for (int p = 0; p < n_phases; ++p) {
         if (pw == 0) {
-            while (staged_n < n_phases && staged_n <= p + SD_STAGE_AHEAD) {
+            while (staged_n < n_phases && staged_n <= p + ahead) {
                 if (staged_n >= SD_NPH) while (*done < staged_n - SD_NPH + 1) { }      // the slot's previous tenant has been left by the consumers
                 StagedPhase & E = ring_ph[staged_n % SD_NPH];
                 sd_copy_phase(&E.P, src + staged_n, lane, 32);
@@ -356,6 +395,7 @@ __device__ __forceinline__ void sd_producer(const SdPhase * src, int n_phases, S
                     *staged = staged_n + 1;
                 }
                 __syncwarp();
+                if (l2pf && E.P.kind == SD_MATVEC) sd_prefetch_l2(E.S, lane, l2shift, pol_last, l2hint);
                 ++staged_n;
             }
         } else {

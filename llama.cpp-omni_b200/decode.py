@@ -207,7 +207,7 @@ class Qwen3Decoder:
             for n in ("wq", "wk", "wv", "wo", "gate", "up", "down"):
                 setattr(layers[i], n, W(lw[n], ty[n]))
             for n in ("attn_norm", "ffn_norm", "q_norm", "k_norm", "k_cache", "v_cache"):
-                setattr(layers[i], n, lw[n].data_ptr())
+                setattr(layers[i], n, lw[n].data_ptr() if lw[n] is not None else None)      # q_norm / k_norm None: llama arch
             layers[i].k_row_bytes = layers[i].v_row_bytes = kvb
         d = ops.DecodeDesc()
         d.n_layer, d.n_embd, d.n_head, d.n_head_kv, d.head_dim, d.n_ff, d.n_vocab = (len(self.L), cfg.n_embd, cfg.n_head, cfg.n_head_kv,

@@ -3,7 +3,9 @@
 // offloaded to the backend loaded from GGML_BACKEND_PATH (libggml-b200.so), greedy sampling, same prompt.  north_star bar: bit-exact
 // token ids for greedy decode, logits within 1e-3 relative.  TEST INFRASTRUCTURE (uses only the reference's public API, include/llama.h).
 //
-//   llama_parity model.gguf [n_prompt=32] [n_gen=32] [n_threads=8] [flash_attn=1] [cpu_self=0]
+//   llama_parity model.gguf [n_prompt=32] [n_gen=32] [n_threads=8] [flash_attn=1] [mode=0]
+//   mode 0: CPU vs B200 (batched prompt)   1: CPU vs CPU-repacked   2: CPU vs CPU 3 threads   3: CPU batched vs CPU incremental
+//        4: B200 batched vs B200 incremental   5: B200 per-op route vs B200 decode engine   6: CPU vs B200, prompt fed token by token (decode only)
 // prints one JSON line: {"tokens_equal": bool, "n_gen": N, "first_mismatch": i, "max_rel_logit_err": x, "prefill_rel_err": y, ...}
 #include "llama.h"
 #include "ggml-backend.h"
@@ -68,13 +70,15 @@ int main(int argc, char ** argv) {
     // mode "cpu-self": the CPU backend against itself (plain vs repacked weights) — how far two correct implementations drift on this model
     const bool cpu_self = argc > 6 && atoi(argv[6]) == 1;
     if (!n_gpu && !cpu_self && !(argc > 6 && (atoi(argv[6]) == 2 || atoi(argv[6]) == 3))) { printf("{\"error\": \"no GPU backend registered (GGML_BACKEND_PATH?)\"}\n"); return 3; }
-    Run cpu = run(argv[1], 0, n_prompt, n_gen, nt, fa, nullptr, false);
-    const int self_mode = argc > 6 ? atoi(argv[6]) : 0;                 // 1: repacked weights; 2: plain weights, 3 threads (must be bit-identical)
+    const int self_mode = argc > 6 ? atoi(argv[6]) : 0;
+    // 6: DECODE-ONLY parity — the prompt is fed one token at a time on BOTH sides, so only n = 1 graphs (the decode path, which carries the
+    //    reference's integer arithmetic) ever run; the batched-prefill kernels (F16 operands on the GPU vs q8_K on the CPU) are out of the picture
+    Run cpu = run(argv[1], 0, n_prompt, n_gen, nt, fa, nullptr, false, self_mode == 6);                 // 1: repacked weights; 2: plain weights, 3 threads (must be bit-identical)
     // 3: CPU batched prompt vs CPU one-token-at-a-time prompt; 4: B200 batched vs B200 one-at-a-time (baseline run also on the GPU)
     if (self_mode == 4) cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false);
     // 5: B200 per-op launches (baseline) vs B200 whole-token decode engine — the plugin reads GGML_B200_DISABLE_ENGINE when a backend is created
     if (self_mode == 5) { setenv("GGML_B200_DISABLE_ENGINE", "1", 1); cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false); setenv("GGML_B200_DISABLE_ENGINE", "0", 1); }
-    Run gpu = run(argv[1], cpu_self || self_mode == 2 || self_mode == 3 ? 0 : 999, n_prompt, n_gen, self_mode == 2 ? 3 : nt, fa, &cpu.toks, cpu_self, self_mode == 3 || self_mode == 4);
+    Run gpu = run(argv[1], cpu_self || self_mode == 2 || self_mode == 3 ? 0 : 999, n_prompt, n_gen, self_mode == 2 ? 3 : nt, fa, &cpu.toks, cpu_self, self_mode == 3 || self_mode == 4 || self_mode == 6);
     if (!cpu.ok || !gpu.ok) { printf("{\"error\": \"run failed\"}\n"); return 4; }
     int first = -1; double max_rel = 0, pre_rel = 0; double step_rel[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n_gen; ++i) if (cpu.toks[i] != gpu.toks[i] && first < 0) first = i;
@@ -83,11 +87,12 @@ int main(int argc, char ** argv) {
         for (size_t v = 0; v < cpu.logits[i].size(); ++v) { mx = std::fmax(mx, std::fabs(cpu.logits[i][v])); err = std::fmax(err, std::fabs(cpu.logits[i][v] - gpu.logits[i][v])); }
         const double rel = err / (mx > 0 ? mx : 1);
         if (i == 0) pre_rel = rel; else max_rel = std::fmax(max_rel, rel);
+        if (i == 0 && self_mode == 6) max_rel = std::fmax(max_rel, rel);   // decode-only mode: the prompt's last logits come from n = 1 graphs too
         if (i >= 1 && i <= 6) step_rel[i - 1] = rel;
     }
     printf("{\"tokens_equal\": %s, \"n_prompt\": %d, \"n_gen\": %d, \"first_mismatch\": %d, \"max_rel_logit_err\": %.3g, \"prefill_rel_err\": %.3g, "
-           "\"decode_step_rel_err\": [%.2g, %.2g, %.2g, %.2g, %.2g, %.2g], \"cpu_tg_tok_s\": %.2f, \"gpu_tg_tok_s\": %.2f, \"cpu_pp_tok_s\": %.1f, \"gpu_pp_tok_s\": %.1f, \"threads\": %d, \"flash_attn\": %d}\n",
+           "\"decode_step_rel_err\": [%.2g, %.2g, %.2g, %.2g, %.2g, %.2g], \"cpu_tg_tok_s\": %.2f, \"gpu_tg_tok_s\": %.2f, \"cpu_pp_tok_s\": %.1f, \"gpu_pp_tok_s\": %.1f, \"threads\": %d, \"flash_attn\": %d, \"mode\": %d}\n",
            first < 0 ? "true" : "false", n_prompt, n_gen, first, max_rel, pre_rel, step_rel[0], step_rel[1], step_rel[2], step_rel[3], step_rel[4], step_rel[5], n_gen * 1e3 / cpu.tg_ms, n_gen * 1e3 / gpu.tg_ms,
-           n_prompt * 1e3 / cpu.pp_ms, n_prompt * 1e3 / gpu.pp_ms, nt, fa);
+           n_prompt * 1e3 / cpu.pp_ms, n_prompt * 1e3 / gpu.pp_ms, nt, fa, self_mode);
     return first < 0 && max_rel <= 1e-3 ? 0 : 1;
 }
