@@ -41,27 +41,27 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
     if (d->rope.n_dims != D || (d->rope.mode != 0 && d->rope.mode != 2)) return B200_ERR_UNSUPPORTED;
     int nsm = sm_count();
     if (HK > nsm) return B200_ERR_UNSUPPORTED;
-    if (E > 24 * 256 || F > 48 * 256 || Q > 48 * 256) return B200_ERR_UNSUPPORTED;        // prologue fast path: normalised vectors in one pass of 2 super-blocks per warp
-    if (E / nsm + 2 > SD_STASH_ROWS) return B200_ERR_UNSUPPORTED;
-    // K-split of ffn_down INSIDE every CTA: slices of at most 4096 so that the activation fragments stay in registers; warp w owns slice w % ksl
-    int ksl = 1;
-    for (int c : { 1, 2, 3, 4, 6 }) if (F % (c * 1024) == 0 && F / c <= 4096) { ksl = c; break; }
+    // K-split of ffn_down: slices of at most 4096 so that the activation fragments stay in registers
+    int ks = 1;
+    while (F / ks > 4096 && ks < 8) ++ks;
+    while (ks < 8 && (F % (ks * 256) || F / ks > 4096)) ++ks;
+    if (F % (ks * 256) || F / ks > 4096) ks = 1;
 
-    // ---- scratch: TAGGED activation vectors between phases (8-byte pairs), attention partials, tickets, launch epoch ---------------------
+    // ---- scratch: activations between phases, K-split partials, attention partials, tickets, grid barrier -------------------------------
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t) 255; return o; };
-    const size_t o_q = take(Q * 8), o_k = take(KV * 8), o_v = take(KV * 8), o_attn = take(Q * 8), o_h = take((size_t) F * 8);
-    const size_t o_x1 = take(E * 8), o_x2 = take(E * 8);
+    const size_t o_q = take(Q * 4), o_k = take(KV * 4), o_v = take(KV * 4), o_attn = take(Q * 4), o_h = take((size_t) F * 4);
+    const size_t o_x1 = take(E * 4), o_x2 = take(E * 4), o_xres = take(E * 4), o_part = take((size_t) 8 * E * 4);
     const int max_splits = nsm / HK;
     const size_t o_pacc = take((size_t) H * max_splits * D * 4), o_pml = take((size_t) H * max_splits * 8), o_tick = take(HK * 4 + 256), o_bar = take(512);
     Decoder * dec = new (std::nothrow) Decoder();
     if (!dec) return B200_ERR_ARG;
     cudaError_t e = cudaMalloc(&dec->scratch, off);
     if (e != cudaSuccess) { delete dec; return -(int) e; }
-    cudaMemset(dec->scratch, 0, off);                                      // tag 0 never matches: epochs start at 1
+    cudaMemset(dec->scratch, 0, off);
     char * S = dec->scratch;
     float * q = (float *) (S + o_q), * k = (float *) (S + o_k), * v = (float *) (S + o_v), * attn = (float *) (S + o_attn), * h = (float *) (S + o_h);
-    float * x1 = (float *) (S + o_x1), * x2 = (float *) (S + o_x2);
+    float * x1 = (float *) (S + o_x1), * x2 = (float *) (S + o_x2), * xres = (float *) (S + o_xres), * part = (float *) (S + o_part);
     dec->gbar = (unsigned *) (S + o_bar);
 
     const float lo = floorf(yarn_dim(D, d->rope.n_ctx_orig, d->rope.beta_fast, d->rope.freq_base));
@@ -69,14 +69,15 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
 
     std::vector<SdPhase> ph;
     bool ok = true;
-    // the residual stream entering a layer: the plain input vector (layer 0) or the tagged x2 of the previous layer's ffn_down phase
-    const float * xin = d->x_in; int xin_tag = 0;
-    auto tag_of_last = [&]() { return (int) ph.size(); };                  // (index of the phase just pushed) + 1
+    // the residual stream entering a layer: one vector, or x1 + K-split partials of the previous ffn_down
+    const float * xin[4] = { d->x_in, nullptr, nullptr, nullptr }; int n_x = 1;
+    auto set_x = [&](SdPhase & P) { for (int i = 0; i < 4; ++i) P.x[i] = xin[i]; P.n_x = n_x; };
     for (int il = 0; il < d->n_layer && ok; ++il) {
         const b200_decode_layer & L = d->layers[il];
-        {   // A: the prologue also stashes this CTA's rows of the layer input (the residual wo adds back in phase C)
+        const float * resid_in = n_x == 1 ? xin[0] : xres;               // what wo adds back: the layer input
+        {   // A
             SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 3; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_RMSNORM_QUANT; P.k = E; P.act_group = 256;
-            P.eps = d->rms_eps; P.ksplit = 1; P.ksl = 1; P.x[0] = xin; P.n_x = 1; P.x_tag = xin_tag; P.norm_w = L.attn_norm; P.y_tagged = 1; P.stash_T = E;
+            P.eps = d->rms_eps; P.ksplit = 1; set_x(P); P.x_out = n_x == 1 ? nullptr : xres; P.norm_w = L.attn_norm;
             ok = ok && L.attn_norm && is_kquant(L.wq.type) && is_kquant(L.wk.type) && is_kquant(L.wv.type);
             ok = ok && sd_fill_mat(P.mat[0], L.wq.data, L.wq.type, L.wq.layout, Q, E, row_bytes(L.wq.type, E), q, nullptr);
             ok = ok && sd_fill_mat(P.mat[1], L.wk.data, L.wk.type, L.wk.layout, KV, E, row_bytes(L.wk.type, E), k, nullptr);
@@ -84,9 +85,9 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
             ok = ok && sd_phase_ok(P); ph.push_back(P);
         }
         {   // B
-            SdPhase P = {}; P.kind = SD_ATTN; P.ksplit = 1; P.ksl = 1;
+            SdPhase P = {}; P.kind = SD_ATTN; P.ksplit = 1;
             SdAttn & A = P.attn;
-            A.q = q; A.k_new = k; A.v_new = v; A.q_norm_w = L.q_norm; A.k_norm_w = L.k_norm; A.in_tag = tag_of_last();
+            A.q = q; A.k_new = k; A.v_new = v; A.q_norm_w = L.q_norm; A.k_norm_w = L.k_norm;
             A.k_cache = (uint8_t *) L.k_cache; A.v_cache = (uint8_t *) L.v_cache; A.k_row_bytes = L.k_row_bytes; A.v_row_bytes = L.v_row_bytes;
             A.out = attn; A.part_acc = (float *) (S + o_pacc); A.part_ml = (float2 *) (S + o_pml); A.tickets = (unsigned *) (S + o_tick);
             A.n_head = H; A.n_head_kv = HK; A.head_dim = D; A.rope_mode = d->rope.mode; A.scale = d->attn_scale; A.eps = d->rms_eps;
@@ -96,33 +97,33 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
             ok = ok && ((uintptr_t) L.k_cache % 16 == 0) && ((uintptr_t) L.v_cache % 16 == 0);
             ph.push_back(P);
         }
-        {   // C: x1 = wo . attn + (stashed layer input)
-            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = Q; P.act_group = 256; P.ksplit = 1; P.ksl = 1;
-            P.x[0] = attn; P.n_x = 1; P.x_tag = tag_of_last(); P.y_tagged = 1; P.resid_stash = 1;
-            ok = ok && is_kquant(L.wo.type) && sd_fill_mat(P.mat[0], L.wo.data, L.wo.type, L.wo.layout, E, Q, row_bytes(L.wo.type, Q), x1, nullptr);
+        {   // C
+            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = Q; P.act_group = 256; P.ksplit = 1;
+            P.x[0] = attn; P.n_x = 1;
+            ok = ok && is_kquant(L.wo.type) && sd_fill_mat(P.mat[0], L.wo.data, L.wo.type, L.wo.layout, E, Q, row_bytes(L.wo.type, Q), x1, resid_in);
             ok = ok && sd_phase_ok(P); ph.push_back(P);
         }
-        {   // D: the prologue stashes this CTA's rows of x1 (the residual ffn_down adds back in phase E)
+        {   // D
             SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 2; P.epilogue = SD_EPI_SWIGLU; P.prologue = SD_PRO_RMSNORM_QUANT; P.k = E; P.act_group = 256;
-            P.eps = d->rms_eps; P.ksplit = 1; P.ksl = 1; P.x[0] = x1; P.n_x = 1; P.x_tag = tag_of_last(); P.norm_w = L.ffn_norm; P.y_tagged = 1; P.stash_T = E;
+            P.eps = d->rms_eps; P.ksplit = 1; P.x[0] = x1; P.n_x = 1; P.norm_w = L.ffn_norm;
             ok = ok && L.ffn_norm && is_kquant(L.gate.type) && L.gate.type == L.up.type;
             ok = ok && sd_fill_mat(P.mat[0], L.gate.data, L.gate.type, L.gate.layout, F, E, row_bytes(L.gate.type, E), h, nullptr);
             ok = ok && sd_fill_mat(P.mat[1], L.up.data, L.up.type, L.up.layout, F, E, row_bytes(L.up.type, E), h, nullptr);
             ok = ok && sd_phase_ok(P); ph.push_back(P);
         }
-        {   // E: x2 = down . h + (stashed x1); every CTA quantises the whole h and K-splits its rows over its warps (no partial vectors cross CTAs)
-            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = F; P.act_group = 256; P.ksplit = 1; P.ksl = ksl;
-            P.x[0] = h; P.n_x = 1; P.x_tag = tag_of_last(); P.y_tagged = 1; P.resid_stash = 1;
+        {   // E
+            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = F; P.act_group = 256; P.ksplit = ks;
+            P.x[0] = h; P.n_x = 1; P.y_part_stride = ks > 1 ? E : 0;
             ok = ok && is_kquant(L.down.type);
-            ok = ok && sd_fill_mat(P.mat[0], L.down.data, L.down.type, L.down.layout, E, F, row_bytes(L.down.type, F), x2, nullptr);
+            ok = ok && sd_fill_mat(P.mat[0], L.down.data, L.down.type, L.down.layout, E, F, row_bytes(L.down.type, F), ks > 1 ? part : x2, ks > 1 ? nullptr : x1);
             ok = ok && sd_phase_ok(P); ph.push_back(P);
         }
-        xin = x2; xin_tag = tag_of_last();
+        if (ks > 1) { xin[0] = x1; for (int s = 0; s < 3; ++s) xin[1 + s] = nullptr; n_x = 1 + ks; if (n_x > 4) ok = false; for (int s = 0; s < ks && s < 3; ++s) xin[1 + s] = part + (size_t) s * E; }
+        else        { xin[0] = x2; n_x = 1; }
     }
-    if (ok) {   // Z: lm_head (or, for a pipeline stage without head, just materialise the residual stream)
-        SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = d->lm_head.data ? 1 : 0; P.epilogue = SD_EPI_STORE; P.k = E; P.act_group = 256; P.ksplit = 1; P.ksl = 1;
-        P.prologue = d->lm_head.data ? SD_PRO_RMSNORM_QUANT : SD_PRO_QUANT; P.eps = d->rms_eps; P.x[0] = xin; P.n_x = 1; P.x_tag = xin_tag;
-        P.x_out = d->x_out; P.norm_w = d->out_norm; P.norm_out = d->hidden_out;
+    if (ok) {   // Z: lm_head (or, for a pipeline stage without head, just materialise the summed residual stream)
+        SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = d->lm_head.data ? 1 : 0; P.epilogue = SD_EPI_STORE; P.k = E; P.act_group = 256; P.ksplit = 1;
+        P.prologue = d->lm_head.data ? SD_PRO_RMSNORM_QUANT : SD_PRO_QUANT; P.eps = d->rms_eps; set_x(P); P.x_out = d->x_out; P.norm_w = d->out_norm; P.norm_out = d->hidden_out;
         if (d->lm_head.data) {
             ok = ok && d->out_norm && d->logits && is_kquant(d->lm_head.type);
             ok = ok && sd_fill_mat(P.mat[0], d->lm_head.data, d->lm_head.type, d->lm_head.layout, d->n_vocab, E, row_bytes(d->lm_head.type, E), d->logits, nullptr);

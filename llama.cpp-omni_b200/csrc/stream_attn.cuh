@@ -7,20 +7,18 @@
 // flash_attn_combine_results of the reference (norm.cu:107-185, rope.cu:83-123, set-rows.cu:264, fattn-vec.cuh:19, fattn-common.cuh).
 //
 // Latency design: the phase is a chain of dependent round trips, not bandwidth, so (1) the chunk's K/V rows are pulled into L2 during the
-// PREVIOUS (qkv matvec) phase — old cache rows do not depend on this token (sa_prefetch_kv); (2) every warp owns 16-position tiles and issues
-// the K, V and mask loads of its first tile before the q-norm/RoPE work; (3) the tile arithmetic runs on the tensor cores (legacy
-// mma.sync.m16n8k16: 4 query heads x 16 positions x 128 dims is far too small for a tcgen05 tile, and at 12 warps per SM the SIMT version was
-// bound by its ~1500 instructions per lane): S = Q.K^T with the 4 GQA heads as the M rows (12 of 16 padded) and P.V with P split into f16
-// hi + lo parts, so the result is the f32-P x f16-V product of the scalar path to ~1e-7; every warp keeps its own online-softmax state, the
-// 12 warps are merged once at the end.  Fragments are loaded straight from global memory with 16-byte loads: a dot product is invariant under
-// a permutation of its reduction index applied to both operands, so a lane's 8 consecutive halves serve as two k-steps of its fragment.
+// PREVIOUS (qkv matvec) phase — old cache rows do not depend on this token (sa_prefetch_kv); (2) the K, V and mask loads of a 144-position
+// tile are all issued together, before the q-norm/RoPE work, into registers; (3) each 16-lane row group keeps its own online-softmax state
+// (m, l, acc), so the tile loop has no CTA barrier; the 24 groups are merged once at the end.
 constexpr int SA_G    = 4;              // query heads per kv head handled together (GQA ratio must be a multiple; Qwen3: 32/8)
-constexpr int SA_TILE = 16;             // KV positions per warp tile (two m16n8k16 column tiles)
+constexpr int SA_U    = 6;              // KV rows per row group and tile
+constexpr int SA_NRG  = SD_WARPS * 2;   // row groups (16 lanes each: 8 head dims per lane)
+constexpr int SA_TILE = SA_NRG * SA_U;  // KV positions per tile
 
 struct SaSmem {                         // carved from the phase scratch (SD_ATTN_BYTES)
-    float red[SD_WARPS][SA_G * 128];    // per-warp un-normalised outputs, merged by the CTA
+    float q[SA_G][128];
+    float red[SD_WARPS][SA_G * 128];
     float2 red_ml[SD_WARPS][SA_G];
-    __half q16[SA_G][128];              // normalised + rotated queries, rounded to f16 exactly as the oracle does before the dot products
     __half knew[128], vnew[128];
     int is_last;
 };
@@ -97,84 +95,49 @@ __device__ __forceinline__ void sa_norm_rope(float (&v)[4], const float * w, flo
     for (int i = 0; i < 4; ++i) v[i] = out[i];
 }
 
-// D(16x8, f32) += A(16x16, f16, row) . B(16x8, f16, col): the legacy warp-level tensor-core op (HMMA.16816.F32)
-__device__ __forceinline__ void mma_f16_16816(float & d0, float & d1, float & d2, float & d3, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t u4_at(const uint4 & v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
-
-// four tagged outputs of one head (16-byte aligned pair address)
-__device__ __forceinline__ void sa_store_out4(float * out_pairs, int idx, float4 v, uint32_t tag) {
-    st_tagged2(out_pairs + 2 * idx, v.x, v.y, tag); st_tagged2(out_pairs + 2 * idx + 4, v.z, v.w, tag);
-}
-
-// Out of line ON PURPOSE: the phase needs ~150 registers of its own (K/V fragments in flight + 32 accumulators); inlined into the phase loop it
-// made the matvec consumer loop spill.  Shared-memory pointers are re-derived from the extern symbol (see the map in stream_decode.cu).
-__device__ __noinline__ void sd_attention(int staged_slot, int n_kv, const int64_t * kv_idx, const __half * mask, int rope_mode, uint32_t tag_base, uint32_t my_tag,
-                                          unsigned long long * pf) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const SdAttn & A = ((const StagedPhase *) (smem + SM_PHASES))[staged_slot].P.attn;
-    SaSmem & sm = *(SaSmem *) (smem + SM_ATTN);
-    const float2 * rope_tab = (const float2 *) (smem + SM_ROPE);
-    constexpr int D = 128;
+__device__ void sd_attention(const SdPhase & P, const SdRuntime & rt, uint8_t * scratch, const float2 * rope_tab, unsigned long long * pf) {
+    const SdAttn & A = P.attn;
+    SaSmem & sm = *(SaSmem *) scratch;
+    constexpr int D = 128, LPR = 16, U = SA_U;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = warp * 2 + lane / LPR, hl = lane % LPR;
     int kvh, split, splits, c0, c1;
-    if (!sa_geometry(A, n_kv, kvh, split, splits, c0, c1)) return;           // idle CTA
+    if (!sa_geometry(A, rt.n_kv, kvh, split, splits, c0, c1)) return;        // idle CTA: straight to the grid barrier
     const int ratio = A.n_head / A.n_head_kv, head0 = kvh * ratio;           // ratio == SA_G (checked on the host)
-    const int64_t slot = kv_idx[0];
+    const int64_t slot = rt.kv_idx[0];
     const bool owner = slot >= c0 && slot < c1;
-    const __half * mrow = mask;
+    const char * kb = (const char *) A.k_cache + (int64_t) kvh * D * 2 + hl * 16;
+    const char * vb = (const char *) A.v_cache + (int64_t) kvh * D * 2 + hl * 16;
+    const __half * mrow = rt.mask;
 
     // ---- the first tile's K, V and mask loads go out before anything else ---------------------------------------------------------------
-    // lane (g, t) = (lane >> 2, lane & 3).  K: B fragments of the two 8-position column tiles: row c0' + 8 nt + g, halves [32 blk + 8 t, +8).
-    // V: the 4 positions {2t, 2t+1, 8+2t, 9+2t} this lane's P fragment multiplies, dims [16 g, 16 g + 16).
-    const int g = lane >> 2, t = lane & 3;
-    uint4 kf[2][4], vf[4][2]; float mv[2][2]; bool live[2][2];
-    auto load_tile = [&](int tile) {
+    uint4 kk[U], vv[U]; float mv[U];
+    auto load_tile = [&](int t0) {
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const int pos = min(tile + 8 * nt + g, c1 - 1);                // out-of-chunk rows are clamped (and masked below)
-            const char * kr = (const char *) A.k_cache + (int64_t) pos * A.k_row_bytes + (int64_t) kvh * D * 2 + t * 16;
-#pragma unroll
-            for (int blk = 0; blk < 4; ++blk) kf[nt][blk] = ldg_stream16(kr + blk * 64);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int pp = tile + 8 * nt + 2 * t + e;
-                const float m = pp < c1 ? __half2float(mrow[pp]) : -INFINITY;
-                mv[nt][e] = m; live[nt][e] = m != -INFINITY;
-                const char * vr = (const char *) A.v_cache + (int64_t) min(pp, c1 - 1) * A.v_row_bytes + (int64_t) kvh * D * 2 + g * 32;
-                vf[2 * nt + e][0] = ldg_stream16(vr); vf[2 * nt + e][1] = ldg_stream16(vr + 16);
-            }
+        for (int u = 0; u < U; ++u) {
+            const int pos = t0 + rg + u * SA_NRG;
+            const bool in = pos < c1;
+            mv[u] = in ? __half2float(mrow[pos]) : -INFINITY;
+            kk[u] = in ? ldg_stream16(kb + (int64_t) pos * A.k_row_bytes) : make_uint4(0, 0, 0, 0);
+            vv[u] = in ? ldg_stream16(vb + (int64_t) pos * A.v_row_bytes) : make_uint4(0, 0, 0, 0);
         }
     };
-    const int tile0 = c0 + warp * SA_TILE;
-    if (tile0 < c1) load_tile(tile0);
+    load_tile(c0);
 
     // ---- q heads (warps 0..3), new K row (warp 4), new V row (warp 5): their loads (and the norm weights') join the same round trip ------
     {
         const bool isq = warp < SA_G, isk = warp == SA_G && owner, isv = warp == SA_G + 1 && owner;
-        const float * srcp = isq ? A.q + 2 * (head0 + warp) * D : isk ? A.k_new + 2 * kvh * D : A.v_new + 2 * kvh * D;     // pairs
+        const float * srcp = isq ? A.q + (head0 + warp) * D : isk ? A.k_new + kvh * D : A.v_new + kvh * D;
         const float * nw = isq ? A.q_norm_w : isk ? A.k_norm_w : nullptr;
         float4 r = make_float4(0, 0, 0, 0), wn = make_float4(1, 1, 1, 1);
+        if (isq || isk || isv) r = __ldcg((const float4 *) (srcp + lane * 4));
         if (nw) wn = __ldg((const float4 *) (nw + lane * 4));
-        if (isq || isk || isv) {                                            // tagged pairs from the qkv phase: poll until this warp's 128 values have landed
-            const uint32_t want = tag_base + (uint32_t) A.in_tag;
-            uint32_t spins = 0; long long t0 = 0;
-            for (;;) {
-                const Pairs4 pr = ld_pairs4(srcp + 2 * (lane * 4));
-                const bool ok = pair_tag(pr.p[0]) == want && pair_tag(pr.p[1]) == want && pair_tag(pr.p[2]) == want && pair_tag(pr.p[3]) == want;
-                r = make_float4(pair_val(pr.p[0]), pair_val(pr.p[1]), pair_val(pr.p[2]), pair_val(pr.p[3]));
-                if (__all_sync(0xffffffffu, ok)) break;
-                sd_spin_guard(spins, t0);
-            }
-        }
         float v[4] = { r.x, r.y, r.z, r.w };
         const float w4[4] = { wn.x, wn.y, wn.z, wn.w };
-        if (isq || isk) sa_norm_rope(v, nw ? w4 : nullptr, A.eps, rope_mode, rope_tab);
+        if (isq || isk) sa_norm_rope(v, nw ? w4 : nullptr, A.eps, rt.rope_mode, rope_tab);
         if (isq) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sm.q16[warp][lane * 4 + i] = __float2half_rn(v[i]);                    // the oracle rounds Q to f16
+            for (int i = 0; i < 4; ++i) sm.q[warp][lane * 4 + i] = __half2float(__float2half_rn(v[i]));       // the oracle rounds Q to f16
         } else if (isk || isv) {
             __half * dst = (__half *) ((isk ? A.k_cache + slot * A.k_row_bytes : A.v_cache + slot * A.v_row_bytes)) + kvh * D + lane * 4;
             __half * snew = isk ? sm.knew : sm.vnew;
@@ -185,96 +148,83 @@ __device__ __noinline__ void sd_attention(int staged_slot, int n_kv, const int64
     cons_sync();
     if (pf) pf[4] = globaltimer();
 
-    // A fragments of Q (rows = the 4 heads; rows 4..15 of the tile are zero) are re-read from shared memory per use: 16 registers matter more here
-    const __half * qrow = &sm.q16[g & (SA_G - 1)][8 * t];
-
-    float o[16][2], m_run = -INFINITY, l_run = 0.0f, zz0 = 0.0f, zz1 = 0.0f;    // o[j] = out[head g][dims 32 t + j, 32 t + 16 + j]
+    float acc[SA_G][8], m[SA_G], l[SA_G];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { o[j][0] = 0.0f; o[j][1] = 0.0f; }
-
-    for (int tile = tile0; tile < c1; ) {
-        // this token's row is not in the cache yet for the loads above: patch it from shared memory
-        if (owner) {
+    for (int g = 0; g < SA_G; ++g) {
+        m[g] = -INFINITY; l[g] = 0.0f;
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                if (tile + 8 * nt + g == slot) {
-#pragma unroll
-                    for (int blk = 0; blk < 4; ++blk) kf[nt][blk] = *(const uint4 *) (sm.knew + 32 * blk + 8 * t);
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) if (tile + 8 * nt + 2 * t + e == slot) {
-                    vf[2 * nt + e][0] = *(const uint4 *) (sm.vnew + 16 * g); vf[2 * nt + e][1] = *(const uint4 *) (sm.vnew + 16 * g + 8);
-                }
-            }
-        }
-        // ---- S[head][pos] = Q . K^T (f16 x f16 -> f32) ----------------------------------------------------------------------------------
-        float sc[2][2];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            float c0_ = 0.0f, c1_ = 0.0f;
-#pragma unroll
-            for (int blk = 0; blk < 4; ++blk) {
-                uint4 qa = *(const uint4 *) (qrow + 32 * blk);
-                if (g >= SA_G) qa = make_uint4(0, 0, 0, 0);
-                mma_f16_16816(c0_, c1_, zz0, zz1, qa.x, 0u, qa.y, 0u, kf[nt][blk].x, kf[nt][blk].y);
-                mma_f16_16816(c0_, c1_, zz0, zz1, qa.z, 0u, qa.w, 0u, kf[nt][blk].z, kf[nt][blk].w);
-            }
-            sc[nt][0] = live[nt][0] ? c0_ * A.scale + mv[nt][0] : -INFINITY;
-            sc[nt][1] = live[nt][1] ? c1_ * A.scale + mv[nt][1] : -INFINITY;
-        }
-        if (pf && tile == tile0) pf[5] = globaltimer();
-        // ---- online softmax of row g over the tile's 16 positions (4 per lane, 4 lanes per row) ------------------------------------------
-        float mx = fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1]));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float m_new = fmaxf(m_run, mx);
-        const float corr = m_new == -INFINITY ? 1.0f : __expf(m_run - m_new);
-        float pr[2][2];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) pr[nt][e] = sc[nt][e] == -INFINITY ? 0.0f : __expf(sc[nt][e] - m_new);
-        }
-        l_run = l_run * corr + (pr[0][0] + pr[0][1]) + (pr[1][0] + pr[1][1]);          // lane-local; summed over the row's 4 lanes at the end
-        m_run = m_new;
-        if (tile != tile0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
-        }
-        // P = hi + lo (two f16 parts: ~22 bits) as the A fragments of P.V; masked positions contribute exactly nothing, so their V rows are
-        // zeroed (they may hold anything: uninitialised cache cells, NaN included)
-        uint32_t ahi[2], alo[2];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const __half2 hi = __floats2half2_rn(pr[nt][0], pr[nt][1]);
-            const float2 hf = __half22float2(hi);
-            const __half2 lo = __floats2half2_rn(pr[nt][0] - hf.x, pr[nt][1] - hf.y);
-            ahi[nt] = *(const uint32_t *) &hi; alo[nt] = *(const uint32_t *) &lo;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) if (!live[nt][e]) { vf[2 * nt + e][0] = make_uint4(0, 0, 0, 0); vf[2 * nt + e][1] = make_uint4(0, 0, 0, 0); }
-        }
-        // ---- out[head][dim] += P . V: column tile j holds dims { 16 c + j } -> B fragment = halves j of this lane's 4 V rows ----------------
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-            const uint32_t b0 = __byte_perm(u4_at(vf[0][j >> 3], (j >> 1) & 3), u4_at(vf[1][j >> 3], (j >> 1) & 3), sel);
-            const uint32_t b1 = __byte_perm(u4_at(vf[2][j >> 3], (j >> 1) & 3), u4_at(vf[3][j >> 3], (j >> 1) & 3), sel);
-            mma_f16_16816(o[j][0], o[j][1], zz0, zz1, ahi[0], 0u, ahi[1], 0u, b0, b1);
-            mma_f16_16816(o[j][0], o[j][1], zz0, zz1, alo[0], 0u, alo[1], 0u, b0, b1);
-        }
-        tile += SD_WARPS * SA_TILE;
-        if (tile < c1) load_tile(tile);
+        for (int i = 0; i < 8; ++i) acc[g][i] = 0.0f;
     }
-    if (pf) pf[6] = globaltimer();
-    // ---- hand this warp's state to the CTA merge: rows g < 4 are real heads -----------------------------------------------------------------
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1); l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-    if (g < SA_G) {
-        float * dstp = &sm.red[warp][g * D + 32 * t];
+
+    for (int t0 = c0; ; ) {
+        // ---- s = scale * K.q + mask for the group's U rows -------------------------------------------------------------------------------
+        float s[U][SA_G];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-            *(float4 *) (dstp + j)      = make_float4(o[j][0], o[j + 1][0], o[j + 2][0], o[j + 3][0]);
-            *(float4 *) (dstp + 16 + j) = make_float4(o[j][1], o[j + 1][1], o[j + 2][1], o[j + 3][1]);
+        for (int u = 0; u < U; ++u) {
+            const int pos = t0 + rg + u * SA_NRG;
+            if (pos == slot) { kk[u] = *(const uint4 *) (sm.knew + hl * 8); vv[u] = *(const uint4 *) (sm.vnew + hl * 8); }   // this token's row: not in the cache yet for the loads above
+            const __half2 * h2 = (const __half2 *) &kk[u];
+            float kf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h2[i]); kf[2 * i] = f.x; kf[2 * i + 1] = f.y; }
+#pragma unroll
+            for (int g = 0; g < SA_G; ++g) {
+                const float4 q0 = *(const float4 *) &sm.q[g][hl * 8], q1 = *(const float4 *) &sm.q[g][hl * 8 + 4];   // re-read per row: keeps 32 registers free
+                float d = kf[0] * q0.x;
+                d = fmaf(kf[1], q0.y, d); d = fmaf(kf[2], q0.z, d); d = fmaf(kf[3], q0.w, d);
+                d = fmaf(kf[4], q1.x, d); d = fmaf(kf[5], q1.y, d); d = fmaf(kf[6], q1.z, d); d = fmaf(kf[7], q1.w, d);
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                s[u][g] = mv[u] != -INFINITY ? d * A.scale + mv[u] : -INFINITY;
+            }
         }
-        if (t == 0) sm.red_ml[warp][g] = make_float2(m_run, l_run);
+        // ---- the group's online softmax + acc = acc * corr + P.V -------------------------------------------------------------------------
+        float pr[U][SA_G];
+#pragma unroll
+        for (int g = 0; g < SA_G; ++g) {
+            float mx = s[0][g];
+#pragma unroll
+            for (int u = 1; u < U; ++u) mx = fmaxf(mx, s[u][g]);
+            const float m_new = fmaxf(m[g], mx);
+            const float corr = m_new == -INFINITY ? 1.0f : __expf(m[g] - m_new);
+            float sum = 0.0f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) { pr[u][g] = s[u][g] == -INFINITY ? 0.0f : __expf(s[u][g] - m_new); sum += pr[u][g]; }
+            m[g] = m_new; l[g] = l[g] * corr + sum;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[g][i] *= corr;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool any = pr[u][0] != 0.0f || pr[u][1] != 0.0f || pr[u][2] != 0.0f || pr[u][3] != 0.0f;
+            if (!any) vv[u] = make_uint4(0, 0, 0, 0);                          // masked rows may hold anything (uninitialised cache)
+            const __half2 * h2 = (const __half2 *) &vv[u];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h2[i]);
+#pragma unroll
+                for (int g = 0; g < SA_G; ++g) { acc[g][2 * i] = fmaf(pr[u][g], f.x, acc[g][2 * i]); acc[g][2 * i + 1] = fmaf(pr[u][g], f.y, acc[g][2 * i + 1]); }
+            }
+        }
+        t0 += SA_TILE;
+        if (t0 >= c1) break;
+        load_tile(t0);
+    }
+    if (pf) pf[5] = globaltimer();
+    // ---- merge the 24 row groups: the two groups of a warp by shuffle, the 12 warps through shared memory (16-byte stores and loads) ---------
+#pragma unroll
+    for (int g = 0; g < SA_G; ++g) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m[g], 16), lo = __shfl_xor_sync(0xffffffffu, l[g], 16);
+        const float M = fmaxf(m[g], mo);
+        const float ws = m[g] == -INFINITY ? 0.0f : __expf(m[g] - M), wo = mo == -INFINITY ? 0.0f : __expf(mo - M);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = acc[g][i] * ws + __shfl_xor_sync(0xffffffffu, acc[g][i], 16) * wo;
+        if (lane < 16) {
+            *(float4 *) &sm.red[warp][g * D + hl * 8]     = make_float4(v[0], v[1], v[2], v[3]);
+            *(float4 *) &sm.red[warp][g * D + hl * 8 + 4] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (lane == 0) sm.red_ml[warp][g] = make_float2(M, l[g] * ws + lo * wo);
     }
     cons_sync();
     if (tid < SA_G * D / 4) {                                               // 128 threads x 4 consecutive outputs of one head
@@ -291,14 +241,16 @@ __device__ __noinline__ void sd_attention(int staged_slot, int n_kv, const int64
             v.x = fmaf(a.x, w, v.x); v.y = fmaf(a.y, w, v.y); v.z = fmaf(a.z, w, v.z); v.w = fmaf(a.w, w, v.w); L = fmaf(ml.y, w, L);
         }
         if (splits == 1) {
-            sa_store_out4(A.out, head * D + d, L == 0.0f ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(v.x / L, v.y / L, v.z / L, v.w / L), tag_base + my_tag);
+            const float inv = L == 0.0f ? 0.0f : 1.0f / L;
+            *(float4 *) &A.out[head * D + d] = L == 0.0f ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(v.x / L, v.y / L, v.z / L, v.w / L);
+            (void) inv;
         } else {
             const int64_t ps = (int64_t) head * splits + split;
             *(float4 *) &A.part_acc[ps * D + d] = v;
             if (d == 0) A.part_ml[ps] = make_float2(M, L);
         }
     }
-    if (pf) pf[7] = globaltimer();
+    if (pf) pf[6] = globaltimer();
     if (splits == 1) return;
     // ---- the last chunk of this kv head to finish merges the partials ---------------------------------------------------------------------
     cons_sync();
@@ -309,6 +261,7 @@ __device__ __noinline__ void sd_attention(int staged_slot, int n_kv, const int64
         if (sm.is_last) { A.tickets[kvh] = 0; __threadfence(); }
     }
     cons_sync();
+    if (pf) pf[7] = globaltimer();
     if (!sm.is_last) return;
     // merge: 128 threads x 4 consecutive output elements; a thread loads its float4 column of partials AND the head's (m, l) pairs in one
     // round trip (18 + 18 requests instead of 36 scalar ones per element: the phase's tail is bound by outstanding requests), then turns them
@@ -338,6 +291,6 @@ __device__ __noinline__ void sd_attention(int staged_slot, int n_kv, const int64
                 v.x = fmaf(t[i].x, w, v.x); v.y = fmaf(t[i].y, w, v.y); v.z = fmaf(t[i].z, w, v.z); v.w = fmaf(t[i].w, w, v.w); L = fmaf(ml[i].y, w, L);
             }
         }
-        sa_store_out4(A.out, head * D + d, L == 0.0f ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(v.x / L, v.y / L, v.z / L, v.w / L), tag_base + my_tag);
+        *(float4 *) &A.out[head * D + d] = L == 0.0f ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(v.x / L, v.y / L, v.z / L, v.w / L);
     }
 }

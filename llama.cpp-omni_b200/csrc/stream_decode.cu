@@ -57,26 +57,6 @@ __device__ __forceinline__ void ld256_cg(const float * p, float4 & lo, float4 & 
     asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
 }
-// ---- tagged pairs { f32 value, u32 tag } (stream_decode.cuh): one 8-byte store per element, 32-byte (4 pair) strong loads through L2
-__device__ __forceinline__ uint64_t pack_tagged(float v, uint32_t tag) { return (uint64_t) __float_as_uint(v) | ((uint64_t) tag << 32); }
-__device__ __forceinline__ void st_tagged(float * pair, float v, uint32_t tag) {        // ONE 64-bit scalar store: value and tag are single-copy atomic
-    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" :: "l"(pair), "l"(pack_tagged(v, tag)) : "memory");
-}
-__device__ __forceinline__ void st_tagged2(float * pair, float v0, float v1, uint32_t tag) {   // two adjacent pairs, 16-byte aligned
-    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" :: "l"(pair), "l"(pack_tagged(v0, tag)), "l"(pack_tagged(v1, tag)) : "memory");
-}
-struct Pairs4 { uint64_t p[4]; };                                                       // 4 tagged pairs: value = low word, tag = high word
-__device__ __forceinline__ Pairs4 ld_pairs4(const float * pair) {                       // pair must be 32-byte aligned
-    Pairs4 r;
-    asm volatile("ld.relaxed.gpu.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(r.p[0]), "=l"(r.p[1]), "=l"(r.p[2]), "=l"(r.p[3]) : "l"(pair) : "memory");
-    return r;
-}
-__device__ __forceinline__ uint32_t pair_tag(uint64_t p) { return (uint32_t) (p >> 32); }
-__device__ __forceinline__ float    pair_val(uint64_t p) { return __uint_as_float((uint32_t) p); }
-// a poll that has been spinning for ~2 s means a protocol bug: trap instead of hanging the device
-__device__ __forceinline__ void sd_spin_guard(uint32_t & spins, long long & t0) {
-    if ((++spins & 0x3ff) == 0) { const long long t = clock64(); if (t0 == 0) t0 = t; else if (t - t0 > 4000000000ll) __trap(); }
-}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned * p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // ---------------------------------------------------------------------------------------------------------------- geometry
@@ -85,10 +65,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned * p) { unsigne
 // 2) consecutive rows of one matrix; unit u of the phase belongs to warp u % SD_WARPS.  Everything is derived arithmetically from u.
 __device__ __forceinline__ void seg_build(SegTab & S, const SdPhase & P, int cta, int ncta) {
     const bool sw = P.epilogue == SD_EPI_SWIGLU;
-    const int nmat = sw ? 1 : P.n_mat, ks = P.ksplit, ksl = P.ksl > 1 ? P.ksl : 1;
+    const int nmat = sw ? 1 : P.n_mat, ks = P.ksplit;
     const int grp = cta / ks, ngrp = ncta / ks;
-    const int ymul = P.y_tagged ? 2 : 1;                                  // tagged outputs: 8-byte pairs
-    S.kpart = cta % ks; S.nm = sw ? 2 : 1; S.ksplit = ks; S.ksl = ksl;
+    S.kpart = cta % ks; S.nm = sw ? 2 : 1; S.ksplit = ks;
     uint32_t T = 0;                                                       // T * ngrp < 2^32 (checked on the host): 32-bit divisions only
     for (int j = 0; j < nmat; ++j) T += (uint32_t) P.mat[j].rows;
     const int r0 = grp < ngrp ? (int) (T * (uint32_t) grp / (uint32_t) ngrp) : 0, r1 = grp < ngrp ? (int) (T * (uint32_t) (grp + 1) / (uint32_t) ngrp) : 0;   // leftover CTAs idle
@@ -98,12 +77,12 @@ __device__ __forceinline__ void seg_build(SegTab & S, const SdPhase & P, int cta
             const SdMat & M = P.mat[j];
             const int lo = max(r0, mb), hi = min(r1, mb + M.rows), first = lo - mb;
             S.nrows[j] = max(0, hi - lo);
-            S.rbp[j] = M.row_bytes_p; S.rbd[j] = M.row_bytes_d; S.sub_p[j] = M.row_bytes_p / (ks * ksl); S.sub_d[j] = M.row_bytes_d / (ks * ksl); S.type[j] = M.type;
+            S.rbp[j] = M.row_bytes_p; S.rbd[j] = M.row_bytes_d; S.sub_p[j] = M.row_bytes_p / ks; S.sub_d[j] = M.row_bytes_d / ks; S.type[j] = M.type;
             const int unit_row = (S.sub_p[j] + S.sub_d[j]) * (sw ? 2 : 1);
             S.rpu[j] = (P.act_group == 256 && unit_row * 2 <= SD_SLOT_BYTES) ? 2 : 1;
             S.pay[j] = M.payload + (int64_t) first * M.row_bytes_p + (int64_t) S.kpart * S.sub_p[j];
             S.dpl[j] = M.dplane ? M.dplane + (int64_t) first * M.row_bytes_d + (int64_t) S.kpart * S.sub_d[j] : nullptr;
-            S.y[j] = M.y + ((int64_t) S.kpart * P.y_part_stride + first) * ymul;
+            S.y[j] = M.y + (int64_t) S.kpart * P.y_part_stride + first;
             S.resid[j] = M.residual ? M.residual + first : nullptr;
             if (sw) {
                 S.pay2 = P.mat[1].payload + (int64_t) first * M.row_bytes_p;
@@ -113,14 +92,11 @@ __device__ __forceinline__ void seg_build(SegTab & S, const SdPhase & P, int cta
         } else { S.nrows[j] = 0; S.rpu[j] = 1; S.sub_p[j] = 0; S.sub_d[j] = 0; S.rbp[j] = 0; S.rbd[j] = 0; S.type[j] = 0; }
         S.upre[j + 1] = S.upre[j] + (S.nrows[j] + S.rpu[j] - 1) / S.rpu[j];
     }
-    S.nunits = S.upre[3] * ksl;                                           // unit u = (row unit u / ksl, K-slice u % ksl): warp u % SD_WARPS always sees slice warp % ksl
 }
-// unit u -> matrix j, first row (relative to this CTA's first row of j), row count, K-slice inside the CTA
-__device__ __forceinline__ void seg_unit(const SegTab & S, int u, int & j, int & off, int & n, int & slice) {
-    int ru = u; slice = 0;
-    if (S.ksl > 1) { ru = u / S.ksl; slice = u - ru * S.ksl; }
-    j = ru < S.upre[1] ? 0 : ru < S.upre[2] ? 1 : 2;
-    off = (ru - S.upre[j]) * S.rpu[j];
+// unit u -> matrix j, first row (relative to this CTA's first row of j), row count
+__device__ __forceinline__ void seg_unit(const SegTab & S, int u, int & j, int & off, int & n) {
+    j = u < S.upre[1] ? 0 : u < S.upre[2] ? 1 : 2;
+    off = (u - S.upre[j]) * S.rpu[j];
     n = min(S.rpu[j], S.nrows[j] - off);
 }
 
@@ -160,111 +136,73 @@ __device__ __forceinline__ ActLayout sd_act_layout(int act_group, int kl) {
     return L;
 }
 
-// engine fast path (every phase of a decode program): ONE input vector — plain f32 (the token's embedding row / the previous pipeline stage's
-// output) or tagged pairs written by an earlier phase of this launch — and at most NB super-blocks per warp, all loaded in ONE round trip.  For a
-// tagged input the load IS the synchronisation: the warp re-loads until every pair carries the producing phase's tag (see stream_decode.cuh).
-// One call handles the super-blocks [b0, b0 + 2 * SD_WARPS) (two per warp: their loads share one round trip); a longer un-normalised vector (the
-// 12288-wide ffn_down input) takes one call per 24 blocks.
-template <bool NORM>
-__device__ __forceinline__ void sd_prologue_one(const SdPhase & P, uint32_t tag_base, uint8_t * act, float * red, float * stash, unsigned long long * pf,
-                                                const ActLayout & L, int k, bool writer, int b0) {
-    constexpr int NB = 2;
+// fast path of sd_prologue (every phase of the decode program): ONE pass over the inputs — each warp keeps its <= 2 super-blocks in registers
+// between the sum of squares and the quantisation.  A round trip to L2 costs ~1 us while the weight stream saturates HBM, so ALL loads of the
+// prologue (NX summands x 2 blocks, and the norm weights) are issued back to back, branch-free, before any use.  NX is a template parameter:
+// the single-input phases (wo, gate/up, down) must not carry the register pressure of the 4-summand layer-entry phase.
+template <int NX>
+__device__ __forceinline__ void sd_prologue_fast(const SdPhase & P, uint8_t * act, float * red, unsigned long long * pf, const ActLayout & L, int k, int kl, int k0,
+                                                 bool norm, bool writer) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nb = k >> 8;
-    int blks[NB]; bool lives[NB];
-#pragma unroll
-    for (int t = 0; t < NB; ++t) { blks[t] = b0 + warp + SD_WARPS * t; lives[t] = blks[t] < nb; }
-    float4 w[NB][2];
-    if (NORM) {
-#pragma unroll
-        for (int t = 0; t < NB; ++t) {
-            w[t][0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); w[t][1] = w[t][0];
-            if (lives[t]) ld256_cg(P.norm_w + blks[t] * 256 + lane * 8, w[t][0], w[t][1]);
-        }
-    }
+    float scale = 1.0f;
+
+    const int nb = kl >> 8, n_x = P.n_x;
+    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 a[2][NX][2], w[2][2];
     if (pf) pf[6] = globaltimer();
-    float v[NB][8];
-    if (P.x_tag == 0) {
 #pragma unroll
-        for (int t = 0; t < NB; ++t) {
-            float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a;
-            if (lives[t]) ld256_cg(P.x[0] + blks[t] * 256 + lane * 8, a, b);
-            v[t][0] = a.x; v[t][1] = a.y; v[t][2] = a.z; v[t][3] = a.w; v[t][4] = b.x; v[t][5] = b.y; v[t][6] = b.z; v[t][7] = b.w;
+    for (int t = 0; t < 2; ++t) {
+        const bool live = warp + SD_WARPS * t < nb;
+        const int e = k0 + (live ? warp + SD_WARPS * t : warp) * 256 + lane * 8;
+#pragma unroll
+        for (int sx = 0; sx < NX; ++sx) {
+            const bool on = live && sx < n_x;
+            const float * px = P.x[on ? sx : 0] + e;
+            a[t][sx][0] = z4; a[t][sx][1] = z4;
+            if (on) ld256_cg(px, a[t][sx][0], a[t][sx][1]);              // ONE 256-bit request per summand and block: the prologue is bound by outstanding requests
         }
-    } else {
-        // Every lane owns 2 chunks of 4 pairs (32 bytes) per block.  The first attempt loads everything in one round trip; a chunk whose four tags
-        // match is kept and never re-loaded, so a CTA that arrives early re-polls only the chunks of the producers that are still working (a
-        // whole-vector re-poll by ~140 waiting CTAs would eat the L2 bandwidth the late CTAs need for their weights).
-        const uint32_t want = tag_base + (uint32_t) P.x_tag;
-        uint32_t need = 0;
+        w[t][0] = z4; w[t][1] = z4;
+        if (norm && live) ld256_cg(P.norm_w + e, w[t][0], w[t][1]);
+    }
+    float v[2][8];
+    float ss = 0.0f;
 #pragma unroll
-        for (int t = 0; t < NB; ++t) { if (lives[t]) need |= 3u << (2 * t); else {
+    for (int t = 0; t < 2; ++t) {
+        v[t][0] = a[t][0][0].x; v[t][1] = a[t][0][0].y; v[t][2] = a[t][0][0].z; v[t][3] = a[t][0][0].w;
+        v[t][4] = a[t][0][1].x; v[t][5] = a[t][0][1].y; v[t][6] = a[t][0][1].z; v[t][7] = a[t][0][1].w;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[t][i] = 0.0f; } }
-        uint32_t spins = 0; long long t0 = 0;
-        for (;;) {
-            Pairs4 pr[NB][2];
-#pragma unroll
-            for (int t = 0; t < NB; ++t) {
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) if (need & (1u << (2 * t + hf))) pr[t][hf] = ld_pairs4(P.x[0] + 2 * (blks[t] * 256 + lane * 8 + 4 * hf));
-            }
-#pragma unroll
-            for (int t = 0; t < NB; ++t) {
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) if (need & (1u << (2 * t + hf))) {
-                    const Pairs4 & c = pr[t][hf];
-                    if (pair_tag(c.p[0]) == want && pair_tag(c.p[1]) == want && pair_tag(c.p[2]) == want && pair_tag(c.p[3]) == want) {
-                        v[t][4 * hf] = pair_val(c.p[0]); v[t][4 * hf + 1] = pair_val(c.p[1]); v[t][4 * hf + 2] = pair_val(c.p[2]); v[t][4 * hf + 3] = pair_val(c.p[3]);
-                        need &= ~(1u << (2 * t + hf));
-                    }
-                }
-            }
-            if (__all_sync(0xffffffffu, need == 0)) break;
-            sd_spin_guard(spins, t0);
+        for (int sx = 1; sx < NX; ++sx) if (sx < n_x) {                 // fixed order x[0] + x[1] + ...: deterministic
+            v[t][0] += a[t][sx][0].x; v[t][1] += a[t][sx][0].y; v[t][2] += a[t][sx][0].z; v[t][3] += a[t][sx][0].w;
+            v[t][4] += a[t][sx][1].x; v[t][5] += a[t][sx][1].y; v[t][6] += a[t][sx][1].z; v[t][7] += a[t][sx][1].w;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
     }
     if (pf) pf[4] = globaltimer();
-    if (P.stash_T) {                                                       // rows of a later phase of THIS CTA whose residual is this vector
-        const uint32_t T = (uint32_t) P.stash_T, c = blockIdx.x, n = gridDim.x;
-        const int r0 = (int) (T * c / n), r1 = (int) (T * (c + 1) / n);
-#pragma unroll
-        for (int t = 0; t < NB; ++t) if (lives[t]) {
-            const int e = blks[t] * 256 + lane * 8;
-            if (e + 8 > r0 && e < r1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) if (e + i >= r0 && e + i < r1) stash[e + i - r0] = v[t][i];
-            }
-        }
-    }
-    float scale = 1.0f;
-    if (NORM) {
-        float ss = 0.0f;
-#pragma unroll
-        for (int t = 0; t < NB; ++t) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ss += v[t][i] * v[t][i];
-        }
-        scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
-    }
+    if (norm) scale = 1.0f / sqrtf(cta_sum(ss, red) / (float) k + P.eps);
     if (pf) pf[5] = globaltimer();
+const int blks[2] = { warp, warp + SD_WARPS };
+    const bool lives[2] = { warp < nb, warp + SD_WARPS < nb };
 #pragma unroll
-    for (int t = 0; t < NB; ++t) if (lives[t]) {
-        const int e = blks[t] * 256 + lane * 8;
-        if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
-        if (NORM) {
-            const float wv[8] = { w[t][0].x, w[t][0].y, w[t][0].z, w[t][0].w, w[t][1].x, w[t][1].y, w[t][1].z, w[t][1].w };
+    for (int t = 0; t < 2; ++t) {
+        if (lives[t]) {
+            const int e = k0 + blks[t] * 256 + lane * 8;
+            if (writer && P.x_out) { *(float4 *) (P.x_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.x_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]); }
+            if (norm) {
+                const float wv[8] = { w[t][0].x, w[t][0].y, w[t][0].z, w[t][0].w, w[t][1].x, w[t][1].y, w[t][1].z, w[t][1].w };
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[t][i] = __fmul_rn(__fmul_rn(v[t][i], scale), wv[i]);
-            if (writer && P.norm_out) {
-                *(float4 *) (P.norm_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]);
+                for (int i = 0; i < 8; ++i) v[t][i] = __fmul_rn(__fmul_rn(v[t][i], scale), wv[i]);
+                if (writer && P.norm_out) {
+                    *(float4 *) (P.norm_out + e) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]); *(float4 *) (P.norm_out + e + 4) = make_float4(v[t][4], v[t][5], v[t][6], v[t][7]);
+                }
             }
         }
     }
-    quant_blocks_q8K<true, NB>(v, blks, lives, act, L.d_off, L.bsum_off);  // both blocks of the warp in lockstep (a dummy block stores nothing)
-}
+    quant_blocks_q8K<true, 2>(v, blks, lives, act, L.d_off, L.bsum_off);     // both blocks of the warp in lockstep (dummy second block for warps 4..11)
+    cons_sync();
+    }
 
-__device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_t * act, float * red, unsigned long long * pf, uint32_t tag_base, float * stash) {
+__device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_t * act, float * red, unsigned long long * pf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = P.k, kl = k / P.ksplit, k0 = kpart * kl;                 // this CTA quantises [k0, k0 + kl)
     const ActLayout L = sd_act_layout(P.act_group, kl);
@@ -281,10 +219,9 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
     }
     float scale = 1.0f;
     const bool norm = P.prologue == SD_PRO_RMSNORM_QUANT;
-    if (P.act_group == 256 && P.n_x == 1 && P.ksplit == 1 && (k >> 8) <= (norm ? 2 : 4) * SD_WARPS) {       // every phase of a decode program
-        if (norm) sd_prologue_one<true>(P, tag_base, act, red, stash, pf, L, k, writer, 0);
-        else for (int b0 = 0; b0 < (k >> 8); b0 += 2 * SD_WARPS) sd_prologue_one<false>(P, tag_base, act, red, stash, pf, L, k, writer, b0);
-        cons_sync();
+    if (P.act_group == 256 && (kl >> 8) <= 2 * SD_WARPS && (P.ksplit == 1 || !norm)) {
+        if (P.n_x == 1) sd_prologue_fast<1>(P, act, red, pf, L, k, kl, k0, norm, writer);
+        else            sd_prologue_fast<4>(P, act, red, pf, L, k, kl, k0, norm, writer);
         return;
     }
     if (norm) {                                                           // generic path: separate sum-of-squares pass over the FULL row
@@ -332,26 +269,26 @@ __device__ __forceinline__ void sd_prologue(const SdPhase & P, int kpart, uint8_
     cons_sync();
 }
 
-// what a consumer warp needs to know about the unit sitting in one of its ring slots (written by the producer before the copy is issued,
-// published by the slot's full-barrier): 32 bytes
-struct alignas(16) SlotDesc { uint32_t type_n; uint32_t sub_p, sub_d; uint32_t aux; float * y; const float * resid; };   // aux = first row of the unit, local to the CTA | K-slice << 16
-
-struct StagedPhase { SdPhase P; SegTab S; };                           // ring of SD_NPH entries in shared memory, entry of phase p: p % SD_NPH
-
-// ---- shared-memory map of the CTA (constexpr offsets from the dynamic shared-memory base: out-of-line phase functions re-derive their
-// pointers from the `extern __shared__` symbol, so the compiler still knows they are shared-memory addresses)
-constexpr int SM_ACT    = SD_RING_BYTES;                                   // q8 activation record of the current phase
-constexpr int SM_ATTN   = SM_ACT + SD_ACT_BYTES;                           // attention scratch (SaSmem)
-constexpr int SM_STASH  = SM_ATTN + SD_ATTN_BYTES;                         // [SD_STASH_ROWS] residual rows of this CTA (sd_prologue_one)
-constexpr int SM_KPARTS = SM_STASH + SD_STASH_ROWS * 4;                    // [SD_STASH_ROWS][SD_KSL_MAX] K-slice partial sums (sd_ksl_finish)
-constexpr int SM_BARS   = SM_KPARTS + SD_STASH_ROWS * SD_KSL_MAX * 4;      // full[warp][slot], then empty[warp][slot]
-constexpr int SM_DESCS  = SM_BARS + 2 * SD_WARPS * SD_DEPTH * 8;
-constexpr int SM_RED    = SM_DESCS + SD_WARPS * SD_DEPTH * (int) sizeof(SlotDesc);
-constexpr int SM_PHASES = SM_RED + 64 * 4;                                 // StagedPhase[SD_NPH]
-constexpr int SM_ROPE   = (SM_PHASES + SD_NPH * (int) sizeof(StagedPhase) + 15) & ~15;   // float2[64]: (cos, sin) of the token's position
-constexpr int SM_FLAGS  = SM_ROPE + 64 * 8;                                // staged, done, tag base
-static_assert(SM_FLAGS + 16 <= SD_SMEM_BYTES, "k_stream shared-memory map");
-static_assert(SM_BARS % 8 == 0 && SM_DESCS % 16 == 0 && SM_PHASES % 16 == 0, "k_stream shared-memory alignment");
+// ---------------------------------------------------------------------------------------------------------------- grid barrier
+// A monotonic arrival counter in global memory: every CTA adds 1 (release) and polls the SAME word (acquire) until it reaches the phase's
+// target — one hop after the last arrival, instead of "last arriver sees the returned count, then flips a generation flag" (two).  The
+// counter is never reset: bar[32] holds the value it had when the launch began (written by CTA 0 at the very end of the previous launch),
+// so a captured CUDA graph can replay the kernel without host help.  `done` (shared) tells the producer warp that this CTA's consumers
+// have left phase `phase_done - 1` (its staging slot may be reused).
+__device__ __forceinline__ void sd_grid_barrier(unsigned * bar, unsigned target, volatile int * done, int phase_done, bool sync_grid) {
+    cons_sync();
+    if (threadIdx.x == 0) {
+        *done = phase_done;
+        if (sync_grid) {
+            // the CTA's writes are ordered before thread 0's release by the bar.sync above (cumulativity); the acquire load orders the other
+            // CTAs' writes before the bar.sync below
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
+            unsigned v;                                                    // (polling relaxed + one acquire fence measured slower)
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int) (v - target) < 0);
+        }
+    }
+    if (sync_grid) cons_sync();
+}
 
 #include "stream_attn.cuh"
 
@@ -362,18 +299,24 @@ __device__ __forceinline__ void sd_copy_phase(SdPhase * dst, const SdPhase * src
     for (int i = lane; i < (int) (sizeof(SdPhase) / 16); i += nlanes) ((uint4 *) dst)[i] = ((const uint4 *) src)[i];
 }
 
+// what a consumer warp needs to know about the unit sitting in one of its ring slots (written by the producer before the copy is issued,
+// published by the slot's full-barrier): 32 bytes
+struct alignas(16) SlotDesc { uint32_t type_n; uint32_t sub_p, sub_d; uint32_t pad_; float * y; const float * resid; };
+
+struct StagedPhase { SdPhase P; SegTab S; };                           // ring of SD_NPH entries in shared memory, entry of phase p: p % SD_NPH
+
 // producer lane (= consumer warp index): request unit u of the staged phase into the warp's ring slot
-__device__ __forceinline__ void sd_issue(const SegTab & S, int u, int ymul, uint32_t dst, uint32_t bar, SlotDesc * desc, uint64_t pol, bool dry) {
-    int j, off, n, slice; seg_unit(S, u, j, off, n, slice);
+__device__ __forceinline__ void sd_issue(const SegTab & S, int u, uint32_t dst, uint32_t bar, SlotDesc * desc, uint64_t pol, bool dry) {
+    int j, off, n; seg_unit(S, u, j, off, n);
     const uint32_t sp = S.sub_p[j], sd = S.sub_d[j];
     const int64_t rbp = S.rbp[j], rbd = S.rbd[j];
-    desc->type_n = (uint32_t) S.type[j] | ((uint32_t) n << 8); desc->sub_p = sp; desc->sub_d = sd; desc->aux = (uint32_t) off | ((uint32_t) slice << 16);
-    desc->y = S.y[j] + off * ymul; desc->resid = S.resid[j] ? S.resid[j] + off : nullptr;
+    desc->type_n = (uint32_t) S.type[j] | ((uint32_t) n << 8); desc->sub_p = sp; desc->sub_d = sd;
+    desc->y = S.y[j] + off; desc->resid = S.resid[j] ? S.resid[j] + off : nullptr;
     if (dry) { mbar_arrive(bar); return; }                                // experiment: control path without any weight traffic
     mbar_expect_tx(bar, (uint32_t) n * (sp + sd) * S.nm);                 // release: orders the descriptor before the consumer's acquire
-    const uint8_t * pay = S.pay[j] + off * rbp + slice * sp;
-    const uint8_t * dpl = S.dpl[j] + off * rbd + slice * sd;
-    if (S.ksplit == 1 && S.ksl == 1) {                                     // full rows are back to back: one copy per plane
+    const uint8_t * pay = S.pay[j] + off * rbp;
+    const uint8_t * dpl = S.dpl[j] + off * rbd;
+    if (S.ksplit == 1) {                                                   // full rows are back to back: one copy per plane
         bulk_g2s(dst, pay, (uint32_t) n * sp, bar, pol); dst += n * sp;
         if (sd) { bulk_g2s(dst, dpl, (uint32_t) n * sd, bar, pol); dst += n * sd; }
         if (S.nm == 2) {
@@ -461,7 +404,7 @@ __device__ __forceinline__ void sd_producer(const SdPhase * src, int n_phases, S
         }
         const StagedPhase & E = ring_ph[p % SD_NPH];
         if (E.P.kind != SD_MATVEC) continue;
-        const int nunits = E.S.nunits;
+        const int nunits = E.S.upre[3];
         if (lane < RPW) {
             const uint32_t ring_w = ring + cw * SD_DEPTH * SD_SLOT_BYTES, full_w = full + cw * SD_DEPTH * 8, empty_w = empty + cw * SD_DEPTH * 8;
             for (int u = cw; u < nunits; u += SD_WARPS) {
@@ -469,7 +412,7 @@ __device__ __forceinline__ void sd_producer(const SdPhase * src, int n_phases, S
                 if (use) mbar_wait(empty_w + 8 * slot, (use - 1) & 1);
                 // pacing: at most `inflight` units of this ring on the wire
                 if (issued >= inflight) { const uint32_t o = issued - inflight; mbar_wait(full_w + 8 * (o % SD_DEPTH), (o / SD_DEPTH) & 1); }
-                sd_issue(E.S, u, E.P.y_tagged ? 2 : 1, ring_w + slot * SD_SLOT_BYTES, full_w + 8 * slot, descs + cw * SD_DEPTH + slot, pol, (rt.flags & 4) != 0);
+                sd_issue(E.S, u, ring_w + slot * SD_SLOT_BYTES, full_w + 8 * slot, descs + cw * SD_DEPTH + slot, pol, (rt.flags & 4) != 0);
                 ++issued;
             }
         }
@@ -477,22 +420,17 @@ __device__ __forceinline__ void sd_producer(const SdPhase * src, int n_phases, S
     }
 }
 
-// what the epilogue of a phase needs beyond the slot descriptor
-struct EpiCtx { uint32_t tag; bool tagged, resid_stash; int ksl; const float * stash; float * kparts; };
-
 // one matvec phase on a consumer warp.  REGS: K-slice <= 4096 and q4_K / q6_K only -> activation fragments live in registers; otherwise
 // fragments are re-read from shared memory (two rows share each read).
 template <bool REGS>
 __device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const ActS & A, uint32_t & consumed, uint32_t ring_w, uint32_t full_w, uint32_t empty_w,
-                                           const SlotDesc * descs_w, const EpiCtx & X, unsigned long long * pf, int flags) {
+                                           const SlotDesc * descs_w, unsigned long long * pf, int flags) {
     long long waited = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kl = P.k / (P.ksplit * X.ksl), nblk = kl >> 8;
+    const int kl = P.k / P.ksplit, nblk = kl >> 8;
     const bool swiglu = P.epilogue == SD_EPI_SWIGLU;
-    ActS As = A;                                                           // K-slice of this warp inside the CTA's record (ksl > 1)
-    if (X.ksl > 1) { const int sl = warp % X.ksl; As.qs += sl * kl; As.d += sl * nblk * 4; As.bsum += sl * nblk * 32; }
     HFrag fr;
-    if (REGS) hfrag_fill(As, nblk, fr);
+    if (REGS) hfrag_fill(A, nblk, fr);
     if (pf && (flags & 512)) pf[4] = globaltimer();                        // finer marks of warp 0's first unit (B200_SD_FLAGS=512)
     bool first = true;
     for (int u = warp; u < nunits; u += SD_WARPS) {
@@ -504,7 +442,7 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const 
         if (pf && (flags & 512) && first) pf[5] = globaltimer();
         const SlotDesc d = descs_w[slot];
         const int type = d.type_n & 0xff, n = d.type_n >> 8;
-        float rz = 0.0f;                                                   // a plain residual's L2 round trip overlaps the dot products
+        float rz = 0.0f;                                                   // the residual's L2 round trip overlaps the dot products
         if (d.resid && lane < n) rz = __ldcg(d.resid + lane);
         const uint32_t rbp = d.sub_p, rbd = d.sub_d;
         const uint32_t bp = (uint32_t) n * rbp, bd = (uint32_t) n * rbd;     // slot: [payload rows][d rows] (+ the same again for `up`)
@@ -514,8 +452,8 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const 
             if (type == B200_Q4_K) { v = krow_regs<B200_Q4_K>(base, rbp, base + bp, rbd, nblk, n, fr); if (swiglu) { g2 = v; v = krow_regs<B200_Q4_K>(base + bp + bd, rbp, base + 2 * bp + bd, rbd, nblk, n, fr); } }
             else                   { v = krow_regs<B200_Q6_K>(base, rbp, base + bp, rbd, nblk, n, fr); if (swiglu) { g2 = v; v = krow_regs<B200_Q6_K>(base + bp + bd, rbp, base + 2 * bp + bd, rbd, nblk, n, fr); } }
         } else {
-            v = unit_dots_lds(type, n, base, rbp, base + bp, rbd, As, kl);
-            if (swiglu) { g2 = v; v = unit_dots_lds(type, n, base + bp + bd, rbp, base + 2 * bp + bd, rbd, As, kl); }
+            v = unit_dots_lds(type, n, base, rbp, base + bp, rbd, A, kl);
+            if (swiglu) { g2 = v; v = unit_dots_lds(type, n, base + bp + bd, rbp, base + 2 * bp + bd, rbd, A, kl); }
         }
         if (pf && (flags & 512) && first) { pf[6] = globaltimer(); first = false; }
         __syncwarp();                                                      // every lane's reads of the slot are done
@@ -523,27 +461,12 @@ __device__ __forceinline__ void sd_consume(const SdPhase & P, int nunits, const 
         if (lane < n) {
             float o = lane == 0 ? v.x : v.y;
             if (swiglu) { const float gg = lane == 0 ? g2.x : g2.y; o = (gg / (1.0f + expf(-gg))) * o; }
-            const int row = (int) (d.aux & 0xffff) + lane;                 // local to the CTA's first row
-            if (X.ksl > 1) X.kparts[row * X.ksl + (int) (d.aux >> 16)] = o;   // partial of this K-slice: summed at the end of the phase
-            else {
-                o += X.resid_stash ? X.stash[row] : rz;
-                if (X.tagged) st_tagged(d.y + 2 * lane, o, X.tag); else d.y[lane] = o;
-            }
+            o += rz;
+            d.y[lane] = o;
         }
         ++consumed;
     }
     if (pf) pf[7] = (unsigned long long) waited;                           // cycles warp 0 spent waiting for weights in this phase
-}
-
-// K-split inside the CTA: y[r] = sum over the slices, in slice order (deterministic), + the stashed residual
-__device__ __forceinline__ void sd_ksl_finish(const SegTab & S, const EpiCtx & X) {
-    cons_sync();                                                           // every warp's partials are in shared memory
-    for (int r = threadIdx.x; r < S.nrows[0]; r += SD_THREADS) {
-        float o = X.kparts[r * X.ksl];
-        for (int sl = 1; sl < X.ksl; ++sl) o += X.kparts[r * X.ksl + sl];
-        if (X.resid_stash) o += X.stash[r];
-        if (X.tagged) st_tagged(S.y[0] + 2 * r, o, X.tag); else S.y[0][r] = o;
-    }
 }
 
 // PROF = false is the production instantiation: `pf` is a compile-time null in every inlined helper and the experiment switches are a compile-time
@@ -556,17 +479,15 @@ __global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * 
     if (!PROF) { rt.flags = 0; rt.prof = nullptr; }
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t  * ring = smem;
-    uint8_t  * act  = smem + SM_ACT;
-    float    * stash  = (float *) (smem + SM_STASH);
-    float    * kparts = (float *) (smem + SM_KPARTS);
-    uint64_t * bars = (uint64_t *) (smem + SM_BARS);
-    SlotDesc * descs = (SlotDesc *) (smem + SM_DESCS);
-    float    * red  = (float *) (smem + SM_RED);
-    StagedPhase * ring_ph = (StagedPhase *) (smem + SM_PHASES);
-    float2   * rope_tab = (float2 *) (smem + SM_ROPE);
-    volatile int * staged = (volatile int *) (smem + SM_FLAGS);          // number of phases staged so far (producer -> consumers)
+    uint8_t  * act  = smem + SD_RING_BYTES;
+    uint8_t  * attn_scratch = act + SD_ACT_BYTES;
+    uint64_t * bars = (uint64_t *) (attn_scratch + SD_ATTN_BYTES);       // full[warp][slot], then empty[warp][slot]
+    SlotDesc * descs = (SlotDesc *) (bars + 2 * SD_WARPS * SD_DEPTH);
+    float    * red  = (float *) (descs + SD_WARPS * SD_DEPTH);
+    StagedPhase * ring_ph = (StagedPhase *) (red + 64);
+    float2   * rope_tab = (float2 *) (((uintptr_t) (ring_ph + SD_NPH) + 15) & ~(uintptr_t) 15);   // [64] (cos, sin) of the token's position
+    volatile int * staged = (volatile int *) (rope_tab + 64);          // number of phases staged so far (producer -> consumers)
     volatile int * done   = staged + 1;                                // number of phases the consumers have left (consumers -> producer)
-    volatile uint32_t * tagbase_s = (volatile uint32_t *) (staged + 2);  // this launch's tag epoch
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SdPhase * src = phases_g ? phases_g : &single;
     const uint32_t full = smem_u32(bars), empty = full + SD_WARPS * SD_DEPTH * 8;
@@ -575,14 +496,8 @@ __global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * 
         for (int s = 0; s < 2 * SD_WARPS * SD_DEPTH; ++s) mbar_init(full + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         *staged = 0; *done = 0;
-        // the tag epoch of this launch: gbar[32] is advanced by n_phases at the very end of every multi-phase launch (by CTA 0, which gets there
-        // only after consuming every CTA's last outputs, i.e. after every CTA has read the old value here)
-        uint32_t tb = 0;
-        if (n_phases > 1) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(gbar + 32) : "memory");
-        *tagbase_s = tb;
     }
     __syncthreads();                                                     // the only CTA-wide barrier: roles split here
-    const uint32_t tag_base = *tagbase_s;
 
     // register reallocation between the warp groups (512 threads start with 128 registers each): the producer group gives most of its
     // registers back, the three consumer groups grow to 152
@@ -599,6 +514,8 @@ __global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * 
     const uint32_t ring_w = smem_u32(ring) + warp * SD_DEPTH * SD_SLOT_BYTES, full_w = full + warp * SD_DEPTH * 8, empty_w = empty + warp * SD_DEPTH * 8;
     const SlotDesc * descs_w = descs + warp * SD_DEPTH;
     uint32_t consumed = 0;
+    unsigned bar_base = 0;                                                // value of the arrival counter when this launch began
+    if (threadIdx.x == 0 && n_phases > 1) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bar_base) : "l"(gbar + 32) : "memory");
     const bool prof = PROF && rt.prof != nullptr && threadIdx.x == 0;
     unsigned long long * const pbase = prof ? rt.prof + (size_t) blockIdx.x * 8 : nullptr;      // [phase][cta][8]
     const size_t pstr = (size_t) gridDim.x * 8;
@@ -610,30 +527,25 @@ __global__ void __launch_bounds__(SD_THREADS + 128, 1) k_stream(const SdPhase * 
         const StagedPhase & E = ring_ph[p % SD_NPH];
         const SdPhase & P = E.P;
         if (P.kind == SD_MATVEC) {
-            sd_prologue(P, E.S.kpart, act, red, PROF && prof ? pbase + p * pstr : nullptr, tag_base, stash);
+            sd_prologue(P, E.S.kpart, act, red, PROF && prof ? pbase + p * pstr : nullptr);
             if (prof) pbase[p * pstr + 1] = globaltimer();
-            const int ksl = E.S.ksl;
-            const int kl = P.k / P.ksplit;                                // the CTA's record; a warp's K-slice is kl / ksl of it
+            const int kl = P.k / P.ksplit;
             const ActLayout L = sd_act_layout(P.act_group, kl);
             ActS A; A.qs = smem_u32(act); A.d = A.qs + (uint32_t) L.d_off; A.bsum = A.qs + (uint32_t) L.bsum_off;
-            bool regs = P.act_group == 256 && kl / ksl <= 4096;           // q8_K fragments of a 4096-wide slice fit in registers
+            bool regs = P.act_group == 256 && kl <= 4096;                 // q8_K fragments of a 4096-wide record fit in registers
             for (int m = 0; m < P.n_mat; ++m) regs = regs && (P.mat[m].type == B200_Q4_K || P.mat[m].type == B200_Q6_K);
-            EpiCtx X; X.tag = tag_base + (uint32_t) p + 1; X.tagged = P.y_tagged != 0; X.resid_stash = P.resid_stash != 0; X.ksl = ksl; X.stash = stash; X.kparts = kparts;
-            if (regs) sd_consume<true >(P, E.S.nunits, A, consumed, ring_w, full_w, empty_w, descs_w, X, PROF && prof ? pbase + p * pstr : nullptr, rt.flags);
-            else      sd_consume<false>(P, E.S.nunits, A, consumed, ring_w, full_w, empty_w, descs_w, X, PROF && prof ? pbase + p * pstr : nullptr, rt.flags);
-            if (ksl > 1) sd_ksl_finish(E.S, X);
+            if (regs) sd_consume<true >(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, PROF && prof ? pbase + p * pstr : nullptr, rt.flags);
+            else      sd_consume<false>(P, E.S.upre[3], A, consumed, ring_w, full_w, empty_w, descs_w, PROF && prof ? pbase + p * pstr : nullptr, rt.flags);
         } else {
             if (prof) pbase[p * pstr + 1] = globaltimer();
-            sd_attention(p % SD_NPH, rt.n_kv, rt.kv_idx, rt.mask, rt.rope_mode, tag_base, (uint32_t) p + 1, PROF && prof ? pbase + p * pstr : nullptr);
+            sd_attention(P, rt, attn_scratch, rope_tab, PROF && prof ? pbase + p * pstr : nullptr);
         }
         if (prof) pbase[p * pstr + 2] = globaltimer();
-        // no grid barrier: the next phase's prologue polls the tagged data itself.  The consumers only close the phase inside the CTA (the
-        // activation record, the stash and the attention scratch are about to be rewritten) and tell the producer its staging slot is free.
-        cons_sync();
-        if (threadIdx.x == 0) *done = p + 1;
+        sd_grid_barrier(gbar, bar_base + (unsigned) (p + 1) * gridDim.x, done, p + 1, p + 1 < n_phases);
         if (prof) pbase[p * pstr + 3] = globaltimer();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n_phases > 1) gbar[32] = tag_base + (unsigned) n_phases;
+    // every CTA read bar[32] before its first barrier, and CTA 0 is past the last one: safe to publish the next launch's base
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_phases > 1) gbar[32] = bar_base + (unsigned) (n_phases - 1) * gridDim.x;
 }
 
 // ---------------------------------------------------------------------------------------------------------------- host side
@@ -654,15 +566,10 @@ bool sd_fill_mat(SdMat & M, const void * w, int type, int layout, int64_t m, int
 // a phase is streamable when one row's K-slice (x2 for gate/up pairs) fits a ring slot and every slice is 16-byte granular
 bool sd_phase_ok(const SdPhase & P) {
     if (P.kind != SD_MATVEC) return true;
-    const int ksl = P.ksl > 1 ? P.ksl : 1;
-    if (P.ksplit < 1 || P.k % P.ksplit) return false;
-    if (ksl > 1 && (P.ksplit != 1 || SD_WARPS % ksl || ksl > SD_KSL_MAX || P.n_mat != 1 || P.epilogue != SD_EPI_STORE || (P.k / ksl) % 1024)) return false;   // (1024: keeps the record's rotation swizzle slice-invariant)
-    if ((P.y_tagged || P.x_tag || P.stash_T || P.resid_stash) &&
-        (P.act_group != 256 || P.n_x != 1 || P.ksplit != 1 || (P.k >> 8) > (P.prologue == SD_PRO_RMSNORM_QUANT ? 2 : 4) * SD_WARPS)) return false;   // tagged hand-off lives in sd_prologue_one
-    if (P.resid_stash && P.n_mat > 1) return false;
-    const int64_t kl = P.k / P.ksplit;
+    const int ks = P.ksplit;
+    if (ks < 1 || P.k % ks) return false;
+    const int64_t kl = P.k / ks;
     if (act_layout(P.act_group == 256 ? B200_Q4_K : B200_Q8_0, kl).bytes + 16 > SD_ACT_BYTES) return false;
-    const int ks = P.ksplit * ksl;                                         // K-slices of a row (across CTAs x inside the CTA)
     const int nm = P.epilogue == SD_EPI_SWIGLU ? 2 : 1;
     for (int j = 0; j < P.n_mat; ++j) {
         const SdMat & M = P.mat[j];
