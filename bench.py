@@ -39,6 +39,41 @@ def peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+REF_BIN = ROOT / "oracle" / "_ref" / "bin" / "llama-bench"
+PLUGIN = ROOT / "llama.cpp-omni_b200" / "lib" / "libggml-b200.so"
+GGUF = Path(os.environ.get("B200_BENCH_GGUF", "/tmp/b200_bench_qwen3_8b_q4_k_m.gguf"))
+
+
+def bench_gguf() -> Path:
+    """The synthetic Qwen3-8B-shaped Q4_K_M GGUF both arms decode (tools/make_gguf.py: random valid quant blocks, the tensor names / types of a
+    llama-quantize file; 5.0 GB, ~20 s to write).  Generated once per box."""
+    if not GGUF.exists() or GGUF.stat().st_size < 5_000_000_000:
+        tmp = GGUF.with_suffix(".tmp")
+        subprocess.check_call([sys.executable, str(ROOT / "tools" / "make_gguf.py"), str(tmp)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        tmp.rename(GGUF)
+    return GGUF
+
+
+def llama_bench(plugin: bool, n_gen: int, depth: int, threads: int, reps: int = 1, timeout: int = 1500) -> dict:
+    """The reference's OWN llama-bench (oracle/_ref, built unmodified from /root/reference by oracle/Makefile), either on its ggml CPU backend
+    (plugin=False, -ngl 0) or with libggml-b200.so loaded through GGML_BACKEND_PATH exactly as a llama.cpp-omni user would (-ngl 99): the whole
+    decode path — graph build, scheduler, input copies from host memory, our backend, logits back to the host — on the same GGUF."""
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = f"{ROOT / 'oracle' / '_ref' / 'lib'}:{PLUGIN.parent}:" + env.get("LD_LIBRARY_PATH", "")
+    if plugin:
+        env["GGML_BACKEND_PATH"] = str(PLUGIN)
+    else:
+        env.pop("GGML_BACKEND_PATH", None)
+    cmd = [str(REF_BIN), "-m", str(bench_gguf()), "-p", "0", "-n", str(n_gen), "-d", str(depth), "-fa", "1", "-ngl", "99" if plugin else "0",
+           "-t", str(threads), "-r", str(reps), "-o", "json"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError(f"llama-bench failed ({out.returncode}): {out.stderr[-600:]}")
+    rows = json.loads(out.stdout)
+    r = [x for x in rows if x.get("n_gen", 0) == n_gen][-1]
+    return {"tok_s": float(r["avg_ts"]), "ms": 1e3 / float(r["avg_ts"]), "backends": r.get("backends"), "n_gen": n_gen, "depth": depth, "reps": reps}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -123,19 +158,31 @@ def reference_layer_sample(cfg, n_layers: int, threads: int, steps: int, warmup:
 
 
 def run_reference(args) -> None:
+    """--impl reference: the reference's own CPU implementation of the path — its llama-bench on its ggml CPU backend, all host threads, WHOLE decoded
+    tokens of the same GGUF at the same KV depth as the B200 arm (same config: nothing is extrapolated).  Bounded: `steps` tokens per run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from __graft_entry__ import load_package
     cfg = load_package().decode.LLMConfig()
     threads = os.cpu_count() or 1
-    r = reference_layer_sample(cfg, 2, threads, max(1, args.steps), max(1, args.warmup))
-    line = {"impl": "reference", "metric": "decode_tok_per_s", "value": round(r["value"], 3), "unit": "tok/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations)", "data": "synthetic",
-            "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}", "timing": "weights (>1 GB sample) exceed the CPU caches"},
-            "cpu_baseline": {"value": round(r["value"], 3), "unit": "tok/s", "cores": threads, "kind": "reference", "sample": r["sample"]},
-            "e2e": {"value": round(r["value"], 3), "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    depth = max(0, min(args.depth, cfg.n_ctx - 2))
+    n_gen = max(4, min(args.steps, 64))
+    if REF_BIN.exists():
+        r = llama_bench(False, n_gen, depth, threads)
+        value, ms = r["tok_s"], r["ms"]
+        sample = (f"{n_gen} whole decoded tokens (36 layers + lm_head, attention at KV depth {depth}) by the reference's llama-bench on its ggml CPU backend "
+                  f"(oracle/_ref, AVX2 build), {threads} threads, after its own 1-token warm-up and a {depth}-token prompt")
+    else:                                                    # reference binaries not built on this box: matvec-only layer sample, extrapolated by bytes
+        r = reference_layer_sample(cfg, 2, threads, max(1, args.steps), max(1, args.warmup))
+        value, ms, sample = r["value"], r["ms_per_step"], r["sample"]
+    line = {"impl": "reference", "metric": "decode_tok_per_s", "value": round(value, 3), "unit": "tok/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations), f16 KV", "data": "synthetic",
+            "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}, KV depth {depth}", "path": "oracle/_ref/bin/llama-bench -ngl 0 (reference CPU backend)",
+                       "timing": "llama-bench's own clock around each llama_decode + synchronize; weights (5 GB) exceed the CPU caches"},
+            "cpu_baseline": {"value": round(value, 3), "unit": "tok/s", "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -196,10 +243,26 @@ def run_b200(args) -> None:
             D.build_engine()
         D.step(n_kv, engine)                               # eager once (module load, attribute setup)
         stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            launches = D.step(n_kv, engine)
+        # N > 1: the stage hop runs ON THE DEVICE (llama.cpp-omni_b200/pipeline.py PeerHop, csrc/hop.cu): wait-for-slot -> copy-in -> stage -> ack -> peer
+        # write + release are kernels of the SAME captured graph, one graph per slot; `--hop nccl` keeps the host-issued NCCL send/recv for comparison
+        hop = None
+        if world > 1 and args.hop == "peer":
+            try:
+                hop = pkg.pipeline.PeerHop(pipe, E, ops, torch, dist, dev, n_slots=2)
+            except Exception as ex:                                  # no IPC / peer access on this box: host-issued NCCL send/recv
+                print(f"[bench] peer hop unavailable ({ex}); using NCCL send/recv", file=sys.stderr)
+                hop = None
+        graphs = []
+        for slot in range(2 if hop is not None else 1):
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=stream):
+                launches = D.step(n_kv, engine) if hop is None else hop.enqueue_recv(slot, D.x_in) + D.step(n_kv, engine)
+                if hop is not None:
+                    launches += hop.enqueue_send(slot, D.x_out)
+            graphs.append(g_)
+        graph = graphs[0]
     hidden = D.x_in
+    item = [0]                                              # stream-items this rank has enqueued (slot = item % 2, identical on every rank)
 
     def pipeline_step(i: int, e2e: bool) -> tuple[int, int]:
         """One step of every in-flight stream through this rank's stage.  Returns (h2d, d2h) bytes when e2e."""
@@ -210,7 +273,12 @@ def run_b200(args) -> None:
             if rank == pipe.first and e2e:
                 D.x_in.copy_(host_embd[i % n_rows], non_blocking=True)
                 h2d += E * 4
-            pipe.stage_step(hidden, D.x_out, graph.replay)          # recv from the previous stage -> one graph replay -> send to the next
+            if hop is not None:
+                if pipe.is_active:
+                    graphs[item[0] % 2].replay()                # wait -> copy-in -> stage -> ack -> send, all on the device
+                item[0] += 1
+            else:
+                pipe.stage_step(hidden, D.x_out, graph.replay)      # recv from the previous stage -> one graph replay -> send to the next
             if last and e2e:
                 host_logits.copy_(D.logits, non_blocking=True)
                 d2h += cfg.n_vocab * 4
@@ -253,6 +321,18 @@ def run_b200(args) -> None:
     ms_total, _, _ = timed(False, args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
     ms_e2e, h2d, d2h = timed(True, args.steps, args.warmup)
+    if hop is not None:
+        if hop.errors():
+            raise RuntimeError("peer hop timed out (see csrc/hop.cu error words)")
+    e2e_cabi = args.steps * n_streams / (ms_e2e / 1e3)
+    e2e_path = "C-ABI with host buffers (pinned H2D inputs, logits D2H per token)"
+    plug = None
+    if world == 1 and not args.tiny and not args.per_op and not args.no_plugin_e2e and REF_BIN.exists() and PLUGIN.exists():
+        # the headline end-to-end number goes THROUGH THE BOUNDARY: the unmodified reference llama-bench with libggml-b200.so as its backend
+        torch.cuda.synchronize()
+        plug = llama_bench(True, max(args.steps, 128), depth, os.cpu_count() or 1, reps=2)
+        e2e_path = ("oracle/_ref/bin/llama-bench -ngl 99 with GGML_BACKEND_PATH=libggml-b200.so (the reference's graph build, scheduler, host input copies and "
+                    f"logits read-back around our backend; {plug['n_gen']} tokens x {plug['reps']} runs at KV depth {depth})")
     if world > 1:
         hb = torch.tensor([h2d, d2h], device=dev)
         dist.all_reduce(hb)
@@ -261,7 +341,10 @@ def run_b200(args) -> None:
     tokens = args.steps * n_streams
     ms_step = ms_total / args.steps
     value = tokens / (ms_total / 1e3)
-    e2e_value = tokens / (ms_e2e / 1e3)
+    e2e_value = plug["tok_s"] if plug else tokens / (ms_e2e / 1e3)
+    if plug:                                                # what the reference's scheduler moves per token (llama-graph.cpp inputs, llama-context.cpp:1144 logits)
+        h2d = cfg.n_embd * 4 + 4 + 64 * n_kv * 4 + 8 + 8 + 4
+        d2h = cfg.n_vocab * 4
     peak, peak_src = peaks()
     # roofline of the dominant kernel class (the weight matvecs + KV reads = the whole step's algorithmic bytes; one launch = one
     # graph replay = one token through this rank's stage).  At N > 1 every rank moves 1/N of the bytes per stream-step.
@@ -280,10 +363,12 @@ def run_b200(args) -> None:
             "dtype": "int8 x int4/int6 -> int32 -> f32 (q8_K activations), f16 KV", "data": "synthetic",
             "config": {"workload": f"{cfg.name} batch=1 decode, ctx={cfg.n_ctx}, KV depth {depth}..{depth + span - 1} (n_kv={n_kv})",
                        "streams_in_flight": n_streams, "parallelism": "single GPU" if world == 1 else f"layer-split pipeline pp{world}, layers per stage {[len(r) for r in ranges]} (+lm_head on the last)",
+                       "hop": None if world == 1 else ("device-side peer write + release flag over NVLink (csrc/hop.cu), captured in the stage's CUDA graph" if hop is not None else "NCCL send/recv issued from the host between graph replays"),
                        "engine": "persistent (1 kernel/token)" if engine else "per-op launches",
                        "timing": f"one CUDA graph per token; weights {w_bytes / 1e9:.2f} GB/rank exceed the 126 MB L2, so no flush is needed"},
             "gpu_launches": launches * args.steps * n_streams,
-            "e2e": {"value": round(e2e_value, 2), "unit": "tok/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": round(e2e_value, 2), "unit": "tok/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "path": e2e_path},
+            "e2e_cabi": {"value": round(e2e_cabi, 2), "unit": "tok/s", "path": "b200_decoder_step through ctypes with pinned host inputs and logits read-back per token"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_step": int(step_bytes),
                          "kernel": ("k_stream (persistent decode engine: all weight matvecs + attention of the token in one launch)" if engine else
@@ -293,10 +378,18 @@ def run_b200(args) -> None:
         line["prefill"] = prefill_leg(D, cfg, dec, torch, dev, args.prefill_tokens)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            r = reference_layer_sample(cfg, 1, os.cpu_count() or 1, 3, 1)
-            line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tok/s", "cores": os.cpu_count() or 1, "kind": "reference",
-                                    "sample": r["sample"]}
+            threads = os.cpu_count() or 1
+            if REF_BIN.exists() and not args.tiny:
+                r = llama_bench(False, 16, 0, threads)
+                line["cpu_baseline"] = {"value": round(r["tok_s"], 3), "unit": "tok/s", "cores": threads, "kind": "reference",
+                                        "sample": "16 whole decoded tokens (36 layers + lm_head) of the same GGUF by the reference's llama-bench on its ggml CPU backend "
+                                                  f"(oracle/_ref), {threads} threads, KV depth 0..15 (bounded sample: `--impl reference` times the full depth)"}
+            else:
+                r = reference_layer_sample(cfg, 1, threads, 3, 1)
+                line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tok/s", "cores": threads, "kind": "reference", "sample": r["sample"]}
         print(json.dumps(line))
+    if hop is not None:
+        hop.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -346,6 +439,8 @@ def main() -> None:
     ap.add_argument("--no-prefill", action="store_true", help="skip the prefill leg (the extra `prefill` object of the JSON line)")
     ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--per-op", action="store_true", help="one launch per (fused) op instead of the persistent decode engine")
+    ap.add_argument("--hop", default="peer", choices=["peer", "nccl"], help="N > 1: how the hidden state crosses a stage boundary")
+    ap.add_argument("--no-plugin-e2e", action="store_true", help="e2e through the C-ABI only (skip the llama-bench + plugin leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

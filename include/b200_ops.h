@@ -206,6 +206,21 @@ B200_API int  b200_decoder_n_phases(void * handle);
 B200_API int  b200_decoder_profile(void * handle, int32_t n_kv, unsigned long long * host_out, void * stream);
 B200_API void b200_decoder_destroy(void * handle);
 
+/* ---- layer-split pipeline hop on the device (csrc/hop.cu; replaces, for one-process-per-GPU launches, the per-boundary copy the reference
+ *      issues from ggml_backend_sched_compute_splits -> cpy_tensor_async, ggml/src/ggml-backend.cpp:1539, ggml-cuda.cu:2598-2620) -------------
+ * b200_ipc_*: device memory another process of the node can map (cudaIpc*); handle64 is the 64-byte cudaIpcMemHandle_t.
+ * b200_hop_send: 1-CTA kernel: wait for the consumer's ack of the slot, write n floats into the PEER's input slot, release its ready word.
+ * b200_hop_wait: 1-CTA kernel in front of a stage's decode step: acquire the ready word the producer writes.
+ * b200_hop_ack : after the step: tell the producer the slot has been consumed.
+ * `state` = 8 zero-initialised device bytes per call site (sequence counter + error word: 1 = ack time-out, 2 = ready time-out). */
+B200_API int b200_ipc_alloc(size_t bytes, void ** ptr, void * handle64);
+B200_API int b200_ipc_open(const void * handle64, void ** ptr);
+B200_API int b200_ipc_close(void * ptr);
+B200_API int b200_ipc_free(void * ptr);
+B200_API int b200_hop_send(const float * src, float * dst_peer, int64_t n, unsigned * ready_peer, const unsigned * ack_local, void * state, void * stream);
+B200_API int b200_hop_wait(const unsigned * ready_local, void * state, void * stream);
+B200_API int b200_hop_ack(unsigned * ack_peer, void * state, void * stream);
+
 #ifdef __cplusplus
 }
 #endif

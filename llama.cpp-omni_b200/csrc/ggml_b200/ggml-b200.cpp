@@ -724,6 +724,10 @@ enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph 
     scratch_for(c, need);                                            // no allocation may happen while capturing
     GraphKey key;
     graph_key_of(g, key);
+    // host-overhead probe (profiles/): GGML_B200_NULL_COMPUTE=1 skips every launch of decode-sized graphs, so `llama-bench -n` then times the
+    // reference's own per-token host work (graph build, scheduling, input copies, logits read-back) plus this function's bookkeeping
+    static const bool null_compute = getenv("GGML_B200_NULL_COMPUTE") && atoi(getenv("GGML_B200_NULL_COMPUTE")) != 0;
+    if (null_compute) return GGML_STATUS_SUCCESS;
     auto run_pre = [&](const std::vector<int> & pre) {                // the engine's per-op prefix, re-resolved from THIS graph by node index
         for (int idx : pre) { int rc = 0; run_node(c, g, idx, rc); if (rc != B200_OK) return false; }
         return true;

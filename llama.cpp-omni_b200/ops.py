@@ -23,7 +23,8 @@ EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b20
            "b200_mul_mat", "b200_mul_mat_ex", "b200_matvec_q", "b200_matvec_q_swiglu", "b200_rms_norm", "b200_rms_norm_quantize", "b200_rope",
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
            "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
-           "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy"]
+           "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy",
+           "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
 
 
 class Tensor(C.Structure):
@@ -82,6 +83,13 @@ def lib():
         L.b200_decoder_step.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.b200_decoder_n_phases.argtypes = [C.c_void_p]
         L.b200_decoder_profile.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+        L.b200_ipc_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.b200_ipc_close.argtypes = [C.c_void_p]
+        L.b200_ipc_free.argtypes = [C.c_void_p]
+        L.b200_hop_send.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200_hop_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200_hop_ack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -84,3 +84,85 @@ class Pipeline:
         stage_fn()
         if self.next is not None:
             self.dist.send(hidden_out, dst=self.next)
+
+
+class PeerHop:
+    """The same hop ON THE DEVICE (csrc/hop.cu): the producer stage writes the hidden state straight into the consumer's input slot over NVLink
+    (cudaIpc-mapped peer memory) and releases a sequence word; the consumer's stream waits for it with a 1-CTA kernel in front of its decode
+    step and acks the slot afterwards.  Everything is stream-ordered kernels, so a stage's whole step (wait -> copy-in -> stage -> ack -> send) can
+    be captured into ONE CUDA graph per slot and replayed without host code between two stages' kernels.  `ops` is the ctypes mirror of the
+    C-ABI, `dist` torch.distributed (only used once, to exchange the 64-byte IPC handles)."""
+
+    SLOT_ALIGN = 256
+
+    def __init__(self, pipe: Pipeline, n_embd: int, ops, torch, dist, device, n_slots: int = 2):
+        import ctypes as C
+        self.pipe, self.ops, self.torch, self.C, self.n, self.n_slots = pipe, ops, torch, C, n_embd, n_slots
+        L = ops.lib()
+        self.slot_bytes = (n_embd * 4 + self.SLOT_ALIGN - 1) // self.SLOT_ALIGN * self.SLOT_ALIGN
+        inbox_bytes = n_slots * (self.slot_bytes + self.SLOT_ALIGN)        # data slots, then one ready word per 256-byte line
+        ack_bytes = n_slots * self.SLOT_ALIGN
+        self.inbox, self.ackbox = C.c_void_p(), C.c_void_p()
+        h_in, h_ack = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
+        ops.check(L.b200_ipc_alloc(inbox_bytes, C.byref(self.inbox), h_in))
+        ops.check(L.b200_ipc_alloc(ack_bytes, C.byref(self.ackbox), h_ack))
+        mine = torch.tensor(list(bytes(h_in)) + list(bytes(h_ack)), dtype=torch.uint8, device=device)
+        allh = [torch.zeros_like(mine) for _ in range(pipe.world)]
+        dist.all_gather(allh, mine)
+        self.peer_inbox, self.peer_ack = C.c_void_p(), C.c_void_p()          # next stage's inbox, previous stage's ack words
+        if pipe.is_active and pipe.next is not None:
+            hb = (C.c_uint8 * 64)(*allh[pipe.next][:64].cpu().tolist())
+            ops.check(L.b200_ipc_open(hb, C.byref(self.peer_inbox)))
+        if pipe.is_active and pipe.prev is not None:
+            hb = (C.c_uint8 * 64)(*allh[pipe.prev][64:].cpu().tolist())
+            ops.check(L.b200_ipc_open(hb, C.byref(self.peer_ack)))
+        dist.barrier()
+        self.state = torch.zeros((3, n_slots, 2), dtype=torch.int32, device=device)      # [wait | ack | send][slot] -> (count, error)
+
+    # addresses inside a mapped inbox / ack box
+    def _data(self, base, slot): return base.value + slot * self.slot_bytes
+    def _ready(self, base, slot): return base.value + self.n_slots * self.slot_bytes + slot * self.SLOT_ALIGN
+    def _ack(self, base, slot): return base.value + slot * self.SLOT_ALIGN
+    def _state(self, which, slot): return self.state[which, slot].data_ptr()
+
+    def enqueue_recv(self, slot: int, x_in) -> int:
+        """wait for the producer's release of `slot`, then bring the hidden state into the stage's input vector.  Returns #launches."""
+        if not self.pipe.is_active or self.pipe.prev is None:
+            return 0
+        C, ops, L = self.C, self.ops, self.ops.lib()
+        ops.check(L.b200_hop_wait(C.c_void_p(self._ready(self.inbox, slot)), C.c_void_p(self._state(0, slot)), ops.stream()))
+        src = ops.Tensor(); dst = ops.T(x_in)
+        src.data, src.type, src.layout = self._data(self.inbox, slot), ops.F32, ops.LAYOUT_NATIVE
+        for i in range(4):
+            src.ne[i], src.nb[i] = dst.ne[i], dst.nb[i]
+        ops.check(L.b200_cpy(C.byref(src), C.byref(dst), ops.stream()))
+        return 2
+
+    def enqueue_send(self, slot: int, x_out) -> int:
+        """after the stage's step: ack the slot just consumed (to the previous stage) and publish x_out into the next stage's slot."""
+        if not self.pipe.is_active:
+            return 0
+        C, ops, L = self.C, self.ops, self.ops.lib()
+        n = 0
+        if self.pipe.prev is not None:
+            ops.check(L.b200_hop_ack(C.c_void_p(self._ack(self.peer_ack, slot)), C.c_void_p(self._state(1, slot)), ops.stream()))
+            n += 1
+        if self.pipe.next is not None:
+            ops.check(L.b200_hop_send(C.c_void_p(x_out.data_ptr()), C.c_void_p(self._data(self.peer_inbox, slot)), self.n,
+                                      C.c_void_p(self._ready(self.peer_inbox, slot)), C.c_void_p(self._ack(self.ackbox, slot)),
+                                      C.c_void_p(self._state(2, slot)), ops.stream()))
+            n += 1
+        return n
+
+    def errors(self) -> int:
+        return int(self.state[:, :, 1].abs().sum().item())
+
+    def close(self):
+        L = self.ops.lib()
+        for p in (self.peer_inbox, self.peer_ack):
+            if p.value:
+                L.b200_ipc_close(p)
+        self.torch.cuda.synchronize()
+        for p in (self.inbox, self.ackbox):
+            if p.value:
+                L.b200_ipc_free(p)
