@@ -206,6 +206,16 @@ B200_API int  b200_decoder_n_phases(void * handle);
 B200_API int  b200_decoder_profile(void * handle, int32_t n_kv, unsigned long long * host_out, void * stream);
 B200_API void b200_decoder_destroy(void * handle);
 
+/* ---- ops of the APM (Whisper) / VPM (SigLip) encoder graphs -----------------------------------------------------------
+ * b200_norm   : GGML_OP_NORM, y = (x - mean) / sqrt(var + eps) per row        replaces norm_f32 (ggml-cuda/norm.cu:5); CPU ggml-cpu/ops.cpp:3450-3495
+ * b200_im2col : GGML_OP_IM2COL (ggml_conv_1d / ggml_conv_2d), F32 input -> F16 or F32 [IC*KH*KW, OW, OH, N]; `kernel` only supplies KW / KH
+ *               replaces im2col_kernel (ggml-cuda/im2col.cu:6); CPU ops.cpp:6160-6301
+ * b200_pool_1d: GGML_OP_POOL_1D, op 0 = max, 1 = avg, k0 == s0, p0 == 0 (all the reference implements, ops.cpp:7212-7280; its CUDA backend has none) */
+B200_API int b200_norm(const b200_tensor * x, const b200_tensor * dst, float eps, void * stream);
+B200_API int b200_im2col(const b200_tensor * kernel, const b200_tensor * x, const b200_tensor * dst, int s0, int s1, int p0, int p1, int d0, int d1,
+                         int is_2d, void * stream);
+B200_API int b200_pool_1d(const b200_tensor * x, const b200_tensor * dst, int op, int k0, int s0, int p0, void * stream);
+
 /* ---- layer-split pipeline hop on the device (csrc/hop.cu; replaces, for one-process-per-GPU launches, the per-boundary copy the reference
  *      issues from ggml_backend_sched_compute_splits -> cpy_tensor_async, ggml/src/ggml-backend.cpp:1539, ggml-cuda.cu:2598-2620) -------------
  * b200_ipc_*: device memory another process of the node can map (cudaIpc*); handle64 is the 64-byte cudaIpcMemHandle_t.

@@ -1,5 +1,6 @@
 // common.cuh — shared device/host helpers for the sm_100a kernel library (libb200ops.so).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -83,11 +84,14 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // cudaFuncSetAttribute is PER DEVICE: a process that drives several GPUs (the ggml scheduler's layer split) must raise the dynamic
 // shared-memory limit of a kernel on each of them.  `mask` is a per-kernel static bit set of devices already done.
-template <class K> inline cudaError_t ensure_dyn_smem(K kernel, int bytes, unsigned long long & mask) {
+// Several host threads may drive backends of one process at once (omni's LLM / TTS / encoder threads): the mask is atomic, and two threads racing on
+// the same device at worst both call cudaFuncSetAttribute, which is idempotent.
+typedef std::atomic<unsigned long long> smem_mask_t;
+template <class K> inline cudaError_t ensure_dyn_smem(K kernel, int bytes, smem_mask_t & mask) {
     int dev = 0; cudaGetDevice(&dev);
-    if (mask >> (dev & 63) & 1ull) return cudaSuccess;
+    if (mask.load(std::memory_order_acquire) >> (dev & 63) & 1ull) return cudaSuccess;
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) mask |= 1ull << (dev & 63);
+    if (e == cudaSuccess) mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
     return e;
 }
 

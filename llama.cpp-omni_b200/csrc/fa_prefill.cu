@@ -242,7 +242,7 @@ size_t fa_prefill_scratch_bytes(const b200_tensor * q, const b200_tensor * mask_
 
 int fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
                void * scratch, cudaStream_t st) {
-    static unsigned long long done128 = 0, done64 = 0;
+    static smem_mask_t done128{0}, done64{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_fa_prefill<128>, 4 * FP_BN * 128 * 2, done128));
     B200_CUDA_TRY(ensure_dyn_smem(k_fa_prefill<64>, 4 * FP_BN * 64 * 2, done64));
     FaPArgs A = {};

@@ -157,7 +157,7 @@ extern "C" int b200_rms_norm_quantize(const float * x, int64_t x_col_stride, con
     if (!x || !w || !act) return B200_ERR_ARG;
     if (!is_quant(weight_type) || k <= 0 || k % blck_size(weight_type) || k % 4 || k > 16384 || ncols <= 0) return B200_ERR_UNSUPPORTED;
     if (((uintptr_t) x | (uintptr_t) w | (uintptr_t) y_f32_or_null | (uintptr_t) act) % 16 || x_col_stride % 4 || y_col_stride % 4) return B200_ERR_UNSUPPORTED;
-    static unsigned long long attr_set = 0;
+    static smem_mask_t attr_set{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_rms_norm_quantize, 16384 * 4, attr_set));
     k_rms_norm_quantize<<<(unsigned) ncols, 512, (size_t) k * 4, (cudaStream_t) stream>>>(x, x_col_stride, w, y_f32_or_null, y_col_stride,
                                                                                         (uint8_t *) act, weight_type, k, eps);

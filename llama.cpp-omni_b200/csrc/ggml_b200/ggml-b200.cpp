@@ -312,8 +312,13 @@ bool b200_dev_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
         }
         case GGML_OP_ADD: case GGML_OP_SUB: case GGML_OP_MUL: case GGML_OP_DIV:
             return floaty(s0) && floaty(s1) && floaty(op) && ggml_are_same_shape(s0, op) && broadcastable(s0, s1);
-        case GGML_OP_RMS_NORM:
+        case GGML_OP_RMS_NORM: case GGML_OP_NORM:
             return f32c(s0) && f32c(op) && ggml_are_same_shape(s0, op);
+        case GGML_OP_IM2COL:
+            return s1 && f32c(s1) && (op->type == GGML_TYPE_F16 || op->type == GGML_TYPE_F32) && ggml_is_contiguous(op);
+        case GGML_OP_POOL_1D:
+            return s0 && (s0->type == GGML_TYPE_F32 || s0->type == GGML_TYPE_F16) && op->type == GGML_TYPE_F32 && ggml_is_contiguous(s0) && ggml_is_contiguous(op) &&
+                   iparam(op, 1) == iparam(op, 2) && iparam(op, 3) == 0 && (iparam(op, 0) == GGML_OP_POOL_MAX || iparam(op, 0) == GGML_OP_POOL_AVG);
         case GGML_OP_ROPE: {
             const int mode = iparam(op, 2), n_dims = iparam(op, 1);
             if (mode != 0 && mode != GGML_ROPE_TYPE_NEOX) return false;
@@ -451,6 +456,13 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             rc = b200_rms_norm(&x, nullptr, nullptr, &d, fparam(n, 0), st);
             return 1;
         }
+        case GGML_OP_NORM: { b200_tensor x = view_of(s0), d = view_of(n); rc = b200_norm(&x, &d, fparam(n, 0), st); return 1; }
+        case GGML_OP_IM2COL: {
+            b200_tensor k = view_of(s0), x = view_of(s1), d = view_of(n);
+            rc = b200_im2col(&k, &x, &d, iparam(n, 0), iparam(n, 1), iparam(n, 2), iparam(n, 3), iparam(n, 4), iparam(n, 5), iparam(n, 6) == 1, st);
+            return 1;
+        }
+        case GGML_OP_POOL_1D: { b200_tensor x = view_of(s0), d = view_of(n); rc = b200_pool_1d(&x, &d, iparam(n, 0), iparam(n, 1), iparam(n, 2), iparam(n, 3), st); return 1; }
         case GGML_OP_ROPE: {
             b200_tensor x = view_of(s0), d = view_of(n);
             b200_rope_params p;
@@ -937,8 +949,7 @@ const ggml_backend_device_i b200_device_iface = {
 };
 
 // ---------------------------------------------------------------------------------------------------------------- registry
-int probe_devices() {
-    if (g_n_devices >= 0) return g_n_devices;
+int probe_devices_once() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { (void) cudaGetLastError(); n = 0; }
     int kept = 0;
@@ -965,6 +976,11 @@ int probe_devices() {
     }
     g_n_devices = kept;
     return kept;
+}
+int probe_devices() {                                                     // any thread, any entry point (omni creates its backends from 3 threads)
+    static std::once_flag once;
+    std::call_once(once, [] { probe_devices_once(); });
+    return g_n_devices;
 }
 
 const char * b200_reg_get_name(ggml_backend_reg_t) { return "B200"; }

@@ -614,7 +614,7 @@ static tc_encode_fn tc_encoder() {
 }
 
 int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st) {
-    static unsigned long long done = 0;
+    static smem_mask_t done{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_mmq_tc, TC_SMEM, done));
     if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
     // the payload plane as a 2-D byte tensor [m rows][row bytes]; box = one quant block x 128 rows
@@ -655,7 +655,7 @@ bool mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t
 }
 
 int mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st) {
-    static unsigned long long done = 0;
+    static smem_mask_t done{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_mm_f16_tc, TF_SMEM, done));
     if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
     CUtensorMap wmap;

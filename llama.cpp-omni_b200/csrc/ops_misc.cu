@@ -486,12 +486,124 @@ extern "C" int b200_soft_max(const b200_tensor * x, const b200_tensor * mask, co
     if (mask && ((mask->type != B200_F32 && mask->type != B200_F16) || mask->ne[0] != x->ne[0] || mask->ne[1] < x->ne[1] ||
                  mask->ne[2] == 0 || mask->ne[3] == 0 || x->ne[2] % mask->ne[2] || x->ne[3] % mask->ne[3])) return B200_ERR_UNSUPPORTED;
     if (x->ne[0] > 24576) return B200_ERR_UNSUPPORTED;
-    static unsigned long long sm_attr = 0;
+    static smem_mask_t sm_attr{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_soft_max, 24576 * 4, sm_attr));
     const int64_t rows = nrows(x);
     if (rows == 0 || x->ne[0] == 0) return B200_OK;
     SmArgs A; A.x = t4(x); A.dst = t4(dst); A.has_mask = mask != nullptr; A.mask = mask ? t4(mask) : A.x; A.scale = scale; A.rows = rows;
     k_soft_max<<<(unsigned) rows, 256, (size_t) x->ne[0] * 4, (cudaStream_t) stream>>>(A);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// ================================================================== ops of the APM (Whisper) / VPM (SigLip) encoder graphs ======================
+// without them every encoder layer bounced to the CPU backend through the scheduler.
+//   NORM    ggml_norm       tools/omni/audition.cpp:449,653,674, vision.cpp:546   (CPU: ggml-cpu/ops.cpp:3450-3495, CUDA: norm.cu:5)
+//   IM2COL  ggml_conv_1d/2d tools/omni/audition.cpp:379,384, vision.cpp:519       (CPU: ops.cpp:6160-6301, CUDA: im2col.cu:6)
+//   POOL_1D ggml_pool_1d    tools/omni/audition.cpp:697                            (CPU: ops.cpp:7212-7260; the reference CUDA backend has no POOL_1D)
+namespace b200 {
+
+// LayerNorm without affine part: y = (x - mean) / sqrt(var + eps), var = mean((x - mean)^2) — two passes over the row like the CPU (mean first, then
+// the centred sum of squares), the row staged in registers when it fits
+template <bool WARP_ROWS>
+__global__ void __launch_bounds__(256) k_norm(const NormArgs A) {
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31;
+    const int64_t row = WARP_ROWS ? (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
+    if (WARP_ROWS && row >= A.rows) return;
+    const int64_t i1 = row % A.x.ne[1], i2 = (row / A.x.ne[1]) % A.x.ne[2], i3 = row / (A.x.ne[1] * A.x.ne[2]);
+    const float * x = (const float *) (A.x.data + i1 * A.x.nb[1] + i2 * A.x.nb[2] + i3 * A.x.nb[3]);
+    float * y = (float *) (A.dst.data + i1 * A.dst.nb[1] + i2 * A.dst.nb[2] + i3 * A.dst.nb[3]);
+    const int64_t n = A.x.ne[0];
+    const int tid = WARP_ROWS ? lane : threadIdx.x, nt = WARP_ROWS ? 32 : blockDim.x;
+    float s = 0.0f;
+    for (int64_t i = tid; i < n; i += nt) s += x[i];
+    s = WARP_ROWS ? warp_sum(s) : block_sum(s, red);
+    const float mean = s / (float) n;
+    float ss = 0.0f;
+    for (int64_t i = tid; i < n; i += nt) { const float d = x[i] - mean; ss += d * d; }
+    ss = WARP_ROWS ? warp_sum(ss) : block_sum(ss, red);
+    const float scale = 1.0f / sqrtf(ss / (float) n + A.eps);
+    for (int64_t i = tid; i < n; i += nt) y[i] = __fmul_rn(x[i] - mean, scale);
+}
+
+struct Im2colArgs {
+    const char * x; char * dst; int dst_f16;
+    int64_t N, IC, IH, IW, KH, KW, OH, OW; int64_t x_nb_n, x_nb_c, x_nb_h;     // byte strides of the F32 input: batch, channel, row
+    int s0, s1, p0, p1, d0, d1;
+};
+// thread = one element of dst [N][OH][OW][IC*KH*KW] (the innermost index is the contiguous one: coalesced stores; the gathers hit a KW-wide window)
+__global__ void __launch_bounds__(256) k_im2col(const Im2colArgs A, int64_t total) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t ckk = A.IC * A.KH * A.KW;
+    const int64_t c = i % ckk, r = i / ckk;
+    const int64_t ikw = c % A.KW, ikh = (c / A.KW) % A.KH, iic = c / (A.KW * A.KH);
+    const int64_t iow = r % A.OW, ioh = (r / A.OW) % A.OH, in = r / (A.OW * A.OH);
+    const int64_t iiw = iow * A.s0 + ikw * A.d0 - A.p0, iih = ioh * A.s1 + ikh * A.d1 - A.p1;
+    float v = 0.0f;
+    if (iih >= 0 && iih < A.IH && iiw >= 0 && iiw < A.IW) v = *(const float *) (A.x + in * A.x_nb_n + iic * A.x_nb_c + iih * A.x_nb_h + iiw * 4);
+    if (A.dst_f16) ((__half *) A.dst)[i] = __float2half_rn(v); else ((float *) A.dst)[i] = v;
+}
+
+struct PoolArgs { const char * x; float * dst; int x_f16, op, k; int64_t rs, x_row_bytes; };
+// thread = one output element: rows of the source are nb[1] apart and walked back to back, exactly as the CPU loop does (k == stride, no padding)
+__global__ void __launch_bounds__(256) k_pool_1d(const PoolArgs A, int64_t total) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t row = i / A.rs, o = i % A.rs;
+    const char * src = A.x + row * A.x_row_bytes;
+    float acc = A.op == 0 ? -3.402823466e+38f : 0.0f;                     // GGML_OP_POOL_MAX = 0, GGML_OP_POOL_AVG = 1
+    for (int ki = 0; ki < A.k; ++ki) {
+        const int64_t j = o * A.k + ki;
+        const float v = A.x_f16 ? __half2float(((const __half *) src)[j]) : ((const float *) src)[j];
+        if (A.op == 0) { if (v > acc) acc = v; } else acc += v;
+    }
+    A.dst[i] = A.op == 0 ? acc : __fdiv_rn(acc, (float) A.k);
+}
+
+} // namespace b200
+
+extern "C" int b200_norm(const b200_tensor * x, const b200_tensor * dst, float eps, void * stream) {
+    if (!x || !dst) return B200_ERR_ARG;
+    if (x->type != B200_F32 || dst->type != B200_F32 || !same_shape(x, dst) || x->nb[0] != 4 || dst->nb[0] != 4) return B200_ERR_UNSUPPORTED;
+    const int64_t rows = nrows(x);
+    if (rows == 0 || x->ne[0] == 0) return B200_OK;
+    NormArgs A; A.x = t4(x); A.dst = t4(dst); A.eps = eps; A.has_w = 0; A.has_add = 0; A.rows = rows; A.w = A.x; A.add = A.x;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (x->ne[0] <= 1024) k_norm<true><<<(unsigned) ((rows + 7) / 8), 256, 0, st>>>(A);
+    else                  k_norm<false><<<(unsigned) rows, 256, 0, st>>>(A);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_im2col(const b200_tensor * kernel, const b200_tensor * x, const b200_tensor * dst, int s0, int s1, int p0, int p1, int d0, int d1,
+                           int is_2d, void * stream) {
+    if (!kernel || !x || !dst) return B200_ERR_ARG;
+    if (x->type != B200_F32 || x->nb[0] != 4 || (dst->type != B200_F16 && dst->type != B200_F32) || !is_contig(dst)) return B200_ERR_UNSUPPORTED;
+    Im2colArgs A;
+    A.x = (const char *) x->data; A.dst = (char *) dst->data; A.dst_f16 = dst->type == B200_F16;
+    A.N = is_2d ? x->ne[3] : x->ne[2]; A.IC = is_2d ? x->ne[2] : x->ne[1]; A.IH = is_2d ? x->ne[1] : 1; A.IW = x->ne[0];
+    A.KH = is_2d ? kernel->ne[1] : 1; A.KW = kernel->ne[0]; A.OH = is_2d ? dst->ne[2] : 1; A.OW = dst->ne[1];
+    A.x_nb_n = is_2d ? x->nb[3] : x->nb[2]; A.x_nb_c = is_2d ? x->nb[2] : x->nb[1]; A.x_nb_h = is_2d ? x->nb[1] : 0;
+    A.s0 = s0; A.s1 = s1; A.p0 = p0; A.p1 = p1; A.d0 = d0; A.d1 = d1;
+    if (dst->ne[0] != A.IC * A.KH * A.KW) return B200_ERR_ARG;
+    const int64_t total = nelem(dst);
+    if (total == 0) return B200_OK;
+    if (total / 256 + 1 > 0x7fffffffll) return B200_ERR_UNSUPPORTED;
+    k_im2col<<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_pool_1d(const b200_tensor * x, const b200_tensor * dst, int op, int k0, int s0, int p0, void * stream) {
+    if (!x || !dst) return B200_ERR_ARG;
+    if ((x->type != B200_F32 && x->type != B200_F16) || dst->type != B200_F32 || !is_contig(dst) || !is_contig(x)) return B200_ERR_UNSUPPORTED;
+    if (k0 != s0 || p0 != 0 || k0 <= 0 || (op != 0 && op != 1)) return B200_ERR_UNSUPPORTED;      // what the reference implements too (ops.cpp:7264-7280)
+    const int64_t total = nelem(dst);
+    if (total == 0) return B200_OK;
+    PoolArgs A; A.x = (const char *) x->data; A.dst = (float *) dst->data; A.x_f16 = x->type == B200_F16; A.op = op; A.k = k0; A.rs = dst->ne[0]; A.x_row_bytes = x->nb[1];
+    k_pool_1d<<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

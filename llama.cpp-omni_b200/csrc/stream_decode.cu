@@ -584,7 +584,7 @@ bool sd_phase_ok(const SdPhase & P) {
 }
 
 static int sd_setup(bool prof) {
-    static unsigned long long done[2] = { 0, 0 };
+    static smem_mask_t done[2] = { {0}, {0} };
     const cudaError_t e = prof ? ensure_dyn_smem(k_stream<true>, SD_SMEM_BYTES, done[1]) : ensure_dyn_smem(k_stream<false>, SD_SMEM_BYTES, done[0]);
     return e == cudaSuccess ? B200_OK : -(int) e;
 }

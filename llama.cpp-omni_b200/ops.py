@@ -24,7 +24,7 @@ EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b20
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
            "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
            "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy",
-           "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
+           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
 
 
 class Tensor(C.Structure):
@@ -329,4 +329,34 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch.Te
         scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=q.device)
     check(L.b200_flash_attn(_ref(qd), _ref(kd), _ref(vd), _ref(md), _ref(od), C.c_float(s), C.c_float(0.0), C.c_float(0.0),
                             C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), stream()))
+    return out
+
+
+def norm(x: torch.Tensor, eps: float) -> torch.Tensor:
+    """GGML_OP_NORM over the last dim."""
+    out = torch.empty_like(x)
+    check(lib().b200_norm(_ref(T(x)), _ref(T(out)), C.c_float(eps), stream()))
+    return out
+
+
+def im2col(kernel: torch.Tensor, x: torch.Tensor, s0: int, s1: int, p0: int, p1: int, d0: int, d1: int, is_2d: bool, dtype=torch.float16) -> torch.Tensor:
+    """GGML_OP_IM2COL.  2-D: kernel [OC, IC, KH, KW], x [N, IC, IH, IW] -> [N, OH, OW, IC*KH*KW]; 1-D: kernel [OC, IC, KW], x [N, IC, IW] -> [N, OW, IC*KW]."""
+    def osz(i, k, s, p, d):
+        return (i + 2 * p - d * (k - 1) - 1) // s + 1
+    if is_2d:
+        N, IC, IH, IW = x.shape
+        KH, KW = kernel.shape[-2:]
+        out = torch.empty((N, osz(IH, KH, s1, p1, d1), osz(IW, KW, s0, p0, d0), IC * KH * KW), dtype=dtype, device=x.device)
+    else:
+        N, IC, IW = x.shape
+        KW = kernel.shape[-1]
+        out = torch.empty((N, osz(IW, KW, s0, p0, d0), IC * KW), dtype=dtype, device=x.device)
+    check(lib().b200_im2col(_ref(T(kernel)), _ref(T(x)), _ref(T(out)), s0, s1, p0, p1, d0, d1, int(is_2d), stream()))
+    return out
+
+
+def pool_1d(x: torch.Tensor, op: int, k: int) -> torch.Tensor:
+    """GGML_OP_POOL_1D along the last dim, kernel == stride, no padding (op 0 = max, 1 = avg)."""
+    out = torch.empty(list(x.shape[:-1]) + [x.shape[-1] // k], dtype=torch.float32, device=x.device)
+    check(lib().b200_pool_1d(_ref(T(x)), _ref(T(out)), op, k, k, 0, stream()))
     return out

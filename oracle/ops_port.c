@@ -141,3 +141,47 @@ void or_flash_attn_f16(const float * q, const uint16_t * k, const uint16_t * v, 
     }
     free(acc32); free(acc16); free(q16);
 }
+
+/* ---- ops of the APM / VPM encoder graphs ---------------------------------------------------------------------------
+ * NORM     ggml/src/ggml-cpu/ops.cpp:3450-3495: mean = sum/n, y = x - mean, variance = sum(y*y)/n (ggml_vec_cvar_f32, vec.cpp:407), y *= 1/sqrtf(var+eps)
+ * IM2COL   ops.cpp:6160-6301: [N, IC, IH, IW] -> [N, OH, OW, IC*KH*KW], zero padding, F32 -> F16 (or F32)
+ * POOL_1D  ops.cpp:7212-7280: kernel == stride, no padding; avg = sequential f32 sum / k, max starts at -FLT_MAX */
+void or_norm(const float * x, float * y, int64_t ncols, int64_t nrows, float eps) {
+    for (int64_t r = 0; r < nrows; ++r, x += ncols, y += ncols) {
+        double s = 0.0;
+        for (int64_t i = 0; i < ncols; ++i) s += (double) x[i];
+        const float mean = (float) s / ncols;
+        double v = 0.0;
+        for (int64_t i = 0; i < ncols; ++i) { y[i] = x[i] - mean; v += (double) (y[i] * y[i]); }
+        const float variance = (float) (v / ncols);
+        const float scale = 1.0f / sqrtf(variance + eps);
+        for (int64_t i = 0; i < ncols; ++i) y[i] *= scale;
+    }
+}
+
+void or_im2col(const float * x, void * dst, int dst_f16, int64_t N, int64_t IC, int64_t IH, int64_t IW, int64_t KH, int64_t KW, int64_t OH, int64_t OW,
+               int s0, int s1, int p0, int p1, int d0, int d1) {
+    for (int64_t in = 0; in < N; ++in) for (int64_t ioh = 0; ioh < OH; ++ioh) for (int64_t iow = 0; iow < OW; ++iow) for (int64_t iic = 0; iic < IC; ++iic) {
+        const int64_t base = (in*OH*OW + ioh*OW + iow) * (IC*KH*KW) + iic*(KH*KW);
+        const float * src = x + (in*IC + iic) * IH*IW;
+        for (int64_t ikh = 0; ikh < KH; ++ikh) for (int64_t ikw = 0; ikw < KW; ++ikw) {
+            const int64_t iiw = iow*s0 + ikw*d0 - p0, iih = ioh*s1 + ikh*d1 - p1;
+            const float v = (iih < 0 || iih >= IH || iiw < 0 || iiw >= IW) ? 0.0f : src[iih*IW + iiw];
+            if (dst_f16) ((uint16_t *) dst)[base + ikh*KW + ikw] = or_f2h(v); else ((float *) dst)[base + ikh*KW + ikw] = v;
+        }
+    }
+}
+
+void or_pool_1d(const float * x, float * dst, int64_t ncols_in, int64_t nrows, int op, int k) {
+    const int64_t rs = ncols_in / k;
+    for (int64_t r = 0; r < nrows; ++r) {
+        const float * srow = x + r * ncols_in;
+        float * drow = dst + r * rs;
+        int64_t j = 0;
+        for (int64_t i = 0; i < rs; ++i) {
+            drow[i] = op == 1 ? 0.0f : -3.402823466e+38f;
+            for (int ki = 0; ki < k; ++ki, ++j) { if (op == 1) drow[i] += srow[j]; else if (srow[j] > drow[i]) drow[i] = srow[j]; }
+            if (op == 1) drow[i] /= k;
+        }
+    }
+}

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 struct Run { std::vector<llama_token> toks; std::vector<std::vector<float>> logits; double tg_ms = 0, pp_ms = 0; bool ok = false; };
@@ -76,6 +77,31 @@ int main(int argc, char ** argv) {
     Run cpu = run(argv[1], 0, n_prompt, n_gen, nt, fa, nullptr, false, self_mode == 6);                 // 1: repacked weights; 2: plain weights, 3 threads (must be bit-identical)
     // 3: CPU batched prompt vs CPU one-token-at-a-time prompt; 4: B200 batched vs B200 one-at-a-time (baseline run also on the GPU)
     if (self_mode == 4) cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false);
+    // 7: RE-ENTRANCY — three host threads, each with its OWN model + context (three backend instances, three streams, three decode engines with their
+    //    cooperative 148-CTA launches) decode the same sequence concurrently on one device; every thread must reproduce the single-threaded B200 run
+    //    BIT FOR BIT (same kernels, deterministic reductions).  This is what omni_init's LLM / TTS / encoder threads do to a backend (omni.h:287).
+    if (self_mode == 7) {
+        Run base = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false);
+        Run th[3];
+        std::thread ts[3];
+        for (int i = 0; i < 3; ++i) ts[i] = std::thread([&, i] { th[i] = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false, i == 2); });
+        for (auto & t : ts) t.join();
+        bool ok = base.ok; double worst = 0; int bad = 0;
+        for (int i = 0; i < 3 && ok; ++i) {
+            ok = ok && th[i].ok;
+            if (!ok) break;
+            const bool incr = i == 2;                                  // thread 2 feeds the prompt token by token (different graphs in flight at the same time)
+            for (size_t s2 = incr ? 1 : 0; s2 < base.logits.size(); ++s2)
+                for (size_t v = 0; v < base.logits[s2].size(); ++v) {
+                    const double e = std::fabs(base.logits[s2][v] - th[i].logits[s2][v]);
+                    if (!incr && e != 0) ++bad;
+                    worst = std::fmax(worst, e);
+                }
+            if (!incr && th[i].toks != base.toks) ++bad;
+        }
+        printf("{\"mode\": 7, \"threads_ok\": %s, \"bitwise_mismatches\": %d, \"max_abs_diff_incl_incremental_thread\": %.3g}\n", ok ? "true" : "false", bad, worst);
+        return ok && bad == 0 ? 0 : 1;
+    }
     // 5: B200 per-op launches (baseline) vs B200 whole-token decode engine — the plugin reads GGML_B200_DISABLE_ENGINE when a backend is created
     if (self_mode == 5) { setenv("GGML_B200_DISABLE_ENGINE", "1", 1); cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false); setenv("GGML_B200_DISABLE_ENGINE", "0", 1); }
     Run gpu = run(argv[1], cpu_self || self_mode == 2 || self_mode == 3 ? 0 : 999, n_prompt, n_gen, self_mode == 2 ? 3 : nt, fa, &cpu.toks, cpu_self, self_mode == 3 || self_mode == 4 || self_mode == 6);

@@ -46,6 +46,9 @@ def lib():
         L.or_swiglu.restype, L.or_swiglu.argtypes = None, [P, P, P, L64]
         L.or_set_rows_f16.restype, L.or_set_rows_f16.argtypes = None, [P, P, P, L64, L64]
         L.or_soft_max.restype, L.or_soft_max.argtypes = None, [P, P, P, L64, L64, F]
+        L.or_norm.restype, L.or_norm.argtypes = None, [P, P, L64, L64, F]
+        L.or_im2col.restype, L.or_im2col.argtypes = None, [P, P, I] + [L64] * 8 + [I] * 6
+        L.or_pool_1d.restype, L.or_pool_1d.argtypes = None, [P, P, L64, L64, I, I]
         L.or_flash_attn_f16.restype = None
         L.or_flash_attn_f16.argtypes = [P, P, P, P, P] + [L64] * 10 + [F, I]
         _lib = L
@@ -152,3 +155,32 @@ def flash_attn(q: np.ndarray, k: np.ndarray, v: np.ndarray, mask: np.ndarray | N
     lib().or_flash_attn_f16(_p(q), _p(k), _p(v), mp, _p(out), D, n_q, n_head, n_head_kv, n_kv,
                             n_head * D, D, n_kv * D, D, ms, scale, int(f16_acc))
     return out
+
+
+def norm(x: np.ndarray, eps: float) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty_like(x)
+    lib().or_norm(_p(x), _p(y), x.shape[-1], x.size // x.shape[-1], eps)
+    return y
+
+
+def conv_out(i: int, k: int, s: int, p: int, d: int) -> int:       # ggml_calc_conv_output_size
+    return (i + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def im2col(x: np.ndarray, KH: int, KW: int, s0, s1, p0, p1, d0, d1, f16: bool = True) -> np.ndarray:
+    """x F32 [N, IC, IH, IW] -> [N, OH, OW, IC*KH*KW] (F16 by default, as ggml_conv_1d / ggml_conv_2d ask for)."""
+    x = np.ascontiguousarray(x, np.float32)
+    N, IC, IH, IW = x.shape
+    OH, OW = (1 if (IH == 1 and KH == 1) else conv_out(IH, KH, s1, p1, d1)), conv_out(IW, KW, s0, p0, d0)      # 1-D: s1 = p1 = d1 = 0
+    y = np.empty((N, OH, OW, IC * KH * KW), np.float16 if f16 else np.float32)
+    lib().or_im2col(_p(x), _p(y), int(f16), N, IC, IH, IW, KH, KW, OH, OW, s0, s1, p0, p1, d0, d1)
+    return y
+
+
+def pool_1d(x: np.ndarray, op: int, k: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    n = x.shape[-1]
+    y = np.empty(list(x.shape[:-1]) + [n // k], np.float32)
+    lib().or_pool_1d(_p(x), _p(y), n, x.size // n, op, k)
+    return y

@@ -65,6 +65,7 @@ def libs():
             "ggml_flash_attn_ext": (P, [P, P, P, P, P, F, F, F][0:5] + [F, F, F]), "ggml_flash_attn_ext_set_prec": (None, [P, I]),
             "ggml_set_rows": (P, [P, P, P, P]), "ggml_get_rows": (P, [P, P, P]),
             "ggml_soft_max_ext": (P, [P, P, P, F, F]),
+            "ggml_norm": (P, [P, P, F]), "ggml_im2col": (P, [P, P, P, I, I, I, I, I, I, C.c_bool, I]), "ggml_pool_1d": (P, [P, P, I, I, I, I]),
             "ggml_permute": (P, [P, P, I, I, I, I]), "ggml_cont": (P, [P, P]),
             "ggml_view_3d": (P, [P, P, L, L, L, S, S, S]),
             "ggml_quantize_chunk": (S, [I, P, P, L, L, L, P]),
@@ -230,3 +231,31 @@ def flash_attn(q: np.ndarray, k: np.ndarray, v: np.ndarray, mask: np.ndarray | N
         out = g.op("ggml_flash_attn_ext", qp, kt, vt, mt, C.c_float(scale), C.c_float(0.0), C.c_float(0.0))
         g.base.ggml_flash_attn_ext_set_prec(out, 10)              # GGML_PREC_F32, as llama-graph.cpp:1347 does
         return g.run(out, n_threads).reshape(n_q, n_head, D)
+
+
+# ---- APM / VPM encoder ops ----------------------------------------------------------------------------------------
+def norm(x: np.ndarray, eps: float) -> np.ndarray:
+    with Graph() as g:
+        a = g.tensor(F32, [x.shape[-1], x.size // x.shape[-1]], x)
+        return g.run(g.op("ggml_norm", a, C.c_float(eps))).reshape(x.shape)
+
+
+def im2col(x: np.ndarray, KH: int, KW: int, OC: int, s0, s1, p0, p1, d0, d1, is_2d: bool, f16: bool = True) -> np.ndarray:
+    """x F32 [N, IC, IH, IW] (IH = 1 for 1-D) -> [N, OH, OW, IC*KH*KW] through ggml_im2col on the reference CPU backend."""
+    N, IC, IH, IW = x.shape
+    with Graph() as g:
+        if is_2d:
+            k = g.tensor(F16, [KW, KH, IC, OC], np.zeros((OC, IC, KH, KW), np.float16))
+            b = g.tensor(F32, [IW, IH, IC, N], x)
+        else:
+            k = g.tensor(F16, [KW, IC, OC], np.zeros((OC, IC, KW), np.float16))
+            b = g.tensor(F32, [IW, IC, N], x.reshape(N, IC, IW))
+        out = g.op("ggml_im2col", k, b, s0, s1, p0, p1, d0, d1, is_2d, F16 if f16 else F32)
+        r = g.run(out, dtype=np.float16 if f16 else np.float32)
+    return r.reshape(N, -1, r.shape[-2], r.shape[-1]) if is_2d else r.reshape(N, 1, r.shape[-2], r.shape[-1])
+
+
+def pool_1d(x: np.ndarray, op: int, k: int) -> np.ndarray:
+    with Graph() as g:
+        a = g.tensor(F32, [x.shape[-1], x.size // x.shape[-1]], x)
+        return g.run(g.op("ggml_pool_1d", a, op, k, k, 0)).reshape(list(x.shape[:-1]) + [x.shape[-1] // k])

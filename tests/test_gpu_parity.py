@@ -665,3 +665,46 @@ def test_decode_engine_whole_token_matches_oracle(ops, variant):
             for c in ("k_cache", "v_cache"):
                 g, r = lw[c][pos].float().cpu().numpy(), ol[c][pos].astype(np.float32)
                 assert np.abs(g - r).max() <= 2e-3 * max(1.0, np.abs(r).max()), (variant, step, c, np.abs(g - r).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------- APM / VPM encoder ops
+def test_norm_matches_oracle(ops):
+    rng = np.random.default_rng(31)
+    for shape in ((9, 1280), (3, 5, 1152), (2, 4096), (1, 7)):
+        x = (rng.standard_normal(shape) * 3 + 0.5).astype(np.float32)
+        got = ops.norm(dev(x), 1e-5).cpu().numpy()
+        assert np.allclose(got, O.norm(x, 1e-5), rtol=2e-6, atol=3e-6), shape
+
+
+@pytest.mark.parametrize("case", ["whisper_conv1_s1", "whisper_conv2_s2", "siglip_patch14", "pad_dilate_f32"])
+def test_im2col_matches_oracle(ops, case):
+    """bit-exact: a gather plus one F32 -> F16 rounding."""
+    rng = np.random.default_rng(32)
+    if case.startswith("whisper"):
+        s = 1 if case.endswith("s1") else 2
+        x = rng.standard_normal((2, 80, 300)).astype(np.float32)                   # [N, IC = mel bins, IW = frames]
+        k = torch.zeros((16, 80, 3), dtype=torch.float16, device="cuda")
+        got = ops.im2col(k, dev(x), s, 0, 1, 0, 1, 0, False).cpu().numpy()
+        ref = O.im2col(x.reshape(2, 80, 1, 300), 1, 3, s, 0, 1, 0, 1, 0)[:, 0]
+    elif case == "siglip_patch14":
+        x = rng.standard_normal((2, 3, 98, 70)).astype(np.float32)
+        k = torch.zeros((8, 3, 14, 14), dtype=torch.float16, device="cuda")
+        got = ops.im2col(k, dev(x), 14, 14, 0, 0, 1, 1, True).cpu().numpy()
+        ref = O.im2col(x, 14, 14, 14, 14, 0, 0, 1, 1)
+    else:
+        x = rng.standard_normal((1, 5, 33, 29)).astype(np.float32)
+        k = torch.zeros((4, 5, 3, 3), dtype=torch.float16, device="cuda")
+        got = ops.im2col(k, dev(x), 2, 1, 1, 2, 2, 1, True, dtype=torch.float32).cpu().numpy()
+        ref = O.im2col(x, 3, 3, 2, 1, 1, 2, 2, 1, f16=False)
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    assert np.array_equal(got.view(np.uint16 if got.dtype == np.float16 else np.uint32), ref.view(np.uint16 if ref.dtype == np.float16 else np.uint32))
+
+
+def test_pool_1d_matches_oracle(ops):
+    """bit-exact: the sequential f32 sum of the CPU loop, then one division."""
+    rng = np.random.default_rng(33)
+    x = rng.standard_normal((3, 1280, 250)).astype(np.float32)                      # audition.cpp:697: k = s = 5 over the token axis
+    for op in (0, 1):
+        assert np.array_equal(ops.pool_1d(dev(x), op, 5).cpu().numpy(), O.pool_1d(x, op, 5))
+    x16 = x[:1].astype(np.float16)
+    assert np.array_equal(ops.pool_1d(dev(x16), 1, 2).cpu().numpy(), O.pool_1d(x16.astype(np.float32), 1, 2))

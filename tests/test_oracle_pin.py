@@ -99,3 +99,20 @@ def test_flash_attn_matches_reference():
     ref = R.flash_attn(q, k, v, mask, 1 / np.sqrt(D))
     got = O.flash_attn(q, k, v, mask, 1 / np.sqrt(D), f16_acc=True)
     assert np.abs(got - ref).max() <= 3e-3 * np.abs(ref).max()
+
+
+def test_encoder_ops_match_reference():
+    """NORM / IM2COL / POOL_1D (the APM / VPM encoder graphs): oracle/ops_port.c against single-op graphs on the live reference CPU backend."""
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal((7, 1280)) * 3 + 0.5).astype(np.float32)
+    assert np.allclose(O.norm(x, 1e-5), R.norm(x, 1e-5), rtol=2e-6, atol=2e-6)
+    # Whisper conv_1d (k = 3, stride 1 and 2, "same" padding) and SigLip patch embedding (14 x 14, stride 14)
+    a = rng.standard_normal((1, 16, 1, 100)).astype(np.float32)
+    for s in (1, 2):
+        assert np.array_equal(O.im2col(a, 1, 3, s, 0, 1, 0, 1, 0).view(np.uint16), R.im2col(a, 1, 3, 8, s, 0, 1, 0, 1, 0, False).view(np.uint16))
+    img = rng.standard_normal((2, 3, 56, 56)).astype(np.float32)
+    assert np.array_equal(O.im2col(img, 14, 14, 14, 14, 0, 0, 1, 1).view(np.uint16), R.im2col(img, 14, 14, 8, 14, 14, 0, 0, 1, 1, True).view(np.uint16))
+    assert np.array_equal(O.im2col(img, 3, 3, 2, 2, 1, 1, 1, 1, f16=False), R.im2col(img, 3, 3, 8, 2, 2, 1, 1, 1, 1, True, f16=False))
+    t = rng.standard_normal((5, 250)).astype(np.float32)
+    for op in (0, 1):
+        assert np.array_equal(O.pool_1d(t, op, 5), R.pool_1d(t, op, 5))
