@@ -84,7 +84,17 @@ __device__ __forceinline__ void ft_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void ft_ld32_issue(uint32_t taddr, float * v) {      // 32 consecutive columns of this thread's TMEM lane; complete after ft_ld_wait()
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+                 "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+                   "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]),
+                   "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void ft_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void ft_sts16(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ float ft_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }      // 2^x, one MUFU op; 2^-inf = +0
 __device__ __forceinline__ uint32_t ft_pack(float lo, float hi) { const __half2 h = __floats2half2_rn(lo, hi); return *(const uint32_t *) &h; }
 
 // ---------------------------------------------------------------------------------------------------------------- the kernel
@@ -194,27 +204,22 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fa_tc(const FaTcArgs A, const
 #pragma unroll
         for (int i = 0; i < FT_D / 2; ++i) acc[i] = 0.0f;
         float m_run = -INFINITY, l_run = 0.0f, corr_prev = 1.0f;
-        // one 32-column chunk of scores (log2 domain, mask applied) of tile j
-        auto load_chunk = [&](int j, int c, bool plain, float (&t)[32]) {
-            ft_ld32(lane_addr + (j & 1) * FT_BN + hf * 64 + c * 32, t);
-            if (plain) {
+        // mask (log2 domain) applied to this thread's 64 scores of tile j; afterwards t holds log2-domain scores, -inf where masked / out of range
+        auto apply_mask = [&](int j, float (&t)[64]) {
+            const int64_t col0 = (int64_t) j * FT_BN + hf * 64;
+            const bool vec = mrow && ((A.m_nb1 | A.m_nb3 | (int64_t) (uintptr_t) A.mask) % 16) == 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) t[i] *= sl2;
-            } else {
-                const int64_t col0 = (int64_t) j * FT_BN + hf * 64 + c * 32;
+            for (int g = 0; g < 8; ++g) {
+                uint4 mk = make_uint4(0, 0, 0, 0);
+                if (vec && col0 + g * 8 + 8 <= A.n_kv) mk = __ldg((const uint4 *) (mrow + (col0 + g * 8) * 2));
+                else if (mrow) { __half hh[8]; for (int i = 0; i < 8; ++i) hh[i] = col0 + g * 8 + i < A.n_kv ? ((const __half *) mrow)[col0 + g * 8 + i] : __float2half(0.0f); mk = *(const uint4 *) hh; }
+                const __half2 * h2 = (const __half2 *) &mk;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 mk = make_uint4(0, 0, 0, 0);
-                    if (mrow && col0 + g * 8 + 8 <= A.n_kv && ((A.m_nb1 | A.m_nb3 | (int64_t) (uintptr_t) A.mask) % 16) == 0) mk = __ldg((const uint4 *) (mrow + (col0 + g * 8) * 2));
-                    else if (mrow) { __half hh[8]; for (int i = 0; i < 8; ++i) hh[i] = col0 + g * 8 + i < A.n_kv ? ((const __half *) mrow)[col0 + g * 8 + i] : __float2half(0.0f); mk = *(const uint4 *) hh; }
-                    const __half2 * h2 = (const __half2 *) &mk;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 f = __half22float2(h2[i]);
-                        const int e = g * 8 + 2 * i;
-                        t[e]     = (col0 + e     >= A.n_kv || f.x == -INFINITY) ? -INFINITY : fmaf(t[e],     sl2, f.x * 1.44269504088896f);
-                        t[e + 1] = (col0 + e + 1 >= A.n_kv || f.y == -INFINITY) ? -INFINITY : fmaf(t[e + 1], sl2, f.y * 1.44269504088896f);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h2[i]);
+                    const int e = g * 8 + 2 * i;
+                    t[e]     = (col0 + e     >= A.n_kv || f.x == -INFINITY) ? -INFINITY : fmaf(t[e],     sl2, f.x * 1.44269504088896f);
+                    t[e + 1] = (col0 + e + 1 >= A.n_kv || f.y == -INFINITY) ? -INFINITY : fmaf(t[e + 1], sl2, f.y * 1.44269504088896f);
                 }
             }
         };
@@ -224,7 +229,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fa_tc(const FaTcArgs A, const
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 float ov[32];
-                ft_ld32(lane_addr + 2 * FT_BN + hf * 64 + c * 32, ov);
+                ft_ld32_issue(lane_addr + 2 * FT_BN + hf * 64 + c * 32, ov);
+                ft_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], corr, ov[i]);
             }
@@ -233,44 +239,41 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fa_tc(const FaTcArgs A, const
         };
         for (int j = 0; j < n_visit; ++j) {
             const uint32_t b = j & 1;
-            const bool plain = j < n_plain;
+            const bool plain = j < n_plain && A.scale > 0.0f;
             ft_mbar_wait(s_full + 8 * b, (j >> 1) & 1);
             ft_fence_after();
-            // ---- pass 1: maximum of this thread's 64 columns (4 independent chains), exchanged with the other half of the row ------------------
+            // ---- this thread's 64 scores: ONE round trip to TMEM, kept in registers for both passes; the S buffer is free again right away ----------
+            float t[64];
+            ft_ld32_issue(lane_addr + b * FT_BN + hf * 64, t);
+            ft_ld32_issue(lane_addr + b * FT_BN + hf * 64 + 32, t + 32);
+            ft_ld_wait();
+            ft_fence_before();
+            ft_mbar_arrive(s_empty + 8 * b);                                    // Q.K of tile j + 2 may overwrite it
+            if (!plain) apply_mask(j, t);
+            // ---- pass 1: maximum (4 independent chains), exchanged with the thread that owns the other half of the row (64-thread named barrier) -----
             float mx4[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float t[32];
-                load_chunk(j, c, plain, t);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], t[i]);
-            }
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], t[i]);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * (plain ? sl2 : 1.0f);     // mask-free tiles keep RAW scores: the positive scale is folded in here and below
             asm volatile("st.shared.f32 [%0], %1;" :: "r"(xch + ((b * 2 + hf) * FT_BM + r) * 4), "f"(mx) : "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");                      // the 8 softmax warps only
+            asm volatile("bar.sync %0, 64;" :: "r"(1 + quarter) : "memory");    // warps w and w + 4 only
             float mo; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mo) : "r"(xch + ((b * 2 + (hf ^ 1)) * FT_BM + r) * 4));
             const float m_new = fmaxf(m_run, fmaxf(mx, mo));
-            const float corr = m_new == -INFINITY ? 1.0f : exp2f(m_run - m_new);
+            const float m_safe = m_new == -INFINITY ? 0.0f : m_new;              // a row with nothing unmasked yet: every p below is 2^-inf = 0
+            const float corr = ft_ex2(m_run - m_safe);
             // ---- the previous tile's P.V result is folded in while the tensor core is busy with this tile's neighbours --------------------------
-            if (j > 0) accumulate(j - 1, corr_prev);                             // (also implies p_empty: P.V of tile j - 1 has consumed the P buffer)
+            if (j > 0) accumulate(j - 1, corr_prev);                             // (also implies that P.V of tile j - 1 has consumed the P buffer)
             // ---- pass 2: p = exp2(t - m) -> F16 P tile (A operand of P.V) ------------------------------------------------------------------------
             float ls4[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float t[32];
-                load_chunk(j, c, plain, t);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float p = (t[i] == -INFINITY || m_new == -INFINITY) ? 0.0f : exp2f(t[i] - m_new);
-                    t[i] = p; ls4[i & 3] += p;
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g)                                     // 8 positions = one 16-byte core-matrix row: K chunk 8 hf + 4 c + g of row r
-                    ft_sts16(p_s + (uint32_t) (hf * 8 + c * 4 + g) * FT_LBO + (uint32_t) (r >> 3) * FT_SBO + (uint32_t) (r & 7) * 16,
-                             make_uint4(ft_pack(t[8 * g], t[8 * g + 1]), ft_pack(t[8 * g + 2], t[8 * g + 3]), ft_pack(t[8 * g + 4], t[8 * g + 5]), ft_pack(t[8 * g + 6], t[8 * g + 7])));
+            for (int i = 0; i < 64; ++i) {
+                const float p = plain ? ft_ex2(fmaf(t[i], sl2, -m_safe)) : ft_ex2(t[i] - m_safe);
+                t[i] = p; ls4[i & 3] += p;
             }
-            ft_fence_before();
-            ft_mbar_arrive(s_empty + 8 * b);                                    // the S buffer may be overwritten by Q.K of tile j + 2
+#pragma unroll
+            for (int g = 0; g < 8; ++g)                                         // 8 positions = one 16-byte core-matrix row: K chunk 8 hf + g of row r
+                ft_sts16(p_s + (uint32_t) (hf * 8 + g) * FT_LBO + (uint32_t) (r >> 3) * FT_SBO + (uint32_t) (r & 7) * 16,
+                         make_uint4(ft_pack(t[8 * g], t[8 * g + 1]), ft_pack(t[8 * g + 2], t[8 * g + 3]), ft_pack(t[8 * g + 4], t[8 * g + 5]), ft_pack(t[8 * g + 6], t[8 * g + 7])));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores of P before the tensor core (async proxy) reads them
             ft_mbar_arrive(p_full);
             l_run = l_run * corr + (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]); m_run = m_new; corr_prev = corr;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fa_tc(const FaTcArgs A, const
         if (n_visit > 0) accumulate(n_visit - 1, corr_prev);
         // combine the two halves' partial row sums (same running maximum), normalise, store this thread's 64 dims
         asm volatile("st.shared.f32 [%0], %1;" :: "r"(xch + ((4 + hf) * FT_BM + r) * 4), "f"(l_run) : "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" :: "r"(1 + quarter) : "memory");
         float lo; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(xch + ((4 + (hf ^ 1)) * FT_BM + r) * 4));
         const float l_tot = l_run + lo;
         if (live) {
