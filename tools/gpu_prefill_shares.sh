@@ -2,7 +2,7 @@
 # kernel shares of one prefill pass (2048 tokens, 36 layers) through the C-ABI mirror: ncu launch list of bench.py's prefill leg
 mkdir -p gpurun_out
 timeout 800 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ --csv --log-file gpurun_out/launches_prefill.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_prefill.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-plugin-e2e > gpurun_out/ncu_prefill.log 2>&1
 tail -1 gpurun_out/ncu_prefill.log | cut -c1-200
 python - <<'PY'
 import csv, collections
