@@ -62,23 +62,42 @@ struct QkvPostArgs {
     float eps, theta_scale, freq_scale, ext_factor, attn_factor, corr0, corr1;
 };
 
-// warp per (token, head); heads [0, n_head) = Q (in place), [n_head, n_head + n_head_kv) = K -> cache, then V -> cache
+// (cos, sin) * mscale of pair p at position posf: the oracle's theta chain (theta *= theta_scale per pair, ops.cpp ggml_rope_cache_init), YaRN mix, accurate sincosf
+__device__ __forceinline__ float2 rope_cs(float posf, int p, float theta_scale, float freq_scale, float ext_factor, float attn_factor, float corr0, float corr1) {
+    float theta = posf;
+    for (int j = 0; j < p; ++j) theta = __fmul_rn(theta, theta_scale);
+    float th = freq_scale * theta, ms = attn_factor;
+    if (ext_factor != 0.0f) {
+        const float yv = ((float) p - corr0) / fmaxf(0.001f, corr1 - corr0);
+        const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * ext_factor;
+        th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(theta, ramp));
+        ms *= 1.0f + 0.1f * logf(1.0f / freq_scale);
+    }
+    float sn, cs; sincosf(th, &sn, &cs);
+    return make_float2(cs * ms, sn * ms);
+}
+
+// CTA per token: the D/2 rotation angles of the token are computed ONCE into shared memory (every head of the token rotates by the same angles: per-element
+// recomputation of the 63-step theta chain + sincosf was 3/4 of this kernel's time), then the warps walk the token's heads:
+// heads [0, n_head) = Q (in place), [n_head, n_head + n_head_kv) = K -> cache, then V -> cache
 template <int D>
-__global__ void __launch_bounds__(128) k_qkv_post(const QkvPostArgs A) {
+__global__ void __launch_bounds__(256) k_qkv_post(const QkvPostArgs A) {
     constexpr int E = D / 32;                                  // elements per lane, contiguous
-    const int lane = threadIdx.x & 31;
-    const int h = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int64_t t = blockIdx.y;
+    __shared__ float2 tab[D / 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t t = blockIdx.x;
+    if (threadIdx.x < D / 2) tab[threadIdx.x] = rope_cs((float) A.pos[t], threadIdx.x, A.theta_scale, A.freq_scale, A.ext_factor, A.attn_factor, A.corr0, A.corr1);
+    __syncthreads();
     const int nqk = A.n_head + A.n_head_kv;
-    if (h >= nqk + A.n_head_kv) return;
     const int64_t row = A.idx_i64 ? ((const int64_t *) A.idx)[t] : (int64_t) ((const int32_t *) A.idx)[t];
+    for (int h = warp; h < nqk + A.n_head_kv; h += nw) {
     if (h >= nqk) {                                            // V head: convert and store
         const int hv = h - nqk;
         const float * src = A.v + t * A.v_tok + (int64_t) hv * D + lane * E;
         __half * dst = (__half *) (A.vc + row * A.vc_row) + (int64_t) hv * D + lane * E;
 #pragma unroll
         for (int i = 0; i < E; ++i) dst[i] = __float2half_rn(src[i]);
-        return;
+        continue;
     }
     const bool is_q = h < A.n_head;
     const int hh = is_q ? h : h - A.n_head;
@@ -97,40 +116,19 @@ __global__ void __launch_bounds__(128) k_qkv_post(const QkvPostArgs A) {
         for (int i = 0; i < E; ++i) v[i] = __fmul_rn(__fmul_rn(v[i], scale), w[lane * E + i]);
     }
     // rotation: neox pairs (p, p + D/2) live in lanes (l, l + 16); norm pairs (2p, 2p + 1) live inside a lane
-    const float posf = (float) A.pos[t];
     float out[E];
     if (A.mode & 2) {
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            const int p = (lane & 15) * E + i;
-            float theta = posf;
-            for (int j = 0; j < p; ++j) theta = __fmul_rn(theta, A.theta_scale);
-            float th = A.freq_scale * theta, ms = A.attn_factor;
-            if (A.ext_factor != 0.0f) {
-                const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
-                const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
-                th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(theta, ramp));
-                ms *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
-            }
-            float sn, cs; sincosf(th, &sn, &cs); sn *= ms; cs *= ms;
+            const float2 cs = tab[(lane & 15) * E + i];
             const float other = __shfl_xor_sync(0xffffffffu, v[i], 16);
-            out[i] = lane < 16 ? v[i] * cs - other * sn : other * sn + v[i] * cs;
+            out[i] = lane < 16 ? v[i] * cs.x - other * cs.y : other * cs.y + v[i] * cs.x;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < E; i += 2) {
-            const int p = (lane * E + i) / 2;
-            float theta = posf;
-            for (int j = 0; j < p; ++j) theta = __fmul_rn(theta, A.theta_scale);
-            float th = A.freq_scale * theta, ms = A.attn_factor;
-            if (A.ext_factor != 0.0f) {
-                const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
-                const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
-                th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(theta, ramp));
-                ms *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
-            }
-            float sn, cs; sincosf(th, &sn, &cs); sn *= ms; cs *= ms;
-            out[i] = v[i] * cs - v[i + 1] * sn; out[i + 1] = v[i] * sn + v[i + 1] * cs;
+            const float2 cs = tab[(lane * E + i) / 2];
+            out[i] = v[i] * cs.x - v[i + 1] * cs.y; out[i + 1] = v[i] * cs.y + v[i + 1] * cs.x;
         }
     }
     if (is_q) {
@@ -141,6 +139,7 @@ __global__ void __launch_bounds__(128) k_qkv_post(const QkvPostArgs A) {
         __half * dst = (__half *) (A.kc + row * A.kc_row) + (int64_t) hh * D + lane * E;
 #pragma unroll
         for (int i = 0; i < E; ++i) dst[i] = __float2half_rn(out[i]);
+    }
     }
 }
 
@@ -185,10 +184,8 @@ extern "C" int b200_qkv_post(float * q, const float * k, const float * v, const 
     const float lo = floorf(yarn_corr_dim_f(p->n_dims, p->n_ctx_orig, p->beta_fast, p->freq_base));
     const float hi = ceilf (yarn_corr_dim_f(p->n_dims, p->n_ctx_orig, p->beta_slow, p->freq_base));
     A.corr0 = lo < 0 ? 0 : lo; A.corr1 = hi > p->n_dims - 1 ? p->n_dims - 1 : hi;
-    const int heads = n_head + 2 * n_head_kv;
-    dim3 grid((unsigned) ((heads + 3) / 4), (unsigned) n_tok);
-    if (head_dim == 128) k_qkv_post<128><<<grid, 128, 0, (cudaStream_t) stream>>>(A);
-    else                 k_qkv_post<64><<<grid, 128, 0, (cudaStream_t) stream>>>(A);
+    if (head_dim == 128) k_qkv_post<128><<<(unsigned) n_tok, 256, 0, (cudaStream_t) stream>>>(A);
+    else                 k_qkv_post<64><<<(unsigned) n_tok, 256, 0, (cudaStream_t) stream>>>(A);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -85,12 +85,36 @@ __global__ void __launch_bounds__(256) k_rms_norm(const NormArgs A) {
     const int64_t n = A.x.ne[0];
     const int tid = WARP_ROWS ? lane : threadIdx.x, nt = WARP_ROWS ? 32 : blockDim.x;
     const bool v4 = (n % 4 == 0) && (((uintptr_t) x | (uintptr_t) y) % 16 == 0);
+    const int64_t wn = A.has_w ? A.w.ne[0] : 1, an = A.has_add ? A.add.ne[0] : 1;
+    // block-per-row fast path (rows of up to 4096: every prefill norm): the row is read ONCE, 4 x 16 bytes per thread stay in registers between the sum of
+    // squares and the scaling (the generic path below re-reads it: 3 passes over memory instead of 2)
+    if (!WARP_ROWS && v4 && n <= 16 * 256 && (!w || (wn == n && (uintptr_t) w % 16 == 0)) && (!ad || (an == n && (uintptr_t) ad % 16 == 0))) {
+        float4 r[4];
+        float s2 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t i = ((int64_t) c * 256 + tid) * 4;
+            r[c] = i < n ? *(const float4 *) (x + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            s2 += r[c].x * r[c].x + r[c].y * r[c].y + r[c].z * r[c].z + r[c].w * r[c].w;
+        }
+        s2 = block_sum(s2, red);
+        const float sc = 1.0f / sqrtf(s2 / (float) n + A.eps);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t i = ((int64_t) c * 256 + tid) * 4;
+            if (i >= n) continue;
+            float4 v = make_float4(__fmul_rn(r[c].x, sc), __fmul_rn(r[c].y, sc), __fmul_rn(r[c].z, sc), __fmul_rn(r[c].w, sc));
+            if (w)  { const float4 q = *(const float4 *) (w + i);  v = make_float4(__fmul_rn(v.x, q.x), __fmul_rn(v.y, q.y), __fmul_rn(v.z, q.z), __fmul_rn(v.w, q.w)); }
+            if (ad) { const float4 q = *(const float4 *) (ad + i); v = make_float4(__fadd_rn(v.x, q.x), __fadd_rn(v.y, q.y), __fadd_rn(v.z, q.z), __fadd_rn(v.w, q.w)); }
+            *(float4 *) (y + i) = v;
+        }
+        return;
+    }
     float ss = 0.0f;
     if (v4) for (int64_t i = tid * 4; i < n; i += nt * 4) { const float4 v = *(const float4 *) (x + i); ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
     else    for (int64_t i = tid; i < n; i += nt) { const float v = x[i]; ss += v * v; }
     ss = WARP_ROWS ? warp_sum(ss) : block_sum(ss, red);
     const float scale = 1.0f / sqrtf(ss / (float) n + A.eps);
-    const int64_t wn = A.has_w ? A.w.ne[0] : 1, an = A.has_add ? A.add.ne[0] : 1;
     for (int64_t i = tid; i < n; i += nt) {
         float v = __fmul_rn(x[i], scale);                                   // separate roundings, like the three CPU ops
         if (w)  v = __fmul_rn(v, w[wn == n ? i : i % wn]);
@@ -135,6 +159,43 @@ __global__ void __launch_bounds__(256) k_rope(const RopeArgs A, int64_t total_pa
         const float x0 = x[a], x1 = x[b];
         y[a] = x0 * cs - x1 * sn;
         y[b] = x0 * sn + x1 * cs;
+    }
+}
+
+// CTA = one (token, batch) slice: every head of the token rotates by the same n_dims/2 angles, so they are computed ONCE per CTA into shared memory
+// (the per-pair theta chain + sincosf was most of k_rope's time at prefill sizes) and the threads then stream the slice's heads.  Same arithmetic.
+constexpr int ROPE_TAB = 256;                                                // rotation pairs held in shared memory
+__global__ void __launch_bounds__(256) k_rope_rows(const RopeArgs A) {
+    __shared__ float2 tab[ROPE_TAB];
+    const int64_t i2 = blockIdx.x, i3 = blockIdx.y;
+    const int np = A.n_dims / 2;
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        float theta = (float) A.pos[i2];
+        for (int j = 0; j < p; ++j) theta = __fmul_rn(theta, A.theta_scale);
+        const float ffv = A.ff ? A.ff[p] : 1.0f;
+        const float th_extrap = theta / ffv;
+        float th = __fmul_rn(A.freq_scale, th_extrap), mscale = A.attn_factor;
+        if (A.ext_factor != 0.0f) {
+            const float yv = ((float) p - A.corr0) / fmaxf(0.001f, A.corr1 - A.corr0);
+            const float ramp = (1.0f - fminf(1.0f, fmaxf(0.0f, yv))) * A.ext_factor;
+            th = __fadd_rn(__fmul_rn(th, 1.0f - ramp), __fmul_rn(th_extrap, ramp));
+            mscale *= 1.0f + 0.1f * logf(1.0f / A.freq_scale);
+        }
+        float sn, cs; sincosf(th, &sn, &cs);
+        tab[p] = make_float2(cs * mscale, sn * mscale);
+    }
+    __syncthreads();
+    const int64_t half_n = A.x.ne[0] / 2, per_slice = half_n * A.x.ne[1];
+    for (int64_t g = threadIdx.x; g < per_slice; g += blockDim.x) {
+        const int64_t p = g % half_n, i1 = g / half_n;
+        const float * x = (const float *) (A.x.data + i1 * A.x.nb[1] + i2 * A.x.nb[2] + i3 * A.x.nb[3]);
+        float * y = (float *) (A.dst.data + i1 * A.dst.nb[1] + i2 * A.dst.nb[2] + i3 * A.dst.nb[3]);
+        if (2 * p >= A.n_dims) { const int64_t i = A.n_dims + 2 * (p - np); y[i] = x[i]; y[i + 1] = x[i + 1]; continue; }
+        const float2 cs = tab[p];
+        const int64_t a = (A.mode & 2) ? p : 2 * p, b = (A.mode & 2) ? p + np : 2 * p + 1;
+        const float x0 = x[a], x1 = x[b];
+        y[a] = x0 * cs.x - x1 * cs.y;
+        y[b] = x0 * cs.y + x1 * cs.x;
     }
 }
 
@@ -361,7 +422,10 @@ extern "C" int b200_rope(const b200_tensor * x, const int32_t * pos, const float
     A.corr0 = lo < 0 ? 0 : lo; A.corr1 = hi > p->n_dims - 1 ? p->n_dims - 1 : hi;
     const int64_t total = nelem(x) / 2;
     if (total == 0) return B200_OK;
-    k_rope<<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
+    if (p->n_dims / 2 <= ROPE_TAB && x->ne[2] <= 0x7fffffff && x->ne[3] <= 65535 && x->ne[1] * x->ne[0] >= 512)
+        k_rope_rows<<<dim3((unsigned) x->ne[2], (unsigned) x->ne[3]), 256, 0, (cudaStream_t) stream>>>(A);
+    else
+        k_rope<<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -534,9 +598,8 @@ struct Im2colArgs {
 };
 // thread = one element of dst [N][OH][OW][IC*KH*KW] (the innermost index is the contiguous one: coalesced stores; the gathers hit a KW-wide window)
 __global__ void __launch_bounds__(256) k_im2col(const Im2colArgs A, int64_t total) {
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
     const int64_t ckk = A.IC * A.KH * A.KW;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {      // grid_for caps the grid
     const int64_t c = i % ckk, r = i / ckk;
     const int64_t ikw = c % A.KW, ikh = (c / A.KW) % A.KH, iic = c / (A.KW * A.KH);
     const int64_t iow = r % A.OW, ioh = (r / A.OW) % A.OH, in = r / (A.OW * A.OH);
@@ -544,13 +607,13 @@ __global__ void __launch_bounds__(256) k_im2col(const Im2colArgs A, int64_t tota
     float v = 0.0f;
     if (iih >= 0 && iih < A.IH && iiw >= 0 && iiw < A.IW) v = *(const float *) (A.x + in * A.x_nb_n + iic * A.x_nb_c + iih * A.x_nb_h + iiw * 4);
     if (A.dst_f16) ((__half *) A.dst)[i] = __float2half_rn(v); else ((float *) A.dst)[i] = v;
+    }
 }
 
 struct PoolArgs { const char * x; float * dst; int x_f16, op, k; int64_t rs, x_row_bytes; };
 // thread = one output element: rows of the source are nb[1] apart and walked back to back, exactly as the CPU loop does (k == stride, no padding)
 __global__ void __launch_bounds__(256) k_pool_1d(const PoolArgs A, int64_t total) {
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
     const int64_t row = i / A.rs, o = i % A.rs;
     const char * src = A.x + row * A.x_row_bytes;
     float acc = A.op == 0 ? -3.402823466e+38f : 0.0f;                     // GGML_OP_POOL_MAX = 0, GGML_OP_POOL_AVG = 1
@@ -560,6 +623,7 @@ __global__ void __launch_bounds__(256) k_pool_1d(const PoolArgs A, int64_t total
         if (A.op == 0) { if (v > acc) acc = v; } else acc += v;
     }
     A.dst[i] = A.op == 0 ? acc : __fdiv_rn(acc, (float) A.k);
+    }
 }
 
 } // namespace b200
