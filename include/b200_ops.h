@@ -206,6 +206,17 @@ B200_API int  b200_decoder_n_phases(void * handle);
 B200_API int  b200_decoder_profile(void * handle, int32_t n_kv, unsigned long long * host_out, void * stream);
 B200_API void b200_decoder_destroy(void * handle);
 
+/* ---- producers that feed a tensor-core MUL_MAT directly: the [n, k] result is written as that MUL_MAT's prepared F16 activation tiles (into ITS scratch buffer)
+ *      instead of (or besides) F32, and the MUL_MAT is then called with B200_MM_REUSE_ACT — no separate conversion pass (k_x_to_f16_tiles), no F32 round trip.
+ *      (The reference converts / quantises the activations inside every MUL_MAT: quantize_mmq_q8_1, ggml-cuda/quantize.cu:50-146.)
+ * b200_rms_norm_tiles  : RMS_NORM(x) [* w] of a 2-D x [k, n], 1024 < k <= 4096, k % 64 == 0; dst->data may be NULL (tiles only)
+ * b200_glu_tiles       : GLU(gate, up) of two contiguous 2-D F32 matrices, k % 64 == 0 (tiles only: the ffn_down MUL_MAT is h's only reader)
+ * b200_flash_attn_tiles: FLASH_ATTN_EXT whose [n_q, n_head * 128] result only feeds wo; tcgen05 kernel only, else B200_ERR_UNSUPPORTED; dst->data is not written */
+B200_API int b200_rms_norm_tiles(const b200_tensor * x, const b200_tensor * w, const b200_tensor * dst, void * tiles, float eps, void * stream);
+B200_API int b200_glu_tiles(int op, const b200_tensor * gate, const b200_tensor * up, void * tiles, void * stream);
+B200_API int b200_flash_attn_tiles(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst,
+                                   float scale, void * scratch, size_t scratch_bytes, void * tiles, void * stream);
+
 /* ---- ops of the APM (Whisper) / VPM (SigLip) encoder graphs -----------------------------------------------------------
  * b200_norm   : GGML_OP_NORM, y = (x - mean) / sqrt(var + eps) per row        replaces norm_f32 (ggml-cuda/norm.cu:5); CPU ggml-cpu/ops.cpp:3450-3495
  * b200_im2col : GGML_OP_IM2COL (ggml_conv_1d / ggml_conv_2d), F32 input -> F16 or F32 [IC*KH*KW, OW, OH, N]; `kernel` only supplies KW / KH

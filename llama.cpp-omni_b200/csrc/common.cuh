@@ -101,4 +101,12 @@ inline int sm_count() {
     return n;
 }
 
+
+// ---- prepared activations of the tensor-core GEMMs (mmq_tc.cu): F16, tiled [row / 256][k / 64][32 KB], each tile in the canonical K-major UMMA layout (8-row x
+// 16-byte core matrices; K direction 4 KB apart, row groups 128 B apart).  Producers that feed a MUL_MAT (RMS_NORM, GLU, FLASH_ATTN_EXT) can write this layout
+// directly instead of F32 + a conversion pass.  Byte offset of the 16-byte core-matrix row that holds columns [col, col + 8) of `row` (col % 8 == 0):
+__host__ __device__ inline int64_t act_tile_off(int64_t row, int64_t col, int64_t k) {
+    return ((row >> 8) * (k >> 6) + (col >> 6)) * 32768 + ((col & 63) >> 3) * 4096 + ((row & 255) >> 3) * 128 + (row & 7) * 16;
+}
+
 } // namespace b200

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(FP_THREADS) k_fa_prefill(const FaPArgs A) {
 // the tcgen05 / TMEM / TMA kernel (fa_tc.cu) takes head size 128 with an F16 K/V cache; this file's mma.sync kernel keeps head size 64 and odd layouts
 bool fa_tc_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst);
 int  fa_tc(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
-           const int32_t * kv_tiles, const int32_t * kv_plain, cudaStream_t st);
+           const int32_t * kv_tiles, const int32_t * kv_plain, void * tiles, cudaStream_t st);
 
 bool fa_prefill_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst) {
     if (q->ne[1] < 16) return false;                                   // few query tokens: the split-KV decode kernel (flash_attn.cu)
@@ -246,7 +246,7 @@ size_t fa_prefill_scratch_bytes(const b200_tensor * q, const b200_tensor * mask_
 }
 
 int fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
-               void * scratch, cudaStream_t st) {
+               void * scratch, cudaStream_t st, void * tiles) {
     static smem_mask_t done128{0}, done64{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_fa_prefill<128>, 4 * FP_BN * 128 * 2, done128));
     B200_CUDA_TRY(ensure_dyn_smem(k_fa_prefill<64>, 4 * FP_BN * 64 * 2, done64));
@@ -268,7 +268,8 @@ int fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor *
             A.kv_tiles = kmax; A.kv_plain = kplain;
         }
     }
-    if (fa_tc_supported(q, k, v, mask, dst)) return fa_tc(q, k, v, mask, dst, scale, A.kv_tiles, A.kv_plain, st);
+    if (fa_tc_supported(q, k, v, mask, dst)) return fa_tc(q, k, v, mask, dst, scale, A.kv_tiles, A.kv_plain, tiles, st);
+    if (tiles) return B200_ERR_UNSUPPORTED;                            // only the tcgen05 kernel writes activation tiles
     const dim3 grid((unsigned) n_q_tiles, (unsigned) A.n_head, (unsigned) q->ne[3]);
     if (q->ne[0] == 128) k_fa_prefill<128><<<grid, FP_THREADS, 4 * FP_BN * 128 * 2, st>>>(A);
     else                 k_fa_prefill<64><<<grid, FP_THREADS, 4 * FP_BN * 64 * 2, st>>>(A);

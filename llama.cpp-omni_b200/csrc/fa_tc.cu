@@ -40,6 +40,7 @@ struct FaTcArgs {
     int kc_pos, kc_head, kc_b;                                             // which TMA coordinate (1..3) carries the position / kv head / batch index
     float scale;
     const int32_t * kv_tiles; const int32_t * kv_plain;                    // per (mask batch, query tile), in units of 64 positions (k_fa_kvmax); null = visit all / mask all
+    uint8_t * tiles;                                                       // optional: the [n_q, n_head * 128] result as F16 activation tiles for the wo MUL_MAT (act_tile_off) instead of F32
 };
 
 // ---------------------------------------------------------------------------------------------------------------- PTX helpers
@@ -284,7 +285,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fa_tc(const FaTcArgs A, const
         asm volatile("bar.sync %0, 64;" :: "r"(1 + quarter) : "memory");
         float lo; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(xch + ((4 + (hf ^ 1)) * FT_BM + r) * 4));
         const float l_tot = l_run + lo;
-        if (live) {
+        if (A.tiles) {                                                          // straight into the next MUL_MAT's operand layout (rows past n_q: zeros)
+            const float inv = (l_tot == 0.0f || !live) ? 0.0f : 1.0f / l_tot;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8)
+                *(uint4 *) (A.tiles + act_tile_off(q0 + r, (int64_t) head * FT_D + hf * 64 + c8 * 8, A.n_head * FT_D)) =
+                    make_uint4(ft_pack(acc[8 * c8] * inv, acc[8 * c8 + 1] * inv), ft_pack(acc[8 * c8 + 2] * inv, acc[8 * c8 + 3] * inv),
+                               ft_pack(acc[8 * c8 + 4] * inv, acc[8 * c8 + 5] * inv), ft_pack(acc[8 * c8 + 6] * inv, acc[8 * c8 + 7] * inv));
+        } else if (live) {
             const float inv = l_tot == 0.0f ? 0.0f : 1.0f / l_tot;
             float * out = (float *) (A.dst + (int64_t) head * A.d_nb1 + (q0 + r) * A.d_nb2 + (int64_t) ib * A.d_nb3) + hf * 64;
 #pragma unroll
@@ -338,7 +346,7 @@ bool fa_tc_supported(const b200_tensor * q, const b200_tensor * k, const b200_te
 }
 
 int fa_tc(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
-          const int32_t * kv_tiles, const int32_t * kv_plain, cudaStream_t st) {
+          const int32_t * kv_tiles, const int32_t * kv_plain, void * tiles, cudaStream_t st) {
     static smem_mask_t done{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_fa_tc, FT_SMEM, done));
     FaTcArgs A = {};
@@ -350,7 +358,7 @@ int fa_tc(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, c
     A.q_nb1 = q->nb[1]; A.q_nb2 = q->nb[2]; A.q_nb3 = q->nb[3]; A.d_nb1 = dst->nb[1]; A.d_nb2 = dst->nb[2]; A.d_nb3 = dst->nb[3];
     A.n_q = q->ne[1]; A.n_kv = k->ne[1]; A.n_head = q->ne[2]; A.n_head_kv = k->ne[2]; A.k_ne3 = k->ne[3]; A.scale = scale; A.m_ne3 = 1;
     if (mask) { A.m_nb1 = mask->nb[1]; A.m_nb3 = mask->nb[3]; A.m_ne3 = mask->ne[3]; }
-    A.kv_tiles = kv_tiles; A.kv_plain = kv_plain;
+    A.kv_tiles = kv_tiles; A.kv_plain = kv_plain; A.tiles = (uint8_t *) tiles;
     const dim3 grid((unsigned) ((A.n_q + FT_BM - 1) / FT_BM), (unsigned) A.n_head, (unsigned) q->ne[3]);
     k_fa_tc<<<grid, FT_THREADS, FT_SMEM, st>>>(A, kmap, vmap);
     B200_LAUNCH_CHECK();

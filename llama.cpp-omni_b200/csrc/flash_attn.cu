@@ -222,7 +222,7 @@ static int fa_launch(const FaArgs & A, int G, int64_t nz, cudaStream_t st) {
 bool   fa_prefill_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst);
 size_t fa_prefill_scratch_bytes(const b200_tensor * q, const b200_tensor * mask_or_null, int64_t m_ne3);
 int    fa_prefill(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale,
-                  void * scratch, cudaStream_t st);
+                  void * scratch, cudaStream_t st, void * tiles);
 
 } // namespace b200
 
@@ -266,16 +266,31 @@ extern "C" size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b20
     return dec;
 }
 
+static int flash_attn_impl(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale, float max_bias,
+                           float logit_softcap, void * scratch, size_t scratch_bytes, void * tiles, void * stream);
 extern "C" int b200_flash_attn(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask,
                                const b200_tensor * dst, float scale, float max_bias, float logit_softcap, void * scratch,
                                size_t scratch_bytes, void * stream) {
+    return flash_attn_impl(q, k, v, mask, dst, scale, max_bias, logit_softcap, scratch, scratch_bytes, nullptr, stream);
+}
+// The [n_q, n_head * 128] result handed to the MUL_MAT that follows (wo) as prepared F16 activation tiles in `tiles` (that MUL_MAT's scratch; call it with
+// B200_MM_REUSE_ACT) instead of F32 in dst->data (which is not written).  Only the tcgen05 prefill kernel does this: B200_ERR_UNSUPPORTED otherwise, and the
+// caller falls back to b200_flash_attn + the MUL_MAT's own conversion pass.  `scratch` (mask pre-scan) must not overlap `tiles`.
+extern "C" int b200_flash_attn_tiles(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask,
+                                     const b200_tensor * dst, float scale, void * scratch, size_t scratch_bytes, void * tiles, void * stream) {
+    if (!tiles || (uintptr_t) tiles % 16 || q->ne[3] != 1) return B200_ERR_UNSUPPORTED;
+    return flash_attn_impl(q, k, v, mask, dst, scale, 0.0f, 0.0f, scratch, scratch_bytes, tiles, stream);
+}
+static int flash_attn_impl(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale, float max_bias,
+                           float logit_softcap, void * scratch, size_t scratch_bytes, void * tiles, void * stream) {
     if (!b200_flash_attn_supported(q, k, v, mask, dst) || max_bias != 0.0f || logit_softcap != 0.0f) return B200_ERR_UNSUPPORTED;
     const int64_t nz = q->ne[1] * q->ne[3];
     if (nz == 0 || q->ne[2] == 0) return B200_OK;
     if (k->ne[1] > 0 && fa_prefill_supported(q, k, v, mask, dst)) {
         const bool have = scratch && scratch_bytes >= fa_prefill_scratch_bytes(q, mask, mask ? mask->ne[3] : 1) && (uintptr_t) scratch % 4 == 0;
-        return fa_prefill(q, k, v, mask, dst, scale, have ? scratch : nullptr, (cudaStream_t) stream);
+        return fa_prefill(q, k, v, mask, dst, scale, have ? scratch : nullptr, (cudaStream_t) stream, tiles);
     }
+    if (tiles) return B200_ERR_UNSUPPORTED;
     if (nz > 65535) return B200_ERR_UNSUPPORTED;
     const FaPlan P = fa_plan(nz, k->ne[1], q->ne[2], k->ne[2]);
     FaArgs A = {};

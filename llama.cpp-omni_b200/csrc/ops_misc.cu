@@ -58,7 +58,7 @@ __device__ __forceinline__ void st_any(char * p, int type, float v) {
 // ================================================================== RMS_NORM (+ MUL + ADD) ====================================
 // One row per warp (ne0 <= 1024) or per CTA.  Sum of squares in f32 with a fixed tree order (the oracle sums in f64; the
 // difference is far below the 1e-7 NMSE the reference's own backend test allows).
-struct NormArgs { T4 x, w, add, dst; float eps; int has_w, has_add; int64_t rows; };
+struct NormArgs { T4 x, w, add, dst; float eps; int has_w, has_add; int64_t rows; uint8_t * tiles; int write_f32; };     // tiles: optional F16 activation tiles (act_tile_off)
 
 __device__ __forceinline__ float block_sum(float v, float * smem) {      // smem: 32 floats
     v = warp_sum(v);
@@ -106,7 +106,11 @@ __global__ void __launch_bounds__(256) k_rms_norm(const NormArgs A) {
             float4 v = make_float4(__fmul_rn(r[c].x, sc), __fmul_rn(r[c].y, sc), __fmul_rn(r[c].z, sc), __fmul_rn(r[c].w, sc));
             if (w)  { const float4 q = *(const float4 *) (w + i);  v = make_float4(__fmul_rn(v.x, q.x), __fmul_rn(v.y, q.y), __fmul_rn(v.z, q.z), __fmul_rn(v.w, q.w)); }
             if (ad) { const float4 q = *(const float4 *) (ad + i); v = make_float4(__fadd_rn(v.x, q.x), __fadd_rn(v.y, q.y), __fadd_rn(v.z, q.z), __fadd_rn(v.w, q.w)); }
-            *(float4 *) (y + i) = v;
+            if (A.write_f32) *(float4 *) (y + i) = v;
+            if (A.tiles) {                                                   // half of a 16-byte core-matrix row: the MUL_MAT that follows needs no conversion pass
+                const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                *(uint2 *) (A.tiles + act_tile_off(row, i & ~(int64_t) 7, n) + (i & 4) * 2) = make_uint2(*(const uint32_t *) &h0, *(const uint32_t *) &h1);
+            }
         }
         return;
     }
@@ -350,6 +354,19 @@ __global__ void __launch_bounds__(256) k_glu_f32x4(const float * __restrict__ g,
     }
 }
 
+// SWIGLU of two contiguous F32 matrices straight into F16 activation tiles (the ffn_down MUL_MAT is the only reader of h): thread = 8 consecutive elements
+__global__ void __launch_bounds__(256) k_glu_tiles(const float * __restrict__ g, const float * __restrict__ u, uint8_t * __restrict__ tiles, int op, int64_t n, int64_t k) {
+    const int64_t k8 = k >> 3;
+    for (int64_t id = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; id < n * k8; id += (int64_t) gridDim.x * blockDim.x) {
+        const int64_t row = id / k8, col = (id % k8) * 8;
+        const float4 a0 = __ldcs((const float4 *) (g + row * k + col)), a1 = __ldcs((const float4 *) (g + row * k + col + 4));
+        const float4 b0 = __ldcs((const float4 *) (u + row * k + col)), b1 = __ldcs((const float4 *) (u + row * k + col + 4));
+        const __half2 h[4] = { __floats2half2_rn(gluop(op, a0.x) * b0.x, gluop(op, a0.y) * b0.y), __floats2half2_rn(gluop(op, a0.z) * b0.z, gluop(op, a0.w) * b0.w),
+                               __floats2half2_rn(gluop(op, a1.x) * b1.x, gluop(op, a1.y) * b1.y), __floats2half2_rn(gluop(op, a1.z) * b1.z, gluop(op, a1.w) * b1.w) };
+        *(uint4 *) (tiles + act_tile_off(row, col, k)) = *(const uint4 *) h;
+    }
+}
+
 // ================================================================== SOFT_MAX ===================================================
 struct SmArgs { T4 x, mask, dst; int has_mask; float scale; int64_t rows; };
 // one CTA per row; row kept in shared memory when it fits (<= 12288 floats), else recomputed from global
@@ -388,8 +405,19 @@ static bool float_type(int t) { return t == B200_F32 || t == B200_F16 || t == B2
 using namespace b200;
 
 // ---------------------------------------------------------------------------------------------------------------- C-ABI
+static int rms_norm_impl(const b200_tensor * x, const b200_tensor * w, const b200_tensor * add, const b200_tensor * dst, float eps, void * tiles, bool write_f32, void * stream);
 extern "C" int b200_rms_norm(const b200_tensor * x, const b200_tensor * w, const b200_tensor * add, const b200_tensor * dst,
-                             float eps, void * stream) {
+                             float eps, void * stream) { return rms_norm_impl(x, w, add, dst, eps, nullptr, true, stream); }
+// y = RMS_NORM(x) [* w] handed to a following tensor-core MUL_MAT as prepared F16 tiles in `tiles` (the MUL_MAT's scratch; call it with B200_MM_REUSE_ACT);
+// x must be a 2-D [k, n] matrix with k % 8 == 0 and k <= 4096.  dst->data may be NULL: tiles only.
+extern "C" int b200_rms_norm_tiles(const b200_tensor * x, const b200_tensor * w, const b200_tensor * dst, void * tiles, float eps, void * stream) {
+    if (!x || !dst || !tiles) return B200_ERR_ARG;
+    if (x->ne[2] * x->ne[3] != 1 || x->ne[0] % 64 || x->ne[0] > 4096 || x->ne[0] <= 1024 || (uintptr_t) tiles % 16) return B200_ERR_UNSUPPORTED;
+    if ((uintptr_t) x->data % 16 || x->nb[1] % 16 || (dst->data && ((uintptr_t) dst->data % 16 || dst->nb[1] % 16))) return B200_ERR_UNSUPPORTED;
+    if (w && (w->ne[0] != x->ne[0] || w->ne[1] * w->ne[2] * w->ne[3] != 1 || (uintptr_t) w->data % 16)) return B200_ERR_UNSUPPORTED;
+    return rms_norm_impl(x, w, nullptr, dst, eps, tiles, dst->data != nullptr, stream);
+}
+static int rms_norm_impl(const b200_tensor * x, const b200_tensor * w, const b200_tensor * add, const b200_tensor * dst, float eps, void * tiles, bool write_f32, void * stream) {
     if (!x || !dst) return B200_ERR_ARG;
     if (x->type != B200_F32 || dst->type != B200_F32 || !same_shape(x, dst) || x->nb[0] != 4 || dst->nb[0] != 4) return B200_ERR_UNSUPPORTED;
     if (w   && (w->type   != B200_F32 || w->nb[0]   != 4 || x->ne[0] % w->ne[0]   || x->ne[1] % w->ne[1]   || x->ne[2] % w->ne[2]   || x->ne[3] % w->ne[3]))   return B200_ERR_UNSUPPORTED;
@@ -397,7 +425,8 @@ extern "C" int b200_rms_norm(const b200_tensor * x, const b200_tensor * w, const
     const int64_t rows = nrows(x);
     if (rows == 0 || x->ne[0] == 0) return B200_OK;
     NormArgs A; A.x = t4(x); A.dst = t4(dst); A.eps = eps; A.has_w = w != nullptr; A.has_add = add != nullptr; A.rows = rows;
-    A.w = w ? t4(w) : A.x; A.add = add ? t4(add) : A.x;
+    A.w = w ? t4(w) : A.x; A.add = add ? t4(add) : A.x; A.tiles = (uint8_t *) tiles; A.write_f32 = write_f32 ? 1 : 0;
+    if (!write_f32) A.dst = A.x;                                          // (never dereferenced)
     cudaStream_t st = (cudaStream_t) stream;
     if (x->ne[0] <= 1024) k_rms_norm<true><<<(unsigned) ((rows + 7) / 8), 256, 0, st>>>(A);
     else                  k_rms_norm<false><<<(unsigned) rows, 256, 0, st>>>(A);
@@ -544,6 +573,19 @@ extern "C" int b200_glu(int op, const b200_tensor * gate_or_x, const b200_tensor
     return B200_OK;
 }
 
+// h = GLU(gate, up) of two contiguous [k, n] F32 matrices as prepared F16 tiles for the MUL_MAT that follows (ffn_down); see b200_rms_norm_tiles
+extern "C" int b200_glu_tiles(int op, const b200_tensor * gate, const b200_tensor * up, void * tiles, void * stream) {
+    if (!gate || !up || !tiles) return B200_ERR_ARG;
+    if (gate->type != B200_F32 || up->type != B200_F32 || !same_shape(gate, up) || !is_contig(gate) || !is_contig(up) || gate->ne[2] * gate->ne[3] != 1) return B200_ERR_UNSUPPORTED;
+    if (gate->ne[0] % 64 || (((uintptr_t) gate->data | (uintptr_t) up->data | (uintptr_t) tiles) % 16)) return B200_ERR_UNSUPPORTED;
+    if (op != B200_GLU_REGLU && op != B200_GLU_GEGLU && op != B200_GLU_SWIGLU && op != B200_GLU_GEGLU_ERF && op != B200_GLU_GEGLU_QUICK) return B200_ERR_UNSUPPORTED;
+    const int64_t n = gate->ne[1], k = gate->ne[0];
+    if (n == 0) return B200_OK;
+    k_glu_tiles<<<grid_for(n * (k >> 3), 256), 256, 0, (cudaStream_t) stream>>>((const float *) gate->data, (const float *) up->data, (uint8_t *) tiles, op, n, k);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 extern "C" int b200_soft_max(const b200_tensor * x, const b200_tensor * mask, const b200_tensor * dst, float scale, float max_bias, void * stream) {
     if (!x || !dst) return B200_ERR_ARG;
     if (x->type != B200_F32 || dst->type != B200_F32 || !same_shape(x, dst) || x->nb[0] != 4 || dst->nb[0] != 4 || max_bias != 0.0f) return B200_ERR_UNSUPPORTED;
@@ -633,7 +675,7 @@ extern "C" int b200_norm(const b200_tensor * x, const b200_tensor * dst, float e
     if (x->type != B200_F32 || dst->type != B200_F32 || !same_shape(x, dst) || x->nb[0] != 4 || dst->nb[0] != 4) return B200_ERR_UNSUPPORTED;
     const int64_t rows = nrows(x);
     if (rows == 0 || x->ne[0] == 0) return B200_OK;
-    NormArgs A; A.x = t4(x); A.dst = t4(dst); A.eps = eps; A.has_w = 0; A.has_add = 0; A.rows = rows; A.w = A.x; A.add = A.x;
+    NormArgs A; A.x = t4(x); A.dst = t4(dst); A.eps = eps; A.has_w = 0; A.has_add = 0; A.rows = rows; A.w = A.x; A.add = A.x; A.tiles = nullptr; A.write_f32 = 1;
     cudaStream_t st = (cudaStream_t) stream;
     if (x->ne[0] <= 1024) k_norm<true><<<(unsigned) ((rows + 7) / 8), 256, 0, st>>>(A);
     else                  k_norm<false><<<(unsigned) rows, 256, 0, st>>>(A);

@@ -233,7 +233,7 @@ class Qwen3Decoder:
         return 2
 
     # ---- prefill: one ubatch of n tokens through the same C-ABI entry points the ggml plugin calls node by node for an n-token graph -------
-    def prefill(self, x: torch.Tensor, pos0: int, n_kv: int) -> tuple[torch.Tensor, int]:
+    def prefill(self, x: torch.Tensor, pos0: int, n_kv: int, fused_tiles: bool = True) -> tuple[torch.Tensor, int]:
         """x [n, n_embd] F32 (embedding rows) at positions pos0 .. pos0+n-1 -> (logits of the LAST token, #launches).  Quantised MUL_MATs with
         n > 8 columns run on the tcgen05 dequant-GEMM (csrc/mmq_tc.cu), attention on k_fa_prefill (csrc/fa_prefill.cu); KV rows are written."""
         cfg, L = self.cfg, ops.lib()
@@ -257,10 +257,16 @@ class Qwen3Decoder:
 
         def mm(w, wtype, m, k, xin, out, reuse=False):
             ops.mul_mat(w, wtype, m, k, xin, layout=ops.LAYOUT_PLANAR if wtype == ops.Q6_K else ops.LAYOUT_NATIVE, out=out, scratch=mm_scratch, reuse_act=reuse)
+        # fused_tiles: RMS_NORM, FLASH_ATTN_EXT and SWIGLU write the NEXT MUL_MAT's F16 activation tiles directly (b200_*_tiles) and every tensor-core MUL_MAT runs
+        # with B200_MM_REUSE_ACT: no F32 round trip and no k_x_to_f16_tiles pass per MUL_MAT (the ggml plugin fuses the same pairs when the use counts allow it)
+        ft = fused_tiles and n >= 64 and 1024 < E <= 4096 and D == 128 and E % 64 == 0 and F % 64 == 0
         for lw in self.L:
             ty = lw["types"]
-            ops.rms_norm(x, cfg.rms_eps, w=lw["attn_norm"], out=bufs["a"])
-            mm(lw["wq"], ty["wq"], q, E, bufs["a"], bufs["q"]); mm(lw["wk"], ty["wk"], kv, E, bufs["a"], bufs["k"], n > 8); mm(lw["wv"], ty["wv"], kv, E, bufs["a"], bufs["v"], n > 8)
+            if ft:
+                ops.rms_norm_tiles(x, cfg.rms_eps, lw["attn_norm"], mm_scratch)
+            else:
+                ops.rms_norm(x, cfg.rms_eps, w=lw["attn_norm"], out=bufs["a"])
+            mm(lw["wq"], ty["wq"], q, E, bufs["a"], bufs["q"], ft); mm(lw["wk"], ty["wk"], kv, E, bufs["a"], bufs["k"], n > 8); mm(lw["wv"], ty["wv"], kv, E, bufs["a"], bufs["v"], n > 8)
             ops.check(L.b200_qkv_post(P(bufs["q"].data_ptr()), P(bufs["k"].data_ptr()), P(bufs["v"].data_ptr()), P(lw["q_norm"].data_ptr()),
                                       P(lw["k_norm"].data_ptr()), P(pos.data_ptr()), P(idx.data_ptr()), ops.I64,
                                       P(lw["k_cache"].data_ptr()), P(lw["v_cache"].data_ptr()), C.c_int64(kv * 2), C.c_int64(kv * 2),
@@ -268,14 +274,23 @@ class Qwen3Decoder:
                                       C.byref(self.rope), C.c_float(cfg.rms_eps), st))
             kview = lw["k_cache"][:n_kv].view(n_kv, cfg.n_head_kv, D).permute(1, 0, 2)
             vview = lw["v_cache"][:n_kv].view(n_kv, cfg.n_head_kv, D).permute(1, 0, 2)
-            ops.flash_attn(bufs["q"].view(n, cfg.n_head, D).permute(1, 0, 2), kview, vview, mask16, 1.0 / D ** 0.5,
-                           out=bufs["attn"].view(n, cfg.n_head, D), scratch=fa_scratch)
-            mm(lw["wo"], ty["wo"], E, q, bufs["attn"], bufs["x1"])
+            if ft:
+                ops.flash_attn_tiles(bufs["q"].view(n, cfg.n_head, D).permute(1, 0, 2), kview, vview, mask16, 1.0 / D ** 0.5, bufs["attn"].view(n, cfg.n_head, D), fa_scratch, mm_scratch)
+            else:
+                ops.flash_attn(bufs["q"].view(n, cfg.n_head, D).permute(1, 0, 2), kview, vview, mask16, 1.0 / D ** 0.5,
+                               out=bufs["attn"].view(n, cfg.n_head, D), scratch=fa_scratch)
+            mm(lw["wo"], ty["wo"], E, q, bufs["attn"], bufs["x1"], ft)
             ops.binary(ops.ADD, bufs["x1"], x, out=bufs["x1"])
-            ops.rms_norm(bufs["x1"], cfg.rms_eps, w=lw["ffn_norm"], out=bufs["a"])
-            mm(lw["gate"], ty["gate"], F, E, bufs["a"], bufs["g"]); mm(lw["up"], ty["up"], F, E, bufs["a"], bufs["u"], n > 8)
-            ops.check(L.b200_glu(ops.GLU_SWIGLU, ops._ref(ops.T(bufs["g"])), ops._ref(ops.T(bufs["u"])), ops._ref(ops.T(bufs["h"])), 0, st))
-            mm(lw["down"], ty["down"], E, F, bufs["h"], bufs["x2"])              # the layer input (x) is dead once x1 exists: x2 may be the same buffer
+            if ft:
+                ops.rms_norm_tiles(bufs["x1"], cfg.rms_eps, lw["ffn_norm"], mm_scratch)
+            else:
+                ops.rms_norm(bufs["x1"], cfg.rms_eps, w=lw["ffn_norm"], out=bufs["a"])
+            mm(lw["gate"], ty["gate"], F, E, bufs["a"], bufs["g"], ft); mm(lw["up"], ty["up"], F, E, bufs["a"], bufs["u"], n > 8)
+            if ft:
+                ops.glu_tiles(ops.GLU_SWIGLU, bufs["g"], bufs["u"], mm_scratch)
+            else:
+                ops.check(L.b200_glu(ops.GLU_SWIGLU, ops._ref(ops.T(bufs["g"])), ops._ref(ops.T(bufs["u"])), ops._ref(ops.T(bufs["h"])), 0, st))
+            mm(lw["down"], ty["down"], E, F, bufs["h"], bufs["x2"], ft)          # the layer input (x) is dead once x1 exists: x2 may be the same buffer
             x = ops.binary(ops.ADD, bufs["x2"], bufs["x1"], out=bufs["x2"])
             nl += 2 * 7 + 8                           # 7 GEMMs (+ their activation tiling), norm x2, qkv_post, kvmax + fa, add x2, glu
         logits = None

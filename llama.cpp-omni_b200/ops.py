@@ -24,7 +24,7 @@ EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b20
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
            "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
            "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy",
-           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
+           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_rms_norm_tiles", "b200_glu_tiles", "b200_flash_attn_tiles", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
 
 
 class Tensor(C.Structure):
@@ -360,3 +360,24 @@ def pool_1d(x: torch.Tensor, op: int, k: int) -> torch.Tensor:
     out = torch.empty(list(x.shape[:-1]) + [x.shape[-1] // k], dtype=torch.float32, device=x.device)
     check(lib().b200_pool_1d(_ref(T(x)), _ref(T(out)), op, k, k, 0, stream()))
     return out
+
+
+# ---- producers that write the following tensor-core MUL_MAT's activation tiles directly (include/b200_ops.h): pass the MUL_MAT's `scratch`, then call
+# mul_mat(..., scratch=scratch, reuse_act=True)
+def rms_norm_tiles(x: torch.Tensor, eps: float, w: torch.Tensor | None, tiles: torch.Tensor, out: torch.Tensor | None = None) -> None:
+    dst = T(out) if out is not None else T(x)
+    if out is None:
+        dst.data = None
+    check(lib().b200_rms_norm_tiles(_ref(T(x)), _ref(T(w)), _ref(dst), C.c_void_p(tiles.data_ptr()), C.c_float(eps), stream()))
+
+
+def glu_tiles(op: int, gate: torch.Tensor, up: torch.Tensor, tiles: torch.Tensor) -> None:
+    check(lib().b200_glu_tiles(op, _ref(T(gate)), _ref(T(up)), C.c_void_p(tiles.data_ptr()), stream()))
+
+
+def flash_attn_tiles(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch.Tensor | None, s: float, out_shape_like: torch.Tensor, scratch: torch.Tensor,
+                     tiles: torch.Tensor) -> None:
+    """as flash_attn, but the [n_q, n_head * D] result goes to `tiles` (the wo MUL_MAT's scratch) as F16 activation tiles; out_shape_like only describes the shape."""
+    qd, kd, vd, md, od = T(q), T(k), T(v), T(mask), T(out_shape_like)
+    check(lib().b200_flash_attn_tiles(_ref(qd), _ref(kd), _ref(vd), _ref(md), _ref(od), C.c_float(s), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()),
+                                      C.c_void_p(tiles.data_ptr()), stream()))

@@ -708,3 +708,20 @@ def test_pool_1d_matches_oracle(ops):
         assert np.array_equal(ops.pool_1d(dev(x), op, 5).cpu().numpy(), O.pool_1d(x, op, 5))
     x16 = x[:1].astype(np.float16)
     assert np.array_equal(ops.pool_1d(dev(x16), 1, 2).cpu().numpy(), O.pool_1d(x16.astype(np.float32), 1, 2))
+
+
+def test_prefill_fused_activation_tiles_are_bit_identical(ops):
+    """RMS_NORM / FLASH_ATTN_EXT / SWIGLU writing the next MUL_MAT's F16 activation tiles directly (b200_*_tiles + B200_MM_REUSE_ACT) must give exactly the logits of
+    the unfused sequence (F32 result + the MUL_MAT's own conversion pass): the tiles hold the same F16 roundings of the same F32 values."""
+    dec = load_package().decode
+    cfg = dec.LLMConfig(name="small", n_embd=2048, n_layer=2, n_head=16, n_head_kv=4, n_ff=6144, n_vocab=4096, n_ctx=512)
+    D = dec.Qwen3Decoder(cfg, "cuda:0", seed=2)
+    x = torch.randn(200, cfg.n_embd, device="cuda") * 0.05
+    a, _ = D.prefill(x, 0, 256, fused_tiles=False)
+    ka = [lw["k_cache"][:200].clone() for lw in D.L]
+    b, _ = D.prefill(x, 0, 256, fused_tiles=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b)
+    for lw, k0 in zip(D.L, ka):
+        assert torch.equal(lw["k_cache"][:200], k0)
