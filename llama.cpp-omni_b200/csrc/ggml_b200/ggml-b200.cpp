@@ -77,6 +77,7 @@ struct BackendCtx {
     bool engine_enabled = true;
     // activation-tile reuse (B200_MM_REUSE_ACT): the tensor whose prepared activations the scratch currently holds, reset per graph_compute
     const ggml_tensor * scratch_act = nullptr; const void * scratch_act_data = nullptr; int scratch_act_type = -1;
+    bool scratch_tiles_fused = false;                        // the tiles in the scratch came from a fused producer (fuse_tiles): the F32 tensor may not exist
 };
 
 DeviceCtx g_devices[MAX_DEVICES];
@@ -414,6 +415,16 @@ bool single_use(const ggml_cgraph * g, int i, const ggml_tensor * n) {
     return n_uses(g, n) == 1 && !n->view_src;
 }
 
+// does this MUL_MAT take the tensor-core path with prepared F16 activation tiles in the scratch?  (same routing conditions as mmq_tc_supported / mm_f16_tc_supported in
+// csrc/mmq_tc.cu: native 16-byte-multiple quant blocks with back-to-back rows, planar planes, or F16 rows; more than 8 activation columns)
+bool mm_tc_class(const ggml_tensor * n) {
+    const ggml_tensor * s0 = n->src[0], * s1 = n->src[1];
+    if (n->op != GGML_OP_MUL_MAT || !s0 || !s1 || s1->type != GGML_TYPE_F32) return false;
+    const bool tc_native = (s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q5_K) && s0->nb[1] == ggml_row_size(s0->type, s0->ne[0]);
+    const bool tc_planar = (s0->type == GGML_TYPE_Q6_K || s0->type == GGML_TYPE_Q8_0 || s0->type == GGML_TYPE_Q4_0) && is_planar(s0);
+    return (tc_native || tc_planar) && (uintptr_t) s0->data % 16 == 0 && s1->ne[1] > 8 && s1->ne[2] * s1->ne[3] == 1 && s0->ne[0] % 256 == 0;
+}
+
 int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool allow_fuse = false) {
     ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, node_idx);
     ggml_tensor * next = allow_fuse && node_idx + 1 < ggml_graph_n_nodes((ggml_cgraph *) g) ? ggml_graph_node((ggml_cgraph *) g, node_idx + 1) : nullptr;
@@ -429,9 +440,7 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             // q/k/v and gate/up share their input: the second and third projection reuse the F16 activation tiles the first one left in scratch
             // (only for the tensor-core path: > 8 columns of q4_K / planar q6_K; the preparation does not depend on which of the two types)
             // (same routing conditions as mmq_tc_supported in csrc/mmq_tc.cu: native 16-byte-multiple blocks with back-to-back rows, or planar planes)
-            const bool tc_native = (s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q5_K) && s0->nb[1] == ggml_row_size(s0->type, s0->ne[0]);
-            const bool tc_planar = (s0->type == GGML_TYPE_Q6_K || s0->type == GGML_TYPE_Q8_0 || s0->type == GGML_TYPE_Q4_0) && is_planar(s0);
-            const bool tc_class = (tc_native || tc_planar) && (uintptr_t) s0->data % 16 == 0 && s1->ne[1] > 8 && s1->ne[2] * s1->ne[3] == 1 && s0->ne[0] % 256 == 0;
+            const bool tc_class = mm_tc_class(n);
             const bool reuse = tc_class && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == 1;
             rc = b200_mul_mat_ex(&w, &x, &d, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
             c->scratch_act = tc_class ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = tc_class ? 1 : 0;
@@ -505,6 +514,88 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
     }
 }
 
+bool is_view_op(const ggml_tensor * t);
+// ---- producer -> MUL_MAT fusion for n-token graphs -------------------------------------------------------------------------------------------------------------
+// RMS_NORM(+MUL), GLU and FLASH_ATTN_EXT whose result only feeds tensor-core MUL_MATs write those MUL_MATs' F16 activation tiles straight into the scratch
+// (b200_*_tiles) instead of F32 + one conversion pass per MUL_MAT; the MUL_MATs then run with B200_MM_REUSE_ACT through the scratch_act bookkeeping below.
+// Whether the F32 tensor can be skipped is decided from the PARENT graph's use counts (a graph view shares them), so a reader in another split is never starved.
+int graph_uses(const ggml_cgraph * g, const ggml_tensor * t) {
+    if (!g->use_counts || !g->visited_hash_set.keys) return -1;
+    const size_t pos = ggml_hash_find(&g->visited_hash_set, t);
+    if (pos == GGML_HASHSET_FULL || !ggml_bitset_get(g->visited_hash_set.used, pos)) return -1;
+    return g->use_counts[pos];
+}
+
+int fuse_tiles(BackendCtx * c, const ggml_cgraph * g, int i, int & rc) {
+    const char * env = getenv("GGML_B200_NO_TILE_FUSION");                  // (read per call: the parity harness toggles it between two runs of one process)
+    const bool off = env && atoi(env) != 0;
+    const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+    ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, i);
+    rc = B200_OK;
+    if (off) return 0;
+    ggml_tensor * out = nullptr; int consumed = 0;
+    if (n->op == GGML_OP_RMS_NORM && i + 1 < nn) {
+        ggml_tensor * mul = ggml_graph_node((ggml_cgraph *) g, i + 1);
+        if (mul->op != GGML_OP_MUL || (mul->src[0] != n && mul->src[1] != n) || (n->flags & GGML_TENSOR_FLAG_OUTPUT) || !single_use(g, i, n)) return 0;
+        const ggml_tensor * wt = mul->src[0] == n ? mul->src[1] : mul->src[0];
+        if (!f32c(wt) || !ggml_are_same_shape(mul, n) || wt->ne[0] != n->ne[0] || ggml_nelements(wt) != wt->ne[0]) return 0;
+        out = mul; consumed = 2;
+    } else if (n->op == GGML_OP_GLU && n->src[1]) { out = n; consumed = 1; }
+    else if (n->op == GGML_OP_FLASH_ATTN_EXT) { out = n; consumed = 1; }
+    else return 0;
+    if (out->flags & GGML_TENSOR_FLAG_OUTPUT) return 0;
+    // readers of `out` (through whole-tensor views) among the nodes that follow
+    const ggml_tensor * alias[4] = { out, nullptr, nullptr, nullptr }; int n_alias = 1, seen[4] = { 0, 0, 0, 0 };
+    const ggml_tensor * mm_first = nullptr; int n_mm = 0;
+    size_t tile_bytes = 0;                                                  // the largest scratch any of the consumers will ask for: the scratch must not move under the tiles
+    bool other_reader = false;
+    for (int j = i + consumed; j < nn && j < i + consumed + 24; ++j) {
+        const ggml_tensor * t = ggml_graph_node((ggml_cgraph *) g, j);
+        int which = -1;
+        for (int s = 0; s < GGML_MAX_SRC && which < 0; ++s) for (int a = 0; a < n_alias; ++a) if (t->src[s] && t->src[s] == alias[a]) { which = a; break; }
+        if (which < 0) continue;
+        if (is_view_op(t) && t->src[0] == alias[which] && ggml_nelements(t) == ggml_nelements(out) && t->data == out->data && n_alias < 4) { ++seen[which]; alias[n_alias++] = t; continue; }
+        if (t->op == GGML_OP_MUL_MAT && t->src[1] == alias[which] && t->src[0] != alias[which] && mm_tc_class(t) && t->src[1]->data == out->data && ggml_is_contiguous(t->src[1]) &&
+            (!mm_first || t->src[1] == mm_first->src[1])) {
+            ++seen[which]; if (!mm_first) mm_first = t; ++n_mm;
+            b200_tensor w = view_of(t->src[0]), xv = view_of(t->src[1]);
+            const size_t sb = b200_mul_mat_scratch_bytes(&w, &xv);
+            if (sb > tile_bytes) tile_bytes = sb;
+            continue;
+        }
+        other_reader = true;
+    }
+    if (!mm_first) return 0;
+    bool all_accounted = !other_reader;
+    for (int a = 0; a < n_alias && all_accounted; ++a) all_accounted = graph_uses(g, alias[a]) == seen[a];
+    const ggml_tensor * x2 = mm_first->src[1];                               // the [k, n] matrix the MUL_MATs read
+    if (tile_bytes == 0) return 0;
+    int rc2 = B200_ERR_UNSUPPORTED;
+    if (n->op == GGML_OP_RMS_NORM) {
+        ggml_tensor * mul = (ggml_tensor *) out;
+        const ggml_tensor * wt = mul->src[0] == n ? mul->src[1] : mul->src[0];
+        void * sc = scratch_for(c, tile_bytes);
+        b200_tensor x = view_of(n->src[0]), wv = view_of(wt), d = view_of(mul);
+        if (all_accounted) d.data = nullptr;                                 // nobody reads the F32 tensor
+        rc2 = b200_rms_norm_tiles(&x, &wv, &d, sc, fparam(n, 0), c->stream);
+    } else if (n->op == GGML_OP_GLU) {
+        if (!all_accounted || iparam(n, 1) != 0) return 0;
+        void * sc = scratch_for(c, tile_bytes);
+        b200_tensor a = view_of(n->src[0]), u = view_of(n->src[1]);
+        rc2 = b200_glu_tiles((int) ggml_get_glu_op(n), &a, &u, sc, c->stream);
+    } else {
+        if (!all_accounted || n->src[4] || fparam(n, 1) != 0.0f || fparam(n, 2) != 0.0f || !n->src[3]) return 0;
+        b200_tensor q = view_of(n->src[0]), k = view_of(n->src[1]), v = view_of(n->src[2]), m = view_of(n->src[3]), d = view_of(n);
+        const size_t fa_sb = b200_flash_attn_scratch_bytes(&q, &k), off2 = (tile_bytes + 255) & ~(size_t) 255;
+        char * sc = (char *) scratch_for(c, off2 + fa_sb);
+        rc2 = b200_flash_attn_tiles(&q, &k, &v, &m, &d, fparam(n, 0), fa_sb ? sc + off2 : nullptr, fa_sb, sc, c->stream);
+    }
+    if (rc2 == B200_ERR_UNSUPPORTED) return 0;                               // shapes the tile producers do not take: the plain path
+    rc = rc2;
+    if (rc == B200_OK) { c->scratch_act = x2; c->scratch_act_data = x2->data; c->scratch_act_type = 1; c->scratch_tiles_fused = true; }
+    return consumed;
+}
+
 enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
     const int nn = ggml_graph_n_nodes(g);
     c->scratch_act = nullptr;
@@ -513,7 +604,8 @@ enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
         if (is_noop(n)) { ++i; continue; }
         if (c->scratch_act && n->data == c->scratch_act_data) c->scratch_act = nullptr;     // an in-place op rewrites the tensor the tiles were made from
         int rc = 0;
-        const int used = run_node(c, g, i, rc, true);                    // RMS_NORM may absorb the MUL right behind it
+        int used = (n->op == GGML_OP_RMS_NORM || n->op == GGML_OP_GLU || n->op == GGML_OP_FLASH_ATTN_EXT) && n->ne[1] * n->ne[2] >= 64 ? fuse_tiles(c, g, i, rc) : 0;
+        if (used == 0) used = run_node(c, g, i, rc, true);               // RMS_NORM may absorb the MUL right behind it
         if (rc != B200_OK) {
             // graph_compute on an op supports_op rejected is a caller bug (the reference asserts, ggml-cuda.cu:3043-3047)
             B200_LOG("op %s (%s) failed: %s", ggml_op_name(n->op), n->name, b200_error_string(rc));

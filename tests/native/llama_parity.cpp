@@ -102,6 +102,9 @@ int main(int argc, char ** argv) {
         printf("{\"mode\": 7, \"threads_ok\": %s, \"bitwise_mismatches\": %d, \"max_abs_diff_incl_incremental_thread\": %.3g}\n", ok ? "true" : "false", bad, worst);
         return ok && bad == 0 ? 0 : 1;
     }
+    // 8: B200 with the producer -> MUL_MAT tile fusion of n-token graphs (RMS_NORM / GLU / FLASH_ATTN_EXT write the next MUL_MAT's F16 tiles) vs without it:
+    //    the fused tiles hold the same F16 roundings of the same F32 values, so the logits must be BIT-IDENTICAL
+    if (self_mode == 8) { setenv("GGML_B200_NO_TILE_FUSION", "1", 1); cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false); setenv("GGML_B200_NO_TILE_FUSION", "0", 1); }
     // 5: B200 per-op launches (baseline) vs B200 whole-token decode engine — the plugin reads GGML_B200_DISABLE_ENGINE when a backend is created
     if (self_mode == 5) { setenv("GGML_B200_DISABLE_ENGINE", "1", 1); cpu = run(argv[1], 999, n_prompt, n_gen, nt, fa, nullptr, false); setenv("GGML_B200_DISABLE_ENGINE", "0", 1); }
     Run gpu = run(argv[1], cpu_self || self_mode == 2 || self_mode == 3 ? 0 : 999, n_prompt, n_gen, self_mode == 2 ? 3 : nt, fa, &cpu.toks, cpu_self, self_mode == 3 || self_mode == 4 || self_mode == 6);

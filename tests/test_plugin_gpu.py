@@ -128,3 +128,11 @@ def test_three_host_threads_three_backends_one_device(small_model):
     assert lines, (r.stdout + r.stderr)[-2000:]
     res = json.loads(lines[-1])
     assert res["threads_ok"] and res["bitwise_mismatches"] == 0 and r.returncode == 0, res
+
+
+def test_prefill_tile_fusion_is_bit_identical(small_model):
+    """The plugin's producer -> MUL_MAT fusion for n-token graphs (RMS_NORM / GLU / FLASH_ATTN_EXT write the next MUL_MAT's F16 activation tiles, no F32 round trip) against
+    the same run with GGML_B200_NO_TILE_FUSION=1 (llama_parity mode 8): a 200-token batched prompt and 8 decoded tokens, logits bit for bit."""
+    r = _parity(small_model, 200, 8, os.cpu_count() or 4, 1, 8)
+    assert "error" not in r, r
+    assert r["tokens_equal"] and r["prefill_rel_err"] == 0 and r["max_rel_logit_err"] == 0, r
