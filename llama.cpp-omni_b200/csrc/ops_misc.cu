@@ -356,14 +356,20 @@ __global__ void __launch_bounds__(256) k_glu_f32x4(const float * __restrict__ g,
 
 // SWIGLU of two contiguous F32 matrices straight into F16 activation tiles (the ffn_down MUL_MAT is the only reader of h): thread = 8 consecutive elements
 __global__ void __launch_bounds__(256) k_glu_tiles(const float * __restrict__ g, const float * __restrict__ u, uint8_t * __restrict__ tiles, int op, int64_t n, int64_t k) {
-    const int64_t k8 = k >> 3;
-    for (int64_t id = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; id < n * k8; id += (int64_t) gridDim.x * blockDim.x) {
-        const int64_t row = id / k8, col = (id % k8) * 8;
-        const float4 a0 = __ldcs((const float4 *) (g + row * k + col)), a1 = __ldcs((const float4 *) (g + row * k + col + 4));
-        const float4 b0 = __ldcs((const float4 *) (u + row * k + col)), b1 = __ldcs((const float4 *) (u + row * k + col + 4));
-        const __half2 h[4] = { __floats2half2_rn(gluop(op, a0.x) * b0.x, gluop(op, a0.y) * b0.y), __floats2half2_rn(gluop(op, a0.z) * b0.z, gluop(op, a0.w) * b0.w),
-                               __floats2half2_rn(gluop(op, a1.x) * b1.x, gluop(op, a1.y) * b1.y), __floats2half2_rn(gluop(op, a1.z) * b1.z, gluop(op, a1.w) * b1.w) };
-        *(uint4 *) (tiles + act_tile_off(row, col, k)) = *(const uint4 *) h;
+    // thread id -> (row within its group of 8, 8-column chunk, row group): the 8 threads of a row group write one 128-byte core matrix back to back, and 4 consecutive
+    // chunks of a row are one 128-byte line of each input (the mapping of k_x_to_f16_tiles)
+    const int64_t k8n = k >> 3, total = ((n + 7) >> 3) * 8 * k8n;
+    for (int64_t id = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t) gridDim.x * blockDim.x) {
+        const int64_t row = ((id >> 3) / k8n) * 8 + (id & 7), col = ((id >> 3) % k8n) * 8;
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (row < n) {
+            const float4 a0 = __ldcs((const float4 *) (g + row * k + col)), a1 = __ldcs((const float4 *) (g + row * k + col + 4));
+            const float4 b0 = __ldcs((const float4 *) (u + row * k + col)), b1 = __ldcs((const float4 *) (u + row * k + col + 4));
+            const __half2 h[4] = { __floats2half2_rn(gluop(op, a0.x) * b0.x, gluop(op, a0.y) * b0.y), __floats2half2_rn(gluop(op, a0.z) * b0.z, gluop(op, a0.w) * b0.w),
+                                   __floats2half2_rn(gluop(op, a1.x) * b1.x, gluop(op, a1.y) * b1.y), __floats2half2_rn(gluop(op, a1.z) * b1.z, gluop(op, a1.w) * b1.w) };
+            out = *(const uint4 *) h;
+        }
+        *(uint4 *) (tiles + act_tile_off(row, col, k)) = out;
     }
 }
 
@@ -581,7 +587,7 @@ extern "C" int b200_glu_tiles(int op, const b200_tensor * gate, const b200_tenso
     if (op != B200_GLU_REGLU && op != B200_GLU_GEGLU && op != B200_GLU_SWIGLU && op != B200_GLU_GEGLU_ERF && op != B200_GLU_GEGLU_QUICK) return B200_ERR_UNSUPPORTED;
     const int64_t n = gate->ne[1], k = gate->ne[0];
     if (n == 0) return B200_OK;
-    k_glu_tiles<<<grid_for(n * (k >> 3), 256), 256, 0, (cudaStream_t) stream>>>((const float *) gate->data, (const float *) up->data, (uint8_t *) tiles, op, n, k);
+    k_glu_tiles<<<grid_for(((n + 7) >> 3) * 8 * (k >> 3), 256), 256, 0, (cudaStream_t) stream>>>((const float *) gate->data, (const float *) up->data, (uint8_t *) tiles, op, n, k);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
