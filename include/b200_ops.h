@@ -98,6 +98,10 @@ B200_API int    b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const
 enum { B200_MM_REUSE_ACT = 1 };
 B200_API int    b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
                                 size_t scratch_bytes, int flags, void * stream);
+/* dst = W . x + residual (the ADD behind wo / ffn_down, ggml-cuda fuses nothing here): rides in the tensor-core GEMM's epilogue when it can (quantised weights, 2-D
+ * operands, no split-K), otherwise MUL_MAT + ADD kernels; residual has dst's shape and row stride and may alias dst. */
+B200_API int    b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, const b200_tensor * residual, const b200_tensor * dst, void * scratch,
+                                 size_t scratch_bytes, int flags, void * stream);
 
 /* Decode fast path: y[m] (+= residual) = W[m, k] . act, activations already quantised by b200_quantize_act /
  * a fused producer.  Up to 4 weight matrices that share the same activation run in ONE launch (q/k/v, gate/up).
@@ -153,6 +157,11 @@ B200_API int b200_binary(int op, const b200_tensor * a, const b200_tensor * b, c
 enum b200_unop { B200_SILU = 0, B200_GELU = 1, B200_RELU = 2, B200_GELU_QUICK = 3, B200_TANH = 4, B200_SIGMOID = 5,
                  B200_GELU_ERF = 6, B200_NEG = 7, B200_EXP = 8, B200_SQR = 9, B200_SQRT = 10, B200_ABS = 11 };
 B200_API int b200_unary(int op, const b200_tensor * x, const b200_tensor * dst, void * stream);
+/* the rest of unary.cu / clamp.cu the Token2Wav graphs use: SIN / COS / LOG (GGML_OP_SIN ...), ELU / STEP / SGN / HARDSWISH / HARDSIGMOID
+ * (GGML_OP_UNARY), LEAKY_RELU (p0 = negative slope; CPU ggml-cpu/ops.cpp:2453-2480), CLAMP (p0 = min, p1 = max; ops.cpp:5309-5340) */
+enum b200_unop_ext { B200_SIN = 12, B200_COS = 13, B200_LOG = 14, B200_ELU = 15, B200_STEP = 16, B200_SGN = 17, B200_HARDSWISH = 18, B200_HARDSIGMOID = 19,
+                     B200_LEAKY_RELU = 20, B200_CLAMP = 21 };
+B200_API int b200_unary_param(int op, const b200_tensor * x, const b200_tensor * dst, float p0, float p1, void * stream);
 enum b200_gluop { B200_GLU_REGLU = 0, B200_GLU_GEGLU = 1, B200_GLU_SWIGLU = 2, B200_GLU_GEGLU_ERF = 4, B200_GLU_GEGLU_QUICK = 5 };
 /* GLU: dst = act(gate) * up.  up == NULL: single-tensor form, halves of x's rows (swapped selects which half gates). */
 B200_API int b200_glu(int op, const b200_tensor * gate_or_x, const b200_tensor * up, const b200_tensor * dst, int swapped,
@@ -226,6 +235,24 @@ B200_API int b200_norm(const b200_tensor * x, const b200_tensor * dst, float eps
 B200_API int b200_im2col(const b200_tensor * kernel, const b200_tensor * x, const b200_tensor * dst, int s0, int s1, int p0, int p1, int d0, int d1,
                          int is_2d, void * stream);
 B200_API int b200_pool_1d(const b200_tensor * x, const b200_tensor * dst, int op, int k0, int s0, int p0, void * stream);
+
+/* ---- ops of the Token2Wav graphs (flow-matching CFM + HiFiGAN; csrc/ops_wave.cu).  tools/omni/token2wav/token2wav-impl.cpp:1905-1916 runs
+ *      them with a direct graph_compute on the first GPU-type device (no CPU fallback), so the whole op set has to exist ------------------------------------------
+ * b200_concat            GGML_OP_CONCAT along dim 0..3, F32 / F16 / BF16 / I32                      replaces ggml-cuda/concat.cu; CPU ggml-cpu/ops.cpp:1839-2040
+ * b200_repeat            GGML_OP_REPEAT (dst.ne[i] a multiple of src.ne[i]), same types             replaces binbcast.cu op_repeat; CPU ops.cpp:1637-1700
+ * b200_arange            GGML_OP_ARANGE dst[i] = start + step*i (F32, 1-D)                          replaces arange.cu; CPU ops.cpp:7762-7785
+ * b200_sum_rows          GGML_OP_SUM_ROWS F32 [ne0, r..] -> [1, r..] (f64 accumulation as the CPU)  replaces sumrows.cu; CPU ops.cpp:1399-1430
+ * b200_pad               GGML_OP_PAD zero padding, lp_rp8 = {lp0, rp0, lp1, rp1, lp2, rp2, lp3, rp3} replaces pad.cu; CPU ops.cpp:7592-7640
+ * b200_pad_reflect_1d    GGML_OP_PAD_REFLECT_1D                                                     replaces pad_reflect_1d.cu; CPU ops.cpp:7664-7692
+ * b200_conv_transpose_1d GGML_OP_CONV_TRANSPOSE_1D (p0 = 0, d0 = 1), kernel [K, Cout, Cin] F32/F16, x [L, Cin] F32 -> [(L-1)*s0 + K, Cout] F32
+ *                                                                                                   replaces conv-transpose-1d.cu; CPU ops.cpp:5952-6130 */
+B200_API int b200_concat(const b200_tensor * a, const b200_tensor * b, const b200_tensor * dst, int dim, void * stream);
+B200_API int b200_repeat(const b200_tensor * src, const b200_tensor * dst, void * stream);
+B200_API int b200_arange(const b200_tensor * dst, float start, float step, void * stream);
+B200_API int b200_sum_rows(const b200_tensor * x, const b200_tensor * dst, void * stream);
+B200_API int b200_pad(const b200_tensor * x, const b200_tensor * dst, const int32_t * lp_rp8, void * stream);
+B200_API int b200_pad_reflect_1d(const b200_tensor * x, const b200_tensor * dst, int p0, int p1, void * stream);
+B200_API int b200_conv_transpose_1d(const b200_tensor * kernel, const b200_tensor * x, const b200_tensor * dst, int s0, void * stream);
 
 /* ---- layer-split pipeline hop on the device (csrc/hop.cu; replaces, for one-process-per-GPU launches, the per-boundary copy the reference
  *      issues from ggml_backend_sched_compute_splits -> cpy_tensor_async, ggml/src/ggml-backend.cpp:1539, ggml-cuda.cu:2598-2620) -------------

@@ -277,7 +277,8 @@ int unary_map(enum ggml_unary_op u) {
         case GGML_UNARY_OP_SILU: return B200_SILU;       case GGML_UNARY_OP_GELU: return B200_GELU;         case GGML_UNARY_OP_RELU: return B200_RELU;
         case GGML_UNARY_OP_GELU_QUICK: return B200_GELU_QUICK; case GGML_UNARY_OP_TANH: return B200_TANH;   case GGML_UNARY_OP_SIGMOID: return B200_SIGMOID;
         case GGML_UNARY_OP_GELU_ERF: return B200_GELU_ERF; case GGML_UNARY_OP_NEG: return B200_NEG;         case GGML_UNARY_OP_EXP: return B200_EXP;
-        case GGML_UNARY_OP_ABS: return B200_ABS;
+        case GGML_UNARY_OP_ABS: return B200_ABS;           case GGML_UNARY_OP_ELU: return B200_ELU;           case GGML_UNARY_OP_STEP: return B200_STEP;
+        case GGML_UNARY_OP_SGN: return B200_SGN;           case GGML_UNARY_OP_HARDSWISH: return B200_HARDSWISH; case GGML_UNARY_OP_HARDSIGMOID: return B200_HARDSIGMOID;
         default: return -1;
     }
 }
@@ -343,8 +344,31 @@ bool b200_dev_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
             return floaty(s0) && floaty(op) && ggml_are_same_shape(s0, op);
         case GGML_OP_UNARY:
             return floaty(s0) && floaty(op) && ggml_are_same_shape(s0, op) && unary_map(ggml_get_unary_op(op)) >= 0;
-        case GGML_OP_SQR: case GGML_OP_SQRT:
+        case GGML_OP_SQR: case GGML_OP_SQRT: case GGML_OP_SIN: case GGML_OP_COS: case GGML_OP_LOG: case GGML_OP_CLAMP: case GGML_OP_LEAKY_RELU:
             return floaty(s0) && floaty(op) && ggml_are_same_shape(s0, op);
+        // ---- Token2Wav op set (csrc/ops_wave.cu): these graphs run without a scheduler, so anything missing here aborts the vocoder (token2wav-impl.cpp:1905-1916)
+        case GGML_OP_CONCAT: {
+            const int dim = iparam(op, 0);
+            if (!s0 || !s1 || s0->type != s1->type || s0->type != op->type || !(floaty(s0) || s0->type == GGML_TYPE_I32) || dim < 0 || dim > 3) return false;
+            for (int d = 0; d < 4; ++d) if (d == dim ? op->ne[d] != s0->ne[d] + s1->ne[d] : (s0->ne[d] != s1->ne[d] || op->ne[d] != s0->ne[d])) return false;
+            return true;
+        }
+        case GGML_OP_REPEAT:
+            return s0 && s0->type == op->type && (floaty(s0) || s0->type == GGML_TYPE_I32) && ggml_can_repeat(s0, op);
+        case GGML_OP_ARANGE:
+            return op->type == GGML_TYPE_F32 && ggml_is_contiguous(op) && ggml_nrows(op) == 1;
+        case GGML_OP_SUM_ROWS:
+            return f32c(s0) && f32c(op) && op->ne[0] == 1 && op->ne[1] == s0->ne[1] && op->ne[2] == s0->ne[2] && op->ne[3] == s0->ne[3];
+        case GGML_OP_PAD: {
+            if (!s0 || s0->type != GGML_TYPE_F32 || op->type != GGML_TYPE_F32) return false;
+            for (int d = 0; d < 4; ++d) if (iparam(op, 2 * d) < 0 || iparam(op, 2 * d + 1) < 0 || op->ne[d] != s0->ne[d] + iparam(op, 2 * d) + iparam(op, 2 * d + 1)) return false;
+            return true;
+        }
+        case GGML_OP_PAD_REFLECT_1D:
+            return s0 && s0->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32 && iparam(op, 0) >= 0 && iparam(op, 1) >= 0 && iparam(op, 0) < s0->ne[0] && iparam(op, 1) < s0->ne[0];
+        case GGML_OP_CONV_TRANSPOSE_1D:
+            return s0 && s1 && (s0->type == GGML_TYPE_F32 || s0->type == GGML_TYPE_F16) && s1->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32 && s0->ne[3] == 1 &&
+                   s1->ne[2] * s1->ne[3] == 1 && s0->ne[2] == s1->ne[1] && iparam(op, 0) > 0 && iparam(op, 1) == 0 && iparam(op, 2) == 1;
         case GGML_OP_GLU: {
             const enum ggml_glu_op g = ggml_get_glu_op(op);
             if (g == GGML_GLU_OP_SWIGLU_OAI || !floaty(s0) || !floaty(op)) return false;
@@ -425,6 +449,10 @@ bool mm_tc_class(const ggml_tensor * n) {
     return (tc_native || tc_planar) && (uintptr_t) s0->data % 16 == 0 && s1->ne[1] > 8 && s1->ne[2] * s1->ne[3] == 1 && s0->ne[0] % 256 == 0;
 }
 
+// GGML_B200_NO_TILE_FUSION=1 switches the n-token fusions off (producer -> MUL_MAT tiles, MUL_MAT -> residual ADD epilogue); read per call: the parity harness
+// toggles it between two runs of one process (llama_parity mode 8)
+bool fusion_off() { const char * env = getenv("GGML_B200_NO_TILE_FUSION"); return env && atoi(env) != 0; }
+
 int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool allow_fuse = false) {
     ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, node_idx);
     ggml_tensor * next = allow_fuse && node_idx + 1 < ggml_graph_n_nodes((ggml_cgraph *) g) ? ggml_graph_node((ggml_cgraph *) g, node_idx + 1) : nullptr;
@@ -442,8 +470,19 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             // (same routing conditions as mmq_tc_supported in csrc/mmq_tc.cu: native 16-byte-multiple blocks with back-to-back rows, or planar planes)
             const bool tc_class = mm_tc_class(n);
             const bool reuse = tc_class && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == 1;
-            rc = b200_mul_mat_ex(&w, &x, &d, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
             c->scratch_act = tc_class ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = tc_class ? 1 : 0;
+            // the residual ADD right behind wo / ffn_down rides in the GEMM epilogue (b200_mul_mat_add) when this MUL_MAT's result has no other reader
+            if (tc_class && next && next->op == GGML_OP_ADD && (next->src[0] == n || next->src[1] == n) && next->src[0] != next->src[1] && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) &&
+                single_use(g, node_idx, n) && !fusion_off()) {
+                const ggml_tensor * other = next->src[0] == n ? next->src[1] : next->src[0];
+                if (other->type == GGML_TYPE_F32 && next->type == GGML_TYPE_F32 && ggml_are_same_shape(other, n) && ggml_are_same_shape(next, n) && ggml_is_contiguous(other) &&
+                    ggml_is_contiguous(next) && ggml_is_contiguous(n)) {
+                    b200_tensor r = view_of(other), dn = view_of(next);
+                    rc = b200_mul_mat_add(&w, &x, &r, &dn, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
+                    if (rc != B200_ERR_UNSUPPORTED) return 2;
+                }
+            }
+            rc = b200_mul_mat_ex(&w, &x, &d, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
             return 1;
         }
         case GGML_OP_ADD: case GGML_OP_SUB: case GGML_OP_MUL: case GGML_OP_DIV: {
@@ -485,9 +524,26 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
         case GGML_OP_GET_ROWS: { b200_tensor a = view_of(s0), i = view_of(s1), d = view_of(n); rc = b200_get_rows(&a, &i, &d, st); return 1; }
         case GGML_OP_CPY: case GGML_OP_CONT: case GGML_OP_DUP: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_cpy(&a, &d, st); return 1; }
         case GGML_OP_SCALE: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_scale(&a, &d, fparam(n, 0), fparam(n, 1), st); return 1; }
-        case GGML_OP_UNARY: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary(unary_map(ggml_get_unary_op(n)), &a, &d, st); return 1; }
+        case GGML_OP_UNARY: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary_param(unary_map(ggml_get_unary_op(n)), &a, &d, 0.0f, 0.0f, st); return 1; }
         case GGML_OP_SQR:  { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary(B200_SQR, &a, &d, st); return 1; }
         case GGML_OP_SQRT: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary(B200_SQRT, &a, &d, st); return 1; }
+        case GGML_OP_SIN:  { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary_param(B200_SIN, &a, &d, 0.0f, 0.0f, st); return 1; }
+        case GGML_OP_COS:  { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary_param(B200_COS, &a, &d, 0.0f, 0.0f, st); return 1; }
+        case GGML_OP_LOG:  { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary_param(B200_LOG, &a, &d, 0.0f, 0.0f, st); return 1; }
+        case GGML_OP_CLAMP: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary_param(B200_CLAMP, &a, &d, fparam(n, 0), fparam(n, 1), st); return 1; }
+        case GGML_OP_LEAKY_RELU: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_unary_param(B200_LEAKY_RELU, &a, &d, fparam(n, 0), 0.0f, st); return 1; }
+        case GGML_OP_CONCAT: { b200_tensor a = view_of(s0), b = view_of(s1), d = view_of(n); rc = b200_concat(&a, &b, &d, iparam(n, 0), st); return 1; }
+        case GGML_OP_REPEAT: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_repeat(&a, &d, st); return 1; }
+        case GGML_OP_ARANGE: { b200_tensor d = view_of(n); rc = b200_arange(&d, fparam(n, 0), fparam(n, 2), st); return 1; }
+        case GGML_OP_SUM_ROWS: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_sum_rows(&a, &d, st); return 1; }
+        case GGML_OP_PAD: {
+            b200_tensor a = view_of(s0), d = view_of(n);
+            int32_t lr[8]; for (int i = 0; i < 8; ++i) lr[i] = iparam(n, i);
+            rc = b200_pad(&a, &d, lr, st);
+            return 1;
+        }
+        case GGML_OP_PAD_REFLECT_1D: { b200_tensor a = view_of(s0), d = view_of(n); rc = b200_pad_reflect_1d(&a, &d, iparam(n, 0), iparam(n, 1), st); return 1; }
+        case GGML_OP_CONV_TRANSPOSE_1D: { b200_tensor k = view_of(s0), x = view_of(s1), d = view_of(n); rc = b200_conv_transpose_1d(&k, &x, &d, iparam(n, 0), st); return 1; }
         case GGML_OP_GLU: {
             b200_tensor a = view_of(s0), d = view_of(n), u;
             if (s1) u = view_of(s1);
@@ -527,8 +583,7 @@ int graph_uses(const ggml_cgraph * g, const ggml_tensor * t) {
 }
 
 int fuse_tiles(BackendCtx * c, const ggml_cgraph * g, int i, int & rc) {
-    const char * env = getenv("GGML_B200_NO_TILE_FUSION");                  // (read per call: the parity harness toggles it between two runs of one process)
-    const bool off = env && atoi(env) != 0;
+    const bool off = fusion_off();
     const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
     ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, i);
     rc = B200_OK;

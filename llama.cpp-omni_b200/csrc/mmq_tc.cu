@@ -44,6 +44,7 @@ struct TcArgs {
     const uint8_t * w; const uint8_t * wd;          // payload plane, f16 d plane (q6_K planar) or null
     const uint8_t * x16;                            // activations, F16, pre-tiled: [n_tiles][k/64][TC_B_BYTES]
     float * dst; int64_t dst_ld;                    // dst[n * dst_ld + m]
+    const float * resid;                            // optional: dst = W.x + resid (same leading dimension as dst; split-K launches never carry it)
     int64_t m, k, n, row_bytes;                     // n = real columns; row_bytes of the payload plane
     int type, tiles_m, tiles_n;
     int span_bytes, n_raw;                          // payload bytes of 256 weights of one row (= TMA box width); raw ring slots
@@ -452,10 +453,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
             const int64_t mrow = (int64_t) mt * TC_M + quarter * 32 + lane;
             int64_t ncols = A.n - (int64_t) ntx * wn; if (ncols > wn) ncols = wn;
             float * out = A.dst + ((int64_t) ntx * wn) * A.dst_ld + mrow;
+            const bool fuse_add = mrow < A.m && A.splitk == 1 && A.resid;  // fused residual ADD (wo / ffn_down of a llama-family layer): one F32 add, as the separate op would do
+            const float * rs = A.resid + ((int64_t) ntx * wn) * A.dst_ld + mrow;
             for (int cc = 0; cc * 32 < ncols; ++cc) {
                 uint32_t v[32];
+                float r[32];
+                // the residual may BE the destination, so the compiler cannot move these loads above the stores below by itself: all 32 are issued up front
+                // (they do not depend on the accumulator and overlap the TMEM read)
+                if (fuse_add) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = cc * 32 + j < ncols ? __ldcg(rs + (int64_t) (cc * 32 + j) * A.dst_ld) : 0.0f;
+                }
                 tc_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + acc * TC_N + cc * 32, v);
-                if (mrow < A.m && A.splitk == 1) {
+                if (fuse_add) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __fadd_rn(__uint_as_float(v[j]), r[j]);
+                } else if (mrow < A.m && A.splitk == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __uint_as_float(v[j]);
                 } else if (mrow < A.m) {
@@ -599,6 +612,8 @@ static int tc_splitk(int tiles_m, int64_t n, int64_t units) {
     const int64_t tiles256 = (int64_t) tiles_m * ((n + TC_N - 1) / TC_N);
     return !off && units % 2 == 0 && units >= 4 && tiles256 * 2 <= sm_count() ? 2 : 1;
 }
+// will mmq_tc carry a residual in its epilogue for this shape?  (not under split-K: three addends would not commute)
+bool mmq_tc_fuses_resid(int64_t m, int64_t k, int64_t n) { return tc_splitk((int) ((m + TC_M - 1) / TC_M), n, k / 256) == 1; }
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n) { return (size_t) ((n + TC_N - 1) / TC_N * TC_N) * (size_t) k * 2; }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
@@ -613,7 +628,9 @@ static tc_encode_fn tc_encoder() {
     return fn;
 }
 
-int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st) {
+int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st,
+           const float * resid, bool * resid_fused) {
+    if (resid_fused) *resid_fused = false;
     static smem_mask_t done{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_mmq_tc, TC_SMEM, done));
     if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
@@ -642,6 +659,8 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
     A.wd = payload_size(type) != type_size(type) ? (const uint8_t *) w + m * A.row_bytes : nullptr;          // planar: f16 d plane behind the payload plane
     A.tiles_m = (int) ((m + TC_M - 1) / TC_M);
     A.splitk = tc_splitk(A.tiles_m, n, k / 256);
+    A.resid = A.splitk == 1 ? resid : nullptr;                                  // three addends would not commute: split-K leaves the ADD to the caller
+    if (resid_fused) *resid_fused = A.resid != nullptr;
     A.nsub = tc_nsub(A.tiles_m * A.splitk, n); A.tiles_n = (int) ((n + TC_N / A.nsub - 1) / (TC_N / A.nsub));
     if (A.splitk > 1) B200_CUDA_TRY(cudaMemset2DAsync(dst, (size_t) dst_ld * 4, 0, (size_t) m * 4, (size_t) n, st));
     int grid = A.tiles_m * A.tiles_n * A.splitk; if (grid > sm_count()) grid = sm_count();

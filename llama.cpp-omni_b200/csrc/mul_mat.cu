@@ -13,7 +13,8 @@ int matvec_q_cols(const void * w, int type, int layout, int64_t m, int64_t row_s
 // mmq_tc.cu: tcgen05 dequant-GEMM for n > 8 columns
 bool   mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void * w, int64_t row_stride);
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n);
-int    mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st);
+int    mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st, const float * resid, bool * resid_fused);
+bool   mmq_tc_fuses_resid(int64_t m, int64_t k, int64_t n);
 bool   mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t row_stride);
 int    mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st);
 static bool tc_disabled() { static const bool off = getenv("B200_DISABLE_TC") && atoi(getenv("B200_DISABLE_TC")) != 0; return off; }
@@ -132,6 +133,31 @@ extern "C" int b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const 
     return b200_mul_mat_ex(w, x, dst, scratch, scratch_bytes, 0, stream);
 }
 
+// dst = W . x + residual: the ADD that follows wo / ffn_down in every llama-family layer rides in the tensor-core GEMM's epilogue (quantised weights, 2-D
+// operands, no split-K); every other case runs the MUL_MAT into dst and then the ADD kernel — which needs a residual that is NOT dst (the MUL_MAT would overwrite
+// it): that combination returns B200_ERR_UNSUPPORTED before anything is launched, and the caller keeps its two separate ops.
+extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, const b200_tensor * residual, const b200_tensor * dst, void * scratch,
+                                size_t scratch_bytes, int flags, void * stream) {
+    if (!residual || !b200_mul_mat_supported(w, x, dst)) return B200_ERR_UNSUPPORTED;
+    if (residual->type != B200_F32 || residual->ne[0] != dst->ne[0] || residual->ne[1] != dst->ne[1] || residual->ne[2] != dst->ne[2] || residual->ne[3] != dst->ne[3]) return B200_ERR_UNSUPPORTED;
+    const int t = w->type;
+    const int64_t k = w->ne[0], m = w->ne[1], n = x->ne[1];
+    const bool fusable = is_quant(t) && !tc_disabled() && mmq_tc_supported(t, w->layout, k, n, w->data, w->nb[1]) && x->ne[2] * x->ne[3] == 1 && w->ne[2] * w->ne[3] == 1 &&
+                         residual->nb[0] == 4 && residual->nb[1] == dst->nb[1] && dst->nb[0] == 4 && scratch && (uintptr_t) scratch % 16 == 0 &&
+                         scratch_bytes >= b200_mul_mat_scratch_bytes(w, x) && m > 0 && n > 0 && mmq_tc_fuses_resid(m, k, n);
+    if (fusable) {
+        bool fused = false;
+        const int rc = mmq_tc(w->data, t, m, k, (const float *) x->data, x->nb[1] / 4, n, (float *) dst->data, dst->nb[1] / 4, scratch, (flags & B200_MM_REUSE_ACT) != 0,
+                              (cudaStream_t) stream, (const float *) residual->data, &fused);
+        return rc ? rc : fused ? B200_OK : B200_ERR_ARG;                    // mmq_tc_fuses_resid and mmq_tc share tc_splitk: not fused here would be a bug
+    }
+    const char * r0 = (const char *) residual->data, * d0 = (const char *) dst->data;
+    const int64_t rbytes = residual->nb[3] * residual->ne[3], dbytes = dst->nb[3] * dst->ne[3];
+    if (r0 < d0 + dbytes && d0 < r0 + rbytes) return B200_ERR_UNSUPPORTED;   // overlapping residual and dst
+    const int rc = b200_mul_mat_ex(w, x, dst, scratch, scratch_bytes, flags, stream);
+    return rc ? rc : b200_binary(B200_ADD, dst, residual, dst, stream);
+}
+
 extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
                                size_t scratch_bytes, int flags, void * stream) {
     if (!b200_mul_mat_supported(w, x, dst)) return B200_ERR_UNSUPPORTED;
@@ -169,7 +195,7 @@ extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, con
         if (tc) {       // prefill / batched: dequant tiles -> tcgen05.mma (mmq_tc.cu)
             const char * wb = (const char *) w->data + (i2 / r2) * w->nb[2] + (i3 / r3) * w->nb[3];
             float * yb = (float *) ((char *) dst->data + i2 * dst->nb[2] + i3 * dst->nb[3]);
-            const int rc = mmq_tc(wb, t, m, k, xs, x->nb[1] / 4, n, yb, dst->nb[1] / 4, scratch, (flags & B200_MM_REUSE_ACT) && x->ne[2] * x->ne[3] == 1, st);
+            const int rc = mmq_tc(wb, t, m, k, xs, x->nb[1] / 4, n, yb, dst->nb[1] / 4, scratch, (flags & B200_MM_REUSE_ACT) && x->ne[2] * x->ne[3] == 1, st, nullptr, nullptr);
             if (rc) return rc;
             continue;
         }

@@ -292,8 +292,18 @@ __global__ void __launch_bounds__(256) k_binary_f32x4(const float * __restrict__
     }
 }
 
-__device__ __forceinline__ float unop(int op, float x) {
+__device__ __forceinline__ float unop(int op, float x, float p0 = 0.0f, float p1 = 0.0f) {
     switch (op) {
+        case B200_SIN:        return sinf(x);
+        case B200_COS:        return cosf(x);
+        case B200_LOG:        return logf(x);
+        case B200_ELU:        return x > 0.0f ? x : expm1f(x);
+        case B200_STEP:       return x > 0.0f ? 1.0f : 0.0f;
+        case B200_SGN:        return x > 0.0f ? 1.0f : x < 0.0f ? -1.0f : 0.0f;
+        case B200_HARDSWISH:  return x * fminf(1.0f, fmaxf(0.0f, (x + 3.0f) / 6.0f));
+        case B200_HARDSIGMOID: return fminf(1.0f, fmaxf(0.0f, (x + 3.0f) / 6.0f));
+        case B200_LEAKY_RELU: return (x > 0.0f ? x : 0.0f) + p0 * (x < 0.0f ? x : 0.0f);
+        case B200_CLAMP:      return x < p0 ? p0 : x > p1 ? p1 : x;
         case B200_SILU:       return x / (1.0f + expf(-x));
         case B200_GELU:       { const float c = 0.044715f, s = 0.79788456080286535587989211986876f; return 0.5f * x * (1.0f + tanhf(s * x * (1.0f + c * x * x))); }
         case B200_RELU:       return fmaxf(x, 0.0f);
@@ -317,7 +327,7 @@ __global__ void __launch_bounds__(256) k_unary(const UnArgs A, int64_t total) {
         const int64_t i1 = r % A.dst.ne[1]; r /= A.dst.ne[1];
         const int64_t i2 = r % A.dst.ne[2]; const int64_t i3 = r / A.dst.ne[2];
         const float x = ld_any(A.x.data + i0 * A.x.nb[0] + i1 * A.x.nb[1] + i2 * A.x.nb[2] + i3 * A.x.nb[3], A.x.type);
-        const float y = A.op < 0 ? x * A.p0 + A.p1 : unop(A.op, x);
+        const float y = A.op < 0 ? x * A.p0 + A.p1 : unop(A.op, x, A.p0, A.p1);
         st_any(A.dst.data + i0 * A.dst.nb[0] + i1 * A.dst.nb[1] + i2 * A.dst.nb[2] + i3 * A.dst.nb[3], A.dst.type, y);
     }
 }
@@ -537,6 +547,17 @@ extern "C" int b200_unary(int op, const b200_tensor * x, const b200_tensor * dst
     const int64_t total = nelem(dst);
     if (total == 0) return B200_OK;
     UnArgs A = { t4(x), t4(dst), op, 0.0f, 0.0f };
+    k_unary<<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_unary_param(int op, const b200_tensor * x, const b200_tensor * dst, float p0, float p1, void * stream) {
+    if (!x || !dst) return B200_ERR_ARG;
+    if (op < B200_SILU || op > B200_CLAMP || !float_type(x->type) || !float_type(dst->type) || !same_shape(x, dst)) return B200_ERR_UNSUPPORTED;
+    const int64_t total = nelem(dst);
+    if (total == 0) return B200_OK;
+    UnArgs A = { t4(x), t4(dst), op, p0, p1 };
     k_unary<<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
     B200_LAUNCH_CHECK();
     return B200_OK;

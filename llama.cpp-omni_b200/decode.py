@@ -279,8 +279,11 @@ class Qwen3Decoder:
             else:
                 ops.flash_attn(bufs["q"].view(n, cfg.n_head, D).permute(1, 0, 2), kview, vview, mask16, 1.0 / D ** 0.5,
                                out=bufs["attn"].view(n, cfg.n_head, D), scratch=fa_scratch)
-            mm(lw["wo"], ty["wo"], E, q, bufs["attn"], bufs["x1"], ft)
-            ops.binary(ops.ADD, bufs["x1"], x, out=bufs["x1"])
+            if ft:                                    # residual ADD in the GEMM epilogue (b200_mul_mat_add)
+                ops.mul_mat_add(lw["wo"], ty["wo"], E, q, bufs["attn"], x, bufs["x1"], layout=ops.LAYOUT_PLANAR if ty["wo"] == ops.Q6_K else ops.LAYOUT_NATIVE, scratch=mm_scratch, reuse_act=True)
+            else:
+                mm(lw["wo"], ty["wo"], E, q, bufs["attn"], bufs["x1"], ft)
+                ops.binary(ops.ADD, bufs["x1"], x, out=bufs["x1"])
             if ft:
                 ops.rms_norm_tiles(bufs["x1"], cfg.rms_eps, lw["ffn_norm"], mm_scratch)
             else:
@@ -290,8 +293,11 @@ class Qwen3Decoder:
                 ops.glu_tiles(ops.GLU_SWIGLU, bufs["g"], bufs["u"], mm_scratch)
             else:
                 ops.check(L.b200_glu(ops.GLU_SWIGLU, ops._ref(ops.T(bufs["g"])), ops._ref(ops.T(bufs["u"])), ops._ref(ops.T(bufs["h"])), 0, st))
-            mm(lw["down"], ty["down"], E, F, bufs["h"], bufs["x2"], ft)          # the layer input (x) is dead once x1 exists: x2 may be the same buffer
-            x = ops.binary(ops.ADD, bufs["x2"], bufs["x1"], out=bufs["x2"])
+            if ft:
+                x = ops.mul_mat_add(lw["down"], ty["down"], E, F, bufs["h"], bufs["x1"], bufs["x2"], layout=ops.LAYOUT_PLANAR if ty["down"] == ops.Q6_K else ops.LAYOUT_NATIVE, scratch=mm_scratch, reuse_act=True)
+            else:
+                mm(lw["down"], ty["down"], E, F, bufs["h"], bufs["x2"], ft)      # the layer input (x) is dead once x1 exists: x2 may be the same buffer
+                x = ops.binary(ops.ADD, bufs["x2"], bufs["x1"], out=bufs["x2"])
             nl += 2 * 7 + 8                           # 7 GEMMs (+ their activation tiling), norm x2, qkv_post, kvmax + fa, add x2, glu
         logits = None
         if self.has_head:

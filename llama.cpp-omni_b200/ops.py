@@ -24,7 +24,7 @@ EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b20
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
            "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
            "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy",
-           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_rms_norm_tiles", "b200_glu_tiles", "b200_flash_attn_tiles", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
+           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_rms_norm_tiles", "b200_glu_tiles", "b200_flash_attn_tiles", "b200_mul_mat_add", "b200_unary_param", "b200_concat", "b200_repeat", "b200_arange", "b200_sum_rows", "b200_pad", "b200_pad_reflect_1d", "b200_conv_transpose_1d", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
 
 
 class Tensor(C.Structure):
@@ -206,6 +206,20 @@ def mul_mat(w: torch.Tensor, wtype: int, m: int, k: int, x: torch.Tensor, layout
     return out
 
 
+def mul_mat_add(w: torch.Tensor, wtype: int, m: int, k: int, x: torch.Tensor, residual: torch.Tensor, out: torch.Tensor, layout: int = LAYOUT_NATIVE,
+                scratch: torch.Tensor | None = None, reuse_act: bool = False) -> torch.Tensor:
+    """out = x . W^T + residual (b200_mul_mat_add: the ADD rides in the tensor-core GEMM's epilogue when it can)."""
+    L = lib()
+    wd, xd, rd, od = T(w, wtype, ne=[k, m], layout=layout), T(x), T(residual), T(out)
+    sb = L.b200_mul_mat_scratch_bytes(C.byref(wd), C.byref(xd))
+    if scratch is None or scratch.numel() < sb:
+        if reuse_act:
+            raise B200Error("mul_mat_add: reuse_act needs the scratch that holds the tiles")
+        scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
+    check(L.b200_mul_mat_add(C.byref(wd), C.byref(xd), C.byref(rd), C.byref(od), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), int(reuse_act), stream()))
+    return out
+
+
 def make_job(w: torch.Tensor, wtype: int, m: int, k: int, y: torch.Tensor, residual: torch.Tensor | None = None,
              layout: int = LAYOUT_NATIVE) -> MatvecJob:
     j = MatvecJob()
@@ -359,6 +373,65 @@ def pool_1d(x: torch.Tensor, op: int, k: int) -> torch.Tensor:
     """GGML_OP_POOL_1D along the last dim, kernel == stride, no padding (op 0 = max, 1 = avg)."""
     out = torch.empty(list(x.shape[:-1]) + [x.shape[-1] // k], dtype=torch.float32, device=x.device)
     check(lib().b200_pool_1d(_ref(T(x)), _ref(T(out)), op, k, k, 0, stream()))
+    return out
+
+
+# ---- Token2Wav op set (csrc/ops_wave.cu; torch shapes are the reversed ggml ne) ---------------------------------------------------------------------------
+SIN, COS, LOG, ELU, STEP, SGN, HARDSWISH, HARDSIGMOID, LEAKY_RELU, CLAMP = range(12, 22)
+
+
+def unary_param(op: int, x: torch.Tensor, p0: float = 0.0, p1: float = 0.0) -> torch.Tensor:
+    out = torch.empty_like(x)
+    check(lib().b200_unary_param(op, _ref(T(x)), _ref(T(out)), C.c_float(p0), C.c_float(p1), stream()))
+    return out
+
+
+def concat(a: torch.Tensor, b: torch.Tensor, ggml_dim: int) -> torch.Tensor:
+    out = torch.empty(torch.cat([a, b], dim=a.dim() - 1 - ggml_dim).shape, dtype=a.dtype, device=a.device)
+    check(lib().b200_concat(_ref(T(a)), _ref(T(b)), _ref(T(out)), ggml_dim, stream()))
+    return out
+
+
+def repeat(x: torch.Tensor, shape) -> torch.Tensor:
+    out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    check(lib().b200_repeat(_ref(T(x)), _ref(T(out)), stream()))
+    return out
+
+
+def arange(start: float, stop: float, step: float, device) -> torch.Tensor:
+    import math
+    out = torch.empty(int(math.ceil((stop - start) / step)), dtype=torch.float32, device=device)
+    check(lib().b200_arange(_ref(T(out)), C.c_float(start), C.c_float(step), stream()))
+    return out
+
+
+def sum_rows(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(list(x.shape[:-1]) + [1], dtype=torch.float32, device=x.device)
+    check(lib().b200_sum_rows(_ref(T(x)), _ref(T(out)), stream()))
+    return out
+
+
+def pad(x: torch.Tensor, lp_rp8) -> torch.Tensor:
+    """lp_rp8 = [lp0, rp0, ..., lp3, rp3] in ggml dimension order (dim 0 = the last torch dim)."""
+    ne = list(x.shape)[::-1] + [1] * (4 - x.dim())
+    out_ne = [ne[d] + lp_rp8[2 * d] + lp_rp8[2 * d + 1] for d in range(4)]
+    out = torch.empty(out_ne[::-1][4 - x.dim():], dtype=torch.float32, device=x.device)
+    arr = (C.c_int32 * 8)(*lp_rp8)
+    check(lib().b200_pad(_ref(T(x)), _ref(T(out)), arr, stream()))
+    return out
+
+
+def pad_reflect_1d(x: torch.Tensor, p0: int, p1: int) -> torch.Tensor:
+    out = torch.empty(list(x.shape[:-1]) + [x.shape[-1] + p0 + p1], dtype=torch.float32, device=x.device)
+    check(lib().b200_pad_reflect_1d(_ref(T(x)), _ref(T(out)), p0, p1, stream()))
+    return out
+
+
+def conv_transpose_1d(kernel: torch.Tensor, x: torch.Tensor, s0: int) -> torch.Tensor:
+    """kernel [Cin, Cout, K] (ggml ne [K, Cout, Cin]) F32 / F16, x [Cin, L] F32 -> [Cout, (L - 1) * s0 + K]."""
+    Cin, Cout, K = kernel.shape
+    out = torch.empty((Cout, (x.shape[-1] - 1) * s0 + K), dtype=torch.float32, device=x.device)
+    check(lib().b200_conv_transpose_1d(_ref(T(kernel)), _ref(T(x)), _ref(T(out)), s0, stream()))
     return out
 
 

@@ -29,7 +29,8 @@ ROOT = Path(__file__).resolve().parent.parent
 REF = ROOT / "oracle" / "_ref"
 pytestmark = pytest.mark.skipif(not (REF / "bin" / "llama-quantize").exists(), reason="oracle/_ref is not built")
 
-CFG = SimpleNamespace(n_embd=2048, n_ff=6144, head_dim=128, n_head=16, n_head_kv=4, n_layer=3, n_vocab=4096, n_ctx=256, rms_eps=1e-6, rope_base=1e6,
+# n_ff = 8192: ffn_down is K-split x2 by the engine and every slice of the planar q6_K d plane must stay a 16-byte multiple (16 blocks x f16) for the bulk copies
+CFG = SimpleNamespace(n_embd=2048, n_ff=8192, head_dim=128, n_head=16, n_head_kv=4, n_layer=3, n_vocab=4096, n_ctx=256, rms_eps=1e-6, rope_base=1e6,
                       n_ctx_orig=40960)
 
 

@@ -188,6 +188,32 @@ def test_mul_mat_prefill_tensor_core(ops, name, m, k, n):
     assert nmse(got.cpu().numpy()[np.ix_(cols, rows)], ref) <= 5e-4
 
 
+@pytest.mark.parametrize("name,m,k,n", [("q4_K", 4096, 4096, 2048), ("q6_K", 4096, 12288, 512), ("q4_K", 1024, 4096, 512), ("q4_K", 200, 512, 17), ("q6_K", 4096, 4096, 3)])
+def test_mul_mat_add_is_mul_mat_then_add(ops, name, m, k, n):
+    """b200_mul_mat_add (the residual ADD behind wo / ffn_down riding in the tcgen05 GEMM's epilogue; split-K launches and matvecs fall back to MUL_MAT + ADD
+    inside the call): bit for bit the two separate ops, also when the residual IS the destination."""
+    t = QT[name]
+    rng = np.random.default_rng(hash((name, m, k, n, "add")) & 0xffff)
+    blocks = rand_blocks(rng, t, m * k // O.BLOCK[t][0])
+    planar = t in ops.PAYLOAD
+    wd = ops.to_planar(t, dev(blocks)) if planar else dev(blocks)
+    lay = ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NATIVE
+    x = dev(rng.standard_normal((n, k)).astype(np.float32))
+    r = dev(rng.standard_normal((n, m)).astype(np.float32))
+    want = ops.binary(ops.ADD, ops.mul_mat(wd, t, m, k, x, layout=lay), r)
+    got = ops.mul_mat_add(wd, t, m, k, x, r, torch.empty_like(r), layout=lay)
+    torch.cuda.synchronize()
+    assert torch.isfinite(want).all()
+    assert torch.equal(got, want)
+    inplace = r.clone()                                # residual == dst: fine in the epilogue (each thread reads its element before writing it); the
+    try:                                               # unfused fall-back would overwrite the residual first and must refuse instead
+        ops.mul_mat_add(wd, t, m, k, x, inplace, inplace, layout=lay)
+        torch.cuda.synchronize()
+        assert torch.equal(inplace, want)
+    except ops.B200Error as e:
+        assert "-1000" in str(e) and torch.equal(inplace, r)
+
+
 def test_mul_mat_lm_head_shape(ops):
     """output.weight of MiniCPM-o-4.5: Q6_K [4096, 151748]; oracle on a row sample, linearity on the full output."""
     m, k = 151748, 4096
@@ -725,3 +751,77 @@ def test_prefill_fused_activation_tiles_are_bit_identical(ops):
     assert torch.equal(a, b)
     for lw, k0 in zip(D.L, ka):
         assert torch.equal(lw["k_cache"][:200], k0)
+
+
+# ---- Token2Wav op set (csrc/ops_wave.cu).  Oracle = numpy restatements of the reference CPU loops (file:line in each case); the live reference checks
+# the same kernels through its own harness in tests/test_plugin_gpu.py::test_reference_backend_ops_harness.
+def test_wave_unary_ops(ops):
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal((3, 5, 77)) * 3).astype(np.float32)
+    xd = dev(x)
+    want = {   # ggml-cpu/unary-ops.cpp op_* and ops.cpp:2453-2480 (leaky_relu), :5309-5340 (clamp)
+        ops.SIN: np.sin(x), ops.COS: np.cos(x), ops.ELU: np.where(x > 0, x, np.expm1(x)), ops.STEP: (x > 0).astype(np.float32), ops.SGN: np.sign(x),
+        ops.HARDSWISH: x * np.clip((x + 3) / 6, 0, 1), ops.HARDSIGMOID: np.clip((x + 3) / 6, 0, 1),
+    }
+    for op, w in want.items():
+        np.testing.assert_allclose(ops.unary_param(op, xd).cpu().numpy(), w.astype(np.float32), rtol=2e-6, atol=2e-6, err_msg=str(op))
+    np.testing.assert_allclose(ops.unary_param(ops.LOG, dev(np.abs(x) + 0.1)).cpu().numpy(), np.log(np.abs(x) + 0.1), rtol=2e-6, atol=2e-6)
+    assert np.array_equal(ops.unary_param(ops.LEAKY_RELU, xd, 0.1).cpu().numpy(), np.maximum(x, 0) + np.float32(0.1) * np.minimum(x, 0))
+    assert np.array_equal(ops.unary_param(ops.CLAMP, xd, -1.5, 2.0).cpu().numpy(), np.clip(x, -1.5, 2.0))
+    h = xd.half()                                                        # F16 in / out: computed in F32, rounded once
+    assert torch.equal(ops.unary_param(ops.CLAMP, h, -1.5, 2.0), h.clamp(-1.5, 2.0))
+    y = ops.unary_param(ops.ELU, xd.permute(2, 0, 1))                   # strided source
+    np.testing.assert_allclose(y.cpu().numpy(), np.where(x > 0, x, np.expm1(x)).transpose(2, 0, 1), rtol=2e-6, atol=2e-6)
+
+
+def test_wave_concat_repeat_pad_arange_sum_rows(ops):
+    rng = np.random.default_rng(22)
+    a = rng.standard_normal((3, 4, 5, 11)).astype(np.float32)
+    for dim in range(4):                                                 # ops.cpp:1968-2010: dst = [a ; b] along ggml dim
+        shp = list(a.shape); shp[3 - dim] = 7
+        b = rng.standard_normal(shp).astype(np.float32)
+        assert np.array_equal(ops.concat(dev(a), dev(b), dim).cpu().numpy(), np.concatenate([a, b], axis=3 - dim))
+    ai = rng.integers(-9, 9, (2, 3, 4), dtype=np.int32); bi = rng.integers(-9, 9, (2, 3, 6), dtype=np.int32)
+    assert np.array_equal(ops.concat(dev(ai), dev(bi), 0).cpu().numpy(), np.concatenate([ai, bi], axis=2))
+    at = dev(a).permute(0, 1, 3, 2)                                      # non-contiguous first operand
+    bt = dev(rng.standard_normal((3, 4, 11, 2)).astype(np.float32))
+    assert torch.equal(ops.concat(at, bt, 0), torch.cat([at, bt], dim=3))
+    for reps in [(1, 1, 1, 2), (2, 1, 3, 1), (1, 2, 1, 1), (2, 2, 2, 2)]:  # ops.cpp:1637-1700: dst[i] = src[i mod ne]
+        out_shape = [s * r for s, r in zip(a.shape, reps)]
+        assert np.array_equal(ops.repeat(dev(a), out_shape).cpu().numpy(), np.tile(a, reps))
+    h = dev(a).half()
+    assert torch.equal(ops.repeat(h, [3, 4, 10, 11]), h.repeat(1, 1, 2, 1))
+    # PAD: ops.cpp:7592-7640
+    lr = [1, 2, 3, 4, 0, 1, 2, 0]
+    want = np.pad(a, [(lr[6], lr[7]), (lr[4], lr[5]), (lr[2], lr[3]), (lr[0], lr[1])])
+    assert np.array_equal(ops.pad(dev(a), lr).cpu().numpy(), want)
+    # PAD_REFLECT_1D: ops.cpp:7664-7692
+    x = rng.standard_normal((2, 80, 300)).astype(np.float32)
+    assert np.array_equal(ops.pad_reflect_1d(dev(x), 7, 3).cpu().numpy(), np.pad(x, [(0, 0), (0, 0), (7, 3)], mode="reflect"))
+    # ARANGE: ops.cpp:7762-7785, value = start + step * i in f32
+    got = ops.arange(0.5, 100.25, 0.75, "cuda").cpu().numpy()
+    i = np.arange(len(got), dtype=np.float32)
+    assert len(got) == int(np.ceil((100.25 - 0.5) / 0.75)) and np.array_equal(got, np.float32(0.5) + np.float32(0.75) * i)
+    # SUM_ROWS: ops.cpp:1399-1430 (f64 accumulator, rounded once)
+    for shape in [(3, 5, 1000), (2, 33), (1, 4097), (7, 1)]:
+        x = rng.standard_normal(shape).astype(np.float32)
+        np.testing.assert_array_equal(ops.sum_rows(dev(x)).cpu().numpy(), x.astype(np.float64).sum(-1, keepdims=True).astype(np.float32))
+
+
+@pytest.mark.parametrize("L,Cin,Cout,K,s0,wt", [(197, 32, 16, 16, 1, "f32"), (3, 2, 3, 2, 3, "f32"), (3, 2, 1, 3, 1, "f32"), (50, 512, 256, 16, 8, "f16"), (121, 64, 32, 11, 5, "f32"),
+                                                 (2, 1, 1, 3, 1, "f32")])
+def test_wave_conv_transpose_1d(ops, L, Cin, Cout, K, s0, wt):
+    """HiFiGAN upsampling (token2wav-impl.cpp ggml_conv_transpose_1d(w, x, stride, 0, 1)); oracle: the scatter form of ops.cpp:6040-6130 in f64."""
+    rng = np.random.default_rng(L * 31 + K)
+    w = rng.standard_normal((Cin, Cout, K)).astype(np.float32)
+    x = rng.standard_normal((Cin, L)).astype(np.float32)
+    wd = dev(w).half() if wt == "f16" else dev(w)
+    w64 = wd.float().cpu().numpy().astype(np.float64)
+    ref = np.zeros((Cout, (L - 1) * s0 + K))
+    for k in range(K):
+        ref[:, k:k + (L - 1) * s0 + 1:s0] += np.einsum("ic,il->cl", w64[:, :, k], x.astype(np.float64))
+    got = ops.conv_transpose_1d(wd, dev(x), s0).cpu().numpy()
+    mag = np.zeros_like(ref)
+    for k in range(K):
+        mag[:, k:k + (L - 1) * s0 + 1:s0] += np.einsum("ic,il->cl", np.abs(w64[:, :, k]), np.abs(x.astype(np.float64)))
+    assert np.all(np.abs(got - ref) <= 2e-6 * mag + 1e-9)
