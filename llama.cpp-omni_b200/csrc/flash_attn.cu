@@ -218,6 +218,7 @@ static int fa_launch(const FaArgs & A, int G, int64_t nz, cudaStream_t st) {
     return B200_OK;
 }
 
+int dequant_rows(const b200_tensor * src, const b200_tensor * idx, const b200_tensor * dst, cudaStream_t st);     // quant_rows.cu
 // fa_prefill.cu: tensor-core tiles for >= 16 query tokens
 bool   fa_prefill_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst);
 size_t fa_prefill_scratch_bytes(const b200_tensor * q, const b200_tensor * mask_or_null, int64_t m_ne3);
@@ -231,13 +232,19 @@ using namespace b200;
 extern "C" int b200_flash_attn_supported(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask,
                                          const b200_tensor * dst) {
     if (!q || !k || !v || !dst) return 0;
-    if (q->type != B200_F32 || k->type != B200_F16 || v->type != B200_F16 || dst->type != B200_F32) return 0;
+    // quantised K / V (-ctk / -ctv q8_0 | q4_0) are staged as F16 in the scratch first, like launch_fattn's to_fp16 pass (fattn-common.cuh); a quantised V needs a
+    // quantised K, because b200_flash_attn_scratch_bytes sizes the staging from K alone
+    const bool kq = k->type == B200_Q8_0 || k->type == B200_Q4_0, vq = v->type == B200_Q8_0 || v->type == B200_Q4_0;
+    if (q->type != B200_F32 || (k->type != B200_F16 && !kq) || (v->type != B200_F16 && !vq) || (vq && !kq) || dst->type != B200_F32) return 0;
     const int64_t D = q->ne[0];
     if ((D != 64 && D != 128) || k->ne[0] != D || v->ne[0] != D) return 0;
     if (k->ne[1] != v->ne[1] || k->ne[2] != v->ne[2] || k->ne[3] != v->ne[3] || k->ne[2] == 0 || k->ne[3] == 0) return 0;
     if (q->ne[2] % k->ne[2] != 0 || q->ne[3] % k->ne[3] != 0) return 0;
-    if (q->nb[0] != 4 || k->nb[0] != 2 || v->nb[0] != 2 || dst->nb[0] != 4) return 0;
-    if (((uintptr_t) k->data | (uintptr_t) v->data) % 16 || (k->nb[1] | k->nb[2] | k->nb[3] | v->nb[1] | v->nb[2] | v->nb[3]) % 16) return 0;
+    if (q->nb[0] != 4 || k->nb[0] != type_size(k->type) || v->nb[0] != type_size(v->type) || dst->nb[0] != 4) return 0;
+    if (!kq && ((uintptr_t) k->data % 16 || (k->nb[1] | k->nb[2] | k->nb[3]) % 16)) return 0;
+    if (!vq && ((uintptr_t) v->data % 16 || (v->nb[1] | v->nb[2] | v->nb[3]) % 16)) return 0;
+    if (kq && (((uintptr_t) k->data | k->nb[1] | k->nb[2] | k->nb[3]) & 1)) return 0;
+    if (vq && (((uintptr_t) v->data | v->nb[1] | v->nb[2] | v->nb[3]) & 1)) return 0;
     if (dst->ne[0] != D || dst->ne[1] != q->ne[2] || dst->ne[2] != q->ne[1] || dst->ne[3] != q->ne[3]) return 0;
     if (mask) {
         if (mask->type != B200_F16 || mask->nb[0] != 2 || mask->ne[0] != k->ne[1] || mask->ne[1] < q->ne[1]) return 0;
@@ -258,12 +265,16 @@ static size_t fa_decode_scratch_bytes(const b200_tensor * q, const b200_tensor *
 
 // Which kernel runs is decided in b200_flash_attn from alignment as well (fa_prefill_supported), which this function cannot see: it
 // returns the LARGER of the two requirements, so the buffer fits whichever path is taken.
+static size_t fa_stage_bytes(const b200_tensor * k) {                       // one F16 copy of a quantised K (and the same again for V)
+    return ((size_t) (k->ne[0] * k->ne[1] * k->ne[2] * k->ne[3]) * 2 + 255) & ~(size_t) 255;
+}
 extern "C" size_t b200_flash_attn_scratch_bytes(const b200_tensor * q, const b200_tensor * k) {
     const int64_t nz = q->ne[1] * q->ne[3];
     if (nz == 0 || k->ne[1] == 0 || k->ne[2] == 0) return 0;
+    const size_t stage = k->type != B200_F16 ? 2 * fa_stage_bytes(k) : 0;
     const size_t dec = nz <= 65535 ? fa_decode_scratch_bytes(q, k) : 0;
-    if (q->ne[1] >= 16) { const size_t pre = fa_prefill_scratch_bytes(q, nullptr, q->ne[3]); return pre > dec ? pre : dec; }   // upper bound for the KV-tile counts (mask batch <= q batch)
-    return dec;
+    if (q->ne[1] >= 16) { const size_t pre = fa_prefill_scratch_bytes(q, nullptr, q->ne[3]); return stage + (pre > dec ? pre : dec); }   // upper bound for the KV-tile counts (mask batch <= q batch)
+    return stage + dec;
 }
 
 static int flash_attn_impl(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, const b200_tensor * mask, const b200_tensor * dst, float scale, float max_bias,
@@ -286,6 +297,21 @@ static int flash_attn_impl(const b200_tensor * q, const b200_tensor * k, const b
     if (!b200_flash_attn_supported(q, k, v, mask, dst) || max_bias != 0.0f || logit_softcap != 0.0f) return B200_ERR_UNSUPPORTED;
     const int64_t nz = q->ne[1] * q->ne[3];
     if (nz == 0 || q->ne[2] == 0) return B200_OK;
+    b200_tensor kf, vf;
+    if (k->type != B200_F16 && k->ne[1] > 0) {                                // stage the quantised cache views as contiguous F16 [D, n_kv, n_head_kv, n_b]
+        const size_t sb = fa_stage_bytes(k);
+        if (!scratch || (uintptr_t) scratch % 16 || scratch_bytes < 2 * sb) return B200_ERR_ARG;
+        auto stage = [&](const b200_tensor * t, b200_tensor & f, char * where) -> int {
+            if (t->type == B200_F16) { f = *t; return B200_OK; }
+            f = *t; f.data = where; f.type = B200_F16; f.layout = B200_LAYOUT_NATIVE;
+            f.nb[0] = 2; f.nb[1] = t->ne[0] * 2; f.nb[2] = f.nb[1] * t->ne[1]; f.nb[3] = f.nb[2] * t->ne[2];
+            return dequant_rows(t, nullptr, &f, (cudaStream_t) stream);
+        };
+        int rc = stage(k, kf, (char *) scratch); if (rc) return rc;
+        rc = stage(v, vf, (char *) scratch + sb); if (rc) return rc;
+        k = &kf; v = &vf;
+        scratch = (char *) scratch + 2 * sb; scratch_bytes -= 2 * sb;
+    }
     if (k->ne[1] > 0 && fa_prefill_supported(q, k, v, mask, dst)) {
         const bool have = scratch && scratch_bytes >= fa_prefill_scratch_bytes(q, mask, mask ? mask->ne[3] : 1) && (uintptr_t) scratch % 4 == 0;
         return fa_prefill(q, k, v, mask, dst, scale, have ? scratch : nullptr, (cudaStream_t) stream, tiles);

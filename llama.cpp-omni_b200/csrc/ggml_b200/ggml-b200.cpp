@@ -324,20 +324,29 @@ bool b200_dev_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
         case GGML_OP_ROPE: {
             const int mode = iparam(op, 2), n_dims = iparam(op, 1);
             if (mode != 0 && mode != GGML_ROPE_TYPE_NEOX) return false;
-            if (!f32c(s0) || !f32c(op) || !s1 || s1->type != GGML_TYPE_I32 || !ggml_is_contiguous(s1)) return false;
+            const bool f16io = s0 && s0->type == GGML_TYPE_F16 && op->type == GGML_TYPE_F16 && s0->nb[0] == 2 && op->nb[0] == 2;      // K-shift of the F16 cache
+            if ((!f16io && (!f32c(s0) || !f32c(op))) || !s1 || s1->type != GGML_TYPE_I32 || !ggml_is_contiguous(s1)) return false;
             if (op->src[2] && (op->src[2]->type != GGML_TYPE_F32 || !ggml_is_contiguous(op->src[2]))) return false;
             return n_dims > 0 && n_dims % 2 == 0 && n_dims <= s0->ne[0] && s0->ne[0] % 2 == 0;
         }
         case GGML_OP_SET_ROWS:
-            if (!s0 || !s1 || s0->type != GGML_TYPE_F32 || !floaty(op) || (s1->type != GGML_TYPE_I64 && s1->type != GGML_TYPE_I32)) return false;
+            if (!s0 || !s1 || s0->type != GGML_TYPE_F32 || (s1->type != GGML_TYPE_I64 && s1->type != GGML_TYPE_I32)) return false;
+            if (op->type == GGML_TYPE_Q8_0 || op->type == GGML_TYPE_Q4_0) { if (s0->ne[0] % 32 || s0->nb[0] != 4) return false; }          // quantised KV cache
+            else if (!floaty(op)) return false;
             return s0->ne[0] == op->ne[0] && s0->ne[2] == op->ne[2] && s0->ne[3] == op->ne[3] && s1->ne[0] == s0->ne[1] &&
                    s1->ne[1] != 0 && s1->ne[2] != 0 && s0->ne[2] % s1->ne[1] == 0 && s0->ne[3] % s1->ne[2] == 0 && op->nb[0] == ggml_type_size(op->type);
         case GGML_OP_GET_ROWS:
-            return floaty(s0) && floaty(op) && s1 && s1->type == GGML_TYPE_I32 && s0->ne[0] == op->ne[0] && op->ne[1] == s1->ne[0] &&
+            if (s0 && ggml_is_quantized(s0->type)) {                        // quantised token_embd: whole, contiguous tensors only (planar planes are addressed by block index)
+                if (op->type != GGML_TYPE_F32 || !ggml_is_contiguous(s0) || s0->view_src) return false;
+            } else if (!floaty(s0)) return false;
+            return floaty(op) && s1 && s1->type == GGML_TYPE_I32 && s0->ne[0] == op->ne[0] && op->ne[1] == s1->ne[0] &&
                    op->ne[2] == s1->ne[1] && op->ne[3] == s1->ne[2];
         case GGML_OP_CPY: case GGML_OP_CONT: case GGML_OP_DUP: {
             if (!s0) return false;
             const bool ints = s0->type == GGML_TYPE_I32 && op->type == GGML_TYPE_I32;
+            const bool to_q = s0->type == GGML_TYPE_F32 && (op->type == GGML_TYPE_Q8_0 || op->type == GGML_TYPE_Q4_0) && ggml_are_same_shape(s0, op) && s0->nb[0] == 4;
+            const bool from_q = ggml_is_quantized(s0->type) && (op->type == GGML_TYPE_F32 || op->type == GGML_TYPE_F16) && ggml_are_same_shape(s0, op) && !is_planar(s0);
+            if (to_q || from_q) return true;
             return (ints || (floaty(s0) && floaty(op))) && ggml_nelements(s0) == ggml_nelements(op);
         }
         case GGML_OP_SCALE:

@@ -134,13 +134,14 @@ struct RopeArgs {
 };
 // thread = one rotation pair of one (head, token, batch) row.  theta follows the oracle's chain (theta *= theta_scale per pair,
 // ops.cpp ggml_rope_cache_init) so that the angle is bit-identical to the CPU backend's; sincosf is the accurate variant.
+template <typename T>
 __global__ void __launch_bounds__(256) k_rope(const RopeArgs A, int64_t total_pairs) {
     const int64_t half_n = A.x.ne[0] / 2;                                  // pairs per row incl. pass-through region
     for (int64_t g = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; g < total_pairs; g += (int64_t) gridDim.x * blockDim.x) {
         const int64_t p = g % half_n, row = g / half_n;
         const int64_t i1 = row % A.x.ne[1], i2 = (row / A.x.ne[1]) % A.x.ne[2], i3 = row / (A.x.ne[1] * A.x.ne[2]);
-        const float * x = (const float *) (A.x.data + i1 * A.x.nb[1] + i2 * A.x.nb[2] + i3 * A.x.nb[3]);
-        float * y = (float *) (A.dst.data + i1 * A.dst.nb[1] + i2 * A.dst.nb[2] + i3 * A.dst.nb[3]);
+        const T * x = (const T *) (A.x.data + i1 * A.x.nb[1] + i2 * A.x.nb[2] + i3 * A.x.nb[3]);
+        T * y = (T *) (A.dst.data + i1 * A.dst.nb[1] + i2 * A.dst.nb[2] + i3 * A.dst.nb[3]);
         if (2 * p >= A.n_dims) {                                            // beyond the rotated dims: copy through
             const int64_t i = A.n_dims + 2 * (p - A.n_dims / 2);
             y[i] = x[i]; y[i + 1] = x[i + 1];
@@ -160,15 +161,16 @@ __global__ void __launch_bounds__(256) k_rope(const RopeArgs A, int64_t total_pa
         float sn, cs; sincosf(th, &sn, &cs);
         cs *= mscale; sn *= mscale;
         const int64_t a = (A.mode & 2) ? p : 2 * p, b = (A.mode & 2) ? p + A.n_dims / 2 : 2 * p + 1;
-        const float x0 = x[a], x1 = x[b];
-        y[a] = x0 * cs - x1 * sn;
-        y[b] = x0 * sn + x1 * cs;
+        const float x0 = ldf<T>(&x[a]), x1 = ldf<T>(&x[b]);
+        stf<T>(&y[a], x0 * cs - x1 * sn);
+        stf<T>(&y[b], x0 * sn + x1 * cs);
     }
 }
 
 // CTA = one (token, batch) slice: every head of the token rotates by the same n_dims/2 angles, so they are computed ONCE per CTA into shared memory
 // (the per-pair theta chain + sincosf was most of k_rope's time at prefill sizes) and the threads then stream the slice's heads.  Same arithmetic.
 constexpr int ROPE_TAB = 256;                                                // rotation pairs held in shared memory
+template <typename T>
 __global__ void __launch_bounds__(256) k_rope_rows(const RopeArgs A) {
     __shared__ float2 tab[ROPE_TAB];
     const int64_t i2 = blockIdx.x, i3 = blockIdx.y;
@@ -192,14 +194,14 @@ __global__ void __launch_bounds__(256) k_rope_rows(const RopeArgs A) {
     const int64_t half_n = A.x.ne[0] / 2, per_slice = half_n * A.x.ne[1];
     for (int64_t g = threadIdx.x; g < per_slice; g += blockDim.x) {
         const int64_t p = g % half_n, i1 = g / half_n;
-        const float * x = (const float *) (A.x.data + i1 * A.x.nb[1] + i2 * A.x.nb[2] + i3 * A.x.nb[3]);
-        float * y = (float *) (A.dst.data + i1 * A.dst.nb[1] + i2 * A.dst.nb[2] + i3 * A.dst.nb[3]);
+        const T * x = (const T *) (A.x.data + i1 * A.x.nb[1] + i2 * A.x.nb[2] + i3 * A.x.nb[3]);
+        T * y = (T *) (A.dst.data + i1 * A.dst.nb[1] + i2 * A.dst.nb[2] + i3 * A.dst.nb[3]);
         if (2 * p >= A.n_dims) { const int64_t i = A.n_dims + 2 * (p - np); y[i] = x[i]; y[i + 1] = x[i + 1]; continue; }
         const float2 cs = tab[p];
         const int64_t a = (A.mode & 2) ? p : 2 * p, b = (A.mode & 2) ? p + np : 2 * p + 1;
-        const float x0 = x[a], x1 = x[b];
-        y[a] = x0 * cs.x - x1 * cs.y;
-        y[b] = x0 * cs.y + x1 * cs.x;
+        const float x0 = ldf<T>(&x[a]), x1 = ldf<T>(&x[b]);
+        stf<T>(&y[a], x0 * cs.x - x1 * cs.y);
+        stf<T>(&y[b], x0 * cs.y + x1 * cs.x);
     }
 }
 
@@ -415,6 +417,9 @@ __global__ void __launch_bounds__(256) k_soft_max(const SmArgs A) {
 }
 
 static bool float_type(int t) { return t == B200_F32 || t == B200_F16 || t == B200_BF16; }
+// quant_rows.cu
+int quant_rows(const b200_tensor * src, const b200_tensor * idx, const b200_tensor * dst, cudaStream_t st);
+int dequant_rows(const b200_tensor * src, const b200_tensor * idx, const b200_tensor * dst, cudaStream_t st);
 
 } // namespace b200
 
@@ -457,7 +462,8 @@ static float yarn_corr_dim(int n_dims, int n_ctx_orig, float n_rot, float base) 
 extern "C" int b200_rope(const b200_tensor * x, const int32_t * pos, const float * freq_factors, const b200_tensor * dst,
                          const b200_rope_params * p, void * stream) {
     if (!x || !dst || !pos || !p) return B200_ERR_ARG;
-    if (x->type != B200_F32 || dst->type != B200_F32 || !same_shape(x, dst) || x->nb[0] != 4 || dst->nb[0] != 4) return B200_ERR_UNSUPPORTED;
+    // F16 in / out: the K-shift of the F16 KV cache (ggml_rope_ext_inplace on a cache view, src/llama-kv-cache.cpp build_rope_shift; CPU ggml_compute_forward_rope_f16)
+    if ((x->type != B200_F32 && x->type != B200_F16) || dst->type != x->type || !same_shape(x, dst) || x->nb[0] != type_size(x->type) || dst->nb[0] != x->nb[0]) return B200_ERR_UNSUPPORTED;
     if ((p->mode != 0 && p->mode != 2) || p->n_dims <= 0 || p->n_dims % 2 || p->n_dims > x->ne[0] || x->ne[0] % 2) return B200_ERR_UNSUPPORTED;
     RopeArgs A; A.x = t4(x); A.dst = t4(dst); A.pos = pos; A.ff = freq_factors; A.n_dims = p->n_dims; A.mode = p->mode;
     A.theta_scale = powf(p->freq_base, -2.0f / p->n_dims);
@@ -467,19 +473,26 @@ extern "C" int b200_rope(const b200_tensor * x, const int32_t * pos, const float
     A.corr0 = lo < 0 ? 0 : lo; A.corr1 = hi > p->n_dims - 1 ? p->n_dims - 1 : hi;
     const int64_t total = nelem(x) / 2;
     if (total == 0) return B200_OK;
-    if (p->n_dims / 2 <= ROPE_TAB && x->ne[2] <= 0x7fffffff && x->ne[3] <= 65535 && x->ne[1] * x->ne[0] >= 512)
-        k_rope_rows<<<dim3((unsigned) x->ne[2], (unsigned) x->ne[3]), 256, 0, (cudaStream_t) stream>>>(A);
-    else
-        k_rope<<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
+    const bool rows = p->n_dims / 2 <= ROPE_TAB && x->ne[2] <= 0x7fffffff && x->ne[3] <= 65535 && x->ne[1] * x->ne[0] >= 512;
+    const dim3 rgrid((unsigned) x->ne[2], (unsigned) x->ne[3]);
+    if (x->type == B200_F32) {
+        if (rows) k_rope_rows<float><<<rgrid, 256, 0, (cudaStream_t) stream>>>(A);
+        else      k_rope<float><<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
+    } else {
+        if (rows) k_rope_rows<__half><<<rgrid, 256, 0, (cudaStream_t) stream>>>(A);
+        else      k_rope<__half><<<grid_for(total, 256), 256, 0, (cudaStream_t) stream>>>(A, total);
+    }
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
 
 extern "C" int b200_set_rows(const b200_tensor * src, const b200_tensor * idx, const b200_tensor * dst, void * stream) {
     if (!src || !idx || !dst) return B200_ERR_ARG;
-    if (src->type != B200_F32 || !float_type(dst->type) || (idx->type != B200_I64 && idx->type != B200_I32)) return B200_ERR_UNSUPPORTED;
+    const bool qdst = dst->type == B200_Q8_0 || dst->type == B200_Q4_0;      // quantised KV cache (-ctk / -ctv): quant_rows.cu
+    if (src->type != B200_F32 || (!float_type(dst->type) && !qdst) || (idx->type != B200_I64 && idx->type != B200_I32)) return B200_ERR_UNSUPPORTED;
     if (src->ne[0] != dst->ne[0] || src->ne[2] != dst->ne[2] || src->ne[3] != dst->ne[3] || idx->ne[0] != src->ne[1]) return B200_ERR_UNSUPPORTED;
     if (idx->ne[1] == 0 || idx->ne[2] == 0 || src->ne[2] % idx->ne[1] || src->ne[3] % idx->ne[2]) return B200_ERR_UNSUPPORTED;
+    if (qdst) return quant_rows(src, idx, dst, (cudaStream_t) stream);
     const int64_t total = nelem(src);
     if (total == 0) return B200_OK;
     RowsArgs A = { t4(src), t4(idx), t4(dst) };
@@ -490,8 +503,9 @@ extern "C" int b200_set_rows(const b200_tensor * src, const b200_tensor * idx, c
 
 extern "C" int b200_get_rows(const b200_tensor * src, const b200_tensor * idx, const b200_tensor * dst, void * stream) {
     if (!src || !idx || !dst) return B200_ERR_ARG;
-    if (!float_type(src->type) || !float_type(dst->type) || idx->type != B200_I32) return B200_ERR_UNSUPPORTED;
-    if (src->ne[0] != dst->ne[0] || dst->ne[1] != idx->ne[0] || dst->ne[2] != idx->ne[1] || dst->ne[3] != idx->ne[2]) return B200_ERR_UNSUPPORTED;
+    if (idx->type != B200_I32 || src->ne[0] != dst->ne[0] || dst->ne[1] != idx->ne[0] || dst->ne[2] != idx->ne[1] || dst->ne[3] != idx->ne[2]) return B200_ERR_UNSUPPORTED;
+    if (is_quant(src->type)) return dst->type == B200_F32 ? dequant_rows(src, idx, dst, (cudaStream_t) stream) : B200_ERR_UNSUPPORTED;      // quantised token_embd
+    if (!float_type(src->type) || !float_type(dst->type)) return B200_ERR_UNSUPPORTED;
     const int64_t total = nelem(dst);
     if (total == 0) return B200_OK;
     RowsArgs A = { t4(src), t4(idx), t4(dst) };
@@ -503,6 +517,9 @@ extern "C" int b200_get_rows(const b200_tensor * src, const b200_tensor * idx, c
 extern "C" int b200_cpy(const b200_tensor * src, const b200_tensor * dst, void * stream) {
     if (!src || !dst) return B200_ERR_ARG;
     const bool ints = src->type == B200_I32 && dst->type == B200_I32;
+    // F32 -> q8_0 / q4_0 and quant -> F32 / F16 between tensors of the same shape (the K-shift of a quantised KV cache casts through F32)
+    if (src->type == B200_F32 && (dst->type == B200_Q8_0 || dst->type == B200_Q4_0)) return same_shape(src, dst) ? quant_rows(src, nullptr, dst, (cudaStream_t) stream) : B200_ERR_UNSUPPORTED;
+    if (is_quant(src->type) && (dst->type == B200_F32 || dst->type == B200_F16))     return same_shape(src, dst) ? dequant_rows(src, nullptr, dst, (cudaStream_t) stream) : B200_ERR_UNSUPPORTED;
     if (!ints && (!float_type(src->type) || !float_type(dst->type))) return B200_ERR_UNSUPPORTED;
     const int64_t total = nelem(src);
     if (total != nelem(dst)) return B200_ERR_UNSUPPORTED;

@@ -108,6 +108,8 @@ def T(t: torch.Tensor | None, type: int | None = None, ne=None, nb=None, layout:
     a uint8 tensor plus type and ne=[k, m(, ...)]; nb is then the packed ggml stride."""
     if t is None:
         return None
+    if isinstance(t, Tensor):                         # a ready descriptor (quantised tensors: T(u8, Q8_0, ne=[...], nb=[...]))
+        return t
     d = Tensor()
     d.data = t.data_ptr()
     d.layout = layout
@@ -274,8 +276,9 @@ def set_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> torch.T
     return dst
 
 
-def get_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-    out = torch.empty(list(idx.shape) + [src.shape[-1]], dtype=torch.float32, device=src.device)
+def get_rows(src, idx: torch.Tensor) -> torch.Tensor:
+    ne0 = int(src.ne[0]) if isinstance(src, Tensor) else src.shape[-1]          # a Tensor descriptor: quantised rows (native or planar)
+    out = torch.empty(list(idx.shape) + [ne0], dtype=torch.float32, device=idx.device)
     check(lib().b200_get_rows(_ref(T(src)), _ref(T(idx)), _ref(T(out)), stream()))
     return out
 
@@ -332,7 +335,7 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch.Te
     """q F32 [n_head, n_q, D] (any strides: pass the permuted view llama builds), k/v F16 [n_head_kv, n_kv, D] (any row strides),
     mask F16 [n_q_pad, n_kv] or None -> F32 [n_q, n_head, D]."""
     L = lib()
-    n_head, n_q, D = q.shape[-3:]
+    n_head, n_q, D = q.shape[-3:]                      # k / v may be Tensor descriptors of a quantised cache (q8_0 / q4_0)
     if out is None:
         out = torch.empty(list(q.shape[:-3]) + [n_q, n_head, D], dtype=torch.float32, device=q.device)
     qd, kd, vd, md, od = T(q), T(k), T(v), T(mask), T(out)

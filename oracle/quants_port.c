@@ -93,6 +93,24 @@ void or_quantize_q8_0(const float * x, void * vy, int64_t n, int variant) {
         }
     }
 }
+/* quantize_row_q4_0_ref, ggml-quants.c:36-71 (what SET_ROWS / CPY into a q4_0 KV cache run on the CPU: type_traits_cpu.from_float = quantize_row_q4_0 -> _ref) */
+void or_quantize_q4_0(const float * x, void * vy, int64_t n) {
+    or_q4_0 * y = vy;
+    for (int64_t b = 0; b < n/32; ++b) {
+        float amax = 0.0f, max = 0.0f;                        /* the FIRST element of largest magnitude keeps its sign */
+        for (int j = 0; j < 32; ++j) { const float v = x[32*b + j]; if (amax < fabsf(v)) { amax = fabsf(v); max = v; } }
+        const float d  = max / -8;
+        const float id = d ? 1.0f/d : 0.0f;
+        y[b].d = or_f2h(d);
+        for (int j = 0; j < 16; ++j) {
+            const float x0 = x[32*b + j]*id, x1 = x[32*b + 16 + j]*id;
+            int q0 = (int8_t) (x0 + 8.5f), q1 = (int8_t) (x1 + 8.5f);
+            if (q0 > 15) q0 = 15;
+            if (q1 > 15) q1 = 15;
+            y[b].qs[j] = (uint8_t) (q0 | (q1 << 4));
+        }
+    }
+}
 void or_quantize_q8_K(const float * x, void * vy, int64_t n) {
     or_q8_K * y = vy;
     for (int64_t b = 0; b < n/256; ++b, x += 256) {

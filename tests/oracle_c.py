@@ -39,6 +39,7 @@ def lib():
         L.or_dequant_row.restype, L.or_dequant_row.argtypes = I, [I, P, P, L64]
         L.or_quantize_q8_0.restype, L.or_quantize_q8_0.argtypes = None, [P, P, L64, I]
         L.or_quantize_q8_K.restype, L.or_quantize_q8_K.argtypes = None, [P, P, L64]
+        L.or_quantize_q4_0.restype, L.or_quantize_q4_0.argtypes = None, [P, P, L64]
         L.or_mul_mat.restype, L.or_mul_mat.argtypes = I, [I, P, P, P, L64, L64, L64, I]
         L.or_rms_norm.restype, L.or_rms_norm.argtypes = None, [P, P, L64, L64, F]
         L.or_rope.restype = None
@@ -77,6 +78,13 @@ def quantize_q8_0(x: np.ndarray, variant: int = 1) -> np.ndarray:
     x = np.ascontiguousarray(x, np.float32).reshape(-1)
     y = np.empty(row_size(Q8_0, x.size), np.uint8)
     lib().or_quantize_q8_0(_p(x), _p(y), x.size, variant)
+    return y
+
+
+def quantize_q4_0(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32).reshape(-1)
+    y = np.empty(row_size(Q4_0, x.size), np.uint8)
+    lib().or_quantize_q4_0(_p(x), _p(y), x.size)
     return y
 
 

@@ -825,3 +825,104 @@ def test_wave_conv_transpose_1d(ops, L, Cin, Cout, K, s0, wt):
     for k in range(K):
         mag[:, k:k + (L - 1) * s0 + 1:s0] += np.einsum("ic,il->cl", np.abs(w64[:, :, k]), np.abs(x.astype(np.float64)))
     assert np.all(np.abs(got - ref) <= 2e-6 * mag + 1e-9)
+
+
+# ---- data formats adjacent to the path (csrc/quant_rows.cu): quantised KV cache, quantised token_embd, K-shift ----------------------------------
+def _kv_desc(ops, buf, t, D, n_kv, n_head_kv):
+    """the view llama builds of a cache tensor [n_embd_kv, kv_size] (src/llama-kv-cache.cpp:981-1009): [D, n_kv, n_head_kv], heads side by side inside a row"""
+    blk, bs = O.BLOCK[t]
+    return ops.T(buf, t, ne=[D, n_kv, n_head_kv], nb=[bs, n_head_kv * D // blk * bs, D // blk * bs, n_kv * n_head_kv * D // blk * bs])
+
+
+@pytest.mark.parametrize("name", ["q8_0", "q4_0"])
+def test_set_rows_and_cpy_into_quantised_cache_bit_exact(ops, name):
+    """SET_ROWS / CPY F32 -> q8_0 | q4_0 (-ctk / -ctv): the blocks the CPU backend's from_float writes (quantize_row_q8_0 x86 flavour / quantize_row_q4_0_ref)."""
+    t = QT[name]
+    rng = np.random.default_rng(31)
+    n_tok, width, kv_size = 37, 1024, 96
+    x = (rng.standard_normal((n_tok, width)) * 2).astype(np.float32)
+    x[3, 64:96] = 0.0                                   # an all-zero block
+    x[5, 0:16] = 3.0; x[5, 16:32] = -3.0                # tied magnitudes of both signs (q4_0 keeps the first one's sign)
+    idx = rng.permutation(kv_size)[:n_tok].astype(np.int64)
+    rb = O.row_size(t, width)
+    cache = torch.zeros((kv_size, rb), dtype=torch.uint8, device="cuda")
+    quant = O.quantize_q8_0 if t == O.Q8_0 else O.quantize_q4_0
+    want = np.zeros((kv_size, rb), np.uint8)
+    for i, r in enumerate(idx):
+        want[r] = quant(x[i])
+    ops.set_rows(dev(x), dev(idx), ops.T(cache, t, ne=[width, kv_size]))
+    torch.cuda.synchronize()
+    assert np.array_equal(cache.cpu().numpy(), want)
+    flat = torch.zeros((n_tok, rb), dtype=torch.uint8, device="cuda")
+    ops.cpy(dev(x), ops.T(flat, t, ne=[width, n_tok]))
+    back = torch.empty((n_tok, width), dtype=torch.float32, device="cuda")
+    ops.cpy(ops.T(flat, t, ne=[width, n_tok]), back)
+    torch.cuda.synchronize()
+    assert np.array_equal(flat.cpu().numpy(), np.stack([quant(r) for r in x]))
+    assert np.array_equal(back.cpu().numpy(), O.dequant(t, flat.cpu().numpy(), width))
+
+
+@pytest.mark.parametrize("name", list(QT))
+def test_get_rows_from_quantised_rows(ops, name):
+    """GET_ROWS on a quantised token_embd, native blocks and (q4_0 / q8_0 / q6_K) the planar weight layout; oracle = dequantize_row_* port."""
+    t = QT[name]
+    rng = np.random.default_rng(41 + t)
+    n_rows, k = 300, 1024
+    blocks = rand_blocks(rng, t, n_rows * k // O.BLOCK[t][0])
+    idx = rng.integers(0, n_rows, (2, 17)).astype(np.int32)
+    want = O.dequant(t, blocks, k)[idx]
+    exact = t in (O.Q4_0, O.Q8_0, O.Q6_K)              # products only; q4_K / q5_K end in d*q - m, which nvcc and gcc may or may not contract to one FMA
+    layouts = [(dev(blocks), ops.LAYOUT_NATIVE)] + ([(ops.to_planar(t, dev(blocks)), ops.LAYOUT_PLANAR)] if t in ops.PAYLOAD else [])
+    for w, lay in layouts:
+        got = ops.get_rows(ops.T(w, t, ne=[k, n_rows], layout=lay), dev(idx[0])).cpu().numpy()
+        if exact:
+            assert np.array_equal(got, want[0]), lay
+        else:
+            np.testing.assert_allclose(got, want[0], rtol=1e-6, atol=1e-7)
+    wb = dev(blocks)                                   # (keep the device copy alive: a descriptor only holds its address)
+    got = ops.get_rows(ops.T(wb, t, ne=[k, n_rows // 2, 2]), dev(idx % (n_rows // 2))).cpu().numpy()      # batched: idx [2, 17] over src [k, 150, 2]
+    ref = O.dequant(t, blocks, k).reshape(2, n_rows // 2, k)
+    for b in range(2):
+        np.testing.assert_allclose(got[b], ref[b][idx[b] % (n_rows // 2)], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,n_q,n_kv,D,n_head,n_head_kv", [("q8_0", 1, 1024, 128, 32, 8), ("q4_0", 1, 512, 128, 8, 2), ("q8_0", 3, 256, 64, 12, 12), ("q8_0", 200, 512, 128, 8, 2),
+                                                               ("q4_0", 64, 256, 128, 8, 2)])
+def test_flash_attn_over_quantised_kv(ops, name, n_q, n_kv, D, n_head, n_head_kv):
+    """FLASH_ATTN_EXT with a q8_0 / q4_0 KV cache: K and V are staged as F16 (the reference's launch_fattn does the same to_fp16 pass), so the result must be bit for bit
+    the F16-cache result on the dequantised, F16-rounded values; that F16 run is itself pinned to the oracle by the tests above."""
+    t = QT[name]
+    rng = np.random.default_rng(n_q * 7 + n_kv)
+    past = n_kv - n_q - 5 if n_q > 1 else n_kv - 9
+    kf = (rng.standard_normal((n_kv, n_head_kv * D)) * 0.5).astype(np.float32)
+    vf = rng.standard_normal((n_kv, n_head_kv * D)).astype(np.float32)
+    quant = O.quantize_q8_0 if t == O.Q8_0 else O.quantize_q4_0
+    kq = np.stack([quant(r) for r in kf]); vq = np.stack([quant(r) for r in vf])
+    k16 = dev(O.dequant(t, kq, n_head_kv * D)).half().view(n_kv, n_head_kv, D).permute(1, 0, 2)
+    v16 = dev(O.dequant(t, vq, n_head_kv * D)).half().view(n_kv, n_head_kv, D).permute(1, 0, 2)
+    q = dev(rng.standard_normal((n_head, n_q, D)).astype(np.float32))
+    n_pad = (n_q + 63) // 64 * 64
+    mask = torch.full((n_pad, n_kv), float("-inf"), dtype=torch.float16, device="cuda")
+    for i in range(n_q):
+        mask[i, :past + i + 1] = 0
+    want = ops.flash_attn(q, k16, v16, mask, 1.0 / D ** 0.5)
+    kqd, vqd = dev(kq), dev(vq)
+    got = ops.flash_attn(q, _kv_desc(ops, kqd, t, D, n_kv, n_head_kv), _kv_desc(ops, vqd, t, D, n_kv, n_head_kv), mask, 1.0 / D ** 0.5)
+    torch.cuda.synchronize()
+    assert torch.isfinite(want).all() and torch.equal(got, want)
+
+
+def test_rope_f16_in_place_is_the_f32_rope_rounded_once(ops):
+    """K-shift of the F16 cache (ggml_rope_ext_inplace on a cache view; CPU ggml_compute_forward_rope_f16: F16 -> F32, rotate, -> F16)."""
+    rng = np.random.default_rng(51)
+    n_tok, n_head, D = 300, 8, 128
+    x = dev(rng.standard_normal((n_tok, n_head, D)).astype(np.float32)).half()
+    pos = dev(rng.integers(-50, 4000, n_tok).astype(np.int32))
+    for mode in (0, 2):
+        want = ops.rope(x.float(), pos, D, mode).half()
+        buf = x.clone()
+        ops.rope(buf, pos, D, mode, out=buf)
+        torch.cuda.synchronize()
+        assert torch.equal(buf, want)
+    small = x[:3, :2].contiguous()                       # the generic (non table) kernel
+    assert torch.equal(ops.rope(small, pos[:3].contiguous(), 64, 2), ops.rope(small.float(), pos[:3].contiguous(), 64, 2).half())

@@ -56,6 +56,9 @@ def test_activation_quantisers(seed):
     assert np.array_equal(_canon_q8K(O.quantize_q8_K(x)), _canon_q8K(R.quantize_act(R.Q8_K, x, simd=True)))
     assert np.array_equal(O.quantize_q8_0(x, 0), R.quantize_act(R.Q8_0, x))
     assert np.array_equal(O.quantize_q8_0(x, 1), R.quantize_act(R.Q8_0, x, simd=True))
+    x[32:64] = -x[0:32]                                       # equal magnitudes, opposite signs: the first largest element wins
+    x[96] = 7.25; x[97] = -7.25
+    assert np.array_equal(O.quantize_q4_0(x), R.quantize(R.Q4_0, x.reshape(1, -1)).reshape(-1))      # ggml_quantize_chunk -> quantize_row_q4_0_ref
 
 
 @pytest.mark.parametrize("t", QT)

@@ -39,7 +39,7 @@ def test_plugin_exports_the_dlsym_entry_points():
     assert {"ggml_backend_init", "ggml_backend_score", "ggml_backend_b200_reg", "ggml_backend_b200_init", "ggml_backend_b200_abi"} <= exported
 
 
-@pytest.mark.parametrize("op", ["MUL_MAT", "FLASH_ATTN_EXT", "RMS_NORM", "ROPE", "SET_ROWS", "GET_ROWS", "GLU", "ADD", "MUL", "CPY", "SOFT_MAX", "NORM", "IM2COL",
+@pytest.mark.parametrize("op", ["MUL_MAT", "FLASH_ATTN_EXT", "RMS_NORM", "ROPE", "SET_ROWS", "GET_ROWS", "GLU", "ADD", "MUL", "CPY", "SOFT_MAX", "NORM", "IM2COL", "CONT,DUP",
                                 "CONCAT,REPEAT,ARANGE,SUM_ROWS,PAD,PAD_REFLECT_1D,CONV_TRANSPOSE_1D",                 # Token2Wav op set (the filter is a comma list)
                                 "SIN,COS,LOG,CLAMP,LEAKY_RELU,ELU,STEP,SGN,HARDSWISH,HARDSIGMOID,SCALE,SQR,SQRT"])
 def test_reference_backend_ops_harness(op):
