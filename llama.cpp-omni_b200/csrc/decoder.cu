@@ -29,6 +29,9 @@ struct Decoder {
 };
 
 static int64_t row_bytes(int type, int64_t k) { return k / blck_size(type) * type_size(type); }
+// activation record a weight type multiplies with: q8_K per 256 for the K-quants, q8_0 per 32 for q4_0 / q8_0 (the CPU backend's vec_dot_type, ggml-cpu.c:196-350);
+// every matrix of one phase must want the same record
+static int act_group_of(int type) { return is_kquant(type) ? 256 : 32; }
 static float yarn_dim(int n_dims, int n_ctx_orig, float n_rot, float base) { return n_dims * logf(n_ctx_orig / (n_rot * 2 * (float) M_PI)) / (2 * logf(base)); }
 } // namespace b200
 
@@ -76,9 +79,9 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
         const b200_decode_layer & L = d->layers[il];
         const float * resid_in = n_x == 1 ? xin[0] : xres;               // what wo adds back: the layer input
         {   // A
-            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 3; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_RMSNORM_QUANT; P.k = E; P.act_group = 256;
+            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 3; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_RMSNORM_QUANT; P.k = E; P.act_group = act_group_of(L.wq.type);
             P.eps = d->rms_eps; P.ksplit = 1; set_x(P); P.x_out = n_x == 1 ? nullptr : xres; P.norm_w = L.attn_norm;
-            ok = ok && L.attn_norm && is_kquant(L.wq.type) && is_kquant(L.wk.type) && is_kquant(L.wv.type);
+            ok = ok && L.attn_norm && is_quant(L.wq.type) && is_quant(L.wk.type) && is_quant(L.wv.type) && act_group_of(L.wk.type) == P.act_group && act_group_of(L.wv.type) == P.act_group;
             ok = ok && sd_fill_mat(P.mat[0], L.wq.data, L.wq.type, L.wq.layout, Q, E, row_bytes(L.wq.type, E), q, nullptr);
             ok = ok && sd_fill_mat(P.mat[1], L.wk.data, L.wk.type, L.wk.layout, KV, E, row_bytes(L.wk.type, E), k, nullptr);
             ok = ok && sd_fill_mat(P.mat[2], L.wv.data, L.wv.type, L.wv.layout, KV, E, row_bytes(L.wv.type, E), v, nullptr);
@@ -98,23 +101,23 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
             ph.push_back(P);
         }
         {   // C
-            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = Q; P.act_group = 256; P.ksplit = 1;
+            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = Q; P.act_group = act_group_of(L.wo.type); P.ksplit = 1;
             P.x[0] = attn; P.n_x = 1;
-            ok = ok && is_kquant(L.wo.type) && sd_fill_mat(P.mat[0], L.wo.data, L.wo.type, L.wo.layout, E, Q, row_bytes(L.wo.type, Q), x1, resid_in);
+            ok = ok && is_quant(L.wo.type) && sd_fill_mat(P.mat[0], L.wo.data, L.wo.type, L.wo.layout, E, Q, row_bytes(L.wo.type, Q), x1, resid_in);
             ok = ok && sd_phase_ok(P); ph.push_back(P);
         }
         {   // D
-            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 2; P.epilogue = SD_EPI_SWIGLU; P.prologue = SD_PRO_RMSNORM_QUANT; P.k = E; P.act_group = 256;
+            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 2; P.epilogue = SD_EPI_SWIGLU; P.prologue = SD_PRO_RMSNORM_QUANT; P.k = E; P.act_group = act_group_of(L.gate.type);
             P.eps = d->rms_eps; P.ksplit = 1; P.x[0] = x1; P.n_x = 1; P.norm_w = L.ffn_norm;
-            ok = ok && L.ffn_norm && is_kquant(L.gate.type) && L.gate.type == L.up.type;
+            ok = ok && L.ffn_norm && is_quant(L.gate.type) && L.gate.type == L.up.type;
             ok = ok && sd_fill_mat(P.mat[0], L.gate.data, L.gate.type, L.gate.layout, F, E, row_bytes(L.gate.type, E), h, nullptr);
             ok = ok && sd_fill_mat(P.mat[1], L.up.data, L.up.type, L.up.layout, F, E, row_bytes(L.up.type, E), h, nullptr);
             ok = ok && sd_phase_ok(P); ph.push_back(P);
         }
         {   // E
-            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = F; P.act_group = 256; P.ksplit = ks;
+            SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = 1; P.epilogue = SD_EPI_STORE; P.prologue = SD_PRO_QUANT; P.k = F; P.act_group = act_group_of(L.down.type); P.ksplit = ks;
             P.x[0] = h; P.n_x = 1; P.y_part_stride = ks > 1 ? E : 0;
-            ok = ok && is_kquant(L.down.type);
+            ok = ok && is_quant(L.down.type);
             ok = ok && sd_fill_mat(P.mat[0], L.down.data, L.down.type, L.down.layout, E, F, row_bytes(L.down.type, F), ks > 1 ? part : x2, ks > 1 ? nullptr : x1);
             ok = ok && sd_phase_ok(P); ph.push_back(P);
         }
@@ -122,10 +125,10 @@ extern "C" int b200_decoder_create(const b200_decode_desc * d, void ** handle) {
         else        { xin[0] = x2; n_x = 1; }
     }
     if (ok) {   // Z: lm_head (or, for a pipeline stage without head, just materialise the summed residual stream)
-        SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = d->lm_head.data ? 1 : 0; P.epilogue = SD_EPI_STORE; P.k = E; P.act_group = 256; P.ksplit = 1;
+        SdPhase P = {}; P.kind = SD_MATVEC; P.n_mat = d->lm_head.data ? 1 : 0; P.epilogue = SD_EPI_STORE; P.k = E; P.act_group = d->lm_head.data ? act_group_of(d->lm_head.type) : 256; P.ksplit = 1;
         P.prologue = d->lm_head.data ? SD_PRO_RMSNORM_QUANT : SD_PRO_QUANT; P.eps = d->rms_eps; set_x(P); P.x_out = d->x_out; P.norm_w = d->out_norm; P.norm_out = d->hidden_out;
         if (d->lm_head.data) {
-            ok = ok && d->out_norm && d->logits && is_kquant(d->lm_head.type);
+            ok = ok && d->out_norm && d->logits && is_quant(d->lm_head.type);
             ok = ok && sd_fill_mat(P.mat[0], d->lm_head.data, d->lm_head.type, d->lm_head.layout, d->n_vocab, E, row_bytes(d->lm_head.type, E), d->logits, nullptr);
         } else ok = ok && d->x_out;
         ok = ok && sd_phase_ok(P); ph.push_back(P);

@@ -4,6 +4,7 @@
 //                   the weight type first exactly like the CPU oracle does (vec_dot_type, ggml-cpu.c:196-350)
 // Batch dims follow ggml broadcast rules: w.ne[2] divides x.ne[2], w.ne[3] divides x.ne[3].
 #include "common.cuh"
+#include <type_traits>
 #include <stdlib.h>
 
 namespace b200 {
@@ -82,8 +83,54 @@ __global__ void __launch_bounds__(256) k_mmvf(const MmvfArgs A, int64_t col0) {
     }
 }
 
+// F16 weights, ONE activation column, 2-D weight: the decode matvec of an F16 model (BASELINE.json configs[4], the TTS llama, the projector) — HBM-bound.
+// The CTA rounds the activation vector to F16 once into shared memory (the oracle's vec_dot_type for F16 weights: ggml-cpu.c type_traits_cpu[F16], products of F16
+// values accumulated in F32); every warp then streams TWO rows at a time with two 16-byte loads per row in flight (4 x 512 B per warp on the wire), so that
+// ~128 KB per SM are outstanding — what 6.4 TB/s x ~1 us of latency needs.  Replaces mul_mat_vec_f (ggml-cuda/mmvf.cu:309) for ncols = 1.
+__device__ __forceinline__ float dot8_f16(const uint4 w, const uint4 x, float acc) {
+    const __half2 * wh = (const __half2 *) &w, * xh = (const __half2 *) &x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 a = __half22float2(wh[i]), b = __half22float2(xh[i]); acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); }
+    return acc;
+}
+__global__ void __launch_bounds__(256) k_mmvf16_stream(const __half * __restrict__ w, int64_t w_ld, const float * __restrict__ x, float * __restrict__ y, int64_t m, int64_t k) {
+    extern __shared__ __align__(16) __half xs[];
+    for (int64_t i = (int64_t) threadIdx.x * 4; i < k; i += 256 * 4) {
+        const float4 v = *(const float4 *) (x + i);
+        *(__half2 *) (xs + i) = __floats2half2_rn(v.x, v.y); *(__half2 *) (xs + i + 2) = __floats2half2_rn(v.z, v.w);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t) gridDim.x * 8;
+    for (int64_t r0 = ((int64_t) blockIdx.x * 8 + (threadIdx.x >> 5)) * 2; r0 < m; r0 += nwarps * 2) {
+        const bool two = r0 + 1 < m;
+        const __half * w0 = w + r0 * w_ld, * w1 = w + (two ? r0 + 1 : r0) * w_ld;
+        float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+        int64_t i = (int64_t) lane * 8;
+        for (; i + 256 < k; i += 512) {
+            const uint4 p0 = ldg_stream16(w0 + i), p1 = ldg_stream16(w1 + i), q0 = ldg_stream16(w0 + i + 256), q1 = ldg_stream16(w1 + i + 256);
+            const uint4 xa = *(const uint4 *) (xs + i), xb = *(const uint4 *) (xs + i + 256);
+            a0 = dot8_f16(p0, xa, a0); a1 = dot8_f16(p1, xa, a1); b0 = dot8_f16(q0, xb, b0); b1 = dot8_f16(q1, xb, b1);
+        }
+        if (i < k) {
+            const uint4 p0 = ldg_stream16(w0 + i), p1 = ldg_stream16(w1 + i);
+            const uint4 xa = *(const uint4 *) (xs + i);
+            a0 = dot8_f16(p0, xa, a0); a1 = dot8_f16(p1, xa, a1);
+        }
+        const float s0 = warp_sum(a0 + b0), s1 = warp_sum(a1 + b1);
+        if (lane == 0) { y[r0] = s0; if (two) y[r0 + 1] = s1; }
+    }
+}
+
 template <typename WT>
 static int run_mmvf(const MmvfArgs & A, cudaStream_t st) {
+    if (sizeof(WT) == 2 && std::is_same<WT, __half>::value && A.n == 1 && A.ne2 * A.ne3 == 1 && A.k % 256 == 0 && A.k <= 24576 && A.w_nb1 % 16 == 0 &&
+        ((uintptr_t) A.w | (uintptr_t) A.x) % 16 == 0 && A.m >= 64) {
+        int64_t g = (A.m / 2 + 7) / 8; const int64_t cap = (int64_t) sm_count() * 8; if (g > cap) g = cap;
+        k_mmvf16_stream<<<(unsigned) g, 256, (size_t) A.k * 2, st>>>((const __half *) A.w, A.w_nb1 / 2, (const float *) A.x, (float *) A.y, A.m, A.k);
+        B200_LAUNCH_CHECK();
+        return B200_OK;
+    }
     const int64_t warps = A.m * A.ne2 * A.ne3;
     const unsigned grid = (unsigned) ((warps + 7) / 8);
     for (int64_t c0 = 0; c0 < A.n; c0 += 8) {

@@ -576,7 +576,7 @@ bool sd_phase_ok(const SdPhase & P) {
         if (M.row_bytes_p % ks || M.row_bytes_d % ks) return false;
         const int sp = M.row_bytes_p / ks, sd = M.row_bytes_d / ks;
         if (sp % 16 || sd % 16 || (sp + sd) * nm > SD_SLOT_BYTES) return false;
-        if (ks > 1 && (kl % 256 || !is_kquant(M.type))) return false;      // K-split: whole super-blocks per slice, K-quants only
+        if (ks > 1 && kl % 256) return false;                              // K-split: whole super-blocks (8 q4_0 / q8_0 blocks) per slice
         if ((is_kquant(M.type) ? 256 : 32) != P.act_group) return false;
     }
     if (nm == 2 && (P.n_mat != 2 || P.mat[0].type != P.mat[1].type || P.mat[0].rows != P.mat[1].rows || P.mat[0].row_bytes_p != P.mat[1].row_bytes_p)) return false;

@@ -200,7 +200,7 @@ class Qwen3Decoder:
         kvb = cfg.n_head_kv * cfg.head_dim * 2
 
         def W(t, wtype):
-            return ops.Weight(t.data_ptr(), wtype, ops.LAYOUT_PLANAR if wtype == ops.Q6_K else ops.LAYOUT_NATIVE)
+            return ops.Weight(t.data_ptr(), wtype, ops.LAYOUT_PLANAR if wtype in ops.PAYLOAD else ops.LAYOUT_NATIVE)     # q6_K / q8_0 / q4_0 stream from the planar layout
         layers = (ops.DecodeLayer * len(self.L))()
         for i, lw in enumerate(self.L):
             ty = lw["types"]

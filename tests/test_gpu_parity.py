@@ -258,6 +258,20 @@ def test_mul_mat_float_weights(ops, dt):
     assert np.abs(got - ref).max() <= 1e-5 * (np.abs(x) @ np.abs(w).T).max()
 
 
+@pytest.mark.parametrize("m,k", [(4096, 4096), (4096, 12288), (151748, 4096), (65, 768), (64, 256), (3072, 768)])
+def test_mul_mat_f16_weights_decode_stream(ops, m, k):
+    """The single-column F16 matvec (k_mmvf16_stream: the decode path of an F16 model and of the TTS llama): products of F16-rounded operands, F32 accumulation."""
+    rng = np.random.default_rng(m + k)
+    w = dev((rng.standard_normal((m, k)) * 0.05).astype(np.float32)).half()
+    x = rng.standard_normal((1, k)).astype(np.float32)
+    got = ops.mul_mat(w, ops.F16, m, k, dev(x), w_ne=[k, m])
+    xr = dev(x).half().double()
+    ref = xr @ w.double().T
+    mag = xr.abs() @ w.double().abs().T
+    torch.cuda.synchronize()
+    assert bool(((got.double() - ref).abs() <= 2e-6 * mag + 1e-12).all())
+
+
 @pytest.mark.parametrize("m,k,n,batch", [(4096, 4096, 512, None), (300, 1024, 77, None), (129, 64, 9, None), (1152, 4304 // 16 * 16 - 4304 % 64, 200, None),
                                           (256, 256, 33, (2, 3))])
 def test_mul_mat_f16_weights_tensor_core(ops, m, k, n, batch):
@@ -617,17 +631,22 @@ def _oracle_model(dec, ops, cfg, rng, variant):
         ty = dict(lw["types"])
         if variant == "q5k":                                                  # the q5_K route of the engine (fragments re-read from shared memory)
             ty.update({"wq": ops.Q5_K, "wk": ops.Q5_K, "wo": ops.Q5_K, "down": ops.Q5_K})     # (a q5_K gate/up PAIR exceeds a ring slot: not streamable)
+        if variant in ("q4_0", "q8_0"):                                       # whole-model Q4_0 / Q8_0 files: q8_0 activation records (group 32), planar weight rows
+            ty = {n: QT[variant] for n in shapes}
         lw["types"] = ty
         ol = {"types": ty}
         for n, (m, k) in shapes.items():
             blocks = rand_blocks(rng, ty[n], m * k // O.BLOCK[ty[n]][0])
             if ty[n] in (O.Q4_K, O.Q5_K):                                     # scales like a real file: d, dmin ~ 1e-4
                 blocks[:, 0:4] = np.frombuffer(rng.uniform(2e-5, 2e-4, (blocks.shape[0], 2)).astype(np.float16).tobytes(), np.uint8).reshape(-1, 4)
-            else:
+            elif ty[n] == O.Q6_K:
                 blocks[:, 208:210] = np.frombuffer(rng.uniform(2e-5, 2e-4, blocks.shape[0]).astype(np.float16).tobytes(), np.uint8).reshape(-1, 2)
+            else:                                                             # q4_0 (codes -8..7) / q8_0 (codes -128..127): d so that the weights are ~1e-2
+                lo, hi = (5e-4, 2e-3) if ty[n] == O.Q4_0 else (3e-5, 1.2e-4)
+                blocks[:, 0:2] = np.frombuffer(rng.uniform(lo, hi, blocks.shape[0]).astype(np.float16).tobytes(), np.uint8).reshape(-1, 2)
             ol[n] = blocks
             wd = dev(blocks.reshape(-1))
-            lw[n] = ops.to_planar(ty[n], wd) if ty[n] == ops.Q6_K else wd
+            lw[n] = ops.to_planar(ty[n], wd) if ty[n] in ops.PAYLOAD else wd
         for n in ("attn_norm", "ffn_norm", "q_norm", "k_norm"):
             ol[n] = lw[n].cpu().numpy().astype(np.float32)
         if variant == "llama":                                                # llm_build_llama: no q/k norm, ROPE mode 0 (adjacent pairs)
@@ -645,7 +664,7 @@ def _oracle_model(dec, ops, cfg, rng, variant):
     return D, o_layers, head
 
 
-@pytest.mark.parametrize("variant", ["qwen3", "llama", "stage", "q5k"])
+@pytest.mark.parametrize("variant", ["qwen3", "llama", "stage", "q5k", "q4_0", "q8_0"])
 def test_decode_engine_whole_token_matches_oracle(ops, variant):
     """north_star parity for the dominant kernel: ONE whole token of k_stream (b200_decoder_step) against the CPU ORACLE chain
     (tests/oracle_decode.py: q8_K quantise -> integer-dot matvec -> RMS_NORM -> ROPE -> F16 cache write -> FLASH_ATTN_EXT -> SWIGLU, every
@@ -656,6 +675,8 @@ def test_decode_engine_whole_token_matches_oracle(ops, variant):
     dec = load_package().decode
     rng = np.random.default_rng(11)
     cfg = dec.LLMConfig(n_layer=4, n_vocab=8192, n_ctx=1024)
+    if variant == "q8_0":                 # a q8_0 gate/up row PAIR must fit one 4608-byte ring slot: n_embd <= 2048 (k + k/16 bytes per row)
+        cfg = dec.LLMConfig(name="q8_0-2048", n_embd=2048, n_layer=3, n_head=16, n_head_kv=4, n_ff=6144, n_vocab=8192, n_ctx=1024)
     D, o_layers, head = _oracle_model(dec, ops, cfg, rng, variant)
     n_kv, depth = 512, 300
     kvw = cfg.n_head_kv * cfg.head_dim
@@ -674,6 +695,20 @@ def test_decode_engine_whole_token_matches_oracle(ops, variant):
         D.x_in.copy_(dev(xs)); D.pos.copy_(hi["pos"]); D.kv_idx.copy_(hi["kv_idx"]); D.mask_f32[:, :n_kv].copy_(hi["mask"])
         D.step_engine(n_kv)
         torch.cuda.synchronize()
+        bar = 1e-3
+        if variant in ("q4_0", "q8_0"):
+            # q8_0 activation records re-quantise every 32 values with their own scale: on these random weights the ORACLE itself moves by more than 1e-3 when its
+            # input is nudged by 2e-6 (what another f32 summation order does; tests/test_chaos_yardstick.py).  The bar is what the oracle differs from its nudged self.
+            import copy
+            yard = []
+            for trial in range(3):
+                ol2 = copy.deepcopy(o_layers)
+                nudged = (xs.astype(np.float64) * (1.0 + 2e-6 * rng.standard_normal(xs.size))).astype(np.float32)
+                pl, _, _ = OD.oracle_token(cfg, ol2, nudged, pos, n_kv, head, rope_mode=2, f16_acc=False)
+                bl, _, _ = OD.oracle_token(cfg, copy.deepcopy(o_layers), xs, pos, n_kv, head, rope_mode=2, f16_acc=False)
+                yard.append(float(np.abs(pl - bl).max() / np.abs(bl).max()))
+            bar = max(1e-3, 2.0 * max(yard))
+            print(variant, "oracle vs nudged oracle:", ["%.2e" % y for y in yard], "bar %.2e" % bar)
         ref_logits, ref_x, ref_hn = OD.oracle_token(cfg, o_layers, xs, pos, n_kv, head, rope_mode=0 if variant == "llama" else 2, f16_acc=False)
         # the residual stream (what a pipeline stage hands to the next one)
         gx = D.engine_x_out.cpu().numpy() if not D.has_head else None
@@ -683,14 +718,16 @@ def test_decode_engine_whole_token_matches_oracle(ops, variant):
             got = D.logits.cpu().numpy()
             assert np.isfinite(got).all()
             rel = np.abs(got - ref_logits).max() / np.abs(ref_logits).max()
-            assert rel <= 1e-3, (variant, step, rel)
-            assert int(got.argmax()) == int(ref_logits.argmax()), (variant, step)
+            assert rel <= bar, (variant, step, rel, bar)
+            top2 = np.sort(ref_logits)[-2:]
+            if bar == 1e-3 or top2[1] - top2[0] > 2 * bar * np.abs(ref_logits).max():
+                assert int(got.argmax()) == int(ref_logits.argmax()), (variant, step)
             hn = hidden.cpu().numpy()
-            assert np.abs(hn - ref_hn).max() <= 1e-3 * np.abs(ref_hn).max(), (variant, step)
+            assert np.abs(hn - ref_hn).max() <= bar * np.abs(ref_hn).max(), (variant, step)
         for lw, ol in zip(D.L, o_layers):                                     # SET_ROWS parity of this token's cache rows
             for c in ("k_cache", "v_cache"):
                 g, r = lw[c][pos].float().cpu().numpy(), ol[c][pos].astype(np.float32)
-                assert np.abs(g - r).max() <= 2e-3 * max(1.0, np.abs(r).max()), (variant, step, c, np.abs(g - r).max())
+                assert np.abs(g - r).max() <= 2e-3 * (bar / 1e-3) * max(1.0, np.abs(r).max()), (variant, step, c, np.abs(g - r).max())
 
 
 # ---------------------------------------------------------------------------------------------------------------- APM / VPM encoder ops
