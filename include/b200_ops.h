@@ -98,6 +98,12 @@ B200_API int    b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const
 enum { B200_MM_REUSE_ACT = 1 };
 B200_API int    b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
                                 size_t scratch_bytes, int flags, void * stream);
+/* dst[i] = W[i] . x for 2 or 3 weight matrices over the SAME activations (q / k / v of a layer): one tcgen05 launch over the concatenated m-tiles when every W[i] is
+ * a K-quant on the tensor-core path and the merged tile count needs no split-K; otherwise the MUL_MATs run one after the other sharing the activation tiles.
+ * (ggml-cuda has no counterpart: ggml_cuda_mul_mat_q is launched once per node, mmq.cu:205.)  scratch >= the largest b200_mul_mat_scratch_bytes of the group. */
+B200_API int    b200_mul_mat_multi_merges(int n_mat, const b200_tensor * const * w, const b200_tensor * x);   /* 1: the group runs as one launch */
+B200_API int    b200_mul_mat_multi(int n_mat, const b200_tensor * const * w, const b200_tensor * x, const b200_tensor * const * dst, void * scratch,
+                                   size_t scratch_bytes, int flags, void * stream);
 /* dst = W . x + residual (the ADD behind wo / ffn_down, ggml-cuda fuses nothing here): rides in the tensor-core GEMM's epilogue when it can (quantised weights, 2-D
  * operands, no split-K), otherwise MUL_MAT + ADD kernels; residual has dst's shape and row stride and may alias dst. */
 B200_API int    b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, const b200_tensor * residual, const b200_tensor * dst, void * scratch,

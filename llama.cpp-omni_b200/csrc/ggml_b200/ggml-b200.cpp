@@ -78,6 +78,10 @@ struct BackendCtx {
     // activation-tile reuse (B200_MM_REUSE_ACT): the tensor whose prepared activations the scratch currently holds, reset per graph_compute
     const ggml_tensor * scratch_act = nullptr; const void * scratch_act_data = nullptr; int scratch_act_type = -1;
     bool scratch_tiles_fused = false;                        // the tiles in the scratch came from a fused producer (fuse_tiles): the F32 tensor may not exist
+    // q / k / v in one launch (b200_mul_mat_multi): the results of the MUL_MAT nodes computed EARLY (with the first of the group) wait here until the graph reaches
+    // their node — their own dst may still hold a live tensor at that point (ggml-alloc reuses buffers in node order)
+    void * hoist_buf = nullptr; size_t hoist_size = 0;
+    const ggml_tensor * hoisted[2] = { nullptr, nullptr }; void * hoisted_at[2] = { nullptr, nullptr };
 };
 
 DeviceCtx g_devices[MAX_DEVICES];
@@ -462,6 +466,7 @@ bool mm_tc_class(const ggml_tensor * n) {
 // toggles it between two runs of one process (llama_parity mode 8)
 bool fusion_off() { const char * env = getenv("GGML_B200_NO_TILE_FUSION"); return env && atoi(env) != 0; }
 
+bool is_weight(const ggml_tensor * t);
 int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool allow_fuse = false) {
     ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, node_idx);
     ggml_tensor * next = allow_fuse && node_idx + 1 < ggml_graph_n_nodes((ggml_cgraph *) g) ? ggml_graph_node((ggml_cgraph *) g, node_idx + 1) : nullptr;
@@ -480,6 +485,43 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             const bool tc_class = mm_tc_class(n);
             const bool reuse = tc_class && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == 1;
             c->scratch_act = tc_class ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = tc_class ? 1 : 0;
+            // q / k / v: the later MUL_MATs over the same activations run with this one (one launch over the concatenated m-tiles); their results are parked in
+            // hoist_buf and copied out when the graph reaches them (run_nodes)
+            if (allow_fuse && tc_class && !fusion_off() && !c->hoisted[0] && x.ne[2] * x.ne[3] == 1) {
+                const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+                const ggml_tensor * later[2] = { nullptr, nullptr }; int n_later = 0;
+                for (int j = node_idx + 1; j < nn && j <= node_idx + 16 && n_later < 2; ++j) {
+                    const ggml_tensor * t = ggml_graph_node((ggml_cgraph *) g, j);
+                    if (t->op == GGML_OP_MUL_MAT && t->src[1] == s1 && t->src[0] != s0 && is_weight(t->src[0]) && mm_tc_class(t) && ggml_is_contiguous(t) && ggml_is_contiguous(n) &&
+                        (t->src[0]->type == GGML_TYPE_Q4_K || t->src[0]->type == GGML_TYPE_Q5_K || t->src[0]->type == GGML_TYPE_Q6_K)) later[n_later++] = t;
+                }
+                if (n_later > 0 && is_weight(s0) && (s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q5_K || s0->type == GGML_TYPE_Q6_K)) {
+                    b200_tensor wv[3] = { w, view_of(later[0]->src[0]), n_later > 1 ? view_of(later[1]->src[0]) : w };
+                    const b200_tensor * wp[3] = { &wv[0], &wv[1], &wv[2] };
+                    if (b200_mul_mat_multi_merges(1 + n_later, wp, &x)) {
+                        size_t need = 0, off[2] = { 0, 0 };
+                        for (int i = 0; i < n_later; ++i) { off[i] = need; need += (ggml_nbytes(later[i]) + 255) & ~(size_t) 255; }
+                        if (need > c->hoist_size) {
+                            CUDA_OK(cudaStreamSynchronize(c->stream));
+                            if (c->hoist_buf) CUDA_OK(cudaFree(c->hoist_buf));
+                            c->hoist_size = need; CUDA_OK(cudaMalloc(&c->hoist_buf, need));
+                        }
+                        b200_tensor dv[3] = { d, view_of(later[0]), n_later > 1 ? view_of(later[1]) : d };
+                        size_t sbm = sb;
+                        for (int i = 0; i < n_later; ++i) {
+                            dv[1 + i].data = (char *) c->hoist_buf + off[i];
+                            const size_t sbi = b200_mul_mat_scratch_bytes(&wv[1 + i], &x); if (sbi > sbm) sbm = sbi;
+                        }
+                        if (sbm <= c->scratch_size || !reuse) {                  // growing the scratch would drop the prepared tiles
+                            void * scm = scratch_for(c, sbm);
+                            const b200_tensor * dp[3] = { &dv[0], &dv[1], &dv[2] };
+                            rc = b200_mul_mat_multi(1 + n_later, wp, &x, dp, scm, sbm, reuse && scm == scratch_before ? B200_MM_REUSE_ACT : 0, st);
+                            if (rc == B200_OK) for (int i = 0; i < n_later; ++i) { c->hoisted[i] = later[i]; c->hoisted_at[i] = dv[1 + i].data; }
+                            return 1;
+                        }
+                    }
+                }
+            }
             // the residual ADD right behind wo / ffn_down rides in the GEMM epilogue (b200_mul_mat_add) when this MUL_MAT's result has no other reader
             if (tc_class && next && next->op == GGML_OP_ADD && (next->src[0] == n || next->src[1] == n) && next->src[0] != next->src[1] && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) &&
                 single_use(g, node_idx, n) && !fusion_off()) {
@@ -663,10 +705,17 @@ int fuse_tiles(BackendCtx * c, const ggml_cgraph * g, int i, int & rc) {
 enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
     const int nn = ggml_graph_n_nodes(g);
     c->scratch_act = nullptr;
+    c->hoisted[0] = c->hoisted[1] = nullptr;
     for (int i = 0; i < nn; ) {
         ggml_tensor * n = ggml_graph_node(g, i);
         if (is_noop(n)) { ++i; continue; }
         if (c->scratch_act && n->data == c->scratch_act_data) c->scratch_act = nullptr;     // an in-place op rewrites the tensor the tiles were made from
+        if (n->op == GGML_OP_MUL_MAT && (n == c->hoisted[0] || n == c->hoisted[1])) {       // computed with the first MUL_MAT of its group: only the copy is left
+            const int h = n == c->hoisted[0] ? 0 : 1;
+            CUDA_OK(cudaMemcpyAsync(n->data, c->hoisted_at[h], ggml_nbytes(n), cudaMemcpyDeviceToDevice, c->stream));
+            c->hoisted[h] = nullptr;
+            ++i; continue;
+        }
         int rc = 0;
         int used = (n->op == GGML_OP_RMS_NORM || n->op == GGML_OP_GLU || n->op == GGML_OP_FLASH_ATTN_EXT) && n->ne[1] * n->ne[2] >= 64 ? fuse_tiles(c, g, i, rc) : 0;
         if (used == 0) used = run_node(c, g, i, rc, true);               // RMS_NORM may absorb the MUL right behind it
@@ -888,13 +937,13 @@ enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph 
         const size_t sb = is_noop(n) ? 0 : node_scratch_bytes(n);
         if (sb > need) need = sb;
     }
-    if (!small) return run_nodes(c, g);
+    // host-overhead probe (profiles/): GGML_B200_NULL_COMPUTE=1 skips every launch of decode-sized graphs (2: of every graph), so `llama-bench -n` / `-p` then times
+    // the reference's own host work (graph build, scheduling, the CPU-side token_embd GET_ROWS, input copies, logits read-back) plus this function's bookkeeping
+    static const int null_compute = getenv("GGML_B200_NULL_COMPUTE") ? atoi(getenv("GGML_B200_NULL_COMPUTE")) : 0;
+    if (!small) return null_compute >= 2 ? GGML_STATUS_SUCCESS : run_nodes(c, g);
     scratch_for(c, need);                                            // no allocation may happen while capturing
     GraphKey key;
     graph_key_of(g, key);
-    // host-overhead probe (profiles/): GGML_B200_NULL_COMPUTE=1 skips every launch of decode-sized graphs, so `llama-bench -n` then times the
-    // reference's own per-token host work (graph build, scheduling, input copies, logits read-back) plus this function's bookkeeping
-    static const bool null_compute = getenv("GGML_B200_NULL_COMPUTE") && atoi(getenv("GGML_B200_NULL_COMPUTE")) != 0;
     if (null_compute) return GGML_STATUS_SUCCESS;
     auto run_pre = [&](const std::vector<int> & pre) {                // the engine's per-op prefix, re-resolved from THIS graph by node index
         for (int idx : pre) { int rc = 0; run_node(c, g, idx, rc); if (rc != B200_OK) return false; }
@@ -957,6 +1006,7 @@ void b200_backend_free(ggml_backend_t backend) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->engine) b200_decoder_destroy(c->engine);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->hoist_buf) cudaFree(c->hoist_buf);
     if (c->hop_event) cudaEventDestroy(c->hop_event);
     cudaStreamDestroy(c->stream);
     delete c;

@@ -52,7 +52,13 @@ struct TcArgs {
                                                     // two addends commute, so the result is still deterministic)
     int nsub;                                       // 1: tiles are 256 columns wide; 2: 128 (twice the tiles when 256-wide ones cannot fill the SMs)
     int flags;                                      // experiment switches (B200_TC_FLAGS): 1 no dequant, 2 no MMA, 4 no B copies
+    // several weight matrices that multiply the SAME activations in one launch (q / k / v: 48 m-tiles instead of 32 + 8 + 8, so the 1024-row wk / wv no longer run
+    // as two launches that cannot fill the SMs).  Segment s owns the m-tiles [seg[s].tile0, seg[s + 1].tile0); the fields above describe segment 0 / the totals.
+    int nseg, raw_stride;                           // raw_stride: bytes of one raw-ring slot (128 rows x the LARGEST 256-weight span of the launch)
+    struct Seg { const uint8_t * wd; float * dst; int64_t dst_ld, m; int type, span_bytes, tile0, pad_; } seg[3];
 };
+// the segment an m-tile belongs to
+__device__ __forceinline__ int tc_seg_of(const TcArgs & A, int mt) { return A.nseg > 2 && mt >= A.seg[2].tile0 ? 2 : A.nseg > 1 && mt >= A.seg[1].tile0 ? 1 : 0; }
 
 // ---------------------------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t tc_smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -336,7 +342,8 @@ __global__ void __launch_bounds__(256) k_x_to_f16_tiles(const float * __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------- the GEMM kernel
-__global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant__ TcArgs A, const __grid_constant__ CUtensorMap wmap) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant__ TcArgs A, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap wmap1,
+                                                          const __grid_constant__ CUtensorMap wmap2) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = tc_smem_u32(smem);
     const uint32_t raw0 = sbase + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);       // raw quant-block ring
@@ -371,15 +378,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
         const int64_t nkb = (A.k >> 8) / A.splitk;                            // 256-weight spans per work item
         uint32_t rit = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it += (uint32_t) nkc, rit += (uint32_t) nkb) {
-            const int mt = (t / A.splitk) % A.tiles_m;
-            int64_t gr = (int64_t) mt * TC_M + row; if (gr >= A.m) gr = A.m - 1;        // tail rows (zero-filled by TMA): any valid d, never stored
-            const uint32_t rrow = raw0 + row * A.span_bytes, rstride = (uint32_t) (TC_M * A.span_bytes), nr = (uint32_t) A.n_raw;
-            switch (A.type) {
+            const int mtg = (t / A.splitk) % A.tiles_m, si = tc_seg_of(A, mtg), mt = mtg - A.seg[si].tile0;
+            const int64_t sm = A.seg[si].m;
+            const uint8_t * swd = A.seg[si].wd;
+            int64_t gr = (int64_t) mt * TC_M + row; if (gr >= sm) gr = sm - 1;          // tail rows (zero-filled by TMA): any valid d, never stored
+            const uint32_t rrow = raw0 + row * A.seg[si].span_bytes, rstride = (uint32_t) A.raw_stride, nr = (uint32_t) A.n_raw;
+            switch (A.seg[si].type) {
                 case B200_Q4_K: tc_produce_tile<RawQ4K>(rrow, rstride, nr, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
                 case B200_Q5_K: tc_produce_tile<RawQ5K>(rrow, rstride, nr, nullptr, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
-                case B200_Q6_K: tc_produce_tile<RawQ6K>(rrow, rstride, nr, A.wd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 2, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
-                case B200_Q8_0: tc_produce_tile<RawQ80>(rrow, rstride, nr, A.wd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
-                default:        tc_produce_tile<RawQ40>(rrow, rstride, nr, A.wd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                case B200_Q6_K: tc_produce_tile<RawQ6K>(rrow, rstride, nr, swd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 2, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                case B200_Q8_0: tc_produce_tile<RawQ80>(rrow, rstride, nr, swd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
+                default:        tc_produce_tile<RawQ40>(rrow, rstride, nr, swd + (gr * nkb * A.splitk + (t % A.splitk) * nkb) * 16, nkb, g, lane, it, rit, stage0, a_full, empty, raw_full, raw_empty, A.flags); break;
             }
         }
     } else if (warp == 8) {
@@ -427,17 +436,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
     } else if (warp == 14) {
         // ================================================================== raw weight producer: one 2-D TMA (128 rows x one quant block) per 4 stages
         if (lane == 0) {
-            const int blk = A.span_bytes;
             const int nkb = (int) (A.k >> 8) / A.splitk;
-            const uint32_t n_raw = (uint32_t) A.n_raw, rstride = (uint32_t) (TC_M * A.span_bytes);
+            const uint32_t n_raw = (uint32_t) A.n_raw, rstride = (uint32_t) A.raw_stride;
             uint32_t ru = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int mt = (t / A.splitk) % A.tiles_m;
+                const int mtg = (t / A.splitk) % A.tiles_m, si = tc_seg_of(A, mtg), mt = mtg - A.seg[si].tile0;
+                const int blk = A.seg[si].span_bytes;
+                const CUtensorMap * map = si == 0 ? &wmap : si == 1 ? &wmap1 : &wmap2;
                 for (int kb = 0; kb < nkb; ++kb, ++ru) {
                     const uint32_t r = ru % n_raw;
                     tc_mbar_wait(raw_empty + 8 * r, ((ru / n_raw) & 1) ^ 1);
-                    tc_mbar_expect_tx(raw_full + 8 * r, rstride);
-                    tc_tma_2d(raw0 + r * rstride, &wmap, ((t % A.splitk) * nkb + kb) * blk, mt * TC_M, raw_full + 8 * r);
+                    tc_mbar_expect_tx(raw_full + 8 * r, (uint32_t) (TC_M * blk));
+                    tc_tma_2d(raw0 + r * rstride, map, ((t % A.splitk) * nkb + kb) * blk, mt * TC_M, raw_full + 8 * r);
                 }
             }
         }
@@ -446,15 +456,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
         const int quarter = warp & 3;
         uint32_t tcount = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
-            const int mt = (t / A.splitk) % A.tiles_m, ntx = (t / A.splitk) / A.tiles_m, wn = TC_N / A.nsub;
+            const int mtg = (t / A.splitk) % A.tiles_m, ntx = (t / A.splitk) / A.tiles_m, wn = TC_N / A.nsub;
+            const int si = tc_seg_of(A, mtg), mt = mtg - A.seg[si].tile0;
+            const int64_t seg_m = A.seg[si].m, seg_ld = A.seg[si].dst_ld;
             const uint32_t acc = tcount & 1;
             tc_mbar_wait(t_full + 8 * acc, (tcount >> 1) & 1);
             tc_fence_after();
             const int64_t mrow = (int64_t) mt * TC_M + quarter * 32 + lane;
             int64_t ncols = A.n - (int64_t) ntx * wn; if (ncols > wn) ncols = wn;
-            float * out = A.dst + ((int64_t) ntx * wn) * A.dst_ld + mrow;
-            const bool fuse_add = mrow < A.m && A.splitk == 1 && A.resid;  // fused residual ADD (wo / ffn_down of a llama-family layer): one F32 add, as the separate op would do
-            const float * rs = A.resid + ((int64_t) ntx * wn) * A.dst_ld + mrow;
+            float * out = A.seg[si].dst + ((int64_t) ntx * wn) * seg_ld + mrow;
+            const bool fuse_add = mrow < seg_m && A.splitk == 1 && A.resid;  // fused residual ADD (wo / ffn_down of a llama-family layer): one F32 add, as the separate op would do (single-matrix launches only)
+            const float * rs = A.resid + ((int64_t) ntx * wn) * seg_ld + mrow;
             for (int cc = 0; cc * 32 < ncols; ++cc) {
                 uint32_t v[32];
                 float r[32];
@@ -462,17 +474,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mmq_tc(const __grid_constant_
                 // (they do not depend on the accumulator and overlap the TMEM read)
                 if (fuse_add) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = cc * 32 + j < ncols ? __ldcg(rs + (int64_t) (cc * 32 + j) * A.dst_ld) : 0.0f;
+                    for (int j = 0; j < 32; ++j) r[j] = cc * 32 + j < ncols ? __ldcg(rs + (int64_t) (cc * 32 + j) * seg_ld) : 0.0f;
                 }
                 tc_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + acc * TC_N + cc * 32, v);
                 if (fuse_add) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __fadd_rn(__uint_as_float(v[j]), r[j]);
-                } else if (mrow < A.m && A.splitk == 1) {
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * seg_ld] = __fadd_rn(__uint_as_float(v[j]), r[j]);
+                } else if (mrow < seg_m && A.splitk == 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * A.dst_ld] = __uint_as_float(v[j]);
-                } else if (mrow < A.m) {
-                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) atomicAdd(out + (int64_t) (cc * 32 + j) * A.dst_ld, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) out[(int64_t) (cc * 32 + j) * seg_ld] = __uint_as_float(v[j]);
+                } else if (mrow < seg_m) {
+                    for (int j = 0; j < 32; ++j) if (cc * 32 + j < ncols) atomicAdd(out + (int64_t) (cc * 32 + j) * seg_ld, __uint_as_float(v[j]));
                 }
             }
             tc_fence_before();
@@ -628,21 +640,32 @@ static tc_encode_fn tc_encoder() {
     return fn;
 }
 
-int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st,
-           const float * resid, bool * resid_fused) {
+static int tc_make_map(CUtensorMap & wmap, const void * w, int type, int64_t m, int64_t k) {
+    // the payload plane as a 2-D byte tensor [m rows][row bytes]; box = one quant block x 128 rows
+    const cuuint64_t blk = (cuuint64_t) (256 / blck_size(type)) * payload_size(type), rowb = (cuuint64_t) (k / 256) * blk;
+    const cuuint64_t gdim[2] = { rowb, (cuuint64_t) m }, gstr[1] = { rowb };
+    const cuuint32_t box[2] = { (cuuint32_t) blk, TC_M }, estr[2] = { 1, 1 };
+    return tc_encoder()(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *) w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        (getenv("B200_TC_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+           ? B200_OK : B200_ERR_UNSUPPORTED;
+}
+
+// can these matrices (all [m_i, k], the same activations) run as ONE launch?  K-quants only (one raw-ring geometry), and only when the merged tile count needs no split-K
+bool mmq_tc_multi_ok(int nseg, const int * type, const int64_t * m, int64_t k, int64_t n) {
+    if (nseg < 2 || nseg > 3) return false;
+    int64_t tiles_m = 0;
+    for (int i = 0; i < nseg; ++i) { if (!is_kquant(type[i]) || m[i] <= 0) return false; tiles_m += (m[i] + TC_M - 1) / TC_M; }
+    return tc_splitk((int) tiles_m, n, k / 256) == 1;
+}
+
+int mmq_tc_multi(int nseg, const void * const * w, const int * type, const int64_t * m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * const * dst, const int64_t * dst_ld,
+                 void * scratch, bool reuse_tiles, cudaStream_t st, const float * resid, bool * resid_fused) {
     if (resid_fused) *resid_fused = false;
     static smem_mask_t done{0};
     B200_CUDA_TRY(ensure_dyn_smem(k_mmq_tc, TC_SMEM, done));
-    if (!tc_encoder()) return B200_ERR_UNSUPPORTED;
-    // the payload plane as a 2-D byte tensor [m rows][row bytes]; box = one quant block x 128 rows
-    CUtensorMap wmap;
-    {
-        const cuuint64_t blk = (cuuint64_t) (256 / blck_size(type)) * payload_size(type), rowb = (cuuint64_t) (k / 256) * blk;
-        const cuuint64_t gdim[2] = { rowb, (cuuint64_t) m }, gstr[1] = { rowb };
-        const cuuint32_t box[2] = { (cuuint32_t) blk, TC_M }, estr[2] = { 1, 1 };
-        if (tc_encoder()(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *) w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                         (getenv("B200_TC_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B200_ERR_UNSUPPORTED;
-    }
+    if (!tc_encoder() || nseg < 1 || nseg > 3) return B200_ERR_UNSUPPORTED;
+    CUtensorMap wmap[3];
+    for (int i = 0; i < 3; ++i) { const int j = i < nseg ? i : 0; if (tc_make_map(wmap[i], w[j], type[j], m[j], k)) return B200_ERR_UNSUPPORTED; }
     const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
     if (!reuse_tiles) {
         k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
@@ -652,21 +675,34 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
     static const int env_flags = getenv("B200_TC_FLAGS") ? atoi(getenv("B200_TC_FLAGS")) : 0;
     A.flags = env_flags;
     const int64_t nkb = k / 256;
-    A.w = (const uint8_t *) w; A.type = type; A.m = m; A.k = k; A.n = n; A.dst = dst; A.dst_ld = dst_ld; A.x16 = (const uint8_t *) scratch;
-    A.span_bytes = (256 / blck_size(type)) * payload_size(type);                // 144, 176, 208, 256 (q8_0), 128 (q4_0)
-    A.n_raw = TC_RAW_REGION / (TC_M * A.span_bytes) >= TC_RAW_MAX ? TC_RAW_MAX : TC_RAW_REGION / (TC_M * A.span_bytes);
-    A.row_bytes = nkb * A.span_bytes;
-    A.wd = payload_size(type) != type_size(type) ? (const uint8_t *) w + m * A.row_bytes : nullptr;          // planar: f16 d plane behind the payload plane
-    A.tiles_m = (int) ((m + TC_M - 1) / TC_M);
+    A.w = (const uint8_t *) w[0]; A.type = type[0]; A.m = m[0]; A.k = k; A.n = n; A.dst = dst[0]; A.dst_ld = dst_ld[0]; A.x16 = (const uint8_t *) scratch;
+    A.nseg = nseg; A.tiles_m = 0; A.n_raw = TC_RAW_MAX; A.raw_stride = 0;
+    for (int i = 0; i < nseg; ++i) {
+        TcArgs::Seg & S = A.seg[i];
+        S.type = type[i]; S.m = m[i]; S.dst = dst[i]; S.dst_ld = dst_ld[i]; S.tile0 = A.tiles_m;
+        S.span_bytes = (256 / blck_size(type[i])) * payload_size(type[i]);       // 144, 176, 208, 256 (q8_0), 128 (q4_0)
+        S.wd = payload_size(type[i]) != type_size(type[i]) ? (const uint8_t *) w[i] + m[i] * nkb * S.span_bytes : nullptr;     // planar: f16 d plane behind the payload plane
+        const int nr = TC_RAW_REGION / (TC_M * S.span_bytes) >= TC_RAW_MAX ? TC_RAW_MAX : TC_RAW_REGION / (TC_M * S.span_bytes);
+        if (nr < A.n_raw) A.n_raw = nr;
+        if (TC_M * S.span_bytes > A.raw_stride) A.raw_stride = TC_M * S.span_bytes;
+        A.tiles_m += (int) ((m[i] + TC_M - 1) / TC_M);
+    }
+    A.span_bytes = A.seg[0].span_bytes; A.row_bytes = nkb * A.span_bytes; A.wd = A.seg[0].wd;
     A.splitk = tc_splitk(A.tiles_m, n, k / 256);
-    A.resid = A.splitk == 1 ? resid : nullptr;                                  // three addends would not commute: split-K leaves the ADD to the caller
+    if (nseg > 1 && A.splitk != 1) return B200_ERR_UNSUPPORTED;                 // (mmq_tc_multi_ok says so beforehand)
+    A.resid = A.splitk == 1 && nseg == 1 ? resid : nullptr;                     // three addends would not commute: split-K leaves the ADD to the caller
     if (resid_fused) *resid_fused = A.resid != nullptr;
     A.nsub = tc_nsub(A.tiles_m * A.splitk, n); A.tiles_n = (int) ((n + TC_N / A.nsub - 1) / (TC_N / A.nsub));
-    if (A.splitk > 1) B200_CUDA_TRY(cudaMemset2DAsync(dst, (size_t) dst_ld * 4, 0, (size_t) m * 4, (size_t) n, st));
+    if (A.splitk > 1) B200_CUDA_TRY(cudaMemset2DAsync(dst[0], (size_t) dst_ld[0] * 4, 0, (size_t) m[0] * 4, (size_t) n, st));
     int grid = A.tiles_m * A.tiles_n * A.splitk; if (grid > sm_count()) grid = sm_count();
-    k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A, wmap);
+    k_mmq_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(A, wmap[0], wmap[1], wmap[2]);
     B200_LAUNCH_CHECK();
     return B200_OK;
+}
+
+int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st,
+           const float * resid, bool * resid_fused) {
+    return mmq_tc_multi(1, &w, &type, &m, k, x, x_ld, n, &dst, &dst_ld, scratch, reuse_tiles, st, resid, resid_fused);
 }
 
 bool mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t row_stride) {

@@ -16,6 +16,9 @@ bool   mmq_tc_supported(int type, int layout, int64_t k, int64_t n, const void *
 size_t mmq_tc_scratch_bytes(int64_t k, int64_t n);
 int    mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st, const float * resid, bool * resid_fused);
 bool   mmq_tc_fuses_resid(int64_t m, int64_t k, int64_t n);
+bool   mmq_tc_multi_ok(int nseg, const int * type, const int64_t * m, int64_t k, int64_t n);
+int    mmq_tc_multi(int nseg, const void * const * w, const int * type, const int64_t * m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * const * dst, const int64_t * dst_ld,
+                    void * scratch, bool reuse_tiles, cudaStream_t st, const float * resid, bool * resid_fused);
 bool   mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t row_stride);
 int    mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st);
 static bool tc_disabled() { static const bool off = getenv("B200_DISABLE_TC") && atoi(getenv("B200_DISABLE_TC")) != 0; return off; }
@@ -203,6 +206,42 @@ extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, co
     if (r0 < d0 + dbytes && d0 < r0 + rbytes) return B200_ERR_UNSUPPORTED;   // overlapping residual and dst
     const int rc = b200_mul_mat_ex(w, x, dst, scratch, scratch_bytes, flags, stream);
     return rc ? rc : b200_binary(B200_ADD, dst, residual, dst, stream);
+}
+
+// dst[i] = W[i] . x for 2 or 3 weight matrices over the SAME activations (q / k / v): ONE tensor-core launch over the concatenated m-tiles when every W[i] is a K-quant
+// on the tcgen05 path (the 1024-row wk / wv alone fill 64 of 148 SMs; merged with wq the launch has 48 x n/256 tiles), otherwise one MUL_MAT after the other with the
+// activation tiles shared.  scratch: the largest b200_mul_mat_scratch_bytes of the group.
+// would b200_mul_mat_multi run this group as ONE launch?  (a caller that has to stage the later results elsewhere — the ggml plugin — only does so when it pays)
+extern "C" int b200_mul_mat_multi_merges(int n_mat, const b200_tensor * const * w, const b200_tensor * x) {
+    if (n_mat < 2 || n_mat > 3 || !w || !x || tc_disabled() || x->ne[2] * x->ne[3] != 1 || x->type != B200_F32) return 0;
+    const int64_t k = x->ne[0], n = x->ne[1];
+    int type[3]; int64_t m[3];
+    for (int i = 0; i < n_mat; ++i) {
+        if (!w[i] || w[i]->ne[0] != k || w[i]->ne[2] * w[i]->ne[3] != 1 || !is_quant(w[i]->type) || !mmq_tc_supported(w[i]->type, w[i]->layout, k, n, w[i]->data, w[i]->nb[1])) return 0;
+        type[i] = w[i]->type; m[i] = w[i]->ne[1];
+    }
+    return mmq_tc_multi_ok(n_mat, type, m, k, n) ? 1 : 0;
+}
+
+extern "C" int b200_mul_mat_multi(int n_mat, const b200_tensor * const * w, const b200_tensor * x, const b200_tensor * const * dst, void * scratch, size_t scratch_bytes,
+                                  int flags, void * stream) {
+    if (n_mat < 1 || n_mat > 3 || !w || !x || !dst) return B200_ERR_ARG;
+    for (int i = 0; i < n_mat; ++i) if (!b200_mul_mat_supported(w[i], x, dst[i])) return B200_ERR_UNSUPPORTED;
+    const int64_t k = x->ne[0], n = x->ne[1];
+    bool merge = n_mat > 1 && !tc_disabled() && x->ne[2] * x->ne[3] == 1 && scratch && (uintptr_t) scratch % 16 == 0 && n > 0;
+    int type[3]; int64_t m[3], ld[3]; const void * wp[3]; float * dp[3];
+    for (int i = 0; i < n_mat && merge; ++i) {
+        type[i] = w[i]->type; m[i] = w[i]->ne[1]; ld[i] = dst[i]->nb[1] / 4; wp[i] = w[i]->data; dp[i] = (float *) dst[i]->data;
+        merge = is_quant(type[i]) && mmq_tc_supported(type[i], w[i]->layout, k, n, w[i]->data, w[i]->nb[1]) && w[i]->ne[2] * w[i]->ne[3] == 1 && dst[i]->nb[0] == 4 &&
+                scratch_bytes >= b200_mul_mat_scratch_bytes(w[i], x);
+    }
+    if (merge && mmq_tc_multi_ok(n_mat, type, m, k, n))
+        return mmq_tc_multi(n_mat, wp, type, m, k, (const float *) x->data, x->nb[1] / 4, n, dp, ld, scratch, (flags & B200_MM_REUSE_ACT) != 0, (cudaStream_t) stream, nullptr, nullptr);
+    for (int i = 0; i < n_mat; ++i) {
+        const int rc = b200_mul_mat_ex(w[i], x, dst[i], scratch, scratch_bytes, i == 0 ? flags : (flags | B200_MM_REUSE_ACT), stream);
+        if (rc) return rc;
+    }
+    return B200_OK;
 }
 
 extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,

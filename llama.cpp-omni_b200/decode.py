@@ -266,7 +266,12 @@ class Qwen3Decoder:
                 ops.rms_norm_tiles(x, cfg.rms_eps, lw["attn_norm"], mm_scratch)
             else:
                 ops.rms_norm(x, cfg.rms_eps, w=lw["attn_norm"], out=bufs["a"])
-            mm(lw["wq"], ty["wq"], q, E, bufs["a"], bufs["q"], ft); mm(lw["wk"], ty["wk"], kv, E, bufs["a"], bufs["k"], n > 8); mm(lw["wv"], ty["wv"], kv, E, bufs["a"], bufs["v"], n > 8)
+            if ft:                                    # q / k / v as ONE launch over the concatenated m-tiles (b200_mul_mat_multi)
+                lay = lambda t: ops.LAYOUT_PLANAR if t == ops.Q6_K else ops.LAYOUT_NATIVE
+                ops.mul_mat_multi([(lw["wq"], ty["wq"], q, lay(ty["wq"])), (lw["wk"], ty["wk"], kv, lay(ty["wk"])), (lw["wv"], ty["wv"], kv, lay(ty["wv"]))],
+                                  bufs["a"], [bufs["q"], bufs["k"], bufs["v"]], scratch=mm_scratch, reuse_act=True)
+            else:
+                mm(lw["wq"], ty["wq"], q, E, bufs["a"], bufs["q"], ft); mm(lw["wk"], ty["wk"], kv, E, bufs["a"], bufs["k"], n > 8); mm(lw["wv"], ty["wv"], kv, E, bufs["a"], bufs["v"], n > 8)
             ops.check(L.b200_qkv_post(P(bufs["q"].data_ptr()), P(bufs["k"].data_ptr()), P(bufs["v"].data_ptr()), P(lw["q_norm"].data_ptr()),
                                       P(lw["k_norm"].data_ptr()), P(pos.data_ptr()), P(idx.data_ptr()), ops.I64,
                                       P(lw["k_cache"].data_ptr()), P(lw["v_cache"].data_ptr()), C.c_int64(kv * 2), C.c_int64(kv * 2),

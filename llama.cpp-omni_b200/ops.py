@@ -24,7 +24,7 @@ EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b20
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
            "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
            "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy",
-           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_rms_norm_tiles", "b200_glu_tiles", "b200_flash_attn_tiles", "b200_mul_mat_add", "b200_unary_param", "b200_concat", "b200_repeat", "b200_arange", "b200_sum_rows", "b200_pad", "b200_pad_reflect_1d", "b200_conv_transpose_1d", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
+           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_rms_norm_tiles", "b200_glu_tiles", "b200_flash_attn_tiles", "b200_mul_mat_add", "b200_mul_mat_multi", "b200_mul_mat_multi_merges", "b200_unary_param", "b200_concat", "b200_repeat", "b200_arange", "b200_sum_rows", "b200_pad", "b200_pad_reflect_1d", "b200_conv_transpose_1d", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
 
 
 class Tensor(C.Structure):
@@ -220,6 +220,24 @@ def mul_mat_add(w: torch.Tensor, wtype: int, m: int, k: int, x: torch.Tensor, re
         scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
     check(L.b200_mul_mat_add(C.byref(wd), C.byref(xd), C.byref(rd), C.byref(od), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), int(reuse_act), stream()))
     return out
+
+
+def mul_mat_multi(ws, x: torch.Tensor, outs, scratch: torch.Tensor | None = None, reuse_act: bool = False):
+    """outs[i] = x . W_i^T for 2-3 weights over the same activations (b200_mul_mat_multi).  ws: list of (tensor, wtype, m, layout)."""
+    L = lib()
+    k = x.shape[-1]
+    wds = [T(w, t, ne=[k, m], layout=lay) for (w, t, m, lay) in ws]
+    xd = T(x)
+    ods = [T(o) for o in outs]
+    sb = max(L.b200_mul_mat_scratch_bytes(C.byref(wd), C.byref(xd)) for wd in wds)
+    if scratch is None or scratch.numel() < sb:
+        if reuse_act:
+            raise B200Error("mul_mat_multi: reuse_act needs the scratch that holds the tiles")
+        scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
+    WP = (C.POINTER(Tensor) * len(wds))(*[C.pointer(wd) for wd in wds])
+    DP = (C.POINTER(Tensor) * len(ods))(*[C.pointer(od) for od in ods])
+    check(L.b200_mul_mat_multi(len(wds), WP, C.byref(xd), DP, C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), int(reuse_act), stream()))
+    return outs
 
 
 def make_job(w: torch.Tensor, wtype: int, m: int, k: int, y: torch.Tensor, residual: torch.Tensor | None = None,

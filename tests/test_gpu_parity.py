@@ -214,6 +214,34 @@ def test_mul_mat_add_is_mul_mat_then_add(ops, name, m, k, n):
         assert "-1000" in str(e) and torch.equal(inplace, r)
 
 
+@pytest.mark.parametrize("names,ms,k,n", [(("q4_K", "q4_K", "q6_K"), (4096, 1024, 1024), 4096, 2048), (("q4_K", "q4_K", "q4_K"), (4096, 1024, 1024), 4096, 512),
+                                           (("q5_K", "q6_K"), (200, 130), 512, 300), (("q4_K", "q8_0"), (256, 256), 512, 64), (("q4_K", "q4_K", "q6_K"), (512, 128, 128), 1024, 40),
+                                           (("q4_K", "q6_K"), (512, 128), 1024, 3)])
+def test_mul_mat_multi_is_the_separate_mul_mats(ops, names, ms, k, n):
+    """b200_mul_mat_multi (q / k / v in one tcgen05 launch over the concatenated m-tiles; groups it cannot merge — split-K shapes, non-K-quants, matvecs — run
+    one after the other inside the call): the separate MUL_MATs — bit for bit, except where the separate launch of a small matrix splits K over two CTAs (two partial
+    sums added in F32) while the merged launch accumulates the whole K in one TMEM accumulator: there the two differ by F32 summation order only."""
+    rng = np.random.default_rng(hash((names, ms, k, n)) & 0xffff)
+    x = dev(rng.standard_normal((n, k)).astype(np.float32))
+    ws, want = [], []
+    for name, m in zip(names, ms):
+        t = QT[name]
+        blocks = rand_blocks(rng, t, m * k // O.BLOCK[t][0])
+        planar = t in ops.PAYLOAD
+        wd = ops.to_planar(t, dev(blocks)) if planar else dev(blocks)
+        lay = ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NATIVE
+        ws.append((wd, t, m, lay))
+        want.append(ops.mul_mat(wd, t, m, k, x, layout=lay))
+    outs = [torch.empty_like(w) for w in want]
+    ops.mul_mat_multi(ws, x, outs)
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+        assert torch.isfinite(w).all()
+        if not torch.equal(o, w):
+            err = float(((o.double() - w.double()) ** 2).sum() / (w.double() ** 2).sum())
+            assert err <= 1e-10, err                    # (tensor-core F32 accumulation of 2 x K/2 vs 1 x K: ~3e-6 relative rms)
+
+
 def test_mul_mat_lm_head_shape(ops):
     """output.weight of MiniCPM-o-4.5: Q6_K [4096, 151748]; oracle on a row sample, linearity on the full output."""
     m, k = 151748, 4096
