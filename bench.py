@@ -6,9 +6,10 @@
 A "step" = one decoded token = one pass of the hot path (36 layers + lm_head) over synthetic weights of the named shape
 (BASELINE.json configs[1]; ctx = 4096, KV depth D, default 2048 = the mean depth of a 4096-token generation).
   value : tok/s, inputs resident in HBM, the step replayed as ONE CUDA graph, CUDA-event timed on the launching stream.
-  e2e   : tok/s through the C-ABI with HOST buffers: per step the token's embedding row, pos, KV index and the F32 KQ mask are
-          copied from pinned host memory (what the ggml scheduler copies per split, ggml-backend.cpp:1435-1442), the graph is
-          replayed, and the logits are read back (llama-context.cpp:1144) — all inside the timed region.
+  e2e   : tok/s through the drop-in boundary: the UNMODIFIED reference llama-bench (oracle/_ref/bin) with libggml-b200.so loaded through
+          GGML_BACKEND_PATH on a synthetic 36-layer GGUF at the same KV depth — graph build, scheduler, host input copies (ggml-backend.cpp:1435-1442),
+          our backend, logits read-back (llama-context.cpp:1144), all inside its timed region.  `e2e_cabi` is the same token through the C-ABI
+          with pinned host buffers from ctypes (--no-plugin-e2e reports only that one).
   roofline : algorithmic bytes/token (weights + KV read/write) / measured time vs MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference : the reference's own ggml CPU backend (oracle/_ref, built from /root/reference by oracle/Makefile)
           on a bounded sample of the same workload (whole layers of the same shapes/types), all host threads.
@@ -427,7 +428,7 @@ def prefill_leg(D, cfg, dec, torch, dev, n_tokens: int) -> dict:
         lw["v_cache"][:n].normal_(0, 1.0)
     return {"metric": "prefill_tok_per_s", "value": round(n / (ms / 1e3), 1), "unit": "tok/s", "n_tokens": n, "ms": round(ms, 2), "gpu_launches_per_pass": launches,
             "roofline": {"bound": "tensor", "achieved": round(flops / (ms / 1e3) / 1e12, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(flops / (ms / 1e3) / 1e12 / peak, 4),
-                         "kernel": "whole pass: k_mmq_tc (tcgen05 dequant-GEMM) + k_fa_prefill + elementwise; algorithmic FLOPs = linear + causal attention (SURVEY.md 8d)"},
+                         "kernel": "whole pass: k_mmq_tc (tcgen05 dequant-GEMM; q/k/v and gate/up merged launches) + k_fa_tc (tcgen05 attention) + elementwise; algorithmic FLOPs = linear + causal attention (SURVEY.md 8d)"},
             "config": {"workload": f"{cfg.name} prefill n_tokens={n} (one ubatch), empty KV cache"}}
 
 

@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fa_tc(const FaTcArgs A, const
                    tmem_slot = bars + 96, xch = bars + 256;                                      // xch: float [2 buffers][2 halves][128 rows]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // heaviest query tiles first (a causal mask gives tile i about i + 1 KV tiles)
-    const int qt = (int) gridDim.x - 1 - (int) blockIdx.x, head = blockIdx.y, ib = blockIdx.z;
+    // longest-processing-time-first over the WHOLE grid: blocks are dispatched in blockIdx.x-fastest order, so the head index is x and the query tile y, last tile
+    // (the causal row block with the most KV tiles) first — every head's heaviest tile starts before any light one, and the last wave holds only 1-tile blocks
+    const int n_qt = (int) gridDim.y, qt = n_qt - 1 - (int) blockIdx.y, head = blockIdx.x, ib = blockIdx.z;
     const int kvh = head / (int) (A.n_head / A.n_head_kv), ibk = (int) (ib % A.k_ne3), ibm = (int) (ib % A.m_ne3);
     const int64_t q0 = (int64_t) qt * FT_BM;
 
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_fa_tc(const FaTcArgs A, const
     const int n_kv_tiles = (int) ((A.n_kv + FT_BN - 1) / FT_BN);
     int n_visit = n_kv_tiles, n_plain = A.mask ? 0 : n_kv_tiles;
     if (A.kv_tiles) {
-        const int ent = ibm * (int) gridDim.x + qt;
+        const int ent = ibm * n_qt + qt;
         n_visit = min(n_kv_tiles, (A.kv_tiles[ent] + 1) / 2);
         n_plain = min(n_visit, A.kv_plain[ent] == 0x7fffffff ? n_visit : A.kv_plain[ent] / 2);
     }
@@ -359,7 +361,7 @@ int fa_tc(const b200_tensor * q, const b200_tensor * k, const b200_tensor * v, c
     A.n_q = q->ne[1]; A.n_kv = k->ne[1]; A.n_head = q->ne[2]; A.n_head_kv = k->ne[2]; A.k_ne3 = k->ne[3]; A.scale = scale; A.m_ne3 = 1;
     if (mask) { A.m_nb1 = mask->nb[1]; A.m_nb3 = mask->nb[3]; A.m_ne3 = mask->ne[3]; }
     A.kv_tiles = kv_tiles; A.kv_plain = kv_plain; A.tiles = (uint8_t *) tiles;
-    const dim3 grid((unsigned) ((A.n_q + FT_BM - 1) / FT_BM), (unsigned) A.n_head, (unsigned) q->ne[3]);
+    const dim3 grid((unsigned) A.n_head, (unsigned) ((A.n_q + FT_BM - 1) / FT_BM), (unsigned) q->ne[3]);
     k_fa_tc<<<grid, FT_THREADS, FT_SMEM, st>>>(A, kmap, vmap);
     B200_LAUNCH_CHECK();
     return B200_OK;

@@ -490,17 +490,21 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             if (allow_fuse && tc_class && !fusion_off() && !c->hoisted[0] && x.ne[2] * x.ne[3] == 1) {
                 const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
                 const ggml_tensor * later[2] = { nullptr, nullptr }; int n_later = 0;
+                bool direct[2] = { false, false };                               // the group member is the NEXT compute node: nothing runs in between, its own dst is safe to write now
+                bool run = true;                                                 // every compute node since this one has been a member of the group
                 for (int j = node_idx + 1; j < nn && j <= node_idx + 16 && n_later < 2; ++j) {
                     const ggml_tensor * t = ggml_graph_node((ggml_cgraph *) g, j);
+                    if (is_noop(t)) continue;
                     if (t->op == GGML_OP_MUL_MAT && t->src[1] == s1 && t->src[0] != s0 && is_weight(t->src[0]) && mm_tc_class(t) && ggml_is_contiguous(t) && ggml_is_contiguous(n) &&
-                        (t->src[0]->type == GGML_TYPE_Q4_K || t->src[0]->type == GGML_TYPE_Q5_K || t->src[0]->type == GGML_TYPE_Q6_K)) later[n_later++] = t;
+                        (t->src[0]->type == GGML_TYPE_Q4_K || t->src[0]->type == GGML_TYPE_Q5_K || t->src[0]->type == GGML_TYPE_Q6_K)) { direct[n_later] = run; later[n_later++] = t; }
+                    else run = false;
                 }
                 if (n_later > 0 && is_weight(s0) && (s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q5_K || s0->type == GGML_TYPE_Q6_K)) {
                     b200_tensor wv[3] = { w, view_of(later[0]->src[0]), n_later > 1 ? view_of(later[1]->src[0]) : w };
                     const b200_tensor * wp[3] = { &wv[0], &wv[1], &wv[2] };
                     if (b200_mul_mat_multi_merges(1 + n_later, wp, &x)) {
                         size_t need = 0, off[2] = { 0, 0 };
-                        for (int i = 0; i < n_later; ++i) { off[i] = need; need += (ggml_nbytes(later[i]) + 255) & ~(size_t) 255; }
+                        for (int i = 0; i < n_later; ++i) { off[i] = need; if (!direct[i]) need += (ggml_nbytes(later[i]) + 255) & ~(size_t) 255; }
                         if (need > c->hoist_size) {
                             CUDA_OK(cudaStreamSynchronize(c->stream));
                             if (c->hoist_buf) CUDA_OK(cudaFree(c->hoist_buf));
@@ -509,14 +513,14 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
                         b200_tensor dv[3] = { d, view_of(later[0]), n_later > 1 ? view_of(later[1]) : d };
                         size_t sbm = sb;
                         for (int i = 0; i < n_later; ++i) {
-                            dv[1 + i].data = (char *) c->hoist_buf + off[i];
+                            if (!direct[i]) dv[1 + i].data = (char *) c->hoist_buf + off[i];
                             const size_t sbi = b200_mul_mat_scratch_bytes(&wv[1 + i], &x); if (sbi > sbm) sbm = sbi;
                         }
                         if (sbm <= c->scratch_size || !reuse) {                  // growing the scratch would drop the prepared tiles
                             void * scm = scratch_for(c, sbm);
                             const b200_tensor * dp[3] = { &dv[0], &dv[1], &dv[2] };
                             rc = b200_mul_mat_multi(1 + n_later, wp, &x, dp, scm, sbm, reuse && scm == scratch_before ? B200_MM_REUSE_ACT : 0, st);
-                            if (rc == B200_OK) for (int i = 0; i < n_later; ++i) { c->hoisted[i] = later[i]; c->hoisted_at[i] = dv[1 + i].data; }
+                            if (rc == B200_OK) for (int i = 0; i < n_later; ++i) { c->hoisted[i] = later[i]; c->hoisted_at[i] = direct[i] ? nullptr : dv[1 + i].data; }
                             return 1;
                         }
                     }
@@ -712,7 +716,7 @@ enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
         if (c->scratch_act && n->data == c->scratch_act_data) c->scratch_act = nullptr;     // an in-place op rewrites the tensor the tiles were made from
         if (n->op == GGML_OP_MUL_MAT && (n == c->hoisted[0] || n == c->hoisted[1])) {       // computed with the first MUL_MAT of its group: only the copy is left
             const int h = n == c->hoisted[0] ? 0 : 1;
-            CUDA_OK(cudaMemcpyAsync(n->data, c->hoisted_at[h], ggml_nbytes(n), cudaMemcpyDeviceToDevice, c->stream));
+            if (c->hoisted_at[h]) CUDA_OK(cudaMemcpyAsync(n->data, c->hoisted_at[h], ggml_nbytes(n), cudaMemcpyDeviceToDevice, c->stream));
             c->hoisted[h] = nullptr;
             ++i; continue;
         }

@@ -211,9 +211,11 @@ extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, co
 // dst[i] = W[i] . x for 2 or 3 weight matrices over the SAME activations (q / k / v): ONE tensor-core launch over the concatenated m-tiles when every W[i] is a K-quant
 // on the tcgen05 path (the 1024-row wk / wv alone fill 64 of 148 SMs; merged with wq the launch has 48 x n/256 tiles), otherwise one MUL_MAT after the other with the
 // activation tiles shared.  scratch: the largest b200_mul_mat_scratch_bytes of the group.
+// B200_NO_MULTI=1 keeps every MUL_MAT of a group in its own launch (read per call: the tests toggle it to compare the merged launch with the separate ones)
+static bool multi_disabled() { const char * e = getenv("B200_NO_MULTI"); return e && atoi(e) != 0; }
 // would b200_mul_mat_multi run this group as ONE launch?  (a caller that has to stage the later results elsewhere — the ggml plugin — only does so when it pays)
 extern "C" int b200_mul_mat_multi_merges(int n_mat, const b200_tensor * const * w, const b200_tensor * x) {
-    if (n_mat < 2 || n_mat > 3 || !w || !x || tc_disabled() || x->ne[2] * x->ne[3] != 1 || x->type != B200_F32) return 0;
+    if (n_mat < 2 || n_mat > 3 || !w || !x || tc_disabled() || multi_disabled() || x->ne[2] * x->ne[3] != 1 || x->type != B200_F32) return 0;
     const int64_t k = x->ne[0], n = x->ne[1];
     int type[3]; int64_t m[3];
     for (int i = 0; i < n_mat; ++i) {
@@ -228,7 +230,7 @@ extern "C" int b200_mul_mat_multi(int n_mat, const b200_tensor * const * w, cons
     if (n_mat < 1 || n_mat > 3 || !w || !x || !dst) return B200_ERR_ARG;
     for (int i = 0; i < n_mat; ++i) if (!b200_mul_mat_supported(w[i], x, dst[i])) return B200_ERR_UNSUPPORTED;
     const int64_t k = x->ne[0], n = x->ne[1];
-    bool merge = n_mat > 1 && !tc_disabled() && x->ne[2] * x->ne[3] == 1 && scratch && (uintptr_t) scratch % 16 == 0 && n > 0;
+    bool merge = n_mat > 1 && !tc_disabled() && !multi_disabled() && x->ne[2] * x->ne[3] == 1 && scratch && (uintptr_t) scratch % 16 == 0 && n > 0;
     int type[3]; int64_t m[3], ld[3]; const void * wp[3]; float * dp[3];
     for (int i = 0; i < n_mat && merge; ++i) {
         type[i] = w[i]->type; m[i] = w[i]->ne[1]; ld[i] = dst[i]->nb[1] / 4; wp[i] = w[i]->data; dp[i] = (float *) dst[i]->data;

@@ -293,7 +293,12 @@ class Qwen3Decoder:
                 ops.rms_norm_tiles(bufs["x1"], cfg.rms_eps, lw["ffn_norm"], mm_scratch)
             else:
                 ops.rms_norm(bufs["x1"], cfg.rms_eps, w=lw["ffn_norm"], out=bufs["a"])
-            mm(lw["gate"], ty["gate"], F, E, bufs["a"], bufs["g"], ft); mm(lw["up"], ty["up"], F, E, bufs["a"], bufs["u"], n > 8)
+            if ft:                                    # gate / up as one launch: 2 x 96 m-tiles share the waves (one round of tiles less per layer)
+                lay = lambda t: ops.LAYOUT_PLANAR if t == ops.Q6_K else ops.LAYOUT_NATIVE
+                ops.mul_mat_multi([(lw["gate"], ty["gate"], F, lay(ty["gate"])), (lw["up"], ty["up"], F, lay(ty["up"]))], bufs["a"], [bufs["g"], bufs["u"]],
+                                  scratch=mm_scratch, reuse_act=True)
+            else:
+                mm(lw["gate"], ty["gate"], F, E, bufs["a"], bufs["g"], ft); mm(lw["up"], ty["up"], F, E, bufs["a"], bufs["u"], n > 8)
             if ft:
                 ops.glu_tiles(ops.GLU_SWIGLU, bufs["g"], bufs["u"], mm_scratch)
             else:

@@ -27,7 +27,8 @@ static Run run(const char * path, int ngl, int n_prompt, int n_gen, int n_thread
     llama_model * model = llama_model_load_from_file(path, mp);
     if (!model) { fprintf(stderr, "load failed\n"); return r; }
     llama_context_params cp = llama_context_default_params();
-    cp.n_ctx = 1024; cp.n_batch = 512; cp.n_ubatch = 512; cp.n_threads = n_threads; cp.n_threads_batch = n_threads;
+    const int nb = n_prompt > 512 ? (n_prompt + 255) / 256 * 256 : 512;                 // the whole prompt as ONE ubatch (exercises the n >= 512 GEMM routing)
+    cp.n_ctx = n_prompt + n_gen + 64 > 1024 ? (n_prompt + n_gen + 64 + 255) / 256 * 256 : 1024; cp.n_batch = nb; cp.n_ubatch = nb; cp.n_threads = n_threads; cp.n_threads_batch = n_threads;
     cp.flash_attn_type = fa ? LLAMA_FLASH_ATTN_TYPE_ENABLED : LLAMA_FLASH_ATTN_TYPE_DISABLED; cp.no_perf = true;
     llama_context * ctx = llama_init_from_model(model, cp);
     if (!ctx) { fprintf(stderr, "context failed\n"); llama_model_free(model); return r; }

@@ -39,6 +39,19 @@ def test_plugin_exports_the_dlsym_entry_points():
     assert {"ggml_backend_init", "ggml_backend_score", "ggml_backend_b200_reg", "ggml_backend_b200_init", "ggml_backend_b200_abi"} <= exported
 
 
+def test_ld_preload_shim_registers_the_backend():
+    """llama-omni-cli never calls ggml_backend_load_all() before loading the LLM (tools/omni/omni-cli.cpp:198-350): libggml-b200-preload.so registers the backend from a
+    constructor instead.  Shown on the reference's test-backend-ops WITHOUT GGML_BACKEND_PATH: the device must be there and pass an op."""
+    shim = PLUGIN.parent / "libggml-b200-preload.so"
+    assert shim.exists()
+    env = _env(plugin=False, LD_PRELOAD=str(shim))
+    r = subprocess.run([str(REF / "bin" / "test-backend-ops"), "test", "-b", "B200:0", "-o", "ADD"], env=env, capture_output=True, text=True, timeout=600)
+    out = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout + r.stderr)
+    assert "Backend B200:0: OK" in out, out[-2000:]
+    r = subprocess.run([str(REF / "bin" / "test-backend-ops"), "test", "-b", "B200:0", "-o", "ADD"], env=_env(plugin=False), capture_output=True, text=True, timeout=600)
+    assert "Backend B200:0: OK" not in r.stdout + r.stderr                 # without the shim (and without GGML_BACKEND_PATH) there is no such device
+
+
 @pytest.mark.parametrize("op", ["MUL_MAT", "FLASH_ATTN_EXT", "RMS_NORM", "ROPE", "SET_ROWS", "GET_ROWS", "GLU", "ADD", "MUL", "CPY", "SOFT_MAX", "NORM", "IM2COL", "CONT,DUP",
                                 "CONCAT,REPEAT,ARANGE,SUM_ROWS,PAD,PAD_REFLECT_1D,CONV_TRANSPOSE_1D",                 # Token2Wav op set (the filter is a comma list)
                                 "SIN,COS,LOG,CLAMP,LEAKY_RELU,ELU,STEP,SGN,HARDSWISH,HARDSIGMOID,SCALE,SQR,SQRT"])
