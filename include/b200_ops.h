@@ -105,9 +105,15 @@ B200_API int    b200_mul_mat_multi_merges(int n_mat, const b200_tensor * const *
 B200_API int    b200_mul_mat_multi(int n_mat, const b200_tensor * const * w, const b200_tensor * x, const b200_tensor * const * dst, void * scratch,
                                    size_t scratch_bytes, int flags, void * stream);
 /* dst = W . x + residual (the ADD behind wo / ffn_down, ggml-cuda fuses nothing here): rides in the tensor-core GEMM's epilogue when it can (quantised weights, 2-D
- * operands, no split-K), otherwise MUL_MAT + ADD kernels; residual has dst's shape and row stride and may alias dst. */
+ * operands, no split-K) and in the decode matvec's epilogue (one activation column, quantised or F16 weights); otherwise MUL_MAT + ADD kernels, which need a
+ * residual that does not overlap dst (B200_ERR_UNSUPPORTED before anything is launched).  residual has dst's shape and row stride. */
 B200_API int    b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, const b200_tensor * residual, const b200_tensor * dst, void * scratch,
                                  size_t scratch_bytes, int flags, void * stream);
+
+/* dst = silu(Wg . x) * (Wu . x) for ONE activation column: the gate / up / SWIGLU triple of a decode graph in one launch (quantised or F16 weights; SWIGLU only).
+ * B200_ERR_UNSUPPORTED otherwise — the caller keeps MUL_MAT, MUL_MAT, GLU.  scratch >= b200_mul_mat_scratch_bytes(w_gate, x). */
+B200_API int    b200_mul_mat_glu(int glu_op, const b200_tensor * w_gate, const b200_tensor * w_up, const b200_tensor * x, const b200_tensor * dst, void * scratch,
+                                 size_t scratch_bytes, void * stream);
 
 /* Decode fast path: y[m] (+= residual) = W[m, k] . act, activations already quantised by b200_quantize_act /
  * a fused producer.  Up to 4 weight matrices that share the same activation run in ONE launch (q/k/v, gate/up).

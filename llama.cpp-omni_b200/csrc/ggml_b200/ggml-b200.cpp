@@ -485,6 +485,33 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             const bool tc_class = mm_tc_class(n);
             const bool reuse = tc_class && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == 1;
             c->scratch_act = tc_class ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = tc_class ? 1 : 0;
+            // ---- decode graphs (ONE activation column; the per-op route of everything the whole-token engine does not take: F16 / Q8_0 models, other head sizes,
+            // a quantised KV cache): launches are what a token costs there, so adjacent nodes share one
+            const bool one_col = allow_fuse && !fusion_off() && s1->ne[1] == 1 && s1->ne[2] * s1->ne[3] == 1 && s0->ne[2] * s0->ne[3] == 1 && is_weight(s0) &&
+                                 (ggml_is_quantized(s0->type) || s0->type == GGML_TYPE_F16) && ggml_is_contiguous(n);
+            if (one_col) {
+                const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+                // [MUL_MAT gate|up, MUL_MAT up|gate, GLU(gate, up)] -> b200_mul_mat_glu
+                ggml_tensor * n1 = node_idx + 1 < nn ? ggml_graph_node((ggml_cgraph *) g, node_idx + 1) : nullptr, * n2 = node_idx + 2 < nn ? ggml_graph_node((ggml_cgraph *) g, node_idx + 2) : nullptr;
+                if (n1 && n2 && n1->op == GGML_OP_MUL_MAT && n1->src[1] == s1 && is_weight(n1->src[0]) && n2->op == GGML_OP_GLU && n2->src[1] && iparam(n2, 1) == 0 &&
+                    ((n2->src[0] == n && n2->src[1] == n1) || (n2->src[0] == n1 && n2->src[1] == n)) && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) && !(n1->flags & GGML_TENSOR_FLAG_OUTPUT) &&
+                    single_use(g, node_idx, n) && single_use(g, node_idx + 1, n1) && ggml_is_contiguous(n2) && n2->type == GGML_TYPE_F32) {
+                    const ggml_tensor * gate = n2->src[0], * up = n2->src[1];
+                    b200_tensor wg = view_of(gate->src[0]), wu = view_of(up->src[0]), dg = view_of(n2);
+                    rc = b200_mul_mat_glu((int) ggml_get_glu_op(n2), &wg, &wu, &x, &dg, sc, sb, st);
+                    if (rc != B200_ERR_UNSUPPORTED) { c->scratch_act = nullptr; return 3; }
+                }
+                // MUL_MAT -> ADD (the residual behind wo / ffn_down) -> the matvec's epilogue
+                if (next && next->op == GGML_OP_ADD && (next->src[0] == n || next->src[1] == n) && next->src[0] != next->src[1] && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) &&
+                    single_use(g, node_idx, n)) {
+                    const ggml_tensor * other = next->src[0] == n ? next->src[1] : next->src[0];
+                    if (other->type == GGML_TYPE_F32 && next->type == GGML_TYPE_F32 && ggml_are_same_shape(other, n) && ggml_are_same_shape(next, n) && ggml_is_contiguous(other) && ggml_is_contiguous(next)) {
+                        b200_tensor r = view_of(other), dn = view_of(next);
+                        rc = b200_mul_mat_add(&w, &x, &r, &dn, sc, sb, 0, st);
+                        if (rc != B200_ERR_UNSUPPORTED) { c->scratch_act = nullptr; return 2; }
+                    }
+                }
+            }
             // q / k / v: the later MUL_MATs over the same activations run with this one (one launch over the concatenated m-tiles); their results are parked in
             // hoist_buf and copied out when the graph reaches them (run_nodes)
             if (allow_fuse && tc_class && !fusion_off() && !c->hoisted[0] && x.ne[2] * x.ne[3] == 1) {

@@ -96,7 +96,11 @@ __device__ __forceinline__ float dot8_f16(const uint4 w, const uint4 x, float ac
     for (int i = 0; i < 4; ++i) { const float2 a = __half22float2(wh[i]), b = __half22float2(xh[i]); acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); }
     return acc;
 }
-__global__ void __launch_bounds__(256) k_mmvf16_stream(const __half * __restrict__ w, int64_t w_ld, const float * __restrict__ x, float * __restrict__ y, int64_t m, int64_t k) {
+// GLU: the two streamed rows are row r of `w` (gate) and row r of `w2` (up), y[r] = silu(gate . x) * (up . x) — the arithmetic of the separate GLU kernel (ops_misc.cu gluop);
+// otherwise rows r0, r0 + 1 of `w`, y = W . x (+ resid: the ADD that follows wo / ffn_down; resid may be y)
+template <bool GLU>
+__global__ void __launch_bounds__(256) k_mmvf16_stream(const __half * __restrict__ w, const __half * __restrict__ w2, int64_t w_ld, const float * __restrict__ x, float * y,
+                                                       const float * resid, int64_t m, int64_t k) {
     extern __shared__ __align__(16) __half xs[];
     for (int64_t i = (int64_t) threadIdx.x * 4; i < k; i += 256 * 4) {
         const float4 v = *(const float4 *) (x + i);
@@ -105,9 +109,10 @@ __global__ void __launch_bounds__(256) k_mmvf16_stream(const __half * __restrict
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t) gridDim.x * 8;
-    for (int64_t r0 = ((int64_t) blockIdx.x * 8 + (threadIdx.x >> 5)) * 2; r0 < m; r0 += nwarps * 2) {
-        const bool two = r0 + 1 < m;
-        const __half * w0 = w + r0 * w_ld, * w1 = w + (two ? r0 + 1 : r0) * w_ld;
+    constexpr int RPW = GLU ? 1 : 2;                                       // output rows per warp pass
+    for (int64_t r0 = ((int64_t) blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW; r0 < m; r0 += nwarps * RPW) {
+        const bool two = !GLU && r0 + 1 < m;
+        const __half * w0 = w + r0 * w_ld, * w1 = GLU ? w2 + r0 * w_ld : w + (two ? r0 + 1 : r0) * w_ld;
         float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
         int64_t i = (int64_t) lane * 8;
         for (; i + 256 < k; i += 512) {
@@ -121,19 +126,34 @@ __global__ void __launch_bounds__(256) k_mmvf16_stream(const __half * __restrict
             a0 = dot8_f16(p0, xa, a0); a1 = dot8_f16(p1, xa, a1);
         }
         const float s0 = warp_sum(a0 + b0), s1 = warp_sum(a1 + b1);
-        if (lane == 0) { y[r0] = s0; if (two) y[r0 + 1] = s1; }
+        if (lane == 0) {
+            if (GLU) y[r0] = (s0 / (1.0f + expf(-s0))) * s1;
+            else if (resid) { const float q0 = resid[r0], q1 = two ? resid[r0 + 1] : 0.0f; y[r0] = s0 + q0; if (two) y[r0 + 1] = s1 + q1; }
+            else { y[r0] = s0; if (two) y[r0 + 1] = s1; }
+        }
     }
+}
+
+// shapes the streaming F16 matvec takes: one column, 2-D weight with 16-byte aligned rows, k a multiple of 256 that fits shared memory as F16
+static bool mmvf16_stream_ok(const MmvfArgs & A) {
+    return A.n == 1 && A.ne2 * A.ne3 == 1 && A.k % 256 == 0 && A.k <= 24576 && A.w_nb1 % 16 == 0 && ((uintptr_t) A.w | (uintptr_t) A.x) % 16 == 0 && A.m >= 64;
+}
+static int run_mmvf16_stream(const MmvfArgs & A, const void * w_up, const float * resid, cudaStream_t st) {
+    const int64_t cap = (int64_t) sm_count() * 8;
+    if (w_up) {
+        int64_t g = (A.m + 7) / 8; if (g > cap) g = cap;
+        k_mmvf16_stream<true><<<(unsigned) g, 256, (size_t) A.k * 2, st>>>((const __half *) A.w, (const __half *) w_up, A.w_nb1 / 2, (const float *) A.x, (float *) A.y, nullptr, A.m, A.k);
+    } else {
+        int64_t g = (A.m / 2 + 7) / 8; if (g > cap) g = cap;
+        k_mmvf16_stream<false><<<(unsigned) g, 256, (size_t) A.k * 2, st>>>((const __half *) A.w, nullptr, A.w_nb1 / 2, (const float *) A.x, (float *) A.y, resid, A.m, A.k);
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
 }
 
 template <typename WT>
 static int run_mmvf(const MmvfArgs & A, cudaStream_t st) {
-    if (sizeof(WT) == 2 && std::is_same<WT, __half>::value && A.n == 1 && A.ne2 * A.ne3 == 1 && A.k % 256 == 0 && A.k <= 24576 && A.w_nb1 % 16 == 0 &&
-        ((uintptr_t) A.w | (uintptr_t) A.x) % 16 == 0 && A.m >= 64) {
-        int64_t g = (A.m / 2 + 7) / 8; const int64_t cap = (int64_t) sm_count() * 8; if (g > cap) g = cap;
-        k_mmvf16_stream<<<(unsigned) g, 256, (size_t) A.k * 2, st>>>((const __half *) A.w, A.w_nb1 / 2, (const float *) A.x, (float *) A.y, A.m, A.k);
-        B200_LAUNCH_CHECK();
-        return B200_OK;
-    }
+    if (std::is_same<WT, __half>::value && mmvf16_stream_ok(A)) return run_mmvf16_stream(A, nullptr, nullptr, st);
     const int64_t warps = A.m * A.ne2 * A.ne3;
     const unsigned grid = (unsigned) ((warps + 7) / 8);
     for (int64_t c0 = 0; c0 < A.n; c0 += 8) {
@@ -201,6 +221,20 @@ extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, co
                               (cudaStream_t) stream, (const float *) residual->data, &fused);
         return rc ? rc : fused ? B200_OK : B200_ERR_ARG;                    // mmq_tc_fuses_resid and mmq_tc share tc_splitk: not fused here would be a bug
     }
+    // decode (ONE column, 2-D weight): the residual rides in the matvec's epilogue — each thread reads residual[i] before it writes y[i], so residual may be dst
+    if (n == 1 && x->ne[2] * x->ne[3] == 1 && w->ne[2] * w->ne[3] == 1 && residual->nb[0] == 4 && dst->nb[0] == 4 && m > 0) {
+        if (is_quant(t) && scratch && (uintptr_t) scratch % 16 == 0 && scratch_bytes >= (size_t) act_layout(t, k).bytes && (uintptr_t) x->data % 16 == 0) {
+            int rc = b200_quantize_act(t, (const float *) x->data, x->nb[1] / 4, scratch, k, 1, stream);
+            if (rc) return rc;
+            b200_matvec_job job = { w->data, t, w->layout, m, w->nb[1], (float *) dst->data, (const float *) residual->data };
+            rc = b200_matvec_q(&job, 1, scratch, k, stream);
+            if (rc != B200_ERR_UNSUPPORTED) return rc;
+        } else if (t == B200_F16) {
+            MmvfArgs A = { (const char *) w->data, (const char *) x->data, (char *) dst->data, m, k, n, w->nb[1], w->nb[2], w->nb[3], x->nb[1], x->nb[2], x->nb[3],
+                           dst->nb[1], dst->nb[2], dst->nb[3], 1, 1, 1, 1 };
+            if (mmvf16_stream_ok(A)) return run_mmvf16_stream(A, nullptr, (const float *) residual->data, (cudaStream_t) stream);
+        }
+    }
     const char * r0 = (const char *) residual->data, * d0 = (const char *) dst->data;
     const int64_t rbytes = residual->nb[3] * residual->ne[3], dbytes = dst->nb[3] * dst->ne[3];
     if (r0 < d0 + dbytes && d0 < r0 + rbytes) return B200_ERR_UNSUPPORTED;   // overlapping residual and dst
@@ -211,6 +245,31 @@ extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, co
 // dst[i] = W[i] . x for 2 or 3 weight matrices over the SAME activations (q / k / v): ONE tensor-core launch over the concatenated m-tiles when every W[i] is a K-quant
 // on the tcgen05 path (the 1024-row wk / wv alone fill 64 of 148 SMs; merged with wq the launch has 48 x n/256 tiles), otherwise one MUL_MAT after the other with the
 // activation tiles shared.  scratch: the largest b200_mul_mat_scratch_bytes of the group.
+// dst = silu(Wg . x) * (Wu . x) for ONE activation column (the gate / up / SWIGLU triple of a decode graph, three adjacent nodes): one launch — the q8 activation
+// record is built once and b200_matvec_q_swiglu streams both matrices (quantised weights), or k_mmvf16_stream<GLU> (F16 weights).  B200_ERR_UNSUPPORTED for everything
+// else (other GLU ops, several columns, batch dims): the caller keeps its three ops.  Replaces mul_mat_vec_q x 2 + unary_gated_op_kernel (mmvq.cu:139, unary.cu:208-228).
+extern "C" int b200_mul_mat_glu(int glu_op, const b200_tensor * w_gate, const b200_tensor * w_up, const b200_tensor * x, const b200_tensor * dst, void * scratch,
+                                size_t scratch_bytes, void * stream) {
+    if (!w_gate || !w_up || !x || !dst) return B200_ERR_ARG;
+    if (glu_op != B200_GLU_SWIGLU || !b200_mul_mat_supported(w_gate, x, dst) || !b200_mul_mat_supported(w_up, x, dst)) return B200_ERR_UNSUPPORTED;
+    const int t = w_gate->type;
+    const int64_t k = w_gate->ne[0], m = w_gate->ne[1];
+    if (w_up->type != t || w_up->ne[1] != m || w_up->layout != w_gate->layout || w_up->nb[1] != w_gate->nb[1] || x->ne[1] != 1 || x->ne[2] * x->ne[3] != 1 ||
+        w_gate->ne[2] * w_gate->ne[3] != 1 || w_up->ne[2] * w_up->ne[3] != 1 || dst->nb[0] != 4 || m <= 0) return B200_ERR_UNSUPPORTED;
+    if (is_quant(t)) {
+        if (!scratch || (uintptr_t) scratch % 16 || scratch_bytes < (size_t) act_layout(t, k).bytes || (uintptr_t) x->data % 16) return B200_ERR_UNSUPPORTED;
+        const int rc = b200_quantize_act(t, (const float *) x->data, x->nb[1] / 4, scratch, k, 1, stream);
+        if (rc) return rc;
+        const b200_matvec_job g = { w_gate->data, t, w_gate->layout, m, w_gate->nb[1], nullptr, nullptr }, u = { w_up->data, t, w_up->layout, m, w_up->nb[1], nullptr, nullptr };
+        return b200_matvec_q_swiglu(&g, &u, (float *) dst->data, scratch, k, stream);
+    }
+    if (t != B200_F16) return B200_ERR_UNSUPPORTED;
+    MmvfArgs A = { (const char *) w_gate->data, (const char *) x->data, (char *) dst->data, m, k, 1, w_gate->nb[1], w_gate->nb[2], w_gate->nb[3], x->nb[1], x->nb[2], x->nb[3],
+                   dst->nb[1], dst->nb[2], dst->nb[3], 1, 1, 1, 1 };
+    if (!mmvf16_stream_ok(A) || (uintptr_t) w_up->data % 16) return B200_ERR_UNSUPPORTED;
+    return run_mmvf16_stream(A, w_up->data, nullptr, (cudaStream_t) stream);
+}
+
 // B200_NO_MULTI=1 keeps every MUL_MAT of a group in its own launch (read per call: the tests toggle it to compare the merged launch with the separate ones)
 static bool multi_disabled() { const char * e = getenv("B200_NO_MULTI"); return e && atoi(e) != 0; }
 // would b200_mul_mat_multi run this group as ONE launch?  (a caller that has to stage the later results elsewhere — the ggml plugin — only does so when it pays)

@@ -24,7 +24,7 @@ EXPORTS = ["b200_abi_version", "b200_error_string", "b200_device_sm_count", "b20
            "b200_set_rows", "b200_get_rows", "b200_cpy", "b200_binary", "b200_unary", "b200_glu", "b200_scale", "b200_soft_max",
            "b200_flash_attn_supported", "b200_flash_attn_scratch_bytes", "b200_flash_attn", "b200_qkv_post",
            "b200_decoder_create", "b200_decoder_step", "b200_decoder_n_phases", "b200_decoder_profile", "b200_decoder_destroy",
-           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_rms_norm_tiles", "b200_glu_tiles", "b200_flash_attn_tiles", "b200_mul_mat_add", "b200_mul_mat_multi", "b200_mul_mat_multi_merges", "b200_unary_param", "b200_concat", "b200_repeat", "b200_arange", "b200_sum_rows", "b200_pad", "b200_pad_reflect_1d", "b200_conv_transpose_1d", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
+           "b200_norm", "b200_im2col", "b200_pool_1d", "b200_rms_norm_tiles", "b200_glu_tiles", "b200_flash_attn_tiles", "b200_mul_mat_add", "b200_mul_mat_multi", "b200_mul_mat_multi_merges", "b200_mul_mat_glu", "b200_unary_param", "b200_concat", "b200_repeat", "b200_arange", "b200_sum_rows", "b200_pad", "b200_pad_reflect_1d", "b200_conv_transpose_1d", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free", "b200_hop_send", "b200_hop_wait", "b200_hop_ack"]
 
 
 class Tensor(C.Structure):
@@ -219,6 +219,17 @@ def mul_mat_add(w: torch.Tensor, wtype: int, m: int, k: int, x: torch.Tensor, re
             raise B200Error("mul_mat_add: reuse_act needs the scratch that holds the tiles")
         scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
     check(L.b200_mul_mat_add(C.byref(wd), C.byref(xd), C.byref(rd), C.byref(od), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), int(reuse_act), stream()))
+    return out
+
+
+def mul_mat_glu(op: int, w_gate: torch.Tensor, w_up: torch.Tensor, wtype: int, m: int, k: int, x: torch.Tensor, layout: int = LAYOUT_NATIVE) -> torch.Tensor:
+    """out[m] = glu(op)(W_gate . x) * (W_up . x) for ONE activation column (b200_mul_mat_glu: the decode graph's gate / up / SWIGLU triple in one launch)."""
+    L = lib()
+    gd, ud, xd = T(w_gate, wtype, ne=[k, m], layout=layout), T(w_up, wtype, ne=[k, m], layout=layout), T(x)
+    out = torch.empty(list(x.shape[:-1]) + [m], dtype=torch.float32, device=x.device)
+    sb = L.b200_mul_mat_scratch_bytes(C.byref(gd), C.byref(xd))
+    scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
+    check(L.b200_mul_mat_glu(op, C.byref(gd), C.byref(ud), C.byref(xd), _ref(T(out)), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), stream()))
     return out
 
 

@@ -214,6 +214,37 @@ def test_mul_mat_add_is_mul_mat_then_add(ops, name, m, k, n):
         assert "-1000" in str(e) and torch.equal(inplace, r)
 
 
+@pytest.mark.parametrize("name,m,k", [("q4_K", 4096, 4096), ("q6_K", 4096, 12288), ("q8_0", 1024, 2048), ("q4_0", 4096, 4096), ("q5_K", 300, 512), ("f16", 4096, 4096), ("f16", 768, 3072),
+                                      ("f16", 70, 256)])
+def test_decode_matvec_epilogues_are_the_separate_ops(ops, name, m, k):
+    """One activation column (the decode graph): b200_mul_mat_add (residual in the matvec's epilogue, also in place) and b200_mul_mat_glu (gate / up / SWIGLU in one launch)
+    against MUL_MAT, ADD and MUL_MAT, MUL_MAT, GLU — bit for bit (the same dot products, then the same single F32 operations)."""
+    rng = np.random.default_rng(hash((name, m, k, "dec")) & 0xffff)
+    x = dev(rng.standard_normal((1, k)).astype(np.float32))
+    r = dev(rng.standard_normal((1, m)).astype(np.float32))
+    if name == "f16":
+        t, lay = ops.F16, ops.LAYOUT_NATIVE
+        wg = (dev(rng.standard_normal((m, k)).astype(np.float32)) * 0.05).half(); wu = (dev(rng.standard_normal((m, k)).astype(np.float32)) * 0.05).half()
+    else:
+        t = QT[name]
+        planar = t in ops.PAYLOAD
+        lay = ops.LAYOUT_PLANAR if planar else ops.LAYOUT_NATIVE
+        mk = lambda: (lambda b: ops.to_planar(t, dev(b)) if planar else dev(b))(rand_blocks(rng, t, m * k // O.BLOCK[t][0]))
+        wg, wu = mk(), mk()
+    g = ops.mul_mat(wg, t, m, k, x, layout=lay, w_ne=[k, m]); u = ops.mul_mat(wu, t, m, k, x, layout=lay, w_ne=[k, m])
+    want_add = ops.binary(ops.ADD, g, r)
+    got_add = ops.mul_mat_add(wg, t, m, k, x, r, torch.empty_like(r), layout=lay)
+    inplace = r.clone()
+    ops.mul_mat_add(wg, t, m, k, x, inplace, inplace, layout=lay)
+    want_glu = torch.empty_like(g)
+    ops.check(ops.lib().b200_glu(ops.GLU_SWIGLU, ops._ref(ops.T(g)), ops._ref(ops.T(u)), ops._ref(ops.T(want_glu)), 0, ops.stream()))
+    got_glu = ops.mul_mat_glu(ops.GLU_SWIGLU, wg, wu, t, m, k, x, layout=lay)
+    torch.cuda.synchronize()
+    assert torch.isfinite(want_add).all() and torch.isfinite(want_glu).all()
+    assert torch.equal(got_add, want_add) and torch.equal(inplace, want_add)
+    assert torch.equal(got_glu, want_glu)
+
+
 @pytest.mark.parametrize("names,ms,k,n", [(("q4_K", "q4_K", "q6_K"), (4096, 1024, 1024), 4096, 2048), (("q4_K", "q4_K", "q4_K"), (4096, 1024, 1024), 4096, 512),
                                            (("q5_K", "q6_K"), (200, 130), 512, 300), (("q4_K", "q8_0"), (256, 256), 512, 64), (("q4_K", "q4_K", "q6_K"), (512, 128, 128), 1024, 40),
                                            (("q4_K", "q6_K"), (512, 128), 1024, 3)])

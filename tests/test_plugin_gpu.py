@@ -107,6 +107,38 @@ def test_llama_decode_only_parity_f16(f16_model):
     assert fa["max_rel_logit_err"] <= 6e-3, fa                            # bounded by the reference's own F16 accumulator
 
 
+def test_tts_llama_shape_f16_and_projector_graph(tmp_path):
+    """(a) the MiniCPM-o TTS transformer is a llama-arch model (no q/k-norm, ROPE norm mode), 768 wide, 12 heads of 64, F16 weights: through
+    libllama the B200 backend must give the reference CPU backend's greedy tokens, decode graphs only (mode 6) and with a batched prompt (mode 0);
+    (b) the projector graph (MUL_MAT F16 -> ADD bias -> RELU -> MUL_MAT -> ADD, tools/omni/omni.cpp:1187-1201) runs WITHOUT a scheduler, straight on
+    ggml_backend_init_by_type(GPU): every node must be supported (tests/native/projector_graph.cpp checks the result against the CPU backend)."""
+    f = tmp_path / "tts_llama_f16.gguf"
+    subprocess.check_call([sys.executable, str(ROOT / "tools" / "make_gguf.py"), str(f), "--arch", "llama", "--ftype", "f16", "--embd", "768", "--ff", "3072", "--heads", "12",
+                           "--kv-heads", "12", "--head-dim", "64", "--layers", "20", "--vocab", "6562"], timeout=600)
+    threads = os.cpu_count() or 4
+    yard = _parity(f, 48, 32, threads, 0, 3, **{"GGML_BACKEND_PATH": ""})        # the CPU backend against itself (batched vs token-by-token prompt): ~7e-4, and on this
+    dec = _parity(f, 48, 32, threads, 0, 6)                                       # random 6562-way head already enough to flip a greedy token, so only the logits are held
+    full = _parity(f, 48, 32, threads, 1, 0)
+    for r in (yard, dec, full):
+        assert "error" not in r, r
+    assert dec["max_rel_logit_err"] <= max(3e-3, 3.0 * yard["max_rel_logit_err"]), (dec, yard)
+    assert full["max_rel_logit_err"] <= 6e-3, full                        # -fa 1: the CPU accumulates V in F16 (ggml-cpu/ops.cpp:8016-8083)
+    for wt, shape in (("f16", (4096, 768, 768, 25)), ("f32", (4096, 768, 768, 1)), ("f16", (768, 768, 768, 300))):
+        r = subprocess.run([str(REF / "bin" / "projector_graph"), *map(str, shape), wt], env=_env(), capture_output=True, text=True, timeout=300)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert lines, (r.stdout + r.stderr)[-2000:]
+        res = json.loads(lines[-1])
+        assert "error" not in res and res["gpu_backend"].startswith("B200") and res["finite"] and res["nmse"] <= 1e-6 and r.returncode == 0, res
+
+
+def test_decode_graph_fusions_are_bit_identical_f16(f16_model):
+    """The per-op route's adjacent-node fusions for decode graphs (MUL_MAT -> ADD in the matvec's epilogue, gate / up / SWIGLU as one launch) against the same run with
+    GGML_B200_NO_TILE_FUSION=1 (llama_parity mode 8) on the F16 model, which the whole-token engine does not take: logits bit for bit."""
+    r = _parity(f16_model, 40, 24, os.cpu_count() or 4, 1, 8)
+    assert "error" not in r, r
+    assert r["tokens_equal"] and r["prefill_rel_err"] == 0 and r["max_rel_logit_err"] == 0, r
+
+
 def test_llama_decode_only_parity_q4_k_m(small_model):
     """Q4_K_M: the decode path keeps the reference's integer arithmetic (q8_K activations, integer sub-block dots), yet through a whole model the logits of any
     two implementations sit at the int8-activation noise floor (tests/test_chaos_yardstick.py: a 2e-6 input perturbation moves the ORACLE's own logits by

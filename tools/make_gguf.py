@@ -83,6 +83,7 @@ def main() -> None:
     ap.add_argument("--ctx", type=int, default=40960)
     ap.add_argument("--ftype", default="q4_k_m", choices=["q4_k_m", "f16", "q8_0", "f32"])
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--arch", default="qwen3", choices=["qwen3", "llama"], help="llama: no q/k-norm tensors, ROPE norm mode (the MiniCPM-o TTS llama: --embd 768 --ff 3072 --heads 12 --kv-heads 12 --head-dim 64 --layers 20)")
     ap.add_argument("--reuse-layers", action="store_true", help="speed-only files: every layer reuses layer 0's random bytes (minutes -> seconds for a 15 GB F16 file)")
     a = ap.parse_args()
     E, F, Q, KV, D, L = a.embd, a.ff, a.heads * a.head_dim, a.kv_heads * a.head_dim, a.head_dim, a.layers
@@ -111,14 +112,19 @@ def main() -> None:
                     (p + "ffn_gate.weight", wtype("ffn_gate", il), E, F, "w"), (p + "ffn_up.weight", wtype("ffn_up", il), E, F, "w"),
                     (p + "ffn_down.weight", wtype("ffn_down", il), F, E, "w")]
     tensors += [("output_norm.weight", F32, E, 1, "norm"), ("output.weight", wtype("output", 0), E, a.vocab, "w")]
+    if a.arch == "llama":
+        tensors = [t for t in tensors if not t[0].endswith(("attn_q_norm.weight", "attn_k_norm.weight"))]
 
     ftype_id = {"q4_k_m": 15, "f16": 1, "q8_0": 7, "f32": 0}[a.ftype]
-    kvs = [kv_str("general.architecture", "qwen3"), kv_str("general.name", f"synthetic-qwen3-{L}L-{a.ftype}"), kv_u32("general.file_type", ftype_id),
-           kv_u32("qwen3.block_count", L), kv_u32("qwen3.context_length", a.ctx), kv_u32("qwen3.embedding_length", E),
-           kv_u32("qwen3.feed_forward_length", F), kv_u32("qwen3.attention.head_count", a.heads), kv_u32("qwen3.attention.head_count_kv", a.kv_heads),
-           kv_u32("qwen3.attention.key_length", D), kv_u32("qwen3.attention.value_length", D), kv_f32("qwen3.attention.layer_norm_rms_epsilon", 1e-6),
-           kv_f32("qwen3.rope.freq_base", 1e6), kv_u32("qwen3.vocab_size", a.vocab), kv_str("tokenizer.ggml.model", "no_vocab"),
+    A = a.arch
+    kvs = [kv_str("general.architecture", A), kv_str("general.name", f"synthetic-{A}-{L}L-{a.ftype}"), kv_u32("general.file_type", ftype_id),
+           kv_u32(f"{A}.block_count", L), kv_u32(f"{A}.context_length", a.ctx), kv_u32(f"{A}.embedding_length", E),
+           kv_u32(f"{A}.feed_forward_length", F), kv_u32(f"{A}.attention.head_count", a.heads), kv_u32(f"{A}.attention.head_count_kv", a.kv_heads),
+           kv_u32(f"{A}.attention.key_length", D), kv_u32(f"{A}.attention.value_length", D), kv_f32(f"{A}.attention.layer_norm_rms_epsilon", 1e-6),
+           kv_f32(f"{A}.rope.freq_base", 1e6), kv_u32(f"{A}.vocab_size", a.vocab), kv_str("tokenizer.ggml.model", "no_vocab"),
            kv_u32("general.alignment", ALIGN)]
+    if A == "llama":
+        kvs.append(kv_u32("llama.rope.dimension_count", D))
 
     infos, off = [], 0
     for name, t, ne0, ne1, _ in tensors:
