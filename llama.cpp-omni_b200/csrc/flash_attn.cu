@@ -46,7 +46,37 @@ static FaPlan fa_plan(int64_t n_q_total, int64_t n_kv, int64_t n_head, int64_t n
     return P;
 }
 
-template <int D, int G>
+// 8 consecutive elements of a K / V row, as raw bits and as floats.  KT = B200_F16: 16 bytes of halves.  KT = B200_Q8_0 / B200_Q4_0 (a quantised KV cache, -ctk / -ctv):
+// the lane's 8 codes (8 int8 bytes, or the low / high nibbles of 8 bytes) and the block's f16 d, fetched with 2-byte loads (34- / 18-byte blocks are only 2-byte aligned)
+// and dequantised in registers as dequantize_row_q8_0 / q4_0 do (ggml-quants.c:390-402, 307-325) — no F16 staging pass, the cache is read once at its quantised size.
+template <int KT> __device__ __forceinline__ uint4 kv_load8(const char * row, int hl) {
+    if (KT == B200_F16) return ldg_stream16(row + hl * 16);
+    const int e0 = hl * 8, blk = e0 >> 5, o = e0 & 31;
+    const uint16_t * b = (const uint16_t *) (row + blk * (KT == B200_Q8_0 ? 34 : 18));
+    const uint16_t * q = b + 1 + (KT == B200_Q8_0 ? o >> 1 : (o & 15) >> 1);
+    uint4 r;
+    r.x = (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 16); r.y = (uint32_t) __ldg(q + 2) | ((uint32_t) __ldg(q + 3) << 16);
+    r.z = __ldg(b); r.w = 0;
+    return r;
+}
+template <int KT> __device__ __forceinline__ void kv_floats8(const uint4 raw, int hl, float (&f)[8]) {
+    if (KT == B200_F16) {
+        const __half2 * h2 = (const __half2 *) &raw;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h2[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+        return;
+    }
+    const float d = h2f((uint16_t) raw.z);
+    const uint32_t w[2] = { raw.x, raw.y };
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xff;
+        const int code = KT == B200_Q8_0 ? (int) (int8_t) byte : (int) (((hl * 8) & 16) ? byte >> 4 : byte & 15) - 8;
+        f[i] = __fmul_rn((float) code, d);
+    }
+}
+
+template <int D, int G, int KT>
 __global__ void __launch_bounds__(FA_THREADS) k_fa_decode(const FaArgs A) {
     constexpr int LPR = D / 8;                 // lanes per K/V row (16 B each)
     constexpr int RPW = 32 / LPR;              // rows per warp-load
@@ -78,8 +108,8 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_decode(const FaArgs A) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[g][i] = 0.0f;
 
-    const char * kb = A.k + (int64_t) kvh * A.k_nb2 + (ib % A.k_ne3) * A.k_nb3 + hl * 16;
-    const char * vb = A.v + (int64_t) kvh * A.v_nb2 + (ib % A.k_ne3) * A.v_nb3 + hl * 16;
+    const char * kb = A.k + (int64_t) kvh * A.k_nb2 + (ib % A.k_ne3) * A.k_nb3;
+    const char * vb = A.v + (int64_t) kvh * A.v_nb2 + (ib % A.k_ne3) * A.v_nb3;
     const __half * mrow = A.mask ? (const __half *) (A.mask + iq * A.m_nb1 + ((int64_t) head0 % A.m_ne2) * A.m_nb2 + (ib % A.m_ne3) * A.m_nb3) : nullptr;
     const int64_t c0 = (int64_t) split * A.chunk, c1 = min(c0 + A.chunk, A.n_kv);
     __syncthreads();
@@ -93,14 +123,12 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_decode(const FaArgs A) {
                 const int64_t pos = t0 + j0 + u * NRG;
                 mv[u] = pos < c1 ? (mrow ? __half2float(mrow[pos]) : 0.0f) : -INFINITY;
                 kk[u] = make_uint4(0, 0, 0, 0);
-                if (mv[u] != -INFINITY) kk[u] = ldg_stream16(kb + pos * A.k_nb1);
+                if (mv[u] != -INFINITY) kk[u] = kv_load8<KT>(kb + pos * A.k_nb1, hl);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const __half2 * h2 = (const __half2 *) &kk[u];
                 float kf[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h2[i]); kf[2 * i] = f.x; kf[2 * i + 1] = f.y; }
+                kv_floats8<KT>(kk[u], hl, kf);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     float d = 0.0f;
@@ -147,17 +175,16 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_decode(const FaArgs A) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) { pv[u][g] = S[j][g]; any |= pv[u][g] != 0.0f; }
                 vv[u] = make_uint4(0, 0, 0, 0);
-                if (any) vv[u] = ldg_stream16(vb + (t0 + j) * A.v_nb1);
+                if (any) vv[u] = kv_load8<KT>(vb + (t0 + j) * A.v_nb1, hl);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const __half2 * h2 = (const __half2 *) &vv[u];
+                float vf[8];
+                kv_floats8<KT>(vv[u], hl, vf);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(h2[i]);
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int g = 0; g < G; ++g) { acc[g][2 * i] = fmaf(pv[u][g], f.x, acc[g][2 * i]); acc[g][2 * i + 1] = fmaf(pv[u][g], f.y, acc[g][2 * i + 1]); }
-                }
+                    for (int g = 0; g < G; ++g) acc[g][i] = fmaf(pv[u][g], vf[i], acc[g][i]);
             }
         }
         __syncthreads();
@@ -204,12 +231,12 @@ __global__ void __launch_bounds__(D) k_fa_combine(const FaArgs A) {
     *(float *) (A.dst + (int64_t) threadIdx.x * 4 + (int64_t) head * A.d_nb1 + iq * A.d_nb2 + ib * A.d_nb3) = L == 0.0f ? 0.0f : v / L;
 }
 
-template <int D>
+template <int D, int KT>
 static int fa_launch(const FaArgs & A, int G, int64_t nz, cudaStream_t st) {
     dim3 grid((unsigned) A.splits, (unsigned) (A.n_head_kv * A.groups), (unsigned) nz);
-    if      (G == 4) k_fa_decode<D, 4><<<grid, FA_THREADS, 0, st>>>(A);
-    else if (G == 2) k_fa_decode<D, 2><<<grid, FA_THREADS, 0, st>>>(A);
-    else             k_fa_decode<D, 1><<<grid, FA_THREADS, 0, st>>>(A);
+    if      (G == 4) k_fa_decode<D, 4, KT><<<grid, FA_THREADS, 0, st>>>(A);
+    else if (G == 2) k_fa_decode<D, 2, KT><<<grid, FA_THREADS, 0, st>>>(A);
+    else             k_fa_decode<D, 1, KT><<<grid, FA_THREADS, 0, st>>>(A);
     B200_LAUNCH_CHECK();
     if (A.splits > 1) {
         k_fa_combine<D><<<dim3((unsigned) A.n_head, (unsigned) nz), D, 0, st>>>(A);
@@ -298,7 +325,9 @@ static int flash_attn_impl(const b200_tensor * q, const b200_tensor * k, const b
     const int64_t nz = q->ne[1] * q->ne[3];
     if (nz == 0 || q->ne[2] == 0) return B200_OK;
     b200_tensor kf, vf;
-    if (k->type != B200_F16 && k->ne[1] > 0) {                                // stage the quantised cache views as contiguous F16 [D, n_kv, n_head_kv, n_b]
+    // decode class (< 16 query tokens) with K and V of the SAME quantised type: k_fa_decode dequantises in its loads, nothing is staged
+    const bool direct_q = k->type != B200_F16 && k->type == v->type && q->ne[1] < 16 && nz <= 65535;
+    if (k->type != B200_F16 && k->ne[1] > 0 && !direct_q) {                   // stage the quantised cache views as contiguous F16 [D, n_kv, n_head_kv, n_b]
         const size_t sb = fa_stage_bytes(k);
         if (!scratch || (uintptr_t) scratch % 16 || scratch_bytes < 2 * sb) return B200_ERR_ARG;
         auto stage = [&](const b200_tensor * t, b200_tensor & f, char * where) -> int {
@@ -337,5 +366,7 @@ static int flash_attn_impl(const b200_tensor * q, const b200_tensor * k, const b
         A.part_ml  = (float2 *) ((char *) scratch + ((slots * q->ne[0] * 4 + 15) & ~(size_t) 15));
     }
     cudaStream_t st = (cudaStream_t) stream;
-    return q->ne[0] == 128 ? fa_launch<128>(A, P.G, nz, st) : fa_launch<64>(A, P.G, nz, st);
+    if (k->type == B200_Q8_0) return q->ne[0] == 128 ? fa_launch<128, B200_Q8_0>(A, P.G, nz, st) : fa_launch<64, B200_Q8_0>(A, P.G, nz, st);
+    if (k->type == B200_Q4_0) return q->ne[0] == 128 ? fa_launch<128, B200_Q4_0>(A, P.G, nz, st) : fa_launch<64, B200_Q4_0>(A, P.G, nz, st);
+    return q->ne[0] == 128 ? fa_launch<128, B200_F16>(A, P.G, nz, st) : fa_launch<64, B200_F16>(A, P.G, nz, st);
 }

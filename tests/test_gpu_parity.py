@@ -994,8 +994,9 @@ def test_get_rows_from_quantised_rows(ops, name):
 @pytest.mark.parametrize("name,n_q,n_kv,D,n_head,n_head_kv", [("q8_0", 1, 1024, 128, 32, 8), ("q4_0", 1, 512, 128, 8, 2), ("q8_0", 3, 256, 64, 12, 12), ("q8_0", 200, 512, 128, 8, 2),
                                                                ("q4_0", 64, 256, 128, 8, 2)])
 def test_flash_attn_over_quantised_kv(ops, name, n_q, n_kv, D, n_head, n_head_kv):
-    """FLASH_ATTN_EXT with a q8_0 / q4_0 KV cache: K and V are staged as F16 (the reference's launch_fattn does the same to_fp16 pass), so the result must be bit for bit
-    the F16-cache result on the dequantised, F16-rounded values; that F16 run is itself pinned to the oracle by the tests above."""
+    """FLASH_ATTN_EXT with a q8_0 / q4_0 KV cache.  >= 16 query tokens: K and V are staged as F16 (the reference's launch_fattn does the same to_fp16 pass), so the result
+    must be bit for bit the F16-cache result on the dequantised, F16-rounded values (that F16 run is itself pinned to the oracle by the tests above).  Decode (< 16 query
+    tokens): k_fa_decode dequantises in its loads (d * code in F32, no F16 rounding of the products), so it agrees with the F16-staged result to that rounding only."""
     t = QT[name]
     rng = np.random.default_rng(n_q * 7 + n_kv)
     past = n_kv - n_q - 5 if n_q > 1 else n_kv - 9
@@ -1014,7 +1015,17 @@ def test_flash_attn_over_quantised_kv(ops, name, n_q, n_kv, D, n_head, n_head_kv
     kqd, vqd = dev(kq), dev(vq)
     got = ops.flash_attn(q, _kv_desc(ops, kqd, t, D, n_kv, n_head_kv), _kv_desc(ops, vqd, t, D, n_kv, n_head_kv), mask, 1.0 / D ** 0.5)
     torch.cuda.synchronize()
-    assert torch.isfinite(want).all() and torch.equal(got, want)
+    assert torch.isfinite(want).all()
+    if n_q >= 16:
+        assert torch.equal(got, want)
+    else:
+        assert float((got - want).abs().max()) <= 1e-3 * float(want.abs().max())
+        # and against the exact dequantised values in f64 (what the CPU's v_to_float + F32 accumulation computes, up to its q8_0-quantised Q): softmax(q.K^T) V
+        kd = dev(O.dequant(t, kq, n_head_kv * D)).double().view(n_kv, n_head_kv, D).permute(1, 0, 2).repeat_interleave(n_head // n_head_kv, 0)
+        vd = dev(O.dequant(t, vq, n_head_kv * D)).double().view(n_kv, n_head_kv, D).permute(1, 0, 2).repeat_interleave(n_head // n_head_kv, 0)
+        sc = (q.half().double() @ kd.transpose(1, 2)) / D ** 0.5 + mask[:n_q].double()[None]
+        ref = (torch.softmax(sc, -1) @ vd).permute(1, 0, 2)
+        assert float((got.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
 
 
 def test_rope_f16_in_place_is_the_f32_rope_rounded_once(ops):
