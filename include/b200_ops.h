@@ -95,7 +95,8 @@ B200_API int    b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const
  * the SAME x from the immediately preceding b200_mul_mat[_ex] call on this scratch, with a weight type of the same preparation class — the
  * q/k/v and gate/up projections of a layer share their input, so only the first of them pays for the conversion.  The caller guarantees
  * that neither x nor scratch changed in between; when the flag cannot be honoured (different path) it is ignored. */
-enum { B200_MM_REUSE_ACT = 1 };
+enum { B200_MM_REUSE_ACT = 1 };   /* the scratch still holds the prepared activations of THIS x from the previous call of the same routing class: F16 tiles (more
+                                   * than 8 columns) or q8 records of the same group (K-quants: q8_K, q4_0 / q8_0: q8_0; at most 8 columns, no batch dims) */
 B200_API int    b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
                                 size_t scratch_bytes, int flags, void * stream);
 /* dst[i] = W[i] . x for 2 or 3 weight matrices over the SAME activations (q / k / v of a layer): one tcgen05 launch over the concatenated m-tiles when every W[i] is

@@ -483,8 +483,12 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             // (only for the tensor-core path: > 8 columns of q4_K / planar q6_K; the preparation does not depend on which of the two types)
             // (same routing conditions as mmq_tc_supported in csrc/mmq_tc.cu: native 16-byte-multiple blocks with back-to-back rows, or planar planes)
             const bool tc_class = mm_tc_class(n);
-            const bool reuse = tc_class && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == 1;
-            c->scratch_act = tc_class ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = tc_class ? 1 : 0;
+            // activation class held in the scratch after this MUL_MAT: 1 = F16 tiles (tensor-core path), 2 / 3 = q8_K / q8_0 records of a matvec (<= 8 columns, no batch dims)
+            const bool rec_class = !tc_class && ggml_is_quantized(s0->type) && s1->ne[1] <= 8 && s1->ne[2] * s1->ne[3] == 1 && s0->ne[2] * s0->ne[3] == 1;
+            const bool kq = s0->type == GGML_TYPE_Q4_K || s0->type == GGML_TYPE_Q5_K || s0->type == GGML_TYPE_Q6_K;
+            const int act_type = tc_class ? 1 : rec_class ? (kq ? 2 : 3) : 0;
+            const bool reuse = act_type != 0 && !(act_type > 1 && fusion_off()) && sc == scratch_before && c->scratch_act == s1 && c->scratch_act_data == s1->data && c->scratch_act_type == act_type;
+            c->scratch_act = act_type ? s1 : nullptr; c->scratch_act_data = s1->data; c->scratch_act_type = act_type;
             // ---- decode graphs (ONE activation column; the per-op route of everything the whole-token engine does not take: F16 / Q8_0 models, other head sizes,
             // a quantised KV cache): launches are what a token costs there, so adjacent nodes share one
             const bool one_col = allow_fuse && !fusion_off() && s1->ne[1] == 1 && s1->ne[2] * s1->ne[3] == 1 && s0->ne[2] * s0->ne[3] == 1 && is_weight(s0) &&
@@ -499,7 +503,7 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
                     const ggml_tensor * gate = n2->src[0], * up = n2->src[1];
                     b200_tensor wg = view_of(gate->src[0]), wu = view_of(up->src[0]), dg = view_of(n2);
                     rc = b200_mul_mat_glu((int) ggml_get_glu_op(n2), &wg, &wu, &x, &dg, sc, sb, st);
-                    if (rc != B200_ERR_UNSUPPORTED) { c->scratch_act = nullptr; return 3; }
+                    if (rc != B200_ERR_UNSUPPORTED) return 3;                 // (it quantised x into the scratch itself: the bookkeeping above already says so)
                 }
                 // MUL_MAT -> ADD (the residual behind wo / ffn_down) -> the matvec's epilogue
                 if (next && next->op == GGML_OP_ADD && (next->src[0] == n || next->src[1] == n) && next->src[0] != next->src[1] && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) &&
@@ -507,8 +511,8 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
                     const ggml_tensor * other = next->src[0] == n ? next->src[1] : next->src[0];
                     if (other->type == GGML_TYPE_F32 && next->type == GGML_TYPE_F32 && ggml_are_same_shape(other, n) && ggml_are_same_shape(next, n) && ggml_is_contiguous(other) && ggml_is_contiguous(next)) {
                         b200_tensor r = view_of(other), dn = view_of(next);
-                        rc = b200_mul_mat_add(&w, &x, &r, &dn, sc, sb, 0, st);
-                        if (rc != B200_ERR_UNSUPPORTED) { c->scratch_act = nullptr; return 2; }
+                        rc = b200_mul_mat_add(&w, &x, &r, &dn, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
+                        if (rc != B200_ERR_UNSUPPORTED) return 2;
                     }
                 }
             }
@@ -577,6 +581,34 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
             b200_tensor x = view_of(s0), d = view_of(n);
             if (next && next->op == GGML_OP_MUL && (next->src[0] == n || next->src[1] == n) && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) && single_use(g, node_idx, n)) {
                 const ggml_tensor * wt = next->src[0] == n ? next->src[1] : next->src[0];
+                // decode graphs: when a quantised matvec reads the normalised vector, the same launch also leaves its q8 record in the scratch (k_rms_norm_quantize),
+                // and that MUL_MAT (and the ones after it on the same activations: q / k / v, gate / up) skip their quantisation pass
+                if (!fusion_off() && f32c(wt) && wt->ne[0] == n->ne[0] && ggml_nelements(wt) == wt->ne[0] && n->ne[1] <= 8 && n->ne[2] * n->ne[3] == 1 && ggml_is_contiguous(next) &&
+                    ggml_is_contiguous(wt)) {
+                    const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+                    const ggml_tensor * mm = nullptr;
+                    for (int j = node_idx + 2, seen = 0; j < nn && seen < 6 && !mm; ++j) {
+                        const ggml_tensor * t = ggml_graph_node((ggml_cgraph *) g, j);
+                        if (is_noop(t)) continue;
+                        ++seen;
+                        if (t->op == GGML_OP_MUL_MAT && t->src[1] == next && ggml_is_quantized(t->src[0]->type) && !mm_tc_class(t) && t->src[0]->ne[2] * t->src[0]->ne[3] == 1) mm = t;
+                    }
+                    if (mm) {
+                        b200_tensor mw = view_of(mm->src[0]), mx = view_of(next);
+                        const size_t sbm = b200_mul_mat_scratch_bytes(&mw, &mx);
+                        void * scm = sbm ? scratch_for(c, sbm) : nullptr;
+                        if (scm) {
+                            rc = b200_rms_norm_quantize((const float *) s0->data, (int64_t) s0->nb[1] / 4, (const float *) wt->data, (float *) next->data, (int64_t) next->nb[1] / 4, scm,
+                                                        (int) mm->src[0]->type, n->ne[0], n->ne[1], fparam(n, 0), st);
+                            if (rc == B200_OK) {
+                                const bool kq = mm->src[0]->type == GGML_TYPE_Q4_K || mm->src[0]->type == GGML_TYPE_Q5_K || mm->src[0]->type == GGML_TYPE_Q6_K;
+                                c->scratch_act = next; c->scratch_act_data = next->data; c->scratch_act_type = kq ? 2 : 3;
+                                return 2;
+                            }
+                            rc = B200_OK;
+                        }
+                    }
+                }
                 if (f32c(wt) && ggml_are_same_shape(next, n) && broadcastable(n, wt)) {
                     b200_tensor w = view_of(wt), dm = view_of(next);
                     rc = b200_rms_norm(&x, &w, nullptr, &dm, fparam(n, 0), st);

@@ -224,7 +224,7 @@ extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, co
     // decode (ONE column, 2-D weight): the residual rides in the matvec's epilogue — each thread reads residual[i] before it writes y[i], so residual may be dst
     if (n == 1 && x->ne[2] * x->ne[3] == 1 && w->ne[2] * w->ne[3] == 1 && residual->nb[0] == 4 && dst->nb[0] == 4 && m > 0) {
         if (is_quant(t) && scratch && (uintptr_t) scratch % 16 == 0 && scratch_bytes >= (size_t) act_layout(t, k).bytes && (uintptr_t) x->data % 16 == 0) {
-            int rc = b200_quantize_act(t, (const float *) x->data, x->nb[1] / 4, scratch, k, 1, stream);
+            int rc = (flags & B200_MM_REUSE_ACT) ? B200_OK : b200_quantize_act(t, (const float *) x->data, x->nb[1] / 4, scratch, k, 1, stream);
             if (rc) return rc;
             b200_matvec_job job = { w->data, t, w->layout, m, w->nb[1], (float *) dst->data, (const float *) residual->data };
             rc = b200_matvec_q(&job, 1, scratch, k, stream);
@@ -347,7 +347,8 @@ extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, con
             continue;
         }
         uint8_t * act = (uint8_t *) scratch + (i3 * x->ne[2] + i2) * n * act_b;
-        int rc = b200_quantize_act(t, xs, x->nb[1] / 4, act, k, n, stream);
+        // B200_MM_REUSE_ACT on the matvec path: the scratch still holds the q8 records of THIS x from the previous MUL_MAT of the same record class (q / k / v)
+        int rc = (flags & B200_MM_REUSE_ACT) && x->ne[2] * x->ne[3] == 1 ? B200_OK : b200_quantize_act(t, xs, x->nb[1] / 4, act, k, n, stream);
         if (rc) return rc;
         const char * wb = (const char *) w->data + (i2 / r2) * w->nb[2] + (i3 / r3) * w->nb[3];
         float * yb = (float *) ((char *) dst->data + i2 * dst->nb[2] + i3 * dst->nb[3]);
