@@ -8,6 +8,7 @@
 //        4: B200 batched vs B200 incremental   5: B200 per-op route vs B200 decode engine   6: CPU vs B200, prompt fed token by token (decode only)
 // prints one JSON line: {"tokens_equal": bool, "n_gen": N, "first_mismatch": i, "max_rel_logit_err": x, "prefill_rel_err": y, ...}
 #include "llama.h"
+#include <cstring>
 #include "ggml-backend.h"
 #include <chrono>
 #include <cmath>
@@ -30,6 +31,11 @@ static Run run(const char * path, int ngl, int n_prompt, int n_gen, int n_thread
     const int nb = n_prompt > 512 ? (n_prompt + 255) / 256 * 256 : 512;                 // the whole prompt as ONE ubatch (exercises the n >= 512 GEMM routing)
     cp.n_ctx = n_prompt + n_gen + 64 > 1024 ? (n_prompt + n_gen + 64 + 255) / 256 * 256 : 1024; cp.n_batch = nb; cp.n_ubatch = nb; cp.n_threads = n_threads; cp.n_threads_batch = n_threads;
     cp.flash_attn_type = fa ? LLAMA_FLASH_ATTN_TYPE_ENABLED : LLAMA_FLASH_ATTN_TYPE_DISABLED; cp.no_perf = true;
+    // PARITY_KV_TYPE=q8_0|q4_0: quantised KV cache on both sides (-ctk / -ctv: SET_ROWS into quant blocks, FLASH_ATTN_EXT over them; needs fa = 1)
+    if (const char * kvt = getenv("PARITY_KV_TYPE")) {
+        const ggml_type t = strcmp(kvt, "q8_0") == 0 ? GGML_TYPE_Q8_0 : strcmp(kvt, "q4_0") == 0 ? GGML_TYPE_Q4_0 : GGML_TYPE_F16;
+        cp.type_k = t; cp.type_v = t;
+    }
     llama_context * ctx = llama_init_from_model(model, cp);
     if (!ctx) { fprintf(stderr, "context failed\n"); llama_model_free(model); return r; }
     const int n_vocab = llama_vocab_n_tokens(llama_model_get_vocab(model));
@@ -42,6 +48,14 @@ static Run run(const char * path, int ngl, int n_prompt, int n_gen, int n_thread
     } else if (llama_decode(ctx, llama_batch_get_one(prompt.data(), n_prompt))) { fprintf(stderr, "prefill failed\n"); return r; }
     const float * lg = llama_get_logits_ith(ctx, -1);
     r.logits.emplace_back(lg, lg + n_vocab);
+    // PARITY_KSHIFT=1: omni's sliding window (tools/omni/omni.cpp:686-820): drop a quarter of the prompt behind the first token and shift the rest down; the next
+    // llama_decode then runs the K-shift graph (ROPE in place on views of the cache: F16 directly, a quantised cache through F32 casts, src/llama-kv-cache.cpp)
+    if (getenv("PARITY_KSHIFT") && atoi(getenv("PARITY_KSHIFT")) != 0 && n_prompt >= 8) {
+        llama_memory_t mem = llama_get_memory(ctx);
+        const int n_discard = n_prompt / 4;
+        llama_memory_seq_rm(mem, 0, 1, 1 + n_discard);
+        llama_memory_seq_add(mem, 0, 1 + n_discard, n_prompt, -n_discard);
+    }
     auto t1 = std::chrono::steady_clock::now();
     r.pp_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     for (int i = 0; i < n_gen; ++i) {

@@ -119,3 +119,23 @@ def test_encoder_ops_match_reference():
     t = rng.standard_normal((5, 250)).astype(np.float32)
     for op in (0, 1):
         assert np.array_equal(O.pool_1d(t, op, 5), R.pool_1d(t, op, 5))
+
+
+def test_make_gguf_llama_arch_loads_in_the_reference(tmp_path):
+    """tools/make_gguf.py --arch llama (the TTS-transformer shape of MiniCPM-o: no q/k-norm, ROPE norm mode) must be a file the unmodified reference loads and decodes:
+    llama_parity mode 3 = the reference CPU backend against itself (batched vs token-by-token prompt), also with the K-shift knob (llama_memory_seq_rm / seq_add)."""
+    import json, os, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "oracle" / "_ref" / "bin" / "llama_parity"
+    if not exe.exists():
+        pytest.skip("oracle/_ref is not built")
+    f = tmp_path / "tiny_llama.gguf"
+    subprocess.check_call([sys.executable, str(root / "tools" / "make_gguf.py"), str(f), "--arch", "llama", "--ftype", "f16", "--embd", "256", "--ff", "512", "--heads", "4",
+                           "--kv-heads", "4", "--head-dim", "64", "--layers", "2", "--vocab", "512"], stderr=subprocess.DEVNULL)
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{root / 'oracle' / '_ref' / 'lib'}:" + os.environ.get("LD_LIBRARY_PATH", ""))
+    env.pop("GGML_BACKEND_PATH", None)
+    for extra in ({}, {"PARITY_KSHIFT": "1"}):
+        r = subprocess.run([str(exe), str(f), "16", "6", "2", "0", "3"], env=dict(env, **extra), capture_output=True, text=True, timeout=300)
+        res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        assert "error" not in res and res["max_rel_logit_err"] <= 5e-3, res

@@ -139,6 +139,21 @@ def test_decode_graph_fusions_are_bit_identical_f16(f16_model):
     assert r["tokens_equal"] and r["prefill_rel_err"] == 0 and r["max_rel_logit_err"] == 0, r
 
 
+def test_kshift_and_quantised_kv_cache_through_libllama(f16_model):
+    """SURVEY §8f rank 4, end to end on the F16 model (no activation-quantisation noise, so the comparison with the reference CPU backend is tight):
+      * K-shift: after the prompt a quarter of the context is dropped and the rest shifted down (llama_memory_seq_rm / seq_add, what omni's sliding window does,
+        tools/omni/omni.cpp:686-820); the next decode runs ROPE in place on views of the F16 cache on the B200 backend;
+      * a q8_0 KV cache (SET_ROWS into quant blocks, attention over them — staged for the prompt, dequantised in the loads for decode);
+      * both at once (the K-shift of a quantised cache: cast to F32, ROPE, CPY back into q8_0 blocks)."""
+    threads = os.cpu_count() or 4
+    for env, bar in (({"PARITY_KSHIFT": "1"}, 6e-3), ({"PARITY_KV_TYPE": "q8_0"}, 2e-2), ({"PARITY_KSHIFT": "1", "PARITY_KV_TYPE": "q8_0"}, 2e-2)):
+        r = _parity(f16_model, 48, 24, threads, 1, 0, **env)
+        assert "error" not in r, (env, r)
+        assert r["max_rel_logit_err"] <= bar, (env, r)          # fa = 1: the CPU accumulates V in F16 (6e-3 on this model, see the F16 test above); q8_0 K/V: the CPU also
+        if "PARITY_KV_TYPE" not in env:                         # quantises Q to q8_0 for its K dot products, we keep Q in F16
+            assert r["tokens_equal"], (env, r)
+
+
 def test_llama_decode_only_parity_q4_k_m(small_model):
     """Q4_K_M: the decode path keeps the reference's integer arithmetic (q8_K activations, integer sub-block dots), yet through a whole model the logits of any
     two implementations sit at the int8-activation noise floor (tests/test_chaos_yardstick.py: a 2e-6 input perturbation moves the ORACLE's own logits by
