@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -82,6 +83,7 @@ struct BackendCtx {
     // their node — their own dst may still hold a live tensor at that point (ggml-alloc reuses buffers in node order)
     void * hoist_buf = nullptr; size_t hoist_size = 0;
     const ggml_tensor * hoisted[2] = { nullptr, nullptr }; void * hoisted_at[2] = { nullptr, nullptr };
+    long long host_ns = 0, host_min_ns = 0, host_calls = 0, host_nodes = 0, sync_ns = 0, sync_calls = 0, evsync_calls = 0;   // GGML_B200_HOST_TIMING
 };
 
 DeviceCtx g_devices[MAX_DEVICES];
@@ -307,6 +309,10 @@ bool b200_dev_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
     if (op_disabled(op)) return false;
     for (int i = 0; i < GGML_MAX_SRC; ++i) if (op->src[i] && !type_known(op->src[i]->type)) return false;
     if (!type_known(op->type)) return false;
+    // a node without elements is never launched (is_noop): claim it whatever the op.  A prompt ubatch that returns no logits has an empty tail (GET_ROWS of zero output
+    // rows, then ADD / norms / MUL_MATs over 0 columns); handing any of those to the CPU backend splits the graph there, and every CPU split behind a device split costs
+    // a ggml_backend_synchronize of the device (no async copy to the CPU) — which serialised the scheduler's ubatch pipeline over the devices of `-sm layer`
+    if (ggml_is_empty(op)) return true;
     switch (op->op) {
         case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
             return true;
@@ -464,7 +470,10 @@ bool mm_tc_class(const ggml_tensor * n) {
 
 // GGML_B200_NO_TILE_FUSION=1 switches the n-token fusions off (producer -> MUL_MAT tiles, MUL_MAT -> residual ADD epilogue); read per call: the parity harness
 // toggles it between two runs of one process (llama_parity mode 8)
-bool fusion_off() { const char * env = getenv("GGML_B200_NO_TILE_FUSION"); return env && atoi(env) != 0; }
+// (read ONCE per graph_compute into g_fusion_off: a getenv per node costs more host time than the launch it decides about)
+thread_local bool g_fusion_off = false;
+void fusion_refresh() { const char * env = getenv("GGML_B200_NO_TILE_FUSION"); g_fusion_off = env && atoi(env) != 0; }
+inline bool fusion_off() { return g_fusion_off; }
 
 bool is_weight(const ggml_tensor * t);
 int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool allow_fuse = false) {
@@ -767,6 +776,7 @@ int fuse_tiles(BackendCtx * c, const ggml_cgraph * g, int i, int & rc) {
 
 enum ggml_status run_nodes(BackendCtx * c, ggml_cgraph * g) {
     const int nn = ggml_graph_n_nodes(g);
+    fusion_refresh();
     c->scratch_act = nullptr;
     c->hoisted[0] = c->hoisted[1] = nullptr;
     for (int i = 0; i < nn; ) {
@@ -985,7 +995,20 @@ void graph_key_of(const ggml_cgraph * g, GraphKey & key) {
     key.h1 = H.a; key.h2 = H.b; key.n = nn;
 }
 
+enum ggml_status b200_backend_graph_compute_impl(ggml_backend_t backend, ggml_cgraph * g);
+// GGML_B200_HOST_TIMING=1: host time spent inside graph_compute (issuing launches; the GPU runs asynchronously), reported per backend when it is freed
 enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph * g) {
+    static const bool timing = getenv("GGML_B200_HOST_TIMING") && atoi(getenv("GGML_B200_HOST_TIMING")) != 0;
+    if (!timing) return b200_backend_graph_compute_impl(backend, g);
+    BackendCtx * c = (BackendCtx *) backend->context;
+    const auto t0 = std::chrono::steady_clock::now();
+    const enum ggml_status st = b200_backend_graph_compute_impl(backend, g);
+    const long long dt = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    c->host_ns += dt; if (c->host_min_ns == 0 || dt < c->host_min_ns) c->host_min_ns = dt;
+    c->host_calls += 1; c->host_nodes += ggml_graph_n_nodes(g);
+    return st;
+}
+enum ggml_status b200_backend_graph_compute_impl(ggml_backend_t backend, ggml_cgraph * g) {
     BackendCtx * c = (BackendCtx *) backend->context;
     CUDA_OK(cudaSetDevice(c->device));
     const int nn = ggml_graph_n_nodes(g);
@@ -1064,6 +1087,9 @@ const char * b200_backend_get_name(ggml_backend_t backend) { return ((BackendCtx
 
 void b200_backend_free(ggml_backend_t backend) {
     BackendCtx * c = (BackendCtx *) backend->context;
+    if (c->host_calls) B200_LOG("%s: synchronize() called %lld times, host blocked %.3f ms in them", c->name.c_str(), c->sync_calls, c->sync_ns / 1e6);
+    if (c->host_calls) B200_LOG("%s: host time inside graph_compute: %.3f ms over %lld calls (%lld nodes): %.1f us per call (fastest call %.1f us), %.2f us per node", c->name.c_str(), c->host_ns / 1e6,
+                                c->host_calls, c->host_nodes, c->host_ns / 1e3 / c->host_calls, c->host_min_ns / 1e3, c->host_ns / 1e3 / (c->host_nodes ? c->host_nodes : 1));
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -1118,7 +1144,10 @@ bool b200_backend_cpy_tensor_async(ggml_backend_t src_backend, ggml_backend_t ds
 void b200_backend_synchronize(ggml_backend_t backend) {
     BackendCtx * c = (BackendCtx *) backend->context;
     CUDA_OK(cudaSetDevice(c->device));
+    static const bool timing = getenv("GGML_B200_HOST_TIMING") && atoi(getenv("GGML_B200_HOST_TIMING")) != 0;
+    const auto t0 = timing ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point();
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (timing) { c->sync_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); c->sync_calls += 1; }
 }
 
 void b200_backend_event_record(ggml_backend_t backend, ggml_backend_event_t event) {

@@ -645,8 +645,9 @@ static int tc_make_map(CUtensorMap & wmap, const void * w, int type, int64_t m, 
     const cuuint64_t blk = (cuuint64_t) (256 / blck_size(type)) * payload_size(type), rowb = (cuuint64_t) (k / 256) * blk;
     const cuuint64_t gdim[2] = { rowb, (cuuint64_t) m }, gstr[1] = { rowb };
     const cuuint32_t box[2] = { (cuuint32_t) blk, TC_M }, estr[2] = { 1, 1 };
+    static const bool nopromo = getenv("B200_TC_NOPROMO") != nullptr;
     return tc_encoder()(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *) w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                        (getenv("B200_TC_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+                        (nopromo ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
            ? B200_OK : B200_ERR_UNSUPPORTED;
 }
 
@@ -665,7 +666,10 @@ int mmq_tc_multi(int nseg, const void * const * w, const int * type, const int64
     B200_CUDA_TRY(ensure_dyn_smem(k_mmq_tc, TC_SMEM, done));
     if (!tc_encoder() || nseg < 1 || nseg > 3) return B200_ERR_UNSUPPORTED;
     CUtensorMap wmap[3];
-    for (int i = 0; i < 3; ++i) { const int j = i < nseg ? i : 0; if (tc_make_map(wmap[i], w[j], type[j], m[j], k)) return B200_ERR_UNSUPPORTED; }
+    for (int i = 0; i < 3; ++i) {                                           // one encode per weight matrix (~2 us of host time each); unused slots repeat segment 0
+        if (i < nseg) { if (tc_make_map(wmap[i], w[i], type[i], m[i], k)) return B200_ERR_UNSUPPORTED; }
+        else wmap[i] = wmap[0];
+    }
     const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
     if (!reuse_tiles) {
         k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
