@@ -970,11 +970,21 @@ bool match_decoder(const ggml_cgraph * g, DecoderMatch & M) {
 // The properties that decide whether a captured graph can be replayed (what the reference compares in
 // ggml_cuda_graph_update_required / is_cuda_graph_update_required, ggml-cuda.cu:2800-2900): op, addresses, shapes, strides, op params —
 // folded on the fly into two independent 64-bit multiply-xor hashes (no per-token allocation; ~900 nodes x ~50 words per decode graph).
+// Four interleaved lanes per hash: one lane is a chain of dependent 64-bit multiplies (~5 cycles each), and ~50 k words per token made that chain ~70 us of the
+// host's serial per-token time (GGML_B200_HOST_TIMING); word i goes to lane i & 3 (still position-sensitive), the lanes are folded at the end.
 struct KeyHasher {
-    uint64_t a = 0x9e3779b97f4a7c15ull, b = 0xc2b2ae3d27d4eb4full;
+    uint64_t a[4] = { 0x9e3779b97f4a7c15ull, 0xbf58476d1ce4e5b9ull, 0x94d049bb133111ebull, 0x2545f4914f6cdd1dull };
+    uint64_t b[4] = { 0xc2b2ae3d27d4eb4full, 0x165667b19e3779f9ull, 0xd6e8feb86659fd93ull, 0xff51afd7ed558ccdull };
+    unsigned i = 0;
     inline void add(uint64_t v) {
-        a = (a ^ v) * 0x100000001b3ull; a ^= a >> 29;
-        b = (b + v) * 0xff51afd7ed558ccdull; b ^= b >> 32;
+        const unsigned l = i++ & 3;
+        a[l] = (a[l] ^ v) * 0x100000001b3ull; a[l] ^= a[l] >> 29;
+        b[l] = (b[l] + v) * 0xff51afd7ed558ccdull; b[l] ^= b[l] >> 32;
+    }
+    inline uint64_t fold(const uint64_t (&x)[4]) const {
+        uint64_t r = x[0];
+        for (int k = 1; k < 4; ++k) { r = (r ^ x[k]) * 0x9e3779b97f4a7c15ull; r ^= r >> 31; }
+        return r;
     }
 };
 void graph_key_of(const ggml_cgraph * g, GraphKey & key) {
@@ -992,7 +1002,7 @@ void graph_key_of(const ggml_cgraph * g, GraphKey & key) {
         const uint64_t * op64 = (const uint64_t *) n->op_params;
         for (size_t w = 0; w < GGML_MAX_OP_PARAMS / sizeof(uint64_t); ++w) H.add(op64[w]);
     }
-    key.h1 = H.a; key.h2 = H.b; key.n = nn;
+    key.h1 = H.fold(H.a); key.h2 = H.fold(H.b); key.n = nn;
 }
 
 enum ggml_status b200_backend_graph_compute_impl(ggml_backend_t backend, ggml_cgraph * g);
