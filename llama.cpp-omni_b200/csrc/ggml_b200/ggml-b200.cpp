@@ -987,11 +987,14 @@ struct KeyHasher {
         return r;
     }
 };
-void graph_key_of(const ggml_cgraph * g, GraphKey & key) {
+// returns whether the graph is decode-sized (every MUL_MAT has <= 8 activation columns): the same pass over the nodes answers both questions
+bool graph_key_of(const ggml_cgraph * g, GraphKey & key) {
     KeyHasher H;
     const int nn = ggml_graph_n_nodes((ggml_cgraph *) g);
+    bool small = true;
     for (int i = 0; i < nn; ++i) {
         const ggml_tensor * n = ggml_graph_node((ggml_cgraph *) g, i);
+        if (n->op == GGML_OP_MUL_MAT && n->src[1]->ne[1] > 8) small = false;
         H.add((uint64_t) n->op | ((uint64_t) n->type << 32)); H.add((uint64_t) (uintptr_t) n->data); H.add((uint64_t) n->flags);
         for (int d = 0; d < 4; ++d) { H.add((uint64_t) n->ne[d]); H.add((uint64_t) n->nb[d]); }
         for (int s = 0; s < GGML_MAX_SRC; ++s) if (n->src[s]) {
@@ -1003,6 +1006,7 @@ void graph_key_of(const ggml_cgraph * g, GraphKey & key) {
         for (size_t w = 0; w < GGML_MAX_OP_PARAMS / sizeof(uint64_t); ++w) H.add(op64[w]);
     }
     key.h1 = H.fold(H.a); key.h2 = H.fold(H.b); key.n = nn;
+    return small;
 }
 
 enum ggml_status b200_backend_graph_compute_impl(ggml_backend_t backend, ggml_cgraph * g);
@@ -1025,22 +1029,27 @@ enum ggml_status b200_backend_graph_compute_impl(ggml_backend_t backend, ggml_cg
     // Decode-sized graphs (every MUL_MAT has <= 8 columns) are launch-bound: capture them once into a CUDA graph and replay while the
     // node list is unchanged (pointers, shapes and parameters; tensor CONTENTS may change) — like the reference's CUDA-graph path,
     // which is also limited to batch-1 graphs (ggml-cuda.cu:2725-2790).
-    bool small = c->graphs_enabled && nn >= 8;
-    size_t need = 0;
-    for (int i = 0; i < nn && small; ++i) {
-        const ggml_tensor * n = ggml_graph_node(g, i);
-        if (n->op == GGML_OP_MUL_MAT && n->src[1]->ne[1] > 8) small = false;
-        const size_t sb = is_noop(n) ? 0 : node_scratch_bytes(n);
-        if (sb > need) need = sb;
-    }
     // host-overhead probe (profiles/): GGML_B200_NULL_COMPUTE=1 skips every launch of decode-sized graphs (2: of every graph), so `llama-bench -n` / `-p` then times
     // the reference's own host work (graph build, scheduling, the CPU-side token_embd GET_ROWS, input copies, logits read-back) plus this function's bookkeeping
     static const int null_compute = getenv("GGML_B200_NULL_COMPUTE") ? atoi(getenv("GGML_B200_NULL_COMPUTE")) : 0;
-    if (!small) return null_compute >= 2 ? GGML_STATUS_SUCCESS : run_nodes(c, g);
-    scratch_for(c, need);                                            // no allocation may happen while capturing
     GraphKey key;
-    graph_key_of(g, key);
+    const bool small = c->graphs_enabled && nn >= 8 && graph_key_of(g, key);       // one pass: the replay key and "every MUL_MAT has <= 8 columns"
+    if (!small) return null_compute >= 2 ? GGML_STATUS_SUCCESS : run_nodes(c, g);
     if (null_compute) return GGML_STATUS_SUCCESS;
+    // the token after token case first: the same graph as last time on the whole-token engine needs nothing else from the host
+    if (c->engine_enabled && c->engine && key == c->engine_key) {
+        for (int idx : c->engine_pre) { int rc = 0; run_node(c, g, idx, rc); if (rc != B200_OK) return GGML_STATUS_FAILED; }
+        const int rc = b200_decoder_step(c->engine, c->engine_n_kv, c->stream);
+        if (rc != B200_OK) { B200_LOG("decoder step failed: %s", b200_error_string(rc)); return GGML_STATUS_FAILED; }
+        return GGML_STATUS_SUCCESS;
+    }
+    size_t need = 0;
+    for (int i = 0; i < nn; ++i) {
+        const ggml_tensor * n = ggml_graph_node(g, i);
+        const size_t sb = is_noop(n) ? 0 : node_scratch_bytes(n);
+        if (sb > need) need = sb;
+    }
+    scratch_for(c, need);                                            // no allocation may happen while capturing
     auto run_pre = [&](const std::vector<int> & pre) {                // the engine's per-op prefix, re-resolved from THIS graph by node index
         for (int idx : pre) { int rc = 0; run_node(c, g, idx, rc); if (rc != B200_OK) return false; }
         return true;
