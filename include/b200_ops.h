@@ -114,7 +114,7 @@ B200_API int    b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, c
 /* dst = silu(Wg . x) * (Wu . x) for ONE activation column: the gate / up / SWIGLU triple of a decode graph in one launch (quantised or F16 weights; SWIGLU only).
  * B200_ERR_UNSUPPORTED otherwise — the caller keeps MUL_MAT, MUL_MAT, GLU.  scratch >= b200_mul_mat_scratch_bytes(w_gate, x). */
 B200_API int    b200_mul_mat_glu(int glu_op, const b200_tensor * w_gate, const b200_tensor * w_up, const b200_tensor * x, const b200_tensor * dst, void * scratch,
-                                 size_t scratch_bytes, void * stream);
+                                 size_t scratch_bytes, int flags /* B200_MM_REUSE_ACT: the scratch already holds x's q8 record */, void * stream);
 
 /* Decode fast path: y[m] (+= residual) = W[m, k] . act, activations already quantised by b200_quantize_act /
  * a fused producer.  Up to 4 weight matrices that share the same activation run in ONE launch (q/k/v, gate/up).

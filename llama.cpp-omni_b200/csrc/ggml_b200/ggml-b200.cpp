@@ -511,8 +511,8 @@ int run_node(BackendCtx * c, const ggml_cgraph * g, int node_idx, int & rc, bool
                     single_use(g, node_idx, n) && single_use(g, node_idx + 1, n1) && ggml_is_contiguous(n2) && n2->type == GGML_TYPE_F32) {
                     const ggml_tensor * gate = n2->src[0], * up = n2->src[1];
                     b200_tensor wg = view_of(gate->src[0]), wu = view_of(up->src[0]), dg = view_of(n2);
-                    rc = b200_mul_mat_glu((int) ggml_get_glu_op(n2), &wg, &wu, &x, &dg, sc, sb, st);
-                    if (rc != B200_ERR_UNSUPPORTED) return 3;                 // (it quantised x into the scratch itself: the bookkeeping above already says so)
+                    rc = b200_mul_mat_glu((int) ggml_get_glu_op(n2), &wg, &wu, &x, &dg, sc, sb, reuse ? B200_MM_REUSE_ACT : 0, st);
+                    if (rc != B200_ERR_UNSUPPORTED) return 3;                 // (the scratch holds x's q8 record either way: the bookkeeping above already says so)
                 }
                 // MUL_MAT -> ADD (the residual behind wo / ffn_down) -> the matvec's epilogue
                 if (next && next->op == GGML_OP_ADD && (next->src[0] == n || next->src[1] == n) && next->src[0] != next->src[1] && !(n->flags & GGML_TENSOR_FLAG_OUTPUT) &&

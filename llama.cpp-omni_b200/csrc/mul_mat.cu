@@ -249,7 +249,7 @@ extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, co
 // record is built once and b200_matvec_q_swiglu streams both matrices (quantised weights), or k_mmvf16_stream<GLU> (F16 weights).  B200_ERR_UNSUPPORTED for everything
 // else (other GLU ops, several columns, batch dims): the caller keeps its three ops.  Replaces mul_mat_vec_q x 2 + unary_gated_op_kernel (mmvq.cu:139, unary.cu:208-228).
 extern "C" int b200_mul_mat_glu(int glu_op, const b200_tensor * w_gate, const b200_tensor * w_up, const b200_tensor * x, const b200_tensor * dst, void * scratch,
-                                size_t scratch_bytes, void * stream) {
+                                size_t scratch_bytes, int flags, void * stream) {
     if (!w_gate || !w_up || !x || !dst) return B200_ERR_ARG;
     if (glu_op != B200_GLU_SWIGLU || !b200_mul_mat_supported(w_gate, x, dst) || !b200_mul_mat_supported(w_up, x, dst)) return B200_ERR_UNSUPPORTED;
     const int t = w_gate->type;
@@ -258,7 +258,7 @@ extern "C" int b200_mul_mat_glu(int glu_op, const b200_tensor * w_gate, const b2
         w_gate->ne[2] * w_gate->ne[3] != 1 || w_up->ne[2] * w_up->ne[3] != 1 || dst->nb[0] != 4 || m <= 0) return B200_ERR_UNSUPPORTED;
     if (is_quant(t)) {
         if (!scratch || (uintptr_t) scratch % 16 || scratch_bytes < (size_t) act_layout(t, k).bytes || (uintptr_t) x->data % 16) return B200_ERR_UNSUPPORTED;
-        const int rc = b200_quantize_act(t, (const float *) x->data, x->nb[1] / 4, scratch, k, 1, stream);
+        const int rc = (flags & B200_MM_REUSE_ACT) ? B200_OK : b200_quantize_act(t, (const float *) x->data, x->nb[1] / 4, scratch, k, 1, stream);
         if (rc) return rc;
         const b200_matvec_job g = { w_gate->data, t, w_gate->layout, m, w_gate->nb[1], nullptr, nullptr }, u = { w_up->data, t, w_up->layout, m, w_up->nb[1], nullptr, nullptr };
         return b200_matvec_q_swiglu(&g, &u, (float *) dst->data, scratch, k, stream);

@@ -48,7 +48,7 @@ extern "C" int b200_repack_gather(int type, const void * src_planar, void * dst_
 }
 
 // ---- library / device ---------------------------------------------------------------------------------------------------
-extern "C" int b200_abi_version(void) { return 2; }
+extern "C" int b200_abi_version(void) { return 3; }          // 3: round 2 (mul_mat_add / _multi / _glu, unary_param, the Token2Wav ops, ...)
 extern "C" const char * b200_error_string(int code) {
     if (code == B200_OK) return "ok";
     if (code == B200_ERR_UNSUPPORTED) return "b200: unsupported type/shape for this kernel";

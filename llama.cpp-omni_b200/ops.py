@@ -229,7 +229,7 @@ def mul_mat_glu(op: int, w_gate: torch.Tensor, w_up: torch.Tensor, wtype: int, m
     out = torch.empty(list(x.shape[:-1]) + [m], dtype=torch.float32, device=x.device)
     sb = L.b200_mul_mat_scratch_bytes(C.byref(gd), C.byref(xd))
     scratch = torch.empty(max(sb, 16), dtype=torch.uint8, device=x.device)
-    check(L.b200_mul_mat_glu(op, C.byref(gd), C.byref(ud), C.byref(xd), _ref(T(out)), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), stream()))
+    check(L.b200_mul_mat_glu(op, C.byref(gd), C.byref(ud), C.byref(xd), _ref(T(out)), C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch.numel()), 0, stream()))
     return out
 
 

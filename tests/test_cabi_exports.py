@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     extra = [s for s in exported if not s.startswith("b200_")]
     assert not extra, f"non-API symbols leak from the library: {extra[:5]}"
     lib = C.CDLL(str(SO))
-    assert lib.b200_abi_version() == 2
+    assert lib.b200_abi_version() == 3
     lib.b200_error_string.restype = C.c_char_p
     assert b"unsupported" in lib.b200_error_string(-1000)
     lib.b200_act_bytes.restype, lib.b200_act_bytes.argtypes = C.c_size_t, [C.c_int, C.c_int64]
