@@ -69,6 +69,11 @@ def libs():
             "ggml_permute": (P, [P, P, I, I, I, I]), "ggml_cont": (P, [P, P]),
             "ggml_view_3d": (P, [P, P, L, L, L, S, S, S]),
             "ggml_quantize_chunk": (S, [I, P, P, L, L, L, P]),
+            # Token2Wav op set
+            "ggml_sin": (P, [P, P]), "ggml_cos": (P, [P, P]), "ggml_log": (P, [P, P]), "ggml_elu": (P, [P, P]), "ggml_step": (P, [P, P]), "ggml_sgn": (P, [P, P]),
+            "ggml_hardswish": (P, [P, P]), "ggml_hardsigmoid": (P, [P, P]), "ggml_leaky_relu": (P, [P, P, F, C.c_bool]), "ggml_clamp": (P, [P, P, F, F]),
+            "ggml_concat": (P, [P, P, P, I]), "ggml_repeat": (P, [P, P, P]), "ggml_arange": (P, [P, F, F, F]), "ggml_sum_rows": (P, [P, P]),
+            "ggml_pad_ext": (P, [P, P] + [I] * 8), "ggml_pad_reflect_1d": (P, [P, P, I, I]), "ggml_conv_transpose_1d": (P, [P, P, P, I, I, I]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(base, name)
@@ -259,3 +264,64 @@ def pool_1d(x: np.ndarray, op: int, k: int) -> np.ndarray:
     with Graph() as g:
         a = g.tensor(F32, [x.shape[-1], x.size // x.shape[-1]], x)
         return g.run(g.op("ggml_pool_1d", a, op, k, k, 0)).reshape(list(x.shape[:-1]) + [x.shape[-1] // k])
+
+
+# ---- Token2Wav op set: single-op graphs on the reference CPU backend; arrays in numpy order (last axis = ggml dim 0) ------------------------
+def _t(g, a: np.ndarray, t: int = F32):
+    return g.tensor(t, list(a.shape)[::-1], a)
+
+
+def wave_unary(name: str, x: np.ndarray, p0: float = 0.0, p1: float = 0.0) -> np.ndarray:
+    with Graph() as g:
+        a = _t(g, x.astype(np.float32))
+        if name == "leaky_relu":
+            out = g.op("ggml_leaky_relu", a, C.c_float(p0), False)
+        elif name == "clamp":
+            out = g.op("ggml_clamp", a, C.c_float(p0), C.c_float(p1))
+        else:
+            out = g.op("ggml_" + name, a)
+        return g.run(out).reshape(x.shape)
+
+
+def wave_concat(a: np.ndarray, b: np.ndarray, dim: int) -> np.ndarray:
+    with Graph() as g:
+        r = g.run(g.op("ggml_concat", _t(g, a), _t(g, b), dim))
+    return r.reshape(np.concatenate([a, b], axis=a.ndim - 1 - dim).shape)
+
+
+def wave_repeat(a: np.ndarray, reps) -> np.ndarray:
+    shape = [s * r for s, r in zip(a.shape, reps)]
+    with Graph() as g:
+        like = g.tensor(F32, shape[::-1])
+        return g.run(g.op("ggml_repeat", _t(g, a), like)).reshape(shape)
+
+
+def wave_pad(a: np.ndarray, lp_rp8) -> np.ndarray:
+    with Graph() as g:
+        r = g.run(g.op("ggml_pad_ext", _t(g, a), *[int(v) for v in lp_rp8]))
+    ne = list(a.shape)[::-1] + [1] * (4 - a.ndim)
+    out_ne = [ne[d] + lp_rp8[2 * d] + lp_rp8[2 * d + 1] for d in range(4)]
+    return r.reshape(out_ne[::-1][4 - a.ndim:])
+
+
+def wave_pad_reflect_1d(a: np.ndarray, p0: int, p1: int) -> np.ndarray:
+    with Graph() as g:
+        return g.run(g.op("ggml_pad_reflect_1d", _t(g, a), p0, p1)).reshape(list(a.shape[:-1]) + [a.shape[-1] + p0 + p1])
+
+
+def wave_arange(start: float, stop: float, step: float) -> np.ndarray:
+    with Graph() as g:
+        return g.run(g.op("ggml_arange", C.c_float(start), C.c_float(stop), C.c_float(step))).reshape(-1)
+
+
+def wave_sum_rows(a: np.ndarray) -> np.ndarray:
+    with Graph() as g:
+        return g.run(g.op("ggml_sum_rows", _t(g, a))).reshape(list(a.shape[:-1]) + [1])
+
+
+def wave_conv_transpose_1d(w: np.ndarray, x: np.ndarray, s0: int, f16: bool = False) -> np.ndarray:
+    """w [Cin, Cout, K], x [Cin, L] -> [Cout, (L - 1) * s0 + K]"""
+    with Graph() as g:
+        wt = _t(g, w.astype(np.float16), F16) if f16 else _t(g, w.astype(np.float32))
+        r = g.run(g.op("ggml_conv_transpose_1d", wt, _t(g, x.astype(np.float32)), s0, 0, 1))
+    return r.reshape(w.shape[1], (x.shape[-1] - 1) * s0 + w.shape[2])

@@ -139,3 +139,41 @@ def test_make_gguf_llama_arch_loads_in_the_reference(tmp_path):
         r = subprocess.run([str(exe), str(f), "16", "6", "2", "0", "3"], env=dict(env, **extra), capture_output=True, text=True, timeout=300)
         res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
         assert "error" not in res and res["max_rel_logit_err"] <= 5e-3, res
+
+
+def test_wave_ops_match_reference():
+    """The numpy restatements of the Token2Wav op set (tests/oracle_wave.py: the oracle of tests/test_gpu_parity.py::test_wave_*) against the live reference CPU backend."""
+    import oracle_wave as W
+    rng = np.random.default_rng(61)
+    x = (rng.standard_normal((3, 5, 77)) * 3).astype(np.float32)
+    for name in ("sin", "cos", "elu", "step", "sgn", "hardswish", "hardsigmoid"):
+        np.testing.assert_allclose(W.unary(name, x), R.wave_unary(name, x), rtol=2e-6, atol=2e-6, err_msg=name)
+    np.testing.assert_allclose(W.unary("log", np.abs(x) + 0.1), R.wave_unary("log", np.abs(x) + 0.1), rtol=2e-6, atol=2e-6)
+    assert np.array_equal(W.unary("leaky_relu", x, 0.1), R.wave_unary("leaky_relu", x, 0.1))
+    assert np.array_equal(W.unary("clamp", x, -1.5, 2.0), R.wave_unary("clamp", x, -1.5, 2.0))
+    a = rng.standard_normal((3, 4, 5, 11)).astype(np.float32)
+    for dim in range(4):
+        shp = list(a.shape); shp[3 - dim] = 7
+        b = rng.standard_normal(shp).astype(np.float32)
+        assert np.array_equal(W.concat(a, b, dim), R.wave_concat(a, b, dim)), dim
+    for reps in [(1, 1, 1, 2), (2, 1, 3, 1), (2, 2, 2, 2)]:
+        assert np.array_equal(W.repeat(a, reps), R.wave_repeat(a, reps)), reps
+    lr = [1, 2, 3, 4, 0, 1, 2, 0]
+    assert np.array_equal(W.pad(a, lr), R.wave_pad(a, lr))
+    y = rng.standard_normal((2, 80, 300)).astype(np.float32)
+    assert np.array_equal(W.pad_reflect_1d(y, 7, 3), R.wave_pad_reflect_1d(y, 7, 3))
+    assert np.array_equal(W.arange(0.5, 100.25, 0.75), R.wave_arange(0.5, 100.25, 0.75))
+    for shape in [(3, 5, 1000), (2, 33), (1, 4097)]:
+        z = rng.standard_normal(shape).astype(np.float32)
+        assert np.array_equal(W.sum_rows(z), R.wave_sum_rows(z)), shape
+    for (L, Cin, Cout, K, s0, f16) in [(197, 32, 16, 16, 1, False), (3, 2, 3, 2, 3, False), (50, 64, 32, 16, 8, True), (121, 16, 8, 11, 5, False)]:
+        w = rng.standard_normal((Cin, Cout, K)).astype(np.float32)
+        if f16:
+            w = w.astype(np.float16).astype(np.float32)
+        xx = rng.standard_normal((Cin, L)).astype(np.float32)
+        if f16:
+            xx = xx.astype(np.float16).astype(np.float32)                 # the CPU's f16-kernel variant rounds x to f16 too (ops.cpp:5993-5999); F16-exact inputs make both sides agree
+        ref = R.wave_conv_transpose_1d(w, xx, s0, f16)
+        got = W.conv_transpose_1d(w, xx, s0)
+        mag = W.conv_transpose_1d(np.abs(w), np.abs(xx), s0)
+        assert np.all(np.abs(got - ref) <= 2e-6 * mag + 1e-9), (L, Cin, Cout, K, s0)
