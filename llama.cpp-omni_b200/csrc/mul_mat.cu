@@ -2,6 +2,8 @@
 //   quantised W : activations -> q8 records (quant_act.cu) -> mmvq (<= 8 columns per pass)
 //   f32/f16/bf16 W: mmvf-style warp-per-row kernel below (replaces mul_mat_vec_f, ggml-cuda/mmvf.cu); activations are rounded to
 //                   the weight type first exactly like the CPU oracle does (vec_dot_type, ggml-cpu.c:196-350)
+//                   more than 8 columns off the tensor-core path (k not a multiple of 64, F32 x F32 attention products of the omni encoders, F16 activations
+//                   of ggml_conv_1d / conv_2d): k_mm_simt, a shared-memory-tiled F32 GEMM, ONE launch over all batch slices
 // Batch dims follow ggml broadcast rules: w.ne[2] divides x.ne[2], w.ne[3] divides x.ne[3].
 #include "common.cuh"
 #include <type_traits>
@@ -22,6 +24,8 @@ int    mmq_tc_multi(int nseg, const void * const * w, const int * type, const in
 bool   mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t row_stride);
 int    mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st);
 static bool tc_disabled() { static const bool off = getenv("B200_DISABLE_TC") && atoi(getenv("B200_DISABLE_TC")) != 0; return off; }
+// B200_NO_SIMT_GEMM=1: float weights with more than 8 columns off the tensor-core path go back to one k_mmvf launch per 8 columns (A/B switch for k_mm_simt; read per call)
+static bool simt_disabled() { const char * e = getenv("B200_NO_SIMT_GEMM"); return e && atoi(e) != 0; }
 
 template <typename WT> __device__ __forceinline__ float w2f(WT v);
 template <> __device__ __forceinline__ float w2f<float>(float v) { return v; }
@@ -167,20 +171,90 @@ static int run_mmvf(const MmvfArgs & A, cudaStream_t st) {
     return B200_OK;
 }
 
+// dst[m, n] = sum_k W[m, k] . X[n, k] for float weights and MORE than 8 columns when the tcgen05 GEMM does not apply (k not a multiple of 64, unaligned rows, F32 or BF16
+// weights) — the attention products of the omni encoders are exactly that: SigLip's K.Q^T / V.softmax are F32 x F32 with k = 72 or n_pos over 16 heads
+// (tools/omni/vision.cpp:662-668), Whisper's V.softmax has k = 50 . (iter + 1) (tools/omni/audition.cpp:620-624), and ggml_conv_1d / conv_2d multiply an F16 im2col matrix
+// by an F16 kernel (ggml.c: ggml_conv_1d -> ggml_mul_mat(im2col, kernel)), i.e. F16 ACTIVATIONS (XT = __half).  Before this kernel those ran as one k_mmvf launch per 8
+// columns (2048 launches per attention product of a 1024-patch frame).  64 x 64 output tile per CTA, K in steps of 32 through shared memory, 4 x 4 outputs per thread,
+// F32 FMA: the CPU oracle's arithmetic (activations rounded to the weight type = vec_dot_type, F32 accumulation), only the summation order differs.  All batch slices in ONE
+// launch (blockIdx.z), any strides (rows of W and X contiguous).  Replaces the cuBLAS route of ggml_cuda_mul_mat (ggml-cuda.cu:2001-2084, ggml_cuda_op_mul_mat_cublas).
+template <typename WT, typename XT>
+__global__ void __launch_bounds__(256) k_mm_simt(const MmvfArgs A) {
+    constexpr int BM = 64, BN = 64, BK = 32;
+    __shared__ float Ws[BK][BM + 1], Xs[BK][BN + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t) blockIdx.x * BM, n0 = (int64_t) blockIdx.y * BN;
+    const int64_t i2 = blockIdx.z % A.ne2, i3 = blockIdx.z / A.ne2;
+    const char * wb = A.w + (i2 / A.r2) * A.w_nb2 + (i3 / A.r3) * A.w_nb3;
+    const char * xb = A.x + i2 * A.x_nb2 + i3 * A.x_nb3;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int64_t k0 = 0; k0 < A.k; k0 += BK) {
+        // a warp loads 32 consecutive k of one row (coalesced) and stores them down a column of the transposed tile (stride BM + 1: conflict-free)
+#pragma unroll
+        for (int e = 0; e < BM * BK / 256; ++e) {
+            const int idx = e * 256 + tid, r = idx >> 5, kk = idx & 31;
+            const bool kin = k0 + kk < A.k;
+            Ws[kk][r] = kin && m0 + r < A.m ? w2f<WT>(((const WT *) (wb + (m0 + r) * A.w_nb1))[k0 + kk]) : 0.0f;
+            Xs[kk][r] = kin && n0 + r < A.n ? round_like<WT>(w2f<XT>(((const XT *) (xb + (n0 + r) * A.x_nb1))[k0 + kk])) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = Ws[kk][tx + 16 * i]; b[i] = Xs[kk][ty + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    char * yb = A.y + i2 * A.y_nb2 + i3 * A.y_nb3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t c = n0 + ty + 16 * j;
+        if (c >= A.n) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = m0 + tx + 16 * i;
+            if (r < A.m) *(float *) (yb + c * A.y_nb1 + r * 4) = acc[i][j];
+        }
+    }
+}
+
+template <typename WT>
+static int run_mm_simt(const MmvfArgs & A, bool x_f16, cudaStream_t st) {
+    const int64_t nz = A.ne2 * A.ne3, gy = (A.n + 63) / 64;
+    if (nz > 65535 || gy > 65535) return B200_ERR_UNSUPPORTED;
+    const dim3 grid((unsigned) ((A.m + 63) / 64), (unsigned) gy, (unsigned) nz);
+    if (x_f16) k_mm_simt<WT, __half><<<grid, 256, 0, st>>>(A);
+    else       k_mm_simt<WT, float><<<grid, 256, 0, st>>>(A);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 } // namespace b200
 
 using namespace b200;
 
 extern "C" int b200_mul_mat_supported(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst) {
     if (!w || !x || !dst) return 0;
-    if (x->type != B200_F32 || dst->type != B200_F32) return 0;
     const int t = w->type;
     if (!(is_quant(t) || t == B200_F32 || t == B200_F16 || t == B200_BF16)) return 0;
+    // F16 activations: the im2col matrix x kernel product of ggml_conv_1d / conv_2d (F16 x F16 only, as the CPU backend: k_mm_simt reads them in place)
+    const bool x16 = x->type == B200_F16 && t == B200_F16;          // (the only F16-activation product the CPU backend has: src1 type == vec_dot_type)
+    if ((x->type != B200_F32 && !x16) || dst->type != B200_F32) return 0;
     const int64_t k = w->ne[0];
     if (k != x->ne[0] || k % blck_size(t) != 0) return 0;
     if (dst->ne[0] != w->ne[1] || dst->ne[1] != x->ne[1] || dst->ne[2] != x->ne[2] || dst->ne[3] != x->ne[3]) return 0;
     if (w->ne[2] == 0 || w->ne[3] == 0 || x->ne[2] % w->ne[2] != 0 || x->ne[3] % w->ne[3] != 0) return 0;
-    if (w->nb[0] != type_size(t) || x->nb[0] != 4 || dst->nb[0] != 4) return 0;       // rows contiguous
+    if (w->nb[0] != type_size(t) || x->nb[0] != (x16 ? 2 : 4) || dst->nb[0] != 4) return 0;       // rows contiguous
+    if (x16 && (x->ne[2] * x->ne[3] > 65535 || (x->ne[1] + 63) / 64 > 65535)) return 0;
     if (is_quant(t)) {
         if ((uintptr_t) x->data % 16 || x->nb[1] % 16 || x->nb[2] % 16 || x->nb[3] % 16) return 0;
         if (dst->nb[1] % 4) return 0;
@@ -190,7 +264,7 @@ extern "C" int b200_mul_mat_supported(const b200_tensor * w, const b200_tensor *
 }
 
 extern "C" size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x) {
-    if (!is_quant(w->type)) return mm_f16_tc_supported(w->type, w->ne[0], x->ne[1], w->data, w->nb[1]) && (uintptr_t) x->data % 16 == 0 && x->nb[1] % 16 == 0 ?
+    if (!is_quant(w->type)) return x->type == B200_F32 && mm_f16_tc_supported(w->type, w->ne[0], x->ne[1], w->data, w->nb[1]) && (uintptr_t) x->data % 16 == 0 && x->nb[1] % 16 == 0 ?
                                    mmq_tc_scratch_bytes(w->ne[0], x->ne[1]) : 0;
     const size_t act = (size_t) act_layout(w->type, w->ne[0]).bytes * (size_t) (x->ne[1] * x->ne[2] * x->ne[3]);
     // the tensor-core path keeps ONE batch slice of F16 activation tiles in the same scratch
@@ -208,7 +282,7 @@ extern "C" int b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const 
 // it): that combination returns B200_ERR_UNSUPPORTED before anything is launched, and the caller keeps its two separate ops.
 extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, const b200_tensor * residual, const b200_tensor * dst, void * scratch,
                                 size_t scratch_bytes, int flags, void * stream) {
-    if (!residual || !b200_mul_mat_supported(w, x, dst)) return B200_ERR_UNSUPPORTED;
+    if (!residual || !b200_mul_mat_supported(w, x, dst) || x->type != B200_F32) return B200_ERR_UNSUPPORTED;
     if (residual->type != B200_F32 || residual->ne[0] != dst->ne[0] || residual->ne[1] != dst->ne[1] || residual->ne[2] != dst->ne[2] || residual->ne[3] != dst->ne[3]) return B200_ERR_UNSUPPORTED;
     const int t = w->type;
     const int64_t k = w->ne[0], m = w->ne[1], n = x->ne[1];
@@ -251,7 +325,7 @@ extern "C" int b200_mul_mat_add(const b200_tensor * w, const b200_tensor * x, co
 extern "C" int b200_mul_mat_glu(int glu_op, const b200_tensor * w_gate, const b200_tensor * w_up, const b200_tensor * x, const b200_tensor * dst, void * scratch,
                                 size_t scratch_bytes, int flags, void * stream) {
     if (!w_gate || !w_up || !x || !dst) return B200_ERR_ARG;
-    if (glu_op != B200_GLU_SWIGLU || !b200_mul_mat_supported(w_gate, x, dst) || !b200_mul_mat_supported(w_up, x, dst)) return B200_ERR_UNSUPPORTED;
+    if (glu_op != B200_GLU_SWIGLU || x->type != B200_F32 || !b200_mul_mat_supported(w_gate, x, dst) || !b200_mul_mat_supported(w_up, x, dst)) return B200_ERR_UNSUPPORTED;
     const int t = w_gate->type;
     const int64_t k = w_gate->ne[0], m = w_gate->ne[1];
     if (w_up->type != t || w_up->ne[1] != m || w_up->layout != w_gate->layout || w_up->nb[1] != w_gate->nb[1] || x->ne[1] != 1 || x->ne[2] * x->ne[3] != 1 ||
@@ -288,6 +362,7 @@ extern "C" int b200_mul_mat_multi(int n_mat, const b200_tensor * const * w, cons
                                   int flags, void * stream) {
     if (n_mat < 1 || n_mat > 3 || !w || !x || !dst) return B200_ERR_ARG;
     for (int i = 0; i < n_mat; ++i) if (!b200_mul_mat_supported(w[i], x, dst[i])) return B200_ERR_UNSUPPORTED;
+    if (x->type != B200_F32) return B200_ERR_UNSUPPORTED;
     const int64_t k = x->ne[0], n = x->ne[1];
     bool merge = n_mat > 1 && !tc_disabled() && !multi_disabled() && x->ne[2] * x->ne[3] == 1 && scratch && (uintptr_t) scratch % 16 == 0 && n > 0;
     int type[3]; int64_t m[3], ld[3]; const void * wp[3]; float * dp[3];
@@ -315,7 +390,11 @@ extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, con
     const int64_t r2 = x->ne[2] / w->ne[2], r3 = x->ne[3] / w->ne[3];
     if (!is_quant(t)) {
         // F16 weights, more than 8 columns: TMA-fed tcgen05 GEMM (mmq_tc.cu k_mm_f16_tc), one launch per batch slice
-        if (!tc_disabled() && mm_f16_tc_supported(t, k, n, w->data, w->nb[1]) && scratch && (uintptr_t) scratch % 16 == 0 &&
+        const bool x16 = x->type == B200_F16;
+        // many SMALL batch slices (attention products per head: Whisper's K.Q^T is 16 heads x [T x 50 x 64]) are launch-bound on the per-slice tensor-core route
+        // (tile conversion + GEMM launch per slice): below ~50 MFLOP per slice the one-launch SIMT GEMM is faster
+        const bool small_slices = x->ne[2] * x->ne[3] > 1 && 2.0 * (double) m * (double) n * (double) k < 5e7 && !simt_disabled() && x->ne[2] * x->ne[3] <= 65535;
+        if (!x16 && !small_slices && !tc_disabled() && mm_f16_tc_supported(t, k, n, w->data, w->nb[1]) && scratch && (uintptr_t) scratch % 16 == 0 &&
             scratch_bytes >= mmq_tc_scratch_bytes(k, n) && (uintptr_t) x->data % 16 == 0 && x->nb[1] % 16 == 0 && x->nb[2] % 16 == 0 && x->nb[3] % 16 == 0 &&
             w->nb[2] % 16 == 0 && w->nb[3] % 16 == 0 && dst->nb[1] % 4 == 0) {
             for (int64_t i3 = 0; i3 < x->ne[3]; ++i3) for (int64_t i2 = 0; i2 < x->ne[2]; ++i2) {
@@ -330,6 +409,12 @@ extern "C" int b200_mul_mat_ex(const b200_tensor * w, const b200_tensor * x, con
         MmvfArgs A = { (const char *) w->data, (const char *) x->data, (char *) dst->data, m, k, n,
                        w->nb[1], w->nb[2], w->nb[3], x->nb[1], x->nb[2], x->nb[3], dst->nb[1], dst->nb[2], dst->nb[3],
                        dst->ne[2], dst->ne[3], r2, r3 };
+        // more than 8 columns (or F16 activations): the tiled GEMM, one launch over all batch slices; up to 8 columns: the warp-per-row matvec
+        if (x16 || (n > 8 && !simt_disabled() && dst->ne[2] * dst->ne[3] <= 65535 && (n + 63) / 64 <= 65535)) {
+            if (t == B200_F32)  return run_mm_simt<float>(A, x16, st);
+            if (t == B200_F16)  return run_mm_simt<__half>(A, x16, st);
+            return run_mm_simt<__nv_bfloat16>(A, x16, st);
+        }
         if (t == B200_F32)  return run_mmvf<float>(A, st);
         if (t == B200_F16)  return run_mmvf<__half>(A, st);
         return run_mmvf<__nv_bfloat16>(A, st);

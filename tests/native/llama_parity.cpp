@@ -17,7 +17,7 @@
 #include <thread>
 #include <vector>
 
-struct Run { std::vector<llama_token> toks; std::vector<std::vector<float>> logits; double tg_ms = 0, pp_ms = 0; bool ok = false; };
+struct Run { std::vector<llama_token> toks; std::vector<std::vector<float>> logits, hidden; double tg_ms = 0, pp_ms = 0; bool ok = false; };
 
 static Run run(const char * path, int ngl, int n_prompt, int n_gen, int n_threads, int fa, const std::vector<llama_token> * force, bool repack, bool incremental = false) {
     Run r;
@@ -39,13 +39,26 @@ static Run run(const char * path, int ngl, int n_prompt, int n_gen, int n_thread
     llama_context * ctx = llama_init_from_model(model, cp);
     if (!ctx) { fprintf(stderr, "context failed\n"); llama_model_free(model); return r; }
     const int n_vocab = llama_vocab_n_tokens(llama_model_get_vocab(model));
+    // PARITY_EMBEDDINGS=1: omni's stream_decode pattern (tools/omni/omni.cpp:889-916, eval_id_with_hidden): llama_set_embeddings(ctx, true) around every llama_decode, so
+    // the graph also outputs result_norm (src/llama-model.cpp:9395-9396) and the caller reads the hidden state next to the logits (the TTS input)
+    const bool want_hidden = getenv("PARITY_EMBEDDINGS") && atoi(getenv("PARITY_EMBEDDINGS")) != 0;
+    const int n_embd = llama_model_n_embd(model);
+    auto decode = [&](llama_batch b) {
+        if (want_hidden) llama_set_embeddings(ctx, true);
+        const int rc = llama_decode(ctx, b);
+        if (want_hidden) {
+            if (rc == 0) { const float * e = llama_get_embeddings_ith(ctx, -1); if (e) r.hidden.emplace_back(e, e + n_embd); }
+            llama_set_embeddings(ctx, false);
+        }
+        return rc;
+    };
     std::vector<llama_token> prompt(n_prompt);
     uint32_t s = 12345;
     for (auto & t : prompt) { s = s * 1664525u + 1013904223u; t = (llama_token) ((s >> 8) % (uint32_t) n_vocab); }
     auto t0 = std::chrono::steady_clock::now();
     if (incremental) {                                                  // the same prompt one token at a time (n = 1 graphs only)
-        for (int i = 0; i < n_prompt; ++i) if (llama_decode(ctx, llama_batch_get_one(&prompt[i], 1))) { fprintf(stderr, "prefill failed\n"); return r; }
-    } else if (llama_decode(ctx, llama_batch_get_one(prompt.data(), n_prompt))) { fprintf(stderr, "prefill failed\n"); return r; }
+        for (int i = 0; i < n_prompt; ++i) if (decode(llama_batch_get_one(&prompt[i], 1))) { fprintf(stderr, "prefill failed\n"); return r; }
+    } else if (decode(llama_batch_get_one(prompt.data(), n_prompt))) { fprintf(stderr, "prefill failed\n"); return r; }
     const float * lg = llama_get_logits_ith(ctx, -1);
     r.logits.emplace_back(lg, lg + n_vocab);
     // PARITY_KSHIFT=1: omni's sliding window (tools/omni/omni.cpp:686-820): drop a quarter of the prompt behind the first token and shift the rest down; the next
@@ -65,7 +78,7 @@ static Run run(const char * path, int ngl, int n_prompt, int n_gen, int n_thread
         r.toks.push_back(best);
         // teacher forcing on the second run keeps the two runs on the same sequence even after a (reported) mismatch
         llama_token feed = force && i < (int) force->size() ? (*force)[i] : best;
-        if (llama_decode(ctx, llama_batch_get_one(&feed, 1))) { fprintf(stderr, "decode failed\n"); return r; }
+        if (decode(llama_batch_get_one(&feed, 1))) { fprintf(stderr, "decode failed\n"); return r; }
         lg = llama_get_logits_ith(ctx, -1);
         r.logits.emplace_back(lg, lg + n_vocab);
     }
@@ -134,9 +147,20 @@ int main(int argc, char ** argv) {
         if (i == 0 && self_mode == 6) max_rel = std::fmax(max_rel, rel);   // decode-only mode: the prompt's last logits come from n = 1 graphs too
         if (i >= 1 && i <= 6) step_rel[i - 1] = rel;
     }
+    // hidden states (PARITY_EMBEDDINGS=1): one per llama_decode on both sides, compared relative to each vector's largest magnitude
+    double hid_rel = -1;
+    if (!cpu.hidden.empty() && cpu.hidden.size() == gpu.hidden.size()) {
+        hid_rel = 0;
+        for (size_t i = 0; i < cpu.hidden.size(); ++i) {
+            double mx = 0, err = 0;
+            for (size_t v = 0; v < cpu.hidden[i].size(); ++v) { mx = std::fmax(mx, std::fabs(cpu.hidden[i][v])); err = std::fmax(err, std::fabs(cpu.hidden[i][v] - gpu.hidden[i][v])); }
+            hid_rel = std::fmax(hid_rel, err / (mx > 0 ? mx : 1));
+        }
+        printf("{\"hidden_states\": %zu, \"max_rel_hidden_err\": %.3g}\n", cpu.hidden.size(), hid_rel);
+    } else if (cpu.hidden.size() != gpu.hidden.size()) { printf("{\"error\": \"hidden state count differs: %zu vs %zu\"}\n", cpu.hidden.size(), gpu.hidden.size()); return 4; }
     printf("{\"tokens_equal\": %s, \"n_prompt\": %d, \"n_gen\": %d, \"first_mismatch\": %d, \"max_rel_logit_err\": %.3g, \"prefill_rel_err\": %.3g, "
            "\"decode_step_rel_err\": [%.2g, %.2g, %.2g, %.2g, %.2g, %.2g], \"cpu_tg_tok_s\": %.2f, \"gpu_tg_tok_s\": %.2f, \"cpu_pp_tok_s\": %.1f, \"gpu_pp_tok_s\": %.1f, \"threads\": %d, \"flash_attn\": %d, \"mode\": %d}\n",
            first < 0 ? "true" : "false", n_prompt, n_gen, first, max_rel, pre_rel, step_rel[0], step_rel[1], step_rel[2], step_rel[3], step_rel[4], step_rel[5], n_gen * 1e3 / cpu.tg_ms, n_gen * 1e3 / gpu.tg_ms,
            n_prompt * 1e3 / cpu.pp_ms, n_prompt * 1e3 / gpu.pp_ms, nt, fa, self_mode);
-    return first < 0 && max_rel <= 1e-3 ? 0 : 1;
+    return first < 0 && max_rel <= 1e-3 && hid_rel <= 1e-3 ? 0 : 1;
 }

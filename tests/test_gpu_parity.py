@@ -7,6 +7,7 @@ MUL_MAT: the integer sub-block dot products are exact, only the order of the fin
 float ops within the tolerance written in each test.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -347,6 +348,47 @@ def test_mul_mat_f16_weights_tensor_core(ops, m, k, n, batch):
     ref = (xr @ wt.double().T).cpu().numpy()
     mag = (np.abs(x.reshape(-1, k)) @ np.abs(w.astype(np.float32)).T).reshape(ref.shape)
     assert np.all(np.abs(got - ref) <= 2e-6 * mag + 1e-9), (np.abs(got - ref) / (mag + 1e-30)).max()
+
+
+@pytest.mark.parametrize("wdt,xdt,m,k,n,wb,xb", [
+    ("f32", "f32", 1024, 72, 1024, (1, 16), (1, 16)),      # SigLip K.Q^T: F32 x F32, k = d_head = 72, one slice per head (vision.cpp:662)
+    ("f32", "f32", 72, 1000, 333, (1, 4), (1, 4)),         # V.softmax: m = d_head, k = n_pos
+    ("f16", "f32", 64, 150, 50, (1, 16), (1, 16)),         # Whisper V.softmax over the F16 encoder cache, k = 50 . (iter + 1) (audition.cpp:620)
+    ("f16", "f32", 300, 64, 50, (1, 16), (1, 16)),         # Whisper K.Q^T: tensor-core eligible but 16 small slices -> the one-launch route
+    ("f16", "f16", 100, 240, 1024, (1, 1), (1, 1)),        # ggml_conv_1d: im2col [IC . K, OL] F16 x kernel [IC . K, OC] F16 (conv1 of the Whisper encoder)
+    ("f16", "f16", 1024, 588, 1152, (1, 1), (1, 1)),       # ggml_conv_2d patch embedding: 3 . 14 . 14 = 588
+    ("f16", "f16", 3, 33, 5, (2, 1), (2, 3)),              # F16 activations with <= 8 columns, broadcast over dim 3
+    ("bf16", "f32", 65, 100, 9, (1, 1), (2, 2)),           # ragged everything, 2-D weight broadcast over both batch dims
+    ("f32", "f32", 129, 31, 65, (3, 2), (3, 2))])
+def test_mul_mat_float_weights_many_columns_simt(ops, wdt, xdt, m, k, n, wb, xb):
+    """Float weights, more than 8 columns, off the tcgen05 route (k % 64 != 0, F32 / BF16 weights, F16 activations, many small slices) -> k_mm_simt: ONE launch over all
+    batch slices.  Arithmetic = the CPU oracle's: activations rounded to the weight type (vec_dot_type), products accumulated in F32.  `wb` / `xb` = (ne3, ne2) of W / x."""
+    rng = np.random.default_rng(m * 7 + k * 3 + n)
+    tdt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+    w = torch.from_numpy((rng.standard_normal(wb + (m, k)) * 0.05).astype(np.float32)).cuda().to(tdt[wdt])
+    x = torch.from_numpy(rng.standard_normal(xb + (n, k)).astype(np.float32)).cuda().to(tdt[xdt])
+    got = ops.mul_mat(w, {"f32": ops.F32, "f16": ops.F16, "bf16": ops.BF16}[wdt], m, k, x, w_ne=[k, m, wb[1], wb[0]],
+                      w_nb=[w.element_size(), k * w.element_size(), m * k * w.element_size(), wb[1] * m * k * w.element_size()]).cpu().numpy()
+    xr = x.to(tdt[wdt]).double()
+    wd = w.double()
+    ref = torch.empty(xb + (n, m), dtype=torch.float64)
+    mag = torch.empty_like(ref)
+    for i3 in range(xb[0]):
+        for i2 in range(xb[1]):
+            ws = wd[i3 // (xb[0] // wb[0]), i2 // (xb[1] // wb[1])]
+            ref[i3, i2] = (xr[i3, i2] @ ws.T).cpu()
+            mag[i3, i2] = (xr[i3, i2].abs() @ ws.abs().T).cpu()
+    assert got.shape == tuple(ref.shape)
+    assert np.all(np.abs(got - ref.numpy()) <= 2e-6 * mag.numpy() + 1e-9), float((np.abs(got - ref.numpy()) / (mag.numpy() + 1e-30)).max())
+    # the A/B switch: one k_mmvf launch per 8 columns gives the same numbers up to the summation order (F32 activations only: k_mmvf reads F32)
+    if xdt == "f32":
+        os.environ["B200_NO_SIMT_GEMM"] = "1"
+        try:
+            old = ops.mul_mat(w, {"f32": ops.F32, "f16": ops.F16, "bf16": ops.BF16}[wdt], m, k, x, w_ne=[k, m, wb[1], wb[0]],
+                              w_nb=[w.element_size(), k * w.element_size(), m * k * w.element_size(), wb[1] * m * k * w.element_size()]).cpu().numpy()
+        finally:
+            del os.environ["B200_NO_SIMT_GEMM"]
+        assert np.all(np.abs(got - old) <= 4e-6 * mag.numpy() + 1e-9)
 
 
 def test_matvec_jobs_residual_swiglu(ops):

@@ -198,3 +198,26 @@ def test_prefill_tile_fusion_is_bit_identical(small_model):
     r = _parity(small_model, 200, 8, os.cpu_count() or 4, 1, 8)
     assert "error" not in r, r
     assert r["tokens_equal"] and r["prefill_rel_err"] == 0 and r["max_rel_logit_err"] == 0, r
+
+
+def _parity_all(model, *args, **env):
+    r = subprocess.run([str(REF / "bin" / "llama_parity"), str(model), *map(str, args)], env=_env(**env), capture_output=True, text=True, timeout=900)
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, (r.stdout + r.stderr)[-2000:]
+    return lines
+
+
+def test_omni_stream_decode_pattern_returns_hidden_states(f16_model, small_model):
+    """omni's stream_decode (tools/omni/omni.cpp:889-916, eval_id_with_hidden): llama_set_embeddings(ctx, true) around every llama_decode, so that the graph outputs
+    result_norm (src/llama-model.cpp:9395-9396) next to the logits and the TTS thread gets the hidden state of every token (PARITY_EMBEDDINGS=1 in llama_parity).
+      * F16 model, CPU vs plugin, prompt token by token (mode 6, -fa 0): hidden states within the F16 bar of the logits test above;
+      * Q4_K_M model, plugin per-op route vs the whole-token decode engine (mode 5), whose last phase writes `hidden_out` (csrc/stream_decode.cu): the hidden states of
+        the two routes must agree as well as their logits do (a mis-wired hidden_out would be off by O(1))."""
+    threads = os.cpu_count() or 4
+    hid, main = _parity_all(f16_model, 24, 16, threads, 0, 6, PARITY_EMBEDDINGS="1")[-2:]
+    assert "error" not in main and "error" not in hid, (hid, main)
+    assert hid["hidden_states"] == 24 + 16 and hid["max_rel_hidden_err"] <= 2e-3 and main["tokens_equal"] and main["max_rel_logit_err"] <= 2e-3, (hid, main)
+    hid, main = _parity_all(small_model, 24, 16, threads, 1, 5, PARITY_EMBEDDINGS="1")[-2:]
+    assert "error" not in main and "error" not in hid, (hid, main)
+    assert hid["hidden_states"] == 1 + 16 and main["prefill_rel_err"] == 0, (hid, main)
+    assert hid["max_rel_hidden_err"] <= 10.0 * main["max_rel_logit_err"] + 1e-2, (hid, main)           # same order as the logits; garbage would be >= 1
