@@ -323,7 +323,8 @@ __device__ __forceinline__ void tc_produce_tile(uint32_t raw_row, uint32_t raw_s
 // ---------------------------------------------------------------------------------------------------------------- activations -> F16 tiles
 // X F32 [n, k] (row stride x_ld elements) -> x16 tiles in the canonical UMMA layout; rows n .. n_pad-1 are zero.  8 consecutive threads
 // write one 128-byte core matrix.
-__global__ void __launch_bounds__(256) k_x_to_f16_tiles(const float * __restrict__ x, int64_t x_ld, uint8_t * __restrict__ x16, int64_t n, int64_t n_pad, int64_t k) {
+// k = the K extent of the tile layout (a multiple of 64), k_real <= k = the columns x has (a multiple of 8): chunks past k_real are zero
+__global__ void __launch_bounds__(256) k_x_to_f16_tiles(const float * __restrict__ x, int64_t x_ld, uint8_t * __restrict__ x16, int64_t n, int64_t n_pad, int64_t k, int64_t k_real) {
     const int64_t id = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t k8n = k >> 3;
     if (id >= n_pad * k8n) return;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(256) k_x_to_f16_tiles(const float * __restrict
     const int64_t k8 = (id >> 3) % k8n, ng = (id >> 3) / k8n;
     const int64_t row = ng * 8 + r;
     uint4 out = make_uint4(0, 0, 0, 0);
-    if (row < n) {
+    if (row < n && k8 * 8 < k_real) {
         const float4 a = __ldg((const float4 *) (x + row * x_ld + k8 * 8)), b = __ldg((const float4 *) (x + row * x_ld + k8 * 8 + 4));
         __half2 h[4] = { __floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w) };
         out = *(const uint4 *) h;
@@ -626,7 +627,7 @@ static int tc_splitk(int tiles_m, int64_t n, int64_t units) {
 }
 // will mmq_tc carry a residual in its epilogue for this shape?  (not under split-K: three addends would not commute)
 bool mmq_tc_fuses_resid(int64_t m, int64_t k, int64_t n) { return tc_splitk((int) ((m + TC_M - 1) / TC_M), n, k / 256) == 1; }
-size_t mmq_tc_scratch_bytes(int64_t k, int64_t n) { return (size_t) ((n + TC_N - 1) / TC_N * TC_N) * (size_t) k * 2; }
+size_t mmq_tc_scratch_bytes(int64_t k, int64_t n) { return (size_t) ((n + TC_N - 1) / TC_N * TC_N) * (size_t) ((k + TC_K - 1) / TC_K * TC_K) * 2; }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
 typedef CUresult (*tc_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -672,7 +673,7 @@ int mmq_tc_multi(int nseg, const void * const * w, const int * type, const int64
     }
     const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
     if (!reuse_tiles) {
-        k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
+        k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k, k);
         B200_LAUNCH_CHECK();
     }
     TcArgs A = {};
@@ -710,7 +711,9 @@ int mmq_tc(const void * w, int type, int64_t m, int64_t k, const float * x, int6
 }
 
 bool mm_f16_tc_supported(int type, int64_t k, int64_t n, const void * w, int64_t row_stride) {
-    return type == B200_F16 && n > 8 && k % 64 == 0 && (uintptr_t) w % 16 == 0 && row_stride == k * 2;
+    // k need not be a multiple of the 64-wide K tile (SigLip's ffn_down has k = 4304): the weight tile's tail is zero-filled by TMA (the tensor map knows the real k), the
+    // activation tiles' tail by k_x_to_f16_tiles; rows must still be 16-byte multiples for the tensor map's global stride
+    return type == B200_F16 && n > 8 && k >= 8 && k % 8 == 0 && (uintptr_t) w % 16 == 0 && row_stride == k * 2;
 }
 
 int mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_ld, int64_t n, float * dst, int64_t dst_ld, void * scratch, bool reuse_tiles, cudaStream_t st) {
@@ -724,15 +727,18 @@ int mm_f16_tc(const void * w, int64_t m, int64_t k, const float * x, int64_t x_l
         if (tc_encoder()(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B200_ERR_UNSUPPORTED;
     }
-    const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k >> 3);
+    const int64_t k_pad = (k + TC_K - 1) / TC_K * TC_K, kt = k_pad / TC_K;
+    const int64_t n_pad = (n + TC_N - 1) / TC_N * TC_N, threads = n_pad * (k_pad >> 3);
     if (!reuse_tiles) {
-        k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k);
+        k_x_to_f16_tiles<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(x, x_ld, (uint8_t *) scratch, n, n_pad, k_pad, k);
         B200_LAUNCH_CHECK();
     }
     TcF16Args A = {};
-    A.x16 = (const uint8_t *) scratch; A.dst = dst; A.dst_ld = dst_ld; A.m = m; A.k = k; A.n = n;
+    A.x16 = (const uint8_t *) scratch; A.dst = dst; A.dst_ld = dst_ld; A.m = m; A.k = k_pad; A.n = n;
     A.tiles_m = (int) ((m + TC_M - 1) / TC_M);
-    A.splitk = tc_splitk(A.tiles_m, n, k / 128);
+    // split-K halves the K TILES between two CTAs: only an even tile count splits (k / 128 used to round an odd count down — k = 576 has 9 tiles — and the second
+    // CTA would have stopped one tile short)
+    A.splitk = tc_splitk(A.tiles_m, n, kt % 2 == 0 ? kt / 2 : 1);
     A.nsub = tc_nsub(A.tiles_m * A.splitk, n); A.tiles_n = (int) ((n + TC_N / A.nsub - 1) / (TC_N / A.nsub));
     if (A.splitk > 1) B200_CUDA_TRY(cudaMemset2DAsync(dst, (size_t) dst_ld * 4, 0, (size_t) m * 4, (size_t) n, st));
     int grid = A.tiles_m * A.tiles_n * A.splitk; if (grid > sm_count()) grid = sm_count();
