@@ -81,12 +81,14 @@ B200_API int    b200_quantize_act(int weight_type, const float * x, int64_t x_co
 
 /* ---- MUL_MAT (replaces ggml_cuda_mul_mat ggml-cuda.cu:2001-2084: mmvq.cu mul_mat_vec_q for n <= 8, mmq.cu mul_mat_q
  *      beyond; oracle: ggml_compute_forward_mul_mat ggml-cpu.c:1210-1402) ------------------------------------------------
- * dst[m, n] (F32) = W[m, k] (any supported type) . X[n, k]^T (F32), batched over ne[2], ne[3] with ggml broadcast rules.
+ * dst[m, n] (F32) = W[m, k] (any supported type) . X[n, k]^T (F32; F16 when W is F16 — the im2col x kernel product of ggml_conv_1d / conv_2d, the one
+ * F16-activation MUL_MAT the CPU backend has), batched over ne[2], ne[3] with ggml broadcast rules.
  * `scratch` must hold b200_mul_mat_scratch_bytes(...) bytes (activation records / tile buffers).
  * Routing: n <= 8 columns -> dequant-in-register matvec on q8_K / q8_0 activation records (the CPU oracle's integer arithmetic);
  *          n >  8 columns, q4_K / q5_K native or q6_K / q8_0 / q4_0 planar, k % 256 == 0 -> tcgen05 dequant-GEMM k_mmq_tc (csrc/mmq_tc.cu:
- *          F16 operands, F32 accumulation in TMEM); F16 weights, n > 8, k % 64 == 0 -> k_mm_f16_tc (TMA-fed tcgen05 GEMM);
- *          everything else -> column-chunked matvec / warp-per-row float kernel. */
+ *          F16 operands, F32 accumulation in TMEM); F16 weights, n > 8, k % 8 == 0 -> k_mm_f16_tc (TMA-fed tcgen05 GEMM; a K tail is zero-filled);
+ *          other float-weight products with n > 8 (F32 x F32, BF16, unaligned rows), many small batch slices, F16 activations -> k_mm_simt (tiled F32 GEMM,
+ *          one launch over all batch slices; replaces the cuBLAS routes of ggml_cuda_mul_mat); everything else -> column-chunked matvec / warp-per-row float kernel. */
 B200_API int    b200_mul_mat_supported(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst);
 B200_API size_t b200_mul_mat_scratch_bytes(const b200_tensor * w, const b200_tensor * x);
 B200_API int    b200_mul_mat(const b200_tensor * w, const b200_tensor * x, const b200_tensor * dst, void * scratch,
