@@ -62,3 +62,42 @@ def test_q4_k_m_recipe_and_bytes_per_token():
         assert cover == list(range(cfg.n_layer))
         total = sum(dec.weight_bytes_per_token(cfg, range(r * per, min(cfg.n_layer, (r + 1) * per)), with_head=(r == world - 1)) for r in range(world))
         assert total == 4_671_134_848
+
+
+@pytest.mark.skipif(not SO.exists(), reason="libb200ops.so not built (run __graft_entry__.build())")
+def test_mul_mat_routing_predicates_for_float_operands():
+    """b200_mul_mat_supported / b200_mul_mat_scratch_bytes are host-only predicates (the plugin's supports_op calls them on tensors without buffers,
+    llama-model.cpp:286-291), so they can be pinned without a GPU: F16 ACTIVATIONS only together with F16 weights (ggml_conv_1d / conv_2d: im2col x kernel — the
+    one F16 x F16 product the reference CPU backend has, ggml-cpu.c type_traits_cpu[F16].vec_dot_type), and the F16 tensor-core GEMM's tile scratch rounds K up to its 64-wide
+    tile (SigLip ffn_down: k = 4304)."""
+    ops = load_package().ops
+    L = ops.lib()
+
+    def desc(type_, ne, elem, nb0=None):
+        d = ops.Tensor()
+        d.data, d.type, d.layout = 0x10000000, type_, ops.LAYOUT_NATIVE
+        ne = list(ne) + [1] * (4 - len(ne))
+        nb = [nb0 or elem, (nb0 or elem) * ne[0]]
+        nb += [nb[1] * ne[1], nb[1] * ne[1] * ne[2]]
+        for i in range(4):
+            d.ne[i], d.nb[i] = ne[i], nb[i]
+        return d
+
+    sup = lambda w, x, y: L.b200_mul_mat_supported(C.byref(w), C.byref(x), C.byref(y))
+    L.b200_mul_mat_scratch_bytes.restype = C.c_size_t
+    # conv1 of the Whisper encoder: im2col [240, 100] F16 x kernel [240, 1024] F16 -> [100, 1024] F32
+    w16, x16, y = desc(ops.F16, [240, 100], 2), desc(ops.F16, [240, 1024], 2), desc(ops.F32, [100, 1024], 4)
+    assert sup(w16, x16, y)
+    assert L.b200_mul_mat_scratch_bytes(C.byref(w16), C.byref(x16)) == 0                              # k_mm_simt reads F16 activations in place
+    assert not sup(desc(ops.F32, [240, 100], 4), x16, y)                                             # F32 x F16: not a product the CPU backend has
+    assert not sup(desc(ops.BF16, [240, 100], 2), x16, y)
+    assert not sup(w16, desc(ops.F16, [240, 1024], 2, nb0=4), y)                                     # activation rows must be contiguous
+    assert not sup(w16, desc(ops.F16, [248, 1024], 2), y)                                            # k mismatch
+    # the F16 tensor-core GEMM: k = 4304 (67.25 K tiles) -> tiles for 68, n padded to 256 columns
+    w, x = desc(ops.F16, [4304, 1152], 2), desc(ops.F32, [4304, 1000], 4)
+    assert sup(w, x, desc(ops.F32, [1152, 1000], 4))
+    assert L.b200_mul_mat_scratch_bytes(C.byref(w), C.byref(x)) == 1024 * 4352 * 2
+    # k = 72 F32 x F32 (SigLip K.Q^T per head): supported, no scratch (k_mm_simt), batch dims broadcast
+    wk, xq = desc(ops.F32, [72, 1024, 16], 4), desc(ops.F32, [72, 1024, 16], 4)
+    assert sup(wk, xq, desc(ops.F32, [1024, 1024, 16], 4)) and L.b200_mul_mat_scratch_bytes(C.byref(wk), C.byref(xq)) == 0
+    assert not sup(wk, desc(ops.F32, [72, 1024, 24], 4), desc(ops.F32, [1024, 1024, 24], 4))        # 24 % 16 != 0: not a ggml broadcast
