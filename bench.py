@@ -75,6 +75,52 @@ def llama_bench(plugin: bool, n_gen: int, depth: int, threads: int, reps: int = 
     return {"tok_s": float(r["avg_ts"]), "ms": 1e3 / float(r["avg_ts"]), "backends": r.get("backends"), "n_gen": n_gen, "depth": depth, "reps": reps}
 
 
+OMNI_BIN = ROOT / "oracle" / "_ref" / "bin" / "omni_encoders"
+
+
+def omni_encoders_leg(threads: int) -> dict:
+    """BASELINE.json configs[3], the encoder half ("APM 1 s audio chunk + VPM frame"): the reference's UNMODIFIED tools/omni/audition.cpp and vision.cpp
+    (oracle/_ref/bin/omni_encoders = tests/native/omni_encoders.cpp around them) on full-size synthetic Whisper / SigLip GGUFs (tools/make_omni_gguf.py), the reference CPU
+    backend and the plugin in ONE process: milliseconds per 1 s chunk / per 448 x 448 frame on both, and how far the plugin's embeddings are from the CPU backend's.  The first
+    chunk / frame (first-launch costs) is left out of the medians.  An extra object of the JSON line; never the headline metric."""
+    if not OMNI_BIN.exists() or not PLUGIN.exists():
+        return {"unavailable": "oracle/_ref/bin/omni_encoders or the plugin is not built"}
+    tmpdir = Path(os.environ.get("TMPDIR", "/tmp"))
+    files, makers = {}, []
+    for what, size in (("apm", 600_000_000), ("vpm", 1_000_000_000)):
+        f = files[what] = tmpdir / f"b200_bench_omni_{what}.gguf"
+        if not f.exists() or f.stat().st_size < size:
+            tmp = f.with_suffix(".tmp")
+            makers.append((subprocess.Popen([sys.executable, str(ROOT / "tools" / "make_omni_gguf.py"), what, str(tmp)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), tmp, f))
+    for proc, tmp, f in makers:
+        if proc.wait(timeout=600) != 0:
+            return {"error": f"tools/make_omni_gguf.py failed for {f.name}"}
+        tmp.rename(f)
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = f"{ROOT / 'oracle' / '_ref' / 'lib'}:{PLUGIN.parent}:" + env.get("LD_LIBRARY_PATH", "")
+    env["GGML_BACKEND_PATH"] = str(PLUGIN)
+    med = lambda v: sorted(v)[len(v) // 2]
+    out = {"path": "oracle/_ref/bin/omni_encoders: audition_audio_encode / vision_image_encode of the unmodified reference, use_gpu = false (ggml CPU backend, "
+                   f"{threads} threads) vs use_gpu = true (libggml-b200.so through GGML_BACKEND_PATH) in one process; synthetic F16 GGUFs; medians without the first call"}
+    for key, what, n in (("apm_1s_audio_chunk", "apm", 9), ("vpm_448x448_frame", "vpm", 3)):
+        r = subprocess.run([str(OMNI_BIN), what, str(files[what]), str(n), str(threads)], env=env, capture_output=True, text=True, timeout=600)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            out[key] = {"error": (r.stderr or r.stdout)[-300:]}
+            continue
+        res = json.loads(lines[-1])
+        if "error" in res:
+            out[key] = res
+            continue
+        on_plugin = "devices:" in r.stderr and "B200" in r.stderr.split("devices:")[-1].splitlines()[0]
+        if not on_plugin:                                    # (no GPU-type device: the harness's second side fell back to the CPU backend — not a plugin number)
+            out[key] = {"error": "no B200 device was registered in the harness process", "reference_cpu_ms": round(med(res["ms_cpu"][1:]), 3)}
+            continue
+        out[key] = {"ms": round(med(res["ms_gpu"][1:]), 3), "reference_cpu_ms": round(med(res["ms_cpu"][1:]), 3), "calls": n, "max_rel_err_vs_cpu": res["max_rel_err"],
+                    "nmse_vs_cpu": res["nmse"], "non_finite": res["non_finite"]}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -401,6 +447,11 @@ def run_b200(args) -> None:
             else:
                 r = reference_layer_sample(cfg, 1, threads, 3, 1)
                 line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tok/s", "cores": threads, "kind": "reference", "sample": r["sample"]}
+        if world == 1 and not args.tiny and not args.no_encoders:
+            try:
+                line["omni_encoders"] = omni_encoders_leg(min(os.cpu_count() or 1, 16))
+            except Exception as e:                           # the line must still be printed
+                line["omni_encoders"] = {"error": str(e)[:300]}
         print(json.dumps(line))
     if hop is not None:
         hop.close()
@@ -455,6 +506,7 @@ def main() -> None:
     ap.add_argument("--per-op", action="store_true", help="one launch per (fused) op instead of the persistent decode engine")
     ap.add_argument("--hop", default="peer", choices=["peer", "nccl"], help="N > 1: how the hidden state crosses a stage boundary")
     ap.add_argument("--no-plugin-e2e", action="store_true", help="e2e through the C-ABI only (skip the llama-bench + plugin leg)")
+    ap.add_argument("--no-encoders", action="store_true", help="skip the omni-encoder leg (the extra `omni_encoders` object: APM 1 s chunk / VPM frame, BASELINE.json configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
