@@ -30,6 +30,15 @@ SMALL = {"apm": ["--layers", "2", "--d-model", "256", "--heads", "4", "--proj", 
 _CACHE = {}
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _remove_the_ggufs_afterwards():
+    yield
+    import shutil
+    for f in _CACHE.values():
+        shutil.rmtree(f.parent, ignore_errors=True)
+    _CACHE.clear()
+
+
 def _gguf(tmp_path, what, full=False):
     """one file per (encoder, size) and session: the full-size ones are 0.7 / 1.1 GB"""
     if (what, full) not in _CACHE:
