@@ -93,7 +93,7 @@ def omni_encoders_leg(threads: int) -> dict:
             tmp = f.with_suffix(".tmp")
             makers.append((subprocess.Popen([sys.executable, str(ROOT / "tools" / "make_omni_gguf.py"), what, str(tmp)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), tmp, f))
     for proc, tmp, f in makers:
-        if proc.wait(timeout=600) != 0:
+        if proc.wait(timeout=240) != 0:
             return {"error": f"tools/make_omni_gguf.py failed for {f.name}"}
         tmp.rename(f)
     env = dict(os.environ)
@@ -103,7 +103,7 @@ def omni_encoders_leg(threads: int) -> dict:
     out = {"path": "oracle/_ref/bin/omni_encoders: audition_audio_encode / vision_image_encode of the unmodified reference, use_gpu = false (ggml CPU backend, "
                    f"{threads} threads) vs use_gpu = true (libggml-b200.so through GGML_BACKEND_PATH) in one process; synthetic F16 GGUFs; medians without the first call"}
     for key, what, n in (("apm_1s_audio_chunk", "apm", 9), ("vpm_448x448_frame", "vpm", 3)):
-        r = subprocess.run([str(OMNI_BIN), what, str(files[what]), str(n), str(threads)], env=env, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([str(OMNI_BIN), what, str(files[what]), str(n), str(threads)], env=env, capture_output=True, text=True, timeout=180)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode != 0 or not lines:
             out[key] = {"error": (r.stderr or r.stdout)[-300:]}
