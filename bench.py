@@ -86,12 +86,16 @@ def omni_encoders_leg(threads: int) -> dict:
     if not OMNI_BIN.exists() or not PLUGIN.exists():
         return {"unavailable": "oracle/_ref/bin/omni_encoders or the plugin is not built"}
     tmpdir = Path(os.environ.get("TMPDIR", "/tmp"))
+    # B200_BENCH_OMNI_SMALL=1: 2-layer encoders (plumbing checks of this leg on a box without a GPU: tests/test_cabi_exports.py); never a bench number
+    small = os.environ.get("B200_BENCH_OMNI_SMALL") == "1"
+    shrink = {"apm": ["--layers", "2", "--d-model", "256", "--heads", "4", "--proj", "512"], "vpm": ["--layers", "2", "--embd", "288", "--heads", "4", "--ff", "512", "--proj", "512"]}
     files, makers = {}, []
     for what, size in (("apm", 600_000_000), ("vpm", 1_000_000_000)):
-        f = files[what] = tmpdir / f"b200_bench_omni_{what}.gguf"
-        if not f.exists() or f.stat().st_size < size:
+        f = files[what] = tmpdir / f"b200_bench_omni_{what}{'_small' if small else ''}.gguf"
+        if not f.exists() or f.stat().st_size < (1_000_000 if small else size):
             tmp = f.with_suffix(".tmp")
-            makers.append((subprocess.Popen([sys.executable, str(ROOT / "tools" / "make_omni_gguf.py"), what, str(tmp)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), tmp, f))
+            makers.append((subprocess.Popen([sys.executable, str(ROOT / "tools" / "make_omni_gguf.py"), what, str(tmp)] + (shrink[what] if small else []),
+                                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), tmp, f))
     for proc, tmp, f in makers:
         if proc.wait(timeout=240) != 0:
             return {"error": f"tools/make_omni_gguf.py failed for {f.name}"}

@@ -101,3 +101,15 @@ def test_mul_mat_routing_predicates_for_float_operands():
     wk, xq = desc(ops.F32, [72, 1024, 16], 4), desc(ops.F32, [72, 1024, 16], 4)
     assert sup(wk, xq, desc(ops.F32, [1024, 1024, 16], 4)) and L.b200_mul_mat_scratch_bytes(C.byref(wk), C.byref(xq)) == 0
     assert not sup(wk, desc(ops.F32, [72, 1024, 24], 4), desc(ops.F32, [1024, 1024, 24], 4))        # 24 % 16 != 0: not a ggml broadcast
+
+
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "bin" / "omni_encoders").exists() or not SO.exists(), reason="oracle/_ref/bin/omni_encoders is not built")
+def test_bench_encoder_leg_never_reports_a_cpu_number_as_the_plugin(monkeypatch, tmp_path):
+    """bench.py's `omni_encoders` object (BASELINE.json configs[3], encoder half): on a box without a GPU the harness's second side falls back to the reference CPU backend —
+    the leg must then say so instead of printing that time as the plugin's (plumbing check with 2-layer encoders)."""
+    import bench
+    monkeypatch.setenv("B200_BENCH_OMNI_SMALL", "1")
+    monkeypatch.setenv("TMPDIR", str(tmp_path))
+    r = bench.omni_encoders_leg(2)
+    for key in ("apm_1s_audio_chunk", "vpm_448x448_frame"):
+        assert "ms" not in r[key] and "no B200 device" in r[key]["error"] and r[key]["reference_cpu_ms"] > 0, r
